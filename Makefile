@@ -1,0 +1,29 @@
+# Builds everything in-tree:
+#   openmmgridforce_b200/lib/libgridforce_b200.so   — CUDA kernels + C ABI (sm_100a only)
+#   openmmgridforce_b200/lib/libOpenMMGridForceB200.so — OpenMM platform plugin (see openmmgridforce_b200/plugin)
+#   oracle/…                                        — test-only parity oracles (see oracle/Makefile)
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Iinclude -Iopenmmgridforce_b200/csrc
+LIBDIR    := openmmgridforce_b200/lib
+CSRC      := openmmgridforce_b200/csrc
+
+all: lib oracle
+
+lib: $(LIBDIR)/libgridforce_b200.so
+
+$(LIBDIR)/libgridforce_b200.so: $(CSRC)/gf_capi.cu $(CSRC)/gf_kernels.cuh $(CSRC)/gf_params.h include/gridforce_b200.h
+	mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/gf_capi.cu
+
+ptxas-info:
+	$(NVCC) $(NVFLAGS) -Xptxas -v -cubin -o /tmp/gf_capi.cubin $(CSRC)/gf_capi.cu
+
+oracle:
+	$(MAKE) -C oracle all
+
+clean:
+	rm -f $(LIBDIR)/*.so
+	$(MAKE) -C oracle clean
+
+.PHONY: all lib oracle clean ptxas-info

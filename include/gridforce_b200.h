@@ -1,0 +1,172 @@
+/* gridforce_b200.h — C ABI of libgridforce_b200.so, the B200 (sm_100a) GridForce evaluation path.
+ *
+ * This is the drop-in boundary. Everything above it (the OpenMM platform plugin in
+ * openmmgridforce_b200/plugin, a SWIG/cgo/ctypes binding, bench.py) talks to the device only through
+ * these entry points: plain pointers and sizes, opaque handles, no C++/torch/OpenMM types.
+ * Every function returns 0 on success or a negative gfb_status; gfb_last_error() gives the text
+ * (thread-local). There is NO CPU fallback: without a usable CUDA device every compute call fails.
+ *
+ * Each entry point names the reference interface it stands in for (paths relative to the reference
+ * tree jimtufts/openmmgridforce).
+ *
+ * Units follow OpenMM: nm, kJ/mol, kJ/mol/nm. Grid values are x-major with z fastest,
+ * idx = (ix*ny + iy)*nz + iz (openmmapi/include/GridData.h:96-98).
+ */
+#ifndef GRIDFORCE_B200_H_
+#define GRIDFORCE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GFB_API __attribute__((visibility("default")))
+#else
+#define GFB_API
+#endif
+
+#define GFB_VERSION 100          /* 0.1.0 */
+#define GFB_MAX_GRIDS 8          /* grids fused into one launch (a System rarely has more than ele/LJr/LJa) */
+
+typedef enum {
+    GFB_OK = 0,
+    GFB_ERR_INVALID = -1,        /* bad argument (message says which) */
+    GFB_ERR_CUDA = -2,           /* CUDA runtime/driver error, incl. "no device" */
+    GFB_ERR_UNSUPPORTED = -3,    /* feature of the reference outside this path (interp method 1-3, tiled mode...) */
+    GFB_ERR_NOMEM = -4
+} gfb_status;
+
+/* Arithmetic mode — OpenMM's "mixed"/"double" precision property (CudaPlatform "Precision").
+ *   MIXED : grid corners stored FP32 (32-byte cell = one L2 sector), index/fraction math FP64 (bit-exact
+ *           cell index), interpolation FP32, energy and force accumulation FP64 / 64-bit fixed point.
+ *   DOUBLE: corners stored FP64 (64-byte cell), everything FP64. */
+typedef enum { GFB_PRECISION_MIXED = 0, GFB_PRECISION_DOUBLE = 1 } gfb_precision;
+
+/* How execute writes forces.
+ *   GFB_FORCE_F64_STORE : double [n_replicas][n_particles][3], plain stores (entries of particles this
+ *                         kernel does not touch are left alone) — ReferencePlatform::PlatformData::forces
+ *                         layout (ReferenceGridForceKernels.cpp:139-142).
+ *   GFB_FORCE_F64_ADD   : same layout, atomically accumulated (forceData[i] -= ..., :1082).
+ *   GFB_FORCE_FIXED_ADD : OpenMM CUDA long-force buffer: unsigned 64-bit, component-planar
+ *                         [3][padded_atoms], value = (long long)(f * 2^32), atomically accumulated
+ *                         (platforms/cuda/src/kernels/gridForce.cu:487-499). padded_atoms is
+ *                         n_replicas*n_particles rounded up to `force_stride` given at execute. */
+typedef enum { GFB_FORCE_F64_STORE = 0, GFB_FORCE_F64_ADD = 1, GFB_FORCE_FIXED_ADD = 2 } gfb_force_mode;
+
+typedef struct gfb_device gfb_device;   /* one GPU: ordinal, default stream, staging buffers */
+typedef struct gfb_grid gfb_grid;       /* one grid, repacked cell-major and resident in HBM */
+typedef struct gfb_kernel gfb_kernel;   /* state of a CalcGridForceKernel after initialize() */
+
+typedef struct {
+    char name[128];
+    int cc_major, cc_minor;
+    int sm_count;
+    int l2_bytes;
+    size_t total_mem_bytes;
+} gfb_device_props;
+
+/* Per-atom classification record (debug/parity): the bit-exact contract of
+ * ReferenceGridForceKernels.cpp:690-696 (inside test) and :708-710 (cell index). */
+typedef struct {
+    int32_t inside;      /* 1 if 0 <= p-origin <= spacing*(counts-1) on all axes (upper face inclusive) */
+    int32_t cell[3];     /* (ix,iy,iz), or -1,-1,-1 when the restraint branch is taken */
+} gfb_class;
+
+GFB_API int gfb_version(void);
+GFB_API const char* gfb_last_error(void);
+GFB_API int gfb_device_count(int* count);
+
+/* Opens GPU `ordinal` (cudaSetDevice + a non-blocking stream). Fails with GFB_ERR_CUDA when there is no
+ * device or it is not compute capability 10.x — the library carries sm_100a code only.
+ * Stands in for CudaPlatform context creation (cu.setAsCurrent(), CudaGridForceKernels.cpp:70). */
+GFB_API int gfb_device_open(int ordinal, gfb_device** out);
+GFB_API int gfb_device_close(gfb_device* dev);
+GFB_API int gfb_device_get_props(gfb_device* dev, gfb_device_props* props);
+GFB_API int gfb_device_synchronize(gfb_device* dev);
+
+/* Uploads one grid and repacks it on the device into cell-major form: cell (ix,iy,iz) holds its 8 corner
+ * values {v000,v001,v010,v011,v100,v101,v110,v111} (last index = z) contiguously, 32 B (MIXED) or 64 B
+ * (DOUBLE), so an atom's whole stencil is one aligned vector load.
+ * Replaces GridForce::getGridParameters (openmmapi/src/GridForce.cpp:355-363) + the CUDA platform's
+ * float upload (CudaGridForceKernels.cpp:482-486). `vals` is a HOST pointer to counts[0]*counts[1]*counts[2]
+ * doubles. counts >= 2 on every axis. */
+GFB_API int gfb_grid_create(gfb_device* dev, const int counts[3], const double spacing[3], const double origin[3],
+                            const double* vals, size_t n_vals, int precision, gfb_grid** out);
+/* Same, from a DEVICE pointer to doubles (x-major); stream-ordered on the device's stream. */
+GFB_API int gfb_grid_create_from_device(gfb_device* dev, const int counts[3], const double spacing[3],
+                                        const double origin[3], const double* d_vals, size_t n_vals,
+                                        int precision, gfb_grid** out);
+GFB_API int gfb_grid_destroy(gfb_grid* grid);
+GFB_API size_t gfb_grid_device_bytes(const gfb_grid* grid);
+
+/* Builds the evaluation state for n_grids GridForces that act on the same atoms — what
+ * CalcGridForceKernel::initialize(System, GridForce) captures (ReferenceGridForceKernels.cpp:147-160),
+ * for several forces at once so that one launch evaluates all of them (ele + LJr + LJa).
+ *   n_atoms    atoms evaluated per replica (the reference's g_scaling_factors.size(), quirk Q6)
+ *   scaling    host [n_grids][n_atoms] (GridForce::addScalingFactor order)
+ *   particles  host [n_atoms] particle index of each atom inside a replica, or NULL for identity
+ *              (GridForce::setLigandAtoms / setParticles). Forces are written at the PARTICLE index
+ *              (what the CUDA platform does, gridForce.cu:497; the Reference platform writes at the
+ *              ordinal, :1082 — identical when particles == NULL).
+ *   inv_power  host [n_grids] or NULL (all 0 = off). > 0: v <- pow(v, n) with the chain rule (:1057-1080).
+ *   oob_k      host [n_grids] out-of-grid restraint constants (GridForce::getOutOfBoundsRestraint).
+ * All grids must have been created on `dev` with the same precision. */
+GFB_API int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int n_atoms,
+                              const double* scaling, const int* particles, const double* inv_power,
+                              const double* oob_k, gfb_kernel** out);
+GFB_API int gfb_kernel_destroy(gfb_kernel* k);
+/* CalcGridForceKernel::copyParametersToContext (ReferenceGridForceKernels.cpp:1123-1127): new scaling
+ * factors [n_grids][n_atoms] and inv_power [n_grids] (NULL = keep). */
+GFB_API int gfb_kernel_update_parameters(gfb_kernel* k, const double* scaling, const double* inv_power);
+
+/* CalcGridForceKernel::execute for host-resident data (Reference-platform style), batched over replicas.
+ *   pos       host [n_replicas][n_particles][3] doubles (std::vector<Vec3> layout)
+ *   energies  host out [n_replicas] (sum over grids) or NULL
+ *   grid_energies host out [n_replicas][n_grids] or NULL
+ *   forces    host [n_replicas][n_particles][3]; force_mode STORE overwrites the evaluated particles'
+ *             entries with the total grid force, ADD adds to what is there. NULL = energy only.
+ * Synchronous: returns after the results are in the host buffers. H2D/D2H go through pinned staging. */
+GFB_API int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, const double* pos,
+                                    double* energies, double* grid_energies, double* forces, int force_mode);
+
+/* CalcGridForceKernel::execute for device-resident data (CUDA-platform style): enqueues ONE kernel on
+ * `stream` (a cudaStream_t; NULL = the device's own stream) and returns without synchronising.
+ *   d_pos          device [n_replicas][n_particles][3] doubles
+ *   d_energies     device [n_replicas] doubles, ACCUMULATED into (caller zeroes), or NULL
+ *   d_grid_energies device [n_replicas][n_grids], accumulated, or NULL
+ *   d_forces       device buffer in the layout `force_mode` names, or NULL
+ *   force_stride   FIXED_ADD only: padded atom count (>= n_replicas*n_particles) = plane stride
+ *   d_order        device [n_replicas*n_atoms] evaluation order (from gfb_kernel_sort_atoms) or NULL */
+GFB_API int gfb_kernel_execute_device(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos,
+                                      double* d_energies, double* d_grid_energies, void* d_forces,
+                                      int force_mode, long long force_stride, const int* d_order, void* stream);
+
+/* Morton order of the atoms by the grid cell they sit in (grid 0), so neighbouring lanes read neighbouring
+ * sectors. Positions move less than a cell per MD step, so the order is reused for many steps.
+ * d_order: device out [n_replicas*n_atoms]. Stream-ordered. */
+GFB_API int gfb_kernel_sort_atoms(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos,
+                                  int* d_order, void* stream);
+
+/* Runs only the classification stage on the device (same device function the evaluation uses) for grid
+ * `grid_index`: host out cls [n_replicas*n_atoms]. Used by the bit-exact index parity tests. */
+GFB_API int gfb_kernel_classify_host(gfb_kernel* k, int grid_index, int n_replicas, int n_particles,
+                                     const double* pos, gfb_class* cls);
+
+/* Converts an OpenMM-style fixed-point force buffer to doubles [n][3] on the device (stream-ordered). */
+GFB_API int gfb_forces_fixed_to_f64(gfb_device* dev, const void* d_fixed, long long force_stride, long long n,
+                                    double* d_out, void* stream);
+
+/* Number of kernels this library has launched on any device since load (bench.py's gpu_launches). */
+GFB_API unsigned long long gfb_launch_count(void);
+
+/* Microbenchmark used for the roofline denominator: random 32-byte-sector gather over `bytes` of device
+ * memory (n_loads loads per launch, `reps` launches, CUDA-event timed). Returns GB/s through *gbs. */
+GFB_API int gfb_bench_sector_gather(gfb_device* dev, size_t bytes, long long n_loads, int reps, double* gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRIDFORCE_B200_H_ */

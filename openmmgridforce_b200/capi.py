@@ -1,0 +1,244 @@
+"""ctypes binding of include/gridforce_b200.h (one Python method per C entry point).
+
+Mirrors what a SWIG/cgo/JNI stub over the same header would do; see INTEGRATION.md for the SWIG form the
+reference's python/gridforceplugin.i would carry. numpy arrays are passed as raw host pointers, torch CUDA
+tensors as raw device pointers (``tensor.data_ptr()``): no torch type crosses the boundary.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+PRECISION_MIXED = 0
+PRECISION_DOUBLE = 1
+FORCE_F64_STORE = 0
+FORCE_F64_ADD = 1
+FORCE_FIXED_ADD = 2
+MAX_GRIDS = 8
+
+_LIB = None
+
+
+class GridForceB200Error(RuntimeError):
+    """Raised for every non-zero status from the C ABI (the reference maps OpenMMException to RuntimeError
+    the same way, python/gridforceplugin.i:49-59)."""
+
+
+class _Props(C.Structure):
+    _fields_ = [("name", C.c_char * 128), ("cc_major", C.c_int), ("cc_minor", C.c_int), ("sm_count", C.c_int),
+                ("l2_bytes", C.c_int), ("total_mem_bytes", C.c_size_t)]
+
+
+CLASS_DTYPE = np.dtype([("inside", np.int32), ("cell", np.int32, (3,))])
+
+# name -> (restype, argtypes); must list every GFB_API symbol of include/gridforce_b200.h
+_vp, _i, _ll, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_size_t
+_pi, _pd = C.POINTER(C.c_int), C.POINTER(C.c_double)
+SIGNATURES = {
+    "gfb_version": (_i, []),
+    "gfb_last_error": (C.c_char_p, []),
+    "gfb_device_count": (_i, [_pi]),
+    "gfb_device_open": (_i, [_i, C.POINTER(_vp)]),
+    "gfb_device_close": (_i, [_vp]),
+    "gfb_device_get_props": (_i, [_vp, C.POINTER(_Props)]),
+    "gfb_device_synchronize": (_i, [_vp]),
+    "gfb_grid_create": (_i, [_vp, _pi, _pd, _pd, _vp, _sz, _i, C.POINTER(_vp)]),
+    "gfb_grid_create_from_device": (_i, [_vp, _pi, _pd, _pd, _vp, _sz, _i, C.POINTER(_vp)]),
+    "gfb_grid_destroy": (_i, [_vp]),
+    "gfb_grid_device_bytes": (_sz, [_vp]),
+    "gfb_kernel_create": (_i, [_vp, _i, C.POINTER(_vp), _i, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "gfb_kernel_destroy": (_i, [_vp]),
+    "gfb_kernel_update_parameters": (_i, [_vp, _vp, _vp]),
+    "gfb_kernel_execute_host": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i]),
+    "gfb_kernel_execute_device": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _ll, _vp, _vp]),
+    "gfb_kernel_sort_atoms": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "gfb_kernel_classify_host": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "gfb_forces_fixed_to_f64": (_i, [_vp, _vp, _ll, _ll, _vp, _vp]),
+    "gfb_launch_count": (C.c_ulonglong, []),
+    "gfb_bench_sector_gather": (_i, [_vp, _sz, _ll, _i, _pd]),
+}
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgridforce_b200.so")
+
+
+def load_library():
+    """dlopen the in-tree CUDA library. There is deliberately no fallback."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise GridForceB200Error(
+                f"{path} is missing: build it with `make lib` (or __graft_entry__.build()); "
+                "there is no CPU/PyTorch fallback for the GridForce path")
+        lib = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise GridForceB200Error(load_library().gfb_last_error().decode() or f"gridforce_b200 status {rc}")
+
+
+def launch_count():
+    return int(load_library().gfb_launch_count())
+
+
+def _host_f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _ptr(a):
+    """Raw pointer of a numpy array / int address / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Device:
+    """gfb_device: one GPU."""
+
+    def __init__(self, ordinal=0):
+        self._h = C.c_void_p()
+        self.ordinal = ordinal
+        _check(load_library().gfb_device_open(ordinal, C.byref(self._h)))
+
+    @staticmethod
+    def count():
+        n = C.c_int(0)
+        _check(load_library().gfb_device_count(C.byref(n)))
+        return n.value
+
+    def props(self):
+        p = _Props()
+        _check(load_library().gfb_device_get_props(self._h, C.byref(p)))
+        return {"name": p.name.decode(), "cc": (p.cc_major, p.cc_minor), "sm_count": p.sm_count,
+                "l2_bytes": p.l2_bytes, "total_mem_bytes": p.total_mem_bytes}
+
+    def synchronize(self):
+        _check(load_library().gfb_device_synchronize(self._h))
+
+    def bench_sector_gather(self, nbytes, n_loads, reps=10):
+        out = C.c_double(0.0)
+        _check(load_library().gfb_bench_sector_gather(self._h, nbytes, n_loads, reps, C.byref(out)))
+        return out.value
+
+    def fixed_to_f64(self, d_fixed, stride, n, d_out, stream=0):
+        _check(load_library().gfb_forces_fixed_to_f64(self._h, _ptr(d_fixed), stride, n, _ptr(d_out), _ptr(stream or None)))
+
+    def close(self):
+        if self._h:
+            load_library().gfb_device_close(self._h)
+            self._h = C.c_void_p()
+
+
+class Grid:
+    """gfb_grid: counts/spacing/origin + values (x-major, z fastest), repacked cell-major on the GPU."""
+
+    def __init__(self, device, counts, spacing, origin, values, precision=PRECISION_MIXED, device_ptr=None):
+        self.device = device
+        self.counts = tuple(int(c) for c in counts)
+        self.spacing = tuple(float(s) for s in spacing)
+        self.origin = tuple(float(o) for o in origin)
+        self.precision = precision
+        self._h = C.c_void_p()
+        cn = (C.c_int * 3)(*self.counts)
+        sp = (C.c_double * 3)(*self.spacing)
+        og = (C.c_double * 3)(*self.origin)
+        lib = load_library()
+        if device_ptr is not None:
+            n = int(np.prod(self.counts))
+            _check(lib.gfb_grid_create_from_device(device._h, cn, sp, og, C.c_void_p(device_ptr), n, precision, C.byref(self._h)))
+        else:
+            v = _host_f64(values).ravel()
+            _check(lib.gfb_grid_create(device._h, cn, sp, og, _ptr(v), v.size, precision, C.byref(self._h)))
+
+    @property
+    def device_bytes(self):
+        return int(load_library().gfb_grid_device_bytes(self._h))
+
+    def close(self):
+        if self._h:
+            load_library().gfb_grid_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class Kernel:
+    """gfb_kernel: the state CalcGridForceKernel::initialize captures, for G grids acting on the same atoms."""
+
+    def __init__(self, device, grids, scaling, particles=None, inv_power=None, oob_k=None):
+        self.device = device
+        self.grids = list(grids)
+        g = len(self.grids)
+        sc = _host_f64(scaling)
+        if sc.ndim == 1:
+            sc = sc.reshape(1, -1)
+        if sc.shape[0] != g:
+            raise GridForceB200Error(f"scaling has {sc.shape[0]} rows for {g} grids")
+        self.n_grids = g
+        self.n_atoms = sc.shape[1]
+        self._scaling = sc
+        ok = _host_f64(oob_k if oob_k is not None else [10000.0] * g).ravel()  # GridForce.cpp:52 default
+        ip = _host_f64(inv_power).ravel() if inv_power is not None else None
+        pa = np.ascontiguousarray(particles, dtype=np.int32) if particles is not None else None
+        handles = (C.c_void_p * g)(*[gr._h for gr in self.grids])
+        self._h = C.c_void_p()
+        _check(load_library().gfb_kernel_create(device._h, g, handles, self.n_atoms, _ptr(sc), _ptr(pa), _ptr(ip), _ptr(ok),
+                                                C.byref(self._h)))
+
+    def update_parameters(self, scaling=None, inv_power=None):
+        sc = _host_f64(scaling).reshape(self.n_grids, self.n_atoms) if scaling is not None else None
+        ip = _host_f64(inv_power).ravel() if inv_power is not None else None
+        _check(load_library().gfb_kernel_update_parameters(self._h, _ptr(sc), _ptr(ip)))
+
+    def execute_host(self, pos, forces=None, force_mode=FORCE_F64_STORE, want_forces=True, want_grid_energies=False,
+                     energies_out=None):
+        """pos: [R, P, 3] (or [P, 3]) float64. Returns (energies[R], forces[R,P,3] or None, grid_energies or None)."""
+        pos = np.asarray(pos)
+        if pos.dtype != np.float64 or not pos.flags.c_contiguous:
+            pos = _host_f64(pos)
+        if pos.ndim == 2:
+            pos = pos.reshape(1, *pos.shape)
+        r, p, _ = pos.shape
+        en = energies_out if energies_out is not None else np.empty(r, dtype=np.float64)
+        ge = np.empty((r, self.n_grids), dtype=np.float64) if want_grid_energies else None
+        if forces is None and want_forces:
+            forces = np.zeros((r, p, 3), dtype=np.float64)
+        _check(load_library().gfb_kernel_execute_host(self._h, r, p, _ptr(pos), _ptr(en), _ptr(ge), _ptr(forces), force_mode))
+        return en, forces, ge
+
+    def execute_device(self, n_replicas, n_particles, d_pos, d_energies=None, d_grid_energies=None, d_forces=None,
+                       force_mode=FORCE_FIXED_ADD, force_stride=0, d_order=None, stream=0):
+        """All d_* are integer device addresses (e.g. torch_tensor.data_ptr()); stream is a cudaStream_t value."""
+        _check(load_library().gfb_kernel_execute_device(self._h, n_replicas, n_particles, _ptr(d_pos), _ptr(d_energies),
+                                                        _ptr(d_grid_energies), _ptr(d_forces), force_mode, force_stride,
+                                                        _ptr(d_order), _ptr(stream or None)))
+
+    def sort_atoms(self, n_replicas, n_particles, d_pos, d_order, stream=0):
+        _check(load_library().gfb_kernel_sort_atoms(self._h, n_replicas, n_particles, _ptr(d_pos), _ptr(d_order),
+                                                    _ptr(stream or None)))
+
+    def classify_host(self, pos, grid_index=0):
+        pos = _host_f64(pos)
+        if pos.ndim == 2:
+            pos = pos.reshape(1, *pos.shape)
+        r, p, _ = pos.shape
+        out = np.empty(r * self.n_atoms, dtype=CLASS_DTYPE)
+        _check(load_library().gfb_kernel_classify_host(self._h, grid_index, r, p, _ptr(pos), _ptr(out)))
+        return out
+
+    def close(self):
+        if self._h:
+            load_library().gfb_kernel_destroy(self._h)
+            self._h = C.c_void_p()

@@ -1,0 +1,718 @@
+// C ABI of libgridforce_b200.so (include/gridforce_b200.h): handles, uploads, launches.
+// Host logic only — every number is produced by the kernels in gf_kernels.cuh. No CPU fallback.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "gf_kernels.cuh"
+#include "gridforce_b200.h"
+
+using namespace gfb;
+
+// ---------------------------------------------------------------------------------------------
+// Errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_error;
+static std::atomic<unsigned long long> g_launches(0);
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t err__ = (expr);                                                                         \
+        if (err__ != cudaSuccess)                                                                           \
+            return fail(GFB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Handles
+// ---------------------------------------------------------------------------------------------
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return GFB_OK;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4;
+        CUDA_TRY(cudaMalloc(&ptr, want));
+        cap = want;
+        return GFB_OK;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinnedBuffer {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return GFB_OK;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4;
+        CUDA_TRY(cudaHostAlloc(&ptr, want, cudaHostAllocDefault));
+        cap = want;
+        return GFB_OK;
+    }
+    void release() {
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+struct gfb_device {
+    int ordinal;
+    cudaStream_t stream;
+    cudaStream_t copy_stream;   // D2H of chunk i overlaps the kernel of chunk i+1
+    cudaDeviceProp prop;
+};
+
+struct gfb_grid {
+    gfb_device* dev;
+    int counts[3];
+    double spacing[3], origin[3];
+    int precision;
+    void* cells;
+    size_t bytes;
+};
+
+struct gfb_kernel {
+    gfb_device* dev;
+    int n_grids, n_atoms, precision;
+    bool same_geom;
+    gfb_grid* grids[GFB_MAX_GRIDS];
+    double inv_power[GFB_MAX_GRIDS], oob_k[GFB_MAX_GRIDS];
+    void* d_scaling;      // [n_grids][n_atoms] float|double
+    int* d_particles;     // [n_atoms] or null
+    int max_particle;     // largest particle index referenced (+1 = minimum n_particles)
+    // host-path scratch
+    DeviceBuffer d_pos, d_forces, d_energy, d_cls, d_sort;
+    PinnedBuffer h_stage, h_energy;
+};
+
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Library / device
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int gfb_version(void) { return GFB_VERSION; }
+const char* gfb_last_error(void) { return g_error.c_str(); }
+unsigned long long gfb_launch_count(void) { return g_launches.load(); }
+
+int gfb_device_count(int* count) {
+    if (!count) return fail(GFB_ERR_INVALID, "gfb_device_count: count is NULL");
+    *count = 0;
+    CUDA_TRY(cudaGetDeviceCount(count));
+    return GFB_OK;
+}
+
+int gfb_device_open(int ordinal, gfb_device** out) {
+    if (!out) return fail(GFB_ERR_INVALID, "gfb_device_open: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    CUDA_TRY(cudaGetDeviceCount(&n));
+    if (ordinal < 0 || ordinal >= n) return fail(GFB_ERR_CUDA, "gfb_device_open: no CUDA device %d (found %d)", ordinal, n);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, ordinal));
+    if (prop.major != 10)
+        return fail(GFB_ERR_CUDA, "gfb_device_open: device %d (%s, sm_%d%d) is not Blackwell sm_100; this library has no other code path",
+                    ordinal, prop.name, prop.major, prop.minor);
+    CUDA_TRY(cudaSetDevice(ordinal));
+    gfb_device* d = new (std::nothrow) gfb_device();
+    if (!d) return fail(GFB_ERR_NOMEM, "gfb_device_open: out of host memory");
+    d->ordinal = ordinal;
+    d->prop = prop;
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    *out = d;
+    return GFB_OK;
+}
+
+int gfb_device_close(gfb_device* dev) {
+    if (!dev) return GFB_OK;
+    cudaSetDevice(dev->ordinal);
+    cudaStreamDestroy(dev->stream);
+    cudaStreamDestroy(dev->copy_stream);
+    delete dev;
+    return GFB_OK;
+}
+
+int gfb_device_get_props(gfb_device* dev, gfb_device_props* props) {
+    if (!dev || !props) return fail(GFB_ERR_INVALID, "gfb_device_get_props: NULL argument");
+    memset(props, 0, sizeof *props);
+    strncpy(props->name, dev->prop.name, sizeof props->name - 1);
+    props->cc_major = dev->prop.major;
+    props->cc_minor = dev->prop.minor;
+    props->sm_count = dev->prop.multiProcessorCount;
+    props->l2_bytes = dev->prop.l2CacheSize;
+    props->total_mem_bytes = dev->prop.totalGlobalMem;
+    return GFB_OK;
+}
+
+int gfb_device_synchronize(gfb_device* dev) {
+    if (!dev) return fail(GFB_ERR_INVALID, "gfb_device_synchronize: NULL device");
+    CUDA_TRY(cudaSetDevice(dev->ordinal));
+    CUDA_TRY(cudaStreamSynchronize(dev->stream));
+    CUDA_TRY(cudaStreamSynchronize(dev->copy_stream));
+    return GFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Grids
+// ---------------------------------------------------------------------------------------------
+static int grid_create_common(gfb_device* dev, const int counts[3], const double spacing[3], const double origin[3],
+                              const double* vals, bool vals_on_device, size_t n_vals, int precision, gfb_grid** out) {
+    if (!dev || !counts || !spacing || !origin || !vals || !out) return fail(GFB_ERR_INVALID, "gfb_grid_create: NULL argument");
+    *out = nullptr;
+    if (precision != GFB_PRECISION_MIXED && precision != GFB_PRECISION_DOUBLE)
+        return fail(GFB_ERR_INVALID, "gfb_grid_create: unknown precision %d", precision);
+    for (int k = 0; k < 3; k++) {
+        if (counts[k] < 2) return fail(GFB_ERR_INVALID, "gfb_grid_create: counts[%d]=%d, need >= 2 points per axis", k, counts[k]);
+        if (!(spacing[k] > 0.0) || !std::isfinite(spacing[k]))
+            return fail(GFB_ERR_INVALID, "gfb_grid_create: spacing[%d]=%g must be positive and finite", k, spacing[k]);
+    }
+    const size_t n_points = (size_t) counts[0] * counts[1] * counts[2];
+    if (n_vals != n_points)
+        return fail(GFB_ERR_INVALID, "gfb_grid_create: %zu values given for a %dx%dx%d grid (%zu points)", n_vals, counts[0],
+                    counts[1], counts[2], n_points);
+    CUDA_TRY(cudaSetDevice(dev->ordinal));
+
+    gfb_grid* g = new (std::nothrow) gfb_grid();
+    if (!g) return fail(GFB_ERR_NOMEM, "gfb_grid_create: out of host memory");
+    g->dev = dev;
+    g->precision = precision;
+    for (int k = 0; k < 3; k++) {
+        g->counts[k] = counts[k];
+        g->spacing[k] = spacing[k];
+        g->origin[k] = origin[k];
+    }
+    const size_t n_cells = (size_t) (counts[0] - 1) * (counts[1] - 1) * (counts[2] - 1);
+    const size_t cell_bytes = precision == GFB_PRECISION_MIXED ? 32 : 64;
+    g->bytes = n_cells * cell_bytes;
+    g->cells = nullptr;
+
+    const double* d_vals = vals;
+    void* d_tmp = nullptr;
+    cudaError_t err = cudaMalloc(&g->cells, g->bytes);
+    if (err == cudaSuccess && !vals_on_device) {
+        err = cudaMalloc(&d_tmp, n_points * sizeof(double));
+        if (err == cudaSuccess) err = cudaMemcpyAsync(d_tmp, vals, n_points * sizeof(double), cudaMemcpyHostToDevice, dev->stream);
+        d_vals = static_cast<const double*>(d_tmp);
+    }
+    if (err == cudaSuccess) {
+        const int blocks = (int) std::min<size_t>((n_cells + 255) / 256, (size_t) dev->prop.multiProcessorCount * 32);
+        if (precision == GFB_PRECISION_MIXED)
+            gf_repack_kernel<float><<<blocks, 256, 0, dev->stream>>>(d_vals, static_cast<float*>(g->cells), counts[0], counts[1], counts[2]);
+        else
+            gf_repack_kernel<double><<<blocks, 256, 0, dev->stream>>>(d_vals, static_cast<double*>(g->cells), counts[0], counts[1], counts[2]);
+        g_launches++;
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaStreamSynchronize(dev->stream);
+    if (d_tmp) cudaFree(d_tmp);
+    if (err != cudaSuccess) {
+        if (g->cells) cudaFree(g->cells);
+        delete g;
+        return fail(GFB_ERR_CUDA, "gfb_grid_create: %s", cudaGetErrorString(err));
+    }
+    *out = g;
+    return GFB_OK;
+}
+
+int gfb_grid_create(gfb_device* dev, const int counts[3], const double spacing[3], const double origin[3],
+                    const double* vals, size_t n_vals, int precision, gfb_grid** out) {
+    return grid_create_common(dev, counts, spacing, origin, vals, false, n_vals, precision, out);
+}
+
+int gfb_grid_create_from_device(gfb_device* dev, const int counts[3], const double spacing[3], const double origin[3],
+                                const double* d_vals, size_t n_vals, int precision, gfb_grid** out) {
+    return grid_create_common(dev, counts, spacing, origin, d_vals, true, n_vals, precision, out);
+}
+
+int gfb_grid_destroy(gfb_grid* grid) {
+    if (!grid) return GFB_OK;
+    cudaSetDevice(grid->dev->ordinal);
+    cudaFree(grid->cells);
+    delete grid;
+    return GFB_OK;
+}
+
+size_t gfb_grid_device_bytes(const gfb_grid* grid) { return grid ? grid->bytes : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// Kernel state (= CalcGridForceKernel after initialize)
+// ---------------------------------------------------------------------------------------------
+static int upload_scaling(gfb_kernel* k, const double* scaling) {
+    const size_t n = (size_t) k->n_grids * k->n_atoms;
+    if (k->precision == GFB_PRECISION_DOUBLE) {
+        CUDA_TRY(cudaMemcpyAsync(k->d_scaling, scaling, n * sizeof(double), cudaMemcpyHostToDevice, k->dev->stream));
+    } else {
+        std::vector<float> f(n);
+        for (size_t i = 0; i < n; i++) {
+            f[i] = (float) scaling[i];
+            // The reference branches on scale != 0.0 in FP64 (:706). A nonzero factor that underflows
+            // FP32 must stay nonzero or the atom would change branch.
+            if (scaling[i] != 0.0 && f[i] == 0.0f) f[i] = scaling[i] > 0.0 ? 1.4e-45f : -1.4e-45f;
+        }
+        CUDA_TRY(cudaMemcpyAsync(k->d_scaling, f.data(), n * sizeof(float), cudaMemcpyHostToDevice, k->dev->stream));
+        CUDA_TRY(cudaStreamSynchronize(k->dev->stream));  // f goes out of scope
+    }
+    CUDA_TRY(cudaStreamSynchronize(k->dev->stream));
+    return GFB_OK;
+}
+
+int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int n_atoms, const double* scaling,
+                      const int* particles, const double* inv_power, const double* oob_k, gfb_kernel** out) {
+    if (!dev || !grids || !out || !oob_k) return fail(GFB_ERR_INVALID, "gfb_kernel_create: NULL argument");
+    *out = nullptr;
+    if (n_grids < 1 || n_grids > GFB_MAX_GRIDS)
+        return fail(GFB_ERR_INVALID, "gfb_kernel_create: n_grids=%d, supported 1..%d", n_grids, GFB_MAX_GRIDS);
+    if (n_atoms < 0) return fail(GFB_ERR_INVALID, "gfb_kernel_create: n_atoms=%d", n_atoms);
+    if (n_atoms > 0 && !scaling) return fail(GFB_ERR_INVALID, "gfb_kernel_create: scaling is NULL");
+    for (int g = 0; g < n_grids; g++) {
+        if (!grids[g]) return fail(GFB_ERR_INVALID, "gfb_kernel_create: grids[%d] is NULL", g);
+        if (grids[g]->dev != dev) return fail(GFB_ERR_INVALID, "gfb_kernel_create: grids[%d] lives on another device", g);
+        if (grids[g]->precision != grids[0]->precision)
+            return fail(GFB_ERR_INVALID, "gfb_kernel_create: grids[%d] precision differs from grids[0]", g);
+        if (inv_power && inv_power[g] < 0.0) return fail(GFB_ERR_INVALID, "gfb_kernel_create: inv_power[%d] < 0", g);
+    }
+    CUDA_TRY(cudaSetDevice(dev->ordinal));
+    gfb_kernel* k = new (std::nothrow) gfb_kernel();
+    if (!k) return fail(GFB_ERR_NOMEM, "gfb_kernel_create: out of host memory");
+    k->dev = dev;
+    k->n_grids = n_grids;
+    k->n_atoms = n_atoms;
+    k->precision = grids[0]->precision;
+    k->same_geom = true;
+    k->d_scaling = nullptr;
+    k->d_particles = nullptr;
+    k->max_particle = n_atoms - 1;
+    for (int g = 0; g < n_grids; g++) {
+        k->grids[g] = grids[g];
+        k->inv_power[g] = inv_power ? inv_power[g] : 0.0;
+        k->oob_k[g] = oob_k[g];
+        for (int a = 0; a < 3; a++)
+            if (grids[g]->counts[a] != grids[0]->counts[a] || grids[g]->spacing[a] != grids[0]->spacing[a] ||
+                grids[g]->origin[a] != grids[0]->origin[a])
+                k->same_geom = false;
+    }
+    const size_t elt = k->precision == GFB_PRECISION_DOUBLE ? sizeof(double) : sizeof(float);
+    cudaError_t err = cudaMalloc(&k->d_scaling, std::max<size_t>((size_t) n_grids * n_atoms * elt, 16));
+    if (err == cudaSuccess && particles && n_atoms > 0) {
+        k->max_particle = -1;
+        for (int i = 0; i < n_atoms; i++) {
+            if (particles[i] < 0) {
+                cudaFree(k->d_scaling);
+                delete k;
+                return fail(GFB_ERR_INVALID, "gfb_kernel_create: particles[%d]=%d is negative", i, particles[i]);
+            }
+            k->max_particle = std::max(k->max_particle, particles[i]);
+        }
+        err = cudaMalloc((void**) &k->d_particles, (size_t) n_atoms * sizeof(int));
+        if (err == cudaSuccess)
+            err = cudaMemcpy(k->d_particles, particles, (size_t) n_atoms * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    if (err != cudaSuccess) {
+        if (k->d_scaling) cudaFree(k->d_scaling);
+        if (k->d_particles) cudaFree(k->d_particles);
+        delete k;
+        return fail(GFB_ERR_CUDA, "gfb_kernel_create: %s", cudaGetErrorString(err));
+    }
+    if (n_atoms > 0) {
+        int rc = upload_scaling(k, scaling);
+        if (rc != GFB_OK) {
+            gfb_kernel_destroy(k);
+            return rc;
+        }
+    }
+    *out = k;
+    return GFB_OK;
+}
+
+int gfb_kernel_destroy(gfb_kernel* k) {
+    if (!k) return GFB_OK;
+    cudaSetDevice(k->dev->ordinal);
+    cudaStreamSynchronize(k->dev->stream);
+    cudaStreamSynchronize(k->dev->copy_stream);
+    if (k->d_scaling) cudaFree(k->d_scaling);
+    if (k->d_particles) cudaFree(k->d_particles);
+    k->d_pos.release();
+    k->d_forces.release();
+    k->d_energy.release();
+    k->d_cls.release();
+    k->d_sort.release();
+    k->h_stage.release();
+    k->h_energy.release();
+    delete k;
+    return GFB_OK;
+}
+
+int gfb_kernel_update_parameters(gfb_kernel* k, const double* scaling, const double* inv_power) {
+    if (!k) return fail(GFB_ERR_INVALID, "gfb_kernel_update_parameters: NULL kernel");
+    CUDA_TRY(cudaSetDevice(k->dev->ordinal));
+    if (inv_power)
+        for (int g = 0; g < k->n_grids; g++) {
+            if (inv_power[g] < 0.0) return fail(GFB_ERR_INVALID, "gfb_kernel_update_parameters: inv_power[%d] < 0", g);
+            k->inv_power[g] = inv_power[g];
+        }
+    if (scaling && k->n_atoms > 0) return upload_scaling(k, scaling);
+    return GFB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Launch
+// ---------------------------------------------------------------------------------------------
+static void fill_grid_view(const gfb_kernel* k, int g, GridView& v) {
+    const gfb_grid* gr = k->grids[g];
+    const size_t elt = k->precision == GFB_PRECISION_DOUBLE ? sizeof(double) : sizeof(float);
+    v.cells = gr->cells;
+    v.scaling = static_cast<const char*>(k->d_scaling) + (size_t) g * k->n_atoms * elt;
+    for (int a = 0; a < 3; a++) {
+        v.origin[a] = gr->origin[a];
+        v.spacing[a] = gr->spacing[a];
+        v.inv_spacing[a] = 1.0 / gr->spacing[a];
+        v.hcorner[a] = gr->spacing[a] * (gr->counts[a] - 1);   // ReferenceGridForceKernels.cpp:654-656
+        v.nc[a] = gr->counts[a] - 1;
+    }
+    v.pad_ = 0;
+    v.inv_power = k->inv_power[g];
+    v.oob_k = k->oob_k[g];
+}
+
+template <typename S, int NG, bool SAME, int FMODE>
+static void launch_eval3(const EvalParams& p, cudaStream_t stream) {
+    const unsigned blocks = (unsigned) ((p.total + kBlock - 1) / kBlock);
+    if (p.n_replicas == 1)
+        gf_eval_kernel<S, NG, SAME, FMODE, true><<<blocks, kBlock, 0, stream>>>(p);
+    else
+        gf_eval_kernel<S, NG, SAME, FMODE, false><<<blocks, kBlock, 0, stream>>>(p);
+}
+
+template <typename S, int NG, bool SAME>
+static void launch_eval2(const EvalParams& p, int fmode, cudaStream_t stream) {
+    switch (fmode) {
+        case GFB_FORCE_FIXED_ADD: launch_eval3<S, NG, SAME, GFB_FORCE_FIXED_ADD>(p, stream); break;
+        case GFB_FORCE_F64_ADD: launch_eval3<S, NG, SAME, GFB_FORCE_F64_ADD>(p, stream); break;
+        default: launch_eval3<S, NG, SAME, GFB_FORCE_F64_STORE>(p, stream); break;
+    }
+}
+
+template <typename S>
+static void launch_eval1(const EvalParams& p, bool same, int fmode, cudaStream_t stream) {
+    if (p.n_grids == 1) launch_eval2<S, 1, true>(p, fmode, stream);
+    else if (p.n_grids == 2 && same) launch_eval2<S, 2, true>(p, fmode, stream);
+    else if (p.n_grids == 3 && same) launch_eval2<S, 3, true>(p, fmode, stream);
+    else if (same) launch_eval2<S, 0, true>(p, fmode, stream);
+    else launch_eval2<S, 0, false>(p, fmode, stream);
+}
+
+static int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos, double* d_energies,
+                        double* d_grid_energies, void* d_forces, int force_mode, long long force_stride,
+                        const int* d_order, cudaStream_t stream) {
+    EvalParams p;
+    memset(&p, 0, sizeof p);
+    for (int g = 0; g < k->n_grids; g++) fill_grid_view(k, g, p.grid[g]);
+    p.n_grids = k->n_grids;
+    p.n_atoms = k->n_atoms;
+    p.n_particles = n_particles;
+    p.n_replicas = n_replicas;
+    p.total = (long long) n_replicas * k->n_atoms;
+    p.pos = d_pos;
+    p.particles = k->d_particles;
+    p.order = d_order;
+    p.energies = d_energies;
+    p.grid_energies = d_grid_energies;
+    p.forces = d_forces;
+    p.force_stride = force_stride;
+    if (p.total == 0) return GFB_OK;
+    if (k->precision == GFB_PRECISION_DOUBLE) launch_eval1<double>(p, k->same_geom, force_mode, stream);
+    else launch_eval1<float>(p, k->same_geom, force_mode, stream);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GFB_OK;
+}
+
+static int check_exec_args(const char* fn, gfb_kernel* k, int n_replicas, int n_particles, const void* pos, int force_mode) {
+    if (!k) return fail(GFB_ERR_INVALID, "%s: NULL kernel", fn);
+    if (n_replicas < 0) return fail(GFB_ERR_INVALID, "%s: n_replicas=%d", fn, n_replicas);
+    if (n_particles <= k->max_particle)
+        return fail(GFB_ERR_INVALID, "%s: n_particles=%d but the kernel evaluates particle index %d", fn, n_particles, k->max_particle);
+    if (!pos && (long long) n_replicas * k->n_atoms > 0) return fail(GFB_ERR_INVALID, "%s: positions pointer is NULL", fn);
+    if (force_mode < GFB_FORCE_F64_STORE || force_mode > GFB_FORCE_FIXED_ADD)
+        return fail(GFB_ERR_INVALID, "%s: unknown force_mode %d", fn, force_mode);
+    if ((long long) n_replicas * (long long) n_particles > 2000000000LL)
+        return fail(GFB_ERR_INVALID, "%s: %lld particles in one call; split the batch (limit 2e9)", fn,
+                    (long long) n_replicas * n_particles);
+    return GFB_OK;
+}
+
+extern "C" {
+
+int gfb_kernel_execute_device(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos, double* d_energies,
+                              double* d_grid_energies, void* d_forces, int force_mode, long long force_stride,
+                              const int* d_order, void* stream) {
+    int rc = check_exec_args("gfb_kernel_execute_device", k, n_replicas, n_particles, d_pos, force_mode);
+    if (rc != GFB_OK) return rc;
+    if (force_mode == GFB_FORCE_FIXED_ADD && d_forces && force_stride < (long long) n_replicas * n_particles)
+        return fail(GFB_ERR_INVALID, "gfb_kernel_execute_device: force_stride=%lld < %lld particles", force_stride,
+                    (long long) n_replicas * n_particles);
+    CUDA_TRY(cudaSetDevice(k->dev->ordinal));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : k->dev->stream;
+    return enqueue_eval(k, n_replicas, n_particles, d_pos, d_energies, d_grid_energies, d_forces, force_mode, force_stride,
+                        d_order, s);
+}
+
+// Host path. The batch is cut into replica chunks so that the H2D of chunk i+1, the kernel of chunk i and
+// the D2H of chunk i-1 overlap (two streams + events). Pinned user buffers are DMA'd directly; pageable
+// ones go through the handle's pinned staging buffer.
+int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, const double* pos, double* energies,
+                            double* grid_energies, double* forces, int force_mode) {
+    int rc = check_exec_args("gfb_kernel_execute_host", k, n_replicas, n_particles, pos, force_mode);
+    if (rc != GFB_OK) return rc;
+    if (force_mode == GFB_FORCE_FIXED_ADD)
+        return fail(GFB_ERR_INVALID, "gfb_kernel_execute_host: FIXED_ADD is a device-buffer format; use F64_STORE or F64_ADD");
+    if (n_replicas == 0) return GFB_OK;
+    gfb_device* dev = k->dev;
+    CUDA_TRY(cudaSetDevice(dev->ordinal));
+
+    const size_t np = (size_t) n_replicas * n_particles;
+    const size_t pos_bytes = np * 3 * sizeof(double);
+    const int ng = k->n_grids;
+    const size_t e_count = (size_t) n_replicas * (1 + ng);
+    if ((rc = k->d_pos.ensure(pos_bytes)) != GFB_OK) return rc;
+    if (forces && (rc = k->d_forces.ensure(pos_bytes)) != GFB_OK) return rc;
+    if ((rc = k->d_energy.ensure(e_count * sizeof(double))) != GFB_OK) return rc;
+    if ((rc = k->h_energy.ensure(e_count * sizeof(double))) != GFB_OK) return rc;
+
+    const bool pos_pinned = is_pinned(pos);
+    const bool f_pinned = forces && is_pinned(forces);
+    // staging: [pos | forces] when the user's buffers are pageable
+    const size_t stage_bytes = (pos_pinned ? 0 : pos_bytes) + ((forces && !f_pinned) ? pos_bytes : 0);
+    if (stage_bytes && (rc = k->h_stage.ensure(stage_bytes)) != GFB_OK) return rc;
+    char* stage_pos = static_cast<char*>(k->h_stage.ptr);
+    char* stage_f = stage_pos + (pos_pinned ? 0 : pos_bytes);
+
+    double* d_pos = static_cast<double*>(k->d_pos.ptr);
+    double* d_f = forces ? static_cast<double*>(k->d_forces.ptr) : nullptr;
+    double* d_e = static_cast<double*>(k->d_energy.ptr);
+    double* d_ge = d_e + n_replicas;
+    CUDA_TRY(cudaMemsetAsync(d_e, 0, e_count * sizeof(double), dev->stream));
+
+    // Chunking: aim at ~4 MB of positions per chunk, at most 16 chunks; a single replica is one chunk.
+    int n_chunks = 1;
+    if (n_replicas > 1) {
+        n_chunks = (int) std::min<size_t>(16, std::max<size_t>(1, pos_bytes / (4u << 20)));
+        n_chunks = std::min(n_chunks, n_replicas);
+    }
+    std::vector<cudaEvent_t> done(n_chunks);
+    for (int c = 0; c < n_chunks; c++) CUDA_TRY(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
+
+    int status = GFB_OK;
+    for (int c = 0; c < n_chunks && status == GFB_OK; c++) {
+        const int r0 = (int) ((long long) n_replicas * c / n_chunks);
+        const int r1 = (int) ((long long) n_replicas * (c + 1) / n_chunks);
+        const size_t off = (size_t) r0 * n_particles * 3;            // doubles
+        const size_t cnt = (size_t) (r1 - r0) * n_particles * 3;
+        const double* src = pos + off;
+        if (!pos_pinned) {
+            memcpy(stage_pos + off * sizeof(double), src, cnt * sizeof(double));
+            src = reinterpret_cast<const double*>(stage_pos) + off;
+        }
+        cudaError_t err = cudaMemcpyAsync(d_pos + off, src, cnt * sizeof(double), cudaMemcpyHostToDevice, dev->stream);
+        if (err == cudaSuccess && forces && force_mode == GFB_FORCE_F64_ADD) {
+            // ADD: the caller's current forces are the accumulator's initial value
+            const double* fsrc = forces + off;
+            if (!f_pinned) {
+                memcpy(stage_f + off * sizeof(double), fsrc, cnt * sizeof(double));
+                fsrc = reinterpret_cast<const double*>(stage_f) + off;
+            }
+            err = cudaMemcpyAsync(d_f + off, fsrc, cnt * sizeof(double), cudaMemcpyHostToDevice, dev->stream);
+        } else if (err == cudaSuccess && forces && (k->d_particles || k->n_atoms < n_particles)) {
+            // STORE with a particle subset: untouched entries must come back as they were
+            const double* fsrc = forces + off;
+            if (!f_pinned) {
+                memcpy(stage_f + off * sizeof(double), fsrc, cnt * sizeof(double));
+                fsrc = reinterpret_cast<const double*>(stage_f) + off;
+            }
+            err = cudaMemcpyAsync(d_f + off, fsrc, cnt * sizeof(double), cudaMemcpyHostToDevice, dev->stream);
+        }
+        if (err != cudaSuccess) {
+            status = fail(GFB_ERR_CUDA, "gfb_kernel_execute_host: H2D: %s", cudaGetErrorString(err));
+            break;
+        }
+        status = enqueue_eval(k, r1 - r0, n_particles, d_pos + off, d_e + r0, grid_energies ? d_ge + (size_t) r0 * ng : nullptr,
+                              d_f ? d_f + off : nullptr, force_mode, 0, nullptr, dev->stream);
+        if (status != GFB_OK) break;
+        err = cudaEventRecord(done[c], dev->stream);
+        if (err == cudaSuccess && forces) {
+            err = cudaStreamWaitEvent(dev->copy_stream, done[c], 0);
+            double* dst = f_pinned ? forces + off : reinterpret_cast<double*>(stage_f) + off;
+            if (err == cudaSuccess)
+                err = cudaMemcpyAsync(dst, d_f + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, dev->copy_stream);
+        }
+        if (err != cudaSuccess) status = fail(GFB_ERR_CUDA, "gfb_kernel_execute_host: D2H: %s", cudaGetErrorString(err));
+    }
+    if (status == GFB_OK) {
+        cudaError_t err = cudaMemcpyAsync(k->h_energy.ptr, d_e, e_count * sizeof(double), cudaMemcpyDeviceToHost, dev->stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(dev->stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(dev->copy_stream);
+        if (err != cudaSuccess) status = fail(GFB_ERR_CUDA, "gfb_kernel_execute_host: %s", cudaGetErrorString(err));
+    } else {
+        cudaStreamSynchronize(dev->stream);
+        cudaStreamSynchronize(dev->copy_stream);
+    }
+    for (int c = 0; c < n_chunks; c++) cudaEventDestroy(done[c]);
+    if (status != GFB_OK) return status;
+
+    const double* he = static_cast<const double*>(k->h_energy.ptr);
+    if (energies) memcpy(energies, he, (size_t) n_replicas * sizeof(double));
+    if (grid_energies) memcpy(grid_energies, he + n_replicas, (size_t) n_replicas * ng * sizeof(double));
+    if (forces && !f_pinned) memcpy(forces, stage_f, pos_bytes);
+    return GFB_OK;
+}
+
+int gfb_kernel_classify_host(gfb_kernel* k, int grid_index, int n_replicas, int n_particles, const double* pos, gfb_class* cls) {
+    int rc = check_exec_args("gfb_kernel_classify_host", k, n_replicas, n_particles, pos, GFB_FORCE_F64_STORE);
+    if (rc != GFB_OK) return rc;
+    if (grid_index < 0 || grid_index >= k->n_grids) return fail(GFB_ERR_INVALID, "gfb_kernel_classify_host: grid_index=%d", grid_index);
+    if (!cls) return fail(GFB_ERR_INVALID, "gfb_kernel_classify_host: cls is NULL");
+    const long long total = (long long) n_replicas * k->n_atoms;
+    if (total == 0) return GFB_OK;
+    gfb_device* dev = k->dev;
+    CUDA_TRY(cudaSetDevice(dev->ordinal));
+    const size_t pos_bytes = (size_t) n_replicas * n_particles * 3 * sizeof(double);
+    if ((rc = k->d_pos.ensure(pos_bytes)) != GFB_OK) return rc;
+    if ((rc = k->d_cls.ensure((size_t) total * sizeof(gfb_class))) != GFB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(k->d_pos.ptr, pos, pos_bytes, cudaMemcpyHostToDevice, dev->stream));
+    ClassifyParams p;
+    memset(&p, 0, sizeof p);
+    fill_grid_view(k, grid_index, p.grid);
+    p.n_atoms = k->n_atoms;
+    p.n_particles = n_particles;
+    p.total = total;
+    p.pos = static_cast<const double*>(k->d_pos.ptr);
+    p.particles = k->d_particles;
+    p.out = static_cast<gfb_class*>(k->d_cls.ptr);
+    const unsigned blocks = (unsigned) ((total + 255) / 256);
+    if (k->precision == GFB_PRECISION_DOUBLE) gf_classify_kernel<true><<<blocks, 256, 0, dev->stream>>>(p);
+    else gf_classify_kernel<false><<<blocks, 256, 0, dev->stream>>>(p);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(cls, k->d_cls.ptr, (size_t) total * sizeof(gfb_class), cudaMemcpyDeviceToHost, dev->stream));
+    CUDA_TRY(cudaStreamSynchronize(dev->stream));
+    return GFB_OK;
+}
+
+int gfb_kernel_sort_atoms(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos, int* d_order, void* stream) {
+    int rc = check_exec_args("gfb_kernel_sort_atoms", k, n_replicas, n_particles, d_pos, GFB_FORCE_F64_STORE);
+    if (rc != GFB_OK) return rc;
+    if (!d_order) return fail(GFB_ERR_INVALID, "gfb_kernel_sort_atoms: d_order is NULL");
+    const long long total = (long long) n_replicas * k->n_atoms;
+    if (total == 0) return GFB_OK;
+    if (total > 0x7fffffffLL) return fail(GFB_ERR_INVALID, "gfb_kernel_sort_atoms: %lld atoms exceed the int32 order index", total);
+    gfb_device* dev = k->dev;
+    CUDA_TRY(cudaSetDevice(dev->ordinal));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : dev->stream;
+    const int n = (int) total;
+    size_t tmp_bytes = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (unsigned*) nullptr, (unsigned*) nullptr, (int*) nullptr,
+                                             (int*) nullptr, n, 0, 32, s));
+    const size_t key_bytes = ((size_t) n * sizeof(unsigned) + 255) & ~(size_t) 255;
+    const size_t idx_bytes = ((size_t) n * sizeof(int) + 255) & ~(size_t) 255;
+    if ((rc = k->d_sort.ensure(2 * key_bytes + idx_bytes + tmp_bytes)) != GFB_OK) return rc;
+    char* base = static_cast<char*>(k->d_sort.ptr);
+    unsigned* keys_in = reinterpret_cast<unsigned*>(base);
+    unsigned* keys_out = reinterpret_cast<unsigned*>(base + key_bytes);
+    int* idx_in = reinterpret_cast<int*>(base + 2 * key_bytes);
+    void* tmp = base + 2 * key_bytes + idx_bytes;
+    ClassifyParams p;
+    memset(&p, 0, sizeof p);
+    fill_grid_view(k, 0, p.grid);
+    p.n_atoms = k->n_atoms;
+    p.n_particles = n_particles;
+    p.total = total;
+    p.pos = d_pos;
+    p.particles = k->d_particles;
+    gf_morton_key_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, s>>>(p, keys_in, idx_in);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, idx_in, d_order, n, 0, 32, s));
+    return GFB_OK;
+}
+
+int gfb_forces_fixed_to_f64(gfb_device* dev, const void* d_fixed, long long force_stride, long long n, double* d_out, void* stream) {
+    if (!dev || !d_fixed || !d_out) return fail(GFB_ERR_INVALID, "gfb_forces_fixed_to_f64: NULL argument");
+    if (n <= 0) return GFB_OK;
+    CUDA_TRY(cudaSetDevice(dev->ordinal));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : dev->stream;
+    gf_fixed_to_f64_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(static_cast<const long long*>(d_fixed), force_stride, n, d_out);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GFB_OK;
+}
+
+int gfb_bench_sector_gather(gfb_device* dev, size_t bytes, long long n_loads, int reps, double* gbs) {
+    if (!dev || !gbs) return fail(GFB_ERR_INVALID, "gfb_bench_sector_gather: NULL argument");
+    if (bytes < 32 || n_loads < 1 || reps < 1) return fail(GFB_ERR_INVALID, "gfb_bench_sector_gather: bad sizes");
+    CUDA_TRY(cudaSetDevice(dev->ordinal));
+    float* buf = nullptr;
+    float* sink = nullptr;
+    CUDA_TRY(cudaMalloc((void**) &buf, bytes));
+    CUDA_TRY(cudaMalloc((void**) &sink, 256));
+    CUDA_TRY(cudaMemsetAsync(buf, 0, bytes, dev->stream));
+    const int per_thread = 16;
+    const long long threads = (n_loads + per_thread - 1) / per_thread;
+    const unsigned blocks = (unsigned) ((threads + 255) / 256);
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; i++) gf_sector_gather_kernel<<<blocks, 256, 0, dev->stream>>>(buf, bytes / 32, per_thread, sink);
+    CUDA_TRY(cudaEventRecord(e0, dev->stream));
+    for (int i = 0; i < reps; i++) gf_sector_gather_kernel<<<blocks, 256, 0, dev->stream>>>(buf, bytes / 32, per_thread, sink);
+    CUDA_TRY(cudaEventRecord(e1, dev->stream));
+    g_launches += reps + 3;
+    CUDA_TRY(cudaStreamSynchronize(dev->stream));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    cudaFree(sink);
+    *gbs = (double) blocks * 256.0 * per_thread * 32.0 * reps / (ms * 1e-3) / 1e9;
+    return GFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,54 @@
+// Plain-data launch parameters shared by the host launcher (gf_capi.cu) and the kernels (gf_kernels.cuh).
+#ifndef GF_PARAMS_H_
+#define GF_PARAMS_H_
+
+#include <stdint.h>
+
+#include "gridforce_b200.h"
+
+namespace gfb {
+
+// One grid as the kernel sees it. `cells` points at the packed cell-major array
+// (8 corners per cell, 32 B in MIXED / 64 B in DOUBLE); cell (ix,iy,iz) is at
+// ((ix*nc[1] + iy)*nc[2] + iz) with nc = counts - 1.
+struct GridView {
+    const void* cells;
+    const void* scaling;     // [n_atoms] float (MIXED) or double (DOUBLE), this grid's row
+    double origin[3];
+    double spacing[3];
+    double inv_spacing[3];   // fl(1/spacing): fast-path quotient, re-divided exactly near integers
+    double hcorner[3];       // spacing*(counts-1), computed on the host exactly as the reference does
+    int nc[3];               // cells per axis = counts - 1
+    int pad_;
+    double inv_power;        // 0 = off
+    double oob_k;
+};
+
+struct EvalParams {
+    GridView grid[GFB_MAX_GRIDS];
+    int n_grids;
+    int n_atoms;             // atoms evaluated per replica
+    int n_particles;         // particles per replica (stride of pos/forces)
+    int n_replicas;
+    long long total;         // n_replicas * n_atoms = threads doing work
+    const double* pos;       // [n_replicas][n_particles][3]
+    const int* particles;    // [n_atoms] or null
+    const int* order;        // [total] or null
+    double* energies;        // [n_replicas] or null, accumulated
+    double* grid_energies;   // [n_replicas][n_grids] or null, accumulated
+    void* forces;            // layout per force mode, or null
+    long long force_stride;  // FIXED_ADD plane stride
+};
+
+struct ClassifyParams {
+    GridView grid;
+    int n_atoms, n_particles;
+    long long total;
+    const double* pos;
+    const int* particles;
+    gfb_class* out;
+    int exact_div;
+};
+
+}  // namespace gfb
+#endif

@@ -1,0 +1,147 @@
+/* TEST INFRASTRUCTURE — see gridforce_oracle.h. Plain C99 restatement of
+ * /root/reference/platforms/reference/src/ReferenceGridForceKernels.cpp:646-1121 (trilinear branch).
+ * Build with -ffp-contract=off so a*b+c stays two roundings, as in the reference build. */
+#include "gridforce_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* The inside branch for one atom (:706-1084). pi = position - origin. Returns scale * V and
+ * subtracts scale * grad V from f[3]. */
+static double gfo_interp(const gfo_grid* g, double scale, const double* pi, double* f, gfo_class* cls) {
+    const int nz = g->counts[2];
+    const int nyz = g->counts[1] * nz;                           /* :653 */
+    int k, idx[3];
+    double fr[3];
+    for (k = 0; k < 3; k++) {
+        idx[k] = (int)(pi[k] / g->spacing[k]);                   /* :708-710 */
+        fr[k] = (pi[k] / g->spacing[k]) - idx[k];                /* :713-715 */
+        /* pi == hCorner gives idx == n-1 and the reference reads past the grid (UB, quirk Q2).
+         * The restatement evaluates the same cell the limit from inside would: idx = n-2, f = 1. */
+        if (idx[k] > g->counts[k] - 2) {
+            idx[k] = g->counts[k] - 2;
+            fr[k] = (pi[k] / g->spacing[k]) - idx[k];
+        }
+    }
+    if (cls) { cls->cell[0] = idx[0]; cls->cell[1] = idx[1]; cls->cell[2] = idx[2]; }
+    {
+        {
+            const double* v = g->vals;
+            const int im = idx[0] * nyz + idx[1] * nz + idx[2];  /* :1022 */
+            const int imp = im + nz, ip = im + nyz, ipp = ip + nz; /* :1023-1025 */
+            const double vmmm = v[im], vmmp = v[im + 1], vmpm = v[imp], vmpp = v[imp + 1];   /* :1028-1031 */
+            const double vpmm = v[ip], vpmp = v[ip + 1], vppm = v[ipp], vppp = v[ipp + 1];   /* :1033-1036 */
+            const double fx = fr[0], fy = fr[1], fz = fr[2];
+            const double ax = 1.0 - fx, ay = 1.0 - fy, az = 1.0 - fz;                       /* :1039-1041 */
+            const double vmm = az * vmmm + fz * vmmp;                                       /* :1044-1047 */
+            const double vmp = az * vmpm + fz * vmpp;
+            const double vpm = az * vpmm + fz * vpmp;
+            const double vpp = az * vppm + fz * vppp;
+            const double vm = ay * vmm + fy * vmp;                                          /* :1049-1050 */
+            const double vp = ay * vpm + fy * vpp;
+            double interpolated = ax * vm + fx * vp;                                        /* :1053 */
+            double dvdx, dvdy, dvdz, grd[3], enr;
+            if (g->inv_power > 0.0) interpolated = pow(interpolated, g->inv_power);         /* :1057-1059 */
+            enr = scale * interpolated;                                                     /* :1061 */
+            dvdx = -vm + vp;                                                                /* :1066 */
+            dvdy = (-vmm + vmp) * ax + (-vpm + vpp) * fx;                                   /* :1068 */
+            dvdz = ((-vmmm + vmmp) * ay + (-vmpm + vmpp) * fy) * ax +
+                   ((-vpmm + vpmp) * ay + (-vppm + vppp) * fy) * fx;                        /* :1070-1071 */
+            grd[0] = dvdx / g->spacing[0];                                                  /* :1072 */
+            grd[1] = dvdy / g->spacing[1];
+            grd[2] = dvdz / g->spacing[2];
+            if (g->inv_power > 0.0) {                                                       /* :1076-1080 */
+                const double base = ax * vm + fx * vp;
+                const double pf = g->inv_power * pow(base, g->inv_power - 1.0);
+                grd[0] = grd[0] * pf; grd[1] = grd[1] * pf; grd[2] = grd[2] * pf;
+            }
+            if (f) for (k = 0; k < 3; k++) f[k] -= scale * grd[k];                          /* :1082 */
+            return enr;
+        }
+    }
+}
+
+double gfo_execute(const gfo_grid* grid, const double* scaling, int n_scaling, const int* ligand_atoms,
+                   const double* pos, double* forces, gfo_class* cls) {
+    double energy = 0.0;
+    int ia;
+    for (ia = 0; ia < n_scaling; ia++) {                                                     /* :682 */
+        const int particle = ligand_atoms ? ligand_atoms[ia] : ia;                           /* :684 */
+        const double* p = pos + 3 * (size_t)particle;
+        const double scale = scaling[ia];
+        double h[3], pi[3];
+        int k, inside = 1;
+        for (k = 0; k < 3; k++) {
+            h[k] = grid->spacing[k] * (grid->counts[k] - 1);                                 /* :654-656 hCorner */
+            pi[k] = p[k] - grid->origin[k];                                                  /* :687-688 */
+            if (!(pi[k] >= 0.0 && pi[k] <= h[k])) inside = 0;                                /* :690-696, <= */
+        }
+        if (inside && scale != 0.0) {
+            if (cls) cls[ia].inside = 1;
+            energy += gfo_interp(grid, scale, pi, forces ? forces + 3 * (size_t)ia : 0, cls ? cls + ia : 0);
+        } else {
+            /* :1093-1117 — unscaled harmonic wall. Three separate terms are added to the running
+             * energy (:1112); keep that association so the sum is bit-identical to the reference. */
+            if (cls) { cls[ia].inside = inside; cls[ia].cell[0] = cls[ia].cell[1] = cls[ia].cell[2] = -1; }
+            for (k = 0; k < 3; k++) {
+                double dev = 0.0;
+                if (pi[k] < 0.0) dev = pi[k];
+                else if (pi[k] > h[k]) dev = pi[k] - h[k];
+                energy += 0.5 * grid->oob_k * dev * dev;                                     /* :1112 */
+                if (forces) forces[3 * (size_t)ia + k] -= grid->oob_k * dev;                 /* :1113-1116 */
+            }
+        }
+    }
+    return energy;                                                                           /* :1120 */
+}
+
+typedef struct {
+    const gfo_grid* grids;
+    int n_grids;
+    const double* scaling;
+    int r0, r1, n_atoms;
+    const double* pos;
+    double* forces;
+    double* energies;
+} gfo_job;
+
+static void* gfo_worker(void* arg) {
+    gfo_job* j = (gfo_job*)arg;
+    int r, g;
+    for (r = j->r0; r < j->r1; r++) {
+        const double* p = j->pos + (size_t)r * j->n_atoms * 3;
+        double* f = j->forces ? j->forces + (size_t)r * j->n_atoms * 3 : 0;
+        if (f) memset(f, 0, sizeof(double) * 3 * (size_t)j->n_atoms);
+        for (g = 0; g < j->n_grids; g++) {
+            const double e = gfo_execute(&j->grids[g], j->scaling + (size_t)g * j->n_atoms, j->n_atoms, 0, p, f, 0);
+            if (j->energies) j->energies[(size_t)r * j->n_grids + g] = e;
+        }
+    }
+    return 0;
+}
+
+void gfo_execute_batched(const gfo_grid* grids, int n_grids, const double* scaling, int n_replicas, int n_atoms,
+                         const double* pos, double* forces, double* energies, int n_threads) {
+    int t;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > n_replicas) n_threads = n_replicas > 0 ? n_replicas : 1;
+    {
+        pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * n_threads);
+        gfo_job* jobs = (gfo_job*)malloc(sizeof(gfo_job) * n_threads);
+        for (t = 0; t < n_threads; t++) {
+            gfo_job j;
+            j.grids = grids; j.n_grids = n_grids; j.scaling = scaling; j.n_atoms = n_atoms;
+            j.r0 = (int)((long long)n_replicas * t / n_threads);
+            j.r1 = (int)((long long)n_replicas * (t + 1) / n_threads);
+            j.pos = pos; j.forces = forces; j.energies = energies;
+            jobs[t] = j;
+            if (t > 0) pthread_create(&th[t], 0, gfo_worker, &jobs[t]);
+        }
+        gfo_worker(&jobs[0]);
+        for (t = 1; t < n_threads; t++) pthread_join(th[t], 0);
+        free(th);
+        free(jobs);
+    }
+}

@@ -1,0 +1,164 @@
+// TEST INFRASTRUCTURE — not product code. Nothing under openmmgridforce_b200/ may link this.
+//
+// C-ABI wrapper around the reference's own, unmodified Reference-platform kernel
+// (ReferenceCalcGridForceKernel, /root/reference/platforms/reference/src/
+// ReferenceGridForceKernels.cpp:147-160 initialize, :646-1121 execute), driven the way
+// OpenMM drives it: System -> GridForce -> Context(ReferencePlatform) -> GridForceImpl
+// (openmmapi/src/GridForceImpl.cpp:55-68) -> CalcGridForceKernel::execute.
+// The reference sources are compiled where they lie (see Makefile); only OpenMM itself
+// is replaced by third_party/openmm_shim.
+#include <cstring>
+#include <iostream>
+#include <sstream>
+#include <vector>
+
+#include "GridForce.h"
+#include "GridForceKernels.h"
+#include "openmm/Context.h"
+#include "openmm/Platform.h"
+#include "openmm/System.h"
+#include "openmm/reference/ReferencePlatform.h"
+
+extern "C" void registerKernelFactories();  // ReferenceGridForceKernelFactory.cpp:47
+
+using namespace OpenMM;
+using GridForcePlugin::GridForce;
+using GridForcePlugin::InvPowerMode;
+
+namespace {
+
+// The reference prints debug text from execute() on its first calls (:662-704); swallow it.
+struct CoutSilencer {
+    std::ostringstream sink;
+    std::streambuf* saved;
+    CoutSilencer() : saved(std::cout.rdbuf(sink.rdbuf())) {}
+    ~CoutSilencer() { std::cout.rdbuf(saved); }
+};
+
+Platform& referencePlatform() {
+    static ReferencePlatform* platform = 0;
+    if (!platform) {
+        platform = new ReferencePlatform("Reference");
+        Platform::registerPlatform(platform);
+        registerKernelFactories();
+    }
+    return *platform;
+}
+
+struct Handle {
+    System system;
+    std::vector<GridForce*> forces;  // owned by system
+    Context* context;
+    int numParticles;
+    Handle() : context(0), numParticles(0) {}
+    ~Handle() { delete context; }
+};
+
+thread_local std::string lastError;
+
+}  // namespace
+
+extern "C" {
+
+const char* oracle_ref_last_error() { return lastError.c_str(); }
+
+// One System holding `numParticles` particles; forces are added with oracle_ref_add_grid,
+// then oracle_ref_finalize creates the Context (-> kernel initialize()).
+void* oracle_ref_create(int numParticles) {
+    Handle* h = new Handle();
+    h->numParticles = numParticles;
+    for (int i = 0; i < numParticles; i++) h->system.addParticle(1.0);
+    return h;
+}
+
+// Adds one GridForce the way python/tests/test_grid_force.py:40-64 does (addGridCounts,
+// addGridSpacing, values, scaling factors). ligandAtoms may be NULL (identity mapping).
+int oracle_ref_add_grid(void* handle, const int* counts, const double* spacing, const double* origin,
+                        const double* vals, long long nVals, const double* scaling, int nScaling,
+                        const int* ligandAtoms, int nLigandAtoms, double invPower, double oobK,
+                        int interpolationMethod, int forceGroup) {
+    Handle* h = static_cast<Handle*>(handle);
+    try {
+        GridForce* f = new GridForce();
+        f->addGridCounts(counts[0], counts[1], counts[2]);
+        f->addGridSpacing(spacing[0], spacing[1], spacing[2]);
+        f->setGridOrigin(origin[0], origin[1], origin[2]);
+        f->setGridValues(std::vector<double>(vals, vals + nVals));
+        f->setScalingFactors(std::vector<double>(scaling, scaling + nScaling));
+        if (ligandAtoms && nLigandAtoms > 0)
+            f->setLigandAtoms(std::vector<int>(ligandAtoms, ligandAtoms + nLigandAtoms));
+        if (invPower != 0.0) f->setInvPowerMode(InvPowerMode::STORED, invPower);
+        f->setOutOfBoundsRestraint(oobK);
+        f->setInterpolationMethod(interpolationMethod);
+        f->setForceGroup(forceGroup);
+        h->system.addForce(f);
+        h->forces.push_back(f);
+        return 0;
+    } catch (std::exception& e) {
+        lastError = e.what();
+        return 1;
+    }
+}
+
+int oracle_ref_finalize(void* handle) {
+    Handle* h = static_cast<Handle*>(handle);
+    try {
+        CoutSilencer quiet;
+        h->context = new Context(h->system, referencePlatform());
+        return 0;
+    } catch (std::exception& e) {
+        lastError = e.what();
+        return 1;
+    }
+}
+
+// positions: [numParticles][3] nm. forces (out, may be NULL): [numParticles][3] kJ/mol/nm,
+// zeroed then accumulated by every GridForce whose group bit is set, exactly as
+// forceData[] is in the reference (:1082, :1116). Returns the summed energy through *energy.
+int oracle_ref_execute(void* handle, const double* positions, int groups, double* energy, double* forces) {
+    Handle* h = static_cast<Handle*>(handle);
+    try {
+        std::vector<Vec3> pos(h->numParticles);
+        for (int i = 0; i < h->numParticles; i++)
+            pos[i] = Vec3(positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]);
+        h->context->setPositions(pos);
+        CoutSilencer quiet;
+        *energy = h->context->computeForcesAndEnergy(true, true, groups);
+        if (forces) {
+            const std::vector<Vec3>& f = h->context->getForces();
+            for (int i = 0; i < h->numParticles; i++) {
+                forces[3 * i] = f[i][0];
+                forces[3 * i + 1] = f[i][1];
+                forces[3 * i + 2] = f[i][2];
+            }
+        }
+        return 0;
+    } catch (std::exception& e) {
+        lastError = e.what();
+        return 1;
+    }
+}
+
+// Timing entry point: `reps` back-to-back evaluations on the positions already
+// resident in the Context (no marshalling inside the loop). Returns the last energy.
+int oracle_ref_execute_repeat(void* handle, const double* positions, int reps, double* energy) {
+    Handle* h = static_cast<Handle*>(handle);
+    try {
+        std::vector<Vec3> pos(h->numParticles);
+        for (int i = 0; i < h->numParticles; i++)
+            pos[i] = Vec3(positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]);
+        h->context->setPositions(pos);
+        CoutSilencer quiet;
+        double e = 0.0;
+        for (int r = 0; r < reps; r++) e = h->context->computeForcesAndEnergy(true, true, 0xFFFFFFFF);
+        *energy = e;
+        return 0;
+    } catch (std::exception& e) {
+        lastError = e.what();
+        return 1;
+    }
+}
+
+void oracle_ref_destroy(void* handle) { delete static_cast<Handle*>(handle); }
+
+}  // extern "C"
