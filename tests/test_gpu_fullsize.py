@@ -1,0 +1,87 @@
+"""Full-size configurations of BASELINE.json on the GPU (-m gpu): C3 (1M atoms x 256^3) and C4 (4096 replicas x 3
+grids) compared with the oracle directly (the C restatement finishes these in seconds), C5's shard through
+size-independent properties (ones-grid sum, replica permutation invariance, shard-union = whole)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def test_c3_million_atoms_mixed(gpu_device, oracle_built):
+    import openmmgridforce_b200 as gf
+    from openmmgridforce_b200 import workloads as W
+    w = W.c3_million_atoms()
+    port = oracle_built.PortOracle(w.counts, w.spacing, w.origin, w.grids, w.scaling)
+    e_ref, f_ref, cls_ref = port.execute(w.pos[0], 0, classify=True)
+    g = gf.Grid(gpu_device, w.counts, w.spacing, w.origin, w.grids[0], gf.PRECISION_MIXED)
+    assert g.device_bytes == 255 ** 3 * 32
+    k = gf.Kernel(gpu_device, [g], w.scaling)
+    cls = k.classify_host(w.pos, 0)
+    assert np.array_equal(cls["cell"], cls_ref["cell"]) and np.array_equal(cls["inside"], cls_ref["inside"])
+    en, f, _ = k.execute_host(w.pos)
+    assert abs(en[0] - e_ref) <= 1e-6 * abs(e_ref), (en[0], e_ref)
+    assert _rel(f[0], f_ref) <= 1e-5
+    k.close()
+    g.close()
+
+
+def test_c4_batched_mixed_and_double(gpu_device, oracle_built):
+    import openmmgridforce_b200 as gf
+    from openmmgridforce_b200 import workloads as W
+    w = W.c4_batched_replicas()
+    port = oracle_built.PortOracle(w.counts, w.spacing, w.origin, w.grids, w.scaling, oob_k=w.oob_k)
+    ge_ref, f_ref = port.execute_batched(w.pos, n_threads=8)
+    e_ref = ge_ref.sum(axis=1)
+    for precision, te, tf in ((gf.PRECISION_MIXED, 1e-6, 1e-5), (gf.PRECISION_DOUBLE, 1e-12, 1e-12)):
+        grids = [gf.Grid(gpu_device, w.counts, w.spacing, w.origin, v, precision) for v in w.grids]
+        k = gf.Kernel(gpu_device, grids, w.scaling, oob_k=w.oob_k)
+        en, f, ge = k.execute_host(w.pos, want_grid_energies=True)
+        assert np.abs(ge - ge_ref).max() <= te * np.abs(ge_ref).max()
+        assert np.abs(en - e_ref).max() <= te * np.abs(e_ref).max()
+        assert _rel(f, f_ref) <= tf
+        k.close()
+        for g in grids:
+            g.close()
+
+
+def test_c5_shard_properties(gpu_device):
+    """One rank's shard of C5 at 8 GPUs (8192 replicas x 47 x 3 grids of 192^3) on all-ones grids: every replica
+    fully inside has E = sum over grids of sum(s) exactly representable to 1e-6; permuting replicas permutes the
+    energies; evaluating two half-shards equals evaluating the shard."""
+    import openmmgridforce_b200 as gf
+    from openmmgridforce_b200 import workloads as W
+    n = 192
+    sp = (W.TEST_GRID_SPACING,) * 3
+    half = 0.5 * sp[0] * (n - 1)
+    pos = W.ligand_replicas(8192, (half, half, half), escape_shift=(0.9, 0.0, 0.0))
+    scaling = W._ligand_scaling(3)
+    ones = np.ones((n, n, n))
+    grid = gf.Grid(gpu_device, (n, n, n), sp, (0, 0, 0), ones, gf.PRECISION_MIXED)
+    k = gf.Kernel(gpu_device, [grid, grid, grid], scaling)
+    en, f, _ = k.execute_host(pos)
+    length = sp[0] * (n - 1)
+    inside = ((pos >= 0) & (pos <= length)).all(axis=(1, 2))
+    assert 0.9 < inside.mean() < 1.0
+    assert np.abs(en[inside] - scaling.sum()).max() <= 1e-6 * abs(scaling.sum())
+    assert np.abs(f[inside]).max() == 0.0
+    # closed form for every replica: inside atoms contribute s (ones grid), outside atoms the harmonic wall, per grid
+    atom_in = ((pos >= 0) & (pos <= length)).all(axis=2)                      # [R, A]
+    dev = np.where(pos < 0, pos, np.where(pos > length, pos - length, 0.0))   # [R, A, 3]
+    wall = 0.5 * 10000.0 * (dev ** 2).sum(axis=2)                             # per grid
+    expect = (atom_in[:, None, :] * scaling[None, :, :]).sum(axis=(1, 2)) + 3 * np.where(atom_in, 0.0, wall).sum(axis=1)
+    assert np.abs(en - expect).max() <= 1e-6 * np.abs(expect).max()
+    f_expect = -3 * 10000.0 * np.where(atom_in[..., None], 0.0, dev)
+    assert np.abs(f - f_expect).max() <= 1e-5 * np.abs(f_expect).max()
+    perm = np.random.default_rng(0).permutation(8192)
+    en_p, f_p, _ = k.execute_host(np.ascontiguousarray(pos[perm]))
+    # energies are sums of per-warp partials added atomically: equal up to FP64 re-association
+    assert np.allclose(en_p, en[perm], rtol=1e-12, atol=1e-9) and np.array_equal(f_p, f[perm])
+    en_a, _, _ = k.execute_host(np.ascontiguousarray(pos[:4096]))
+    en_b, _, _ = k.execute_host(np.ascontiguousarray(pos[4096:]))
+    assert np.allclose(np.concatenate([en_a, en_b]), en, rtol=1e-12, atol=1e-9)
+    k.close()
+    grid.close()

@@ -1,0 +1,117 @@
+"""CPU tests of the parity oracle itself (no GPU):
+  * the C restatement (oracle/gridforce_oracle.c) reproduces the committed golden vectors — outputs of the
+    reference's own kernel — bit for bit;
+  * where /root/reference is present (build container) it is also checked bit-for-bit against a fresh build of
+    the reference kernel (oracle/_ref) on random inputs;
+  * closed-form known answers (ones grid, linear field, restraint)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import cases  # noqa: E402
+
+GOLDEN = sorted(cases.CASES)
+
+
+def _port(bindings, c):
+    return bindings.PortOracle(c["counts"], c["spacing"], c["origin"], c["grids"], c["scaling"], oob_k=c["oob_k"],
+                               inv_power=c["inv_power"])
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_port_matches_golden_bit_exact(oracle_built, name):
+    c, ref = cases.load_golden(name)
+    port = _port(oracle_built, c)
+    total_f = np.zeros_like(ref["forces"])
+    for g in range(len(c["grids"])):
+        e, f, _ = port.execute(c["pos"], g)
+        assert e == ref["grid_energies"][g], f"{name} grid {g}: energy differs from the reference kernel"
+        assert np.array_equal(f, ref["grid_forces"][g], equal_nan=True)
+        total_f -= -f        # same accumulation order as forceData[ia] -= ... over forces 0..G-1
+    assert np.array_equal(total_f, ref["forces"], equal_nan=True)
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_inputs_match_generators(name):
+    """The stored inputs are the ones cases.py generates (guards against a stale .npz)."""
+    c, _ = cases.load_golden(name)
+    fresh = cases.CASES[name]()
+    assert c["counts"] == tuple(fresh["counts"])
+    np.testing.assert_array_equal(c["pos"], np.asarray(fresh["pos"], dtype=np.float64))
+    np.testing.assert_array_equal(c["scaling"], np.asarray(fresh["scaling"], dtype=np.float64))
+    for a, b in zip(c["grids"], fresh["grids"]):
+        np.testing.assert_array_equal(a, np.asarray(b, dtype=np.float64))
+
+
+def test_port_matches_reference_build_random(oracle_built):
+    if not oracle_built.ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine); golden vectors cover it")
+    rng = np.random.default_rng(42)
+    for trial in range(6):
+        counts = tuple(int(v) for v in rng.integers(2, 24, size=3))
+        sp = tuple(rng.uniform(0.01, 0.3, size=3))
+        og = tuple(rng.uniform(-2, 2, size=3))
+        n, g = int(rng.integers(1, 400)), int(rng.integers(1, 4))
+        grids = [rng.normal(size=counts) * 10 ** rng.uniform(-2, 4) for _ in range(g)]
+        length = np.array(sp) * (np.array(counts) - 1)
+        pos = np.array(og) + rng.uniform(-0.2, 1.2, size=(n, 3)) * length
+        sc = rng.normal(size=(g, n))
+        sc[:, rng.integers(0, n, size=max(1, n // 10))] = 0.0
+        k = list(rng.uniform(10, 1e5, size=g))
+        ref = oracle_built.RefOracle(n, counts, sp, og, grids, sc, oob_k=k)
+        port = oracle_built.PortOracle(counts, sp, og, grids, sc, oob_k=k)
+        for gi in range(g):
+            er, fr = ref.execute(pos, groups=1 << gi)
+            ep, fp, _ = port.execute(pos, gi)
+            assert er == ep, f"trial {trial} grid {gi}"
+            assert np.array_equal(fr, fp)
+        ref.close()
+
+
+def test_ligand_atoms_quirk_q1(oracle_built):
+    """Position is read at ligand_atoms[ia] but the force is written at ia (ReferenceGridForceKernels.cpp:684 vs :1082)."""
+    if not oracle_built.ref_available():
+        pytest.skip("needs oracle/_ref")
+    rng = np.random.default_rng(3)
+    counts, sp = (8, 8, 8), (0.1, 0.1, 0.1)
+    grid = rng.normal(size=counts)
+    pos = rng.uniform(0.0, 0.7, size=(10, 3))
+    la = [7, 2, 9]
+    sc = np.array([[1.0, -2.0, 0.5]])
+    ref = oracle_built.RefOracle(10, counts, sp, (0, 0, 0), [grid], sc, ligand_atoms=la)
+    er, fr = ref.execute(pos)
+    port = oracle_built.PortOracle(counts, sp, (0, 0, 0), [grid], sc)
+    ep, fp, _ = port.execute(pos, 0, ligand_atoms=la)
+    assert er == ep
+    assert np.array_equal(fr[:3], fp) and not fr[3:].any()
+
+
+def test_known_answers(oracle_built):
+    c = cases.case_ones_grid()
+    e, f, cls = _port(oracle_built, c).execute(c["pos"], 0, classify=True)
+    assert abs(e - c["scaling"].sum()) < 1e-13 and not f.any() and cls["inside"].all()
+    c = cases.case_linear_field()
+    e, f, cls = _port(oracle_built, c).execute(c["pos"], 0, classify=True)
+    np.testing.assert_allclose(f[0], [-20.0, -40.0, -60.0], rtol=1e-12)
+    # atom 1: 0.5 nm beyond +x and 0.01 nm below -y, k = 1e4: F = -k*dev, E = k/2 * dev^2
+    np.testing.assert_allclose(f[1], [-5000.0, 100.0, 0.0], rtol=1e-12)
+    assert list(cls["inside"]) == [1, 0, 1, 1]
+    assert tuple(cls["cell"][0]) == (3, 4, 2) and tuple(cls["cell"][1]) == (-1, -1, -1)
+    assert tuple(cls["cell"][3]) == (-1, -1, -1)        # inside but scale == 0 -> restraint branch (Q3), adds 0
+    v = lambda p: 2 * p[0] + 4 * p[1] + 6 * p[2] + 1    # noqa: E731
+    expect = 10 * v(c["pos"][0]) + 0.5e4 * (0.5 ** 2 + 0.01 ** 2) + 2 * v(c["pos"][2])
+    assert abs(e - expect) < 1e-9
+
+
+def test_batched_threads_agree(oracle_built):
+    c = cases.case_random_aniso()
+    port = _port(oracle_built, c)
+    pos = np.stack([c["pos"] + 0.001 * r for r in range(7)])
+    e1, f1 = port.execute_batched(pos, n_threads=1)
+    e4, f4 = port.execute_batched(pos, n_threads=4)
+    assert np.array_equal(e1, e4) and np.array_equal(f1, f4)
+    e0, f0, _ = port.execute(pos[3], 1)
+    assert e1[3, 1] == e0
