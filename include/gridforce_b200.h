@@ -139,10 +139,13 @@ GFB_API int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particl
  *   d_grid_energies device [n_replicas][n_grids], accumulated, or NULL
  *   d_forces       device buffer in the layout `force_mode` names, or NULL
  *   force_stride   FIXED_ADD only: padded atom count (>= n_replicas*n_particles) = plane stride
- *   d_order        device [n_replicas*n_atoms] evaluation order (from gfb_kernel_sort_atoms) or NULL */
+ *   d_order        device [n_replicas*n_atoms] evaluation order (from gfb_kernel_sort_atoms) or NULL
+ *   d_energies_clear device [n_replicas] buffer zero-filled by this launch, or NULL: the accumulator of the NEXT
+ *                  step when the caller alternates two energy buffers, which saves a memset launch per step */
 GFB_API int gfb_kernel_execute_device(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos,
                                       double* d_energies, double* d_grid_energies, void* d_forces,
-                                      int force_mode, long long force_stride, const int* d_order, void* stream);
+                                      int force_mode, long long force_stride, const int* d_order,
+                                      double* d_energies_clear, void* stream);
 
 /* Morton order of the atoms by the grid cell they sit in (grid 0), so neighbouring lanes read neighbouring
  * sectors. Positions move less than a cell per MD step, so the order is reused for many steps.

@@ -50,7 +50,7 @@ SIGNATURES = {
     "gfb_kernel_destroy": (_i, [_vp]),
     "gfb_kernel_update_parameters": (_i, [_vp, _vp, _vp]),
     "gfb_kernel_execute_host": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i]),
-    "gfb_kernel_execute_device": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _ll, _vp, _vp]),
+    "gfb_kernel_execute_device": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp]),
     "gfb_kernel_sort_atoms": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "gfb_kernel_classify_host": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "gfb_forces_fixed_to_f64": (_i, [_vp, _vp, _ll, _ll, _vp, _vp]),
@@ -219,11 +219,11 @@ class Kernel:
         return en, forces, ge
 
     def execute_device(self, n_replicas, n_particles, d_pos, d_energies=None, d_grid_energies=None, d_forces=None,
-                       force_mode=FORCE_FIXED_ADD, force_stride=0, d_order=None, stream=0):
+                       force_mode=FORCE_FIXED_ADD, force_stride=0, d_order=None, stream=0, d_energies_clear=None):
         """All d_* are integer device addresses (e.g. torch_tensor.data_ptr()); stream is a cudaStream_t value."""
         _check(load_library().gfb_kernel_execute_device(self._h, n_replicas, n_particles, _ptr(d_pos), _ptr(d_energies),
                                                         _ptr(d_grid_energies), _ptr(d_forces), force_mode, force_stride,
-                                                        _ptr(d_order), _ptr(stream or None)))
+                                                        _ptr(d_order), _ptr(d_energies_clear), _ptr(stream or None)))
 
     def sort_atoms(self, n_replicas, n_particles, d_pos, d_order, stream=0):
         _check(load_library().gfb_kernel_sort_atoms(self._h, n_replicas, n_particles, _ptr(d_pos), _ptr(d_order),

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -149,6 +150,10 @@ int gfb_device_open(int ordinal, gfb_device** out) {
         return fail(GFB_ERR_CUDA, "gfb_device_open: device %d (%s, sm_%d%d) is not Blackwell sm_100; this library has no other code path",
                     ordinal, prop.name, prop.major, prop.minor);
     CUDA_TRY(cudaSetDevice(ordinal));
+    if (const char* fg = getenv("GFB_L2_FETCH_GRANULARITY")) {   // tuning probe: 32 | 64 | 128 bytes
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t) atoi(fg));
+        if (e != cudaSuccess) cudaGetLastError();
+    }
     gfb_device* d = new (std::nothrow) gfb_device();
     if (!d) return fail(GFB_ERR_NOMEM, "gfb_device_open: out of host memory");
     d->ordinal = ordinal;
@@ -441,7 +446,7 @@ static void launch_eval1(const EvalParams& p, bool same, int fmode, cudaStream_t
 
 static int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos, double* d_energies,
                         double* d_grid_energies, void* d_forces, int force_mode, long long force_stride,
-                        const int* d_order, cudaStream_t stream) {
+                        const int* d_order, double* d_energies_clear, cudaStream_t stream) {
     EvalParams p;
     memset(&p, 0, sizeof p);
     for (int g = 0; g < k->n_grids; g++) fill_grid_view(k, g, p.grid[g]);
@@ -455,6 +460,7 @@ static int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const do
     p.order = d_order;
     p.energies = d_energies;
     p.grid_energies = d_grid_energies;
+    p.energies_clear = d_energies_clear;
     p.forces = d_forces;
     p.force_stride = force_stride;
     if (p.total == 0) return GFB_OK;
@@ -483,7 +489,7 @@ extern "C" {
 
 int gfb_kernel_execute_device(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos, double* d_energies,
                               double* d_grid_energies, void* d_forces, int force_mode, long long force_stride,
-                              const int* d_order, void* stream) {
+                              const int* d_order, double* d_energies_clear, void* stream) {
     int rc = check_exec_args("gfb_kernel_execute_device", k, n_replicas, n_particles, d_pos, force_mode);
     if (rc != GFB_OK) return rc;
     if (force_mode == GFB_FORCE_FIXED_ADD && d_forces && force_stride < (long long) n_replicas * n_particles)
@@ -492,7 +498,7 @@ int gfb_kernel_execute_device(gfb_kernel* k, int n_replicas, int n_particles, co
     CUDA_TRY(cudaSetDevice(k->dev->ordinal));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : k->dev->stream;
     return enqueue_eval(k, n_replicas, n_particles, d_pos, d_energies, d_grid_energies, d_forces, force_mode, force_stride,
-                        d_order, s);
+                        d_order, d_energies_clear, s);
 }
 
 // Host path. The batch is cut into replica chunks so that the H2D of chunk i+1, the kernel of chunk i and
@@ -574,7 +580,7 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
             break;
         }
         status = enqueue_eval(k, r1 - r0, n_particles, d_pos + off, d_e + r0, grid_energies ? d_ge + (size_t) r0 * ng : nullptr,
-                              d_f ? d_f + off : nullptr, force_mode, 0, nullptr, dev->stream);
+                              d_f ? d_f + off : nullptr, force_mode, 0, nullptr, nullptr, dev->stream);
         if (status != GFB_OK) break;
         err = cudaEventRecord(done[c], dev->stream);
         if (err == cudaSuccess && forces) {
@@ -686,7 +692,7 @@ int gfb_forces_fixed_to_f64(gfb_device* dev, const void* d_fixed, long long forc
 
 int gfb_bench_sector_gather(gfb_device* dev, size_t bytes, long long n_loads, int reps, double* gbs) {
     if (!dev || !gbs) return fail(GFB_ERR_INVALID, "gfb_bench_sector_gather: NULL argument");
-    if (bytes < 32 || n_loads < 1 || reps < 1) return fail(GFB_ERR_INVALID, "gfb_bench_sector_gather: bad sizes");
+    if (bytes < 32 || n_loads < 1 || reps == 0) return fail(GFB_ERR_INVALID, "gfb_bench_sector_gather: bad sizes");
     CUDA_TRY(cudaSetDevice(dev->ordinal));
     float* buf = nullptr;
     float* sink = nullptr;
@@ -699,9 +705,16 @@ int gfb_bench_sector_gather(gfb_device* dev, size_t bytes, long long n_loads, in
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; i++) gf_sector_gather_kernel<<<blocks, 256, 0, dev->stream>>>(buf, bytes / 32, per_thread, sink);
+    // reps < 0: 16-byte loads instead of 32-byte sectors (probe for the row-chunked layouts)
+    const bool chunk16 = reps < 0;
+    if (chunk16) reps = -reps;
+    auto launch = [&]() {
+        if (chunk16) gf_chunk_gather_kernel<<<blocks, 256, 0, dev->stream>>>(reinterpret_cast<const float4*>(buf), bytes / 16, per_thread, sink);
+        else gf_sector_gather_kernel<<<blocks, 256, 0, dev->stream>>>(buf, bytes / 32, per_thread, sink);
+    };
+    for (int i = 0; i < 3; i++) launch();
     CUDA_TRY(cudaEventRecord(e0, dev->stream));
-    for (int i = 0; i < reps; i++) gf_sector_gather_kernel<<<blocks, 256, 0, dev->stream>>>(buf, bytes / 32, per_thread, sink);
+    for (int i = 0; i < reps; i++) launch();
     CUDA_TRY(cudaEventRecord(e1, dev->stream));
     g_launches += reps + 3;
     CUDA_TRY(cudaStreamSynchronize(dev->stream));
@@ -711,7 +724,7 @@ int gfb_bench_sector_gather(gfb_device* dev, size_t bytes, long long n_loads, in
     cudaEventDestroy(e1);
     cudaFree(buf);
     cudaFree(sink);
-    *gbs = (double) blocks * 256.0 * per_thread * 32.0 * reps / (ms * 1e-3) / 1e9;
+    *gbs = (double) blocks * 256.0 * per_thread * (chunk16 ? 16.0 : 32.0) * reps / (ms * 1e-3) / 1e9;
     return GFB_OK;
 }
 

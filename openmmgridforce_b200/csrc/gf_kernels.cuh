@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(kBlock) gf_eval_kernel(const __grid_constant__
     const long long t = (long long) blockIdx.x * kBlock + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool active = t < p.total;
+    if (p.energies_clear && t < p.n_replicas) p.energies_clear[t] = 0.0;
 
     int rep = -1;
     long long gidx = 0;
@@ -394,6 +395,22 @@ __global__ void __launch_bounds__(256) gf_sector_gather_kernel(const float* __re
         acc += v[0] + v[3] + v[5] + v[7];
     }
     if (acc == 123.456f) sink[0] = acc;  // keeps the loads alive; practically never taken
+}
+
+// Same, with 16-byte (LDG.E.128) loads: the unit of the row-chunked layouts.
+__global__ void __launch_bounds__(256) gf_chunk_gather_kernel(const float4* __restrict__ buf, unsigned long long n_chunks,
+                                                              int loads_per_thread, float* __restrict__ sink) {
+    unsigned long long h = ((unsigned long long) blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < loads_per_thread; i++) {
+        h ^= h >> 29;
+        h *= 0xBF58476D1CE4E5B9ull;
+        h ^= h >> 32;
+        const float4 v = __ldg(buf + __umul64hi(h, n_chunks));
+        acc += v.x + v.y + v.z + v.w;
+    }
+    if (acc == 123.456f) sink[0] = acc;
 }
 
 }  // namespace gfb

@@ -36,6 +36,7 @@ struct EvalParams {
     const int* order;        // [total] or null
     double* energies;        // [n_replicas] or null, accumulated
     double* grid_energies;   // [n_replicas][n_grids] or null, accumulated
+    double* energies_clear;  // [n_replicas] or null: zero-filled by this launch (next step's accumulator)
     void* forces;            // layout per force mode, or null
     long long force_stride;  // FIXED_ADD plane stride
 };
