@@ -40,10 +40,21 @@ typedef enum {
 } gfb_status;
 
 /* Arithmetic mode — OpenMM's "mixed"/"double" precision property (CudaPlatform "Precision").
- *   MIXED : grid corners stored FP32 (32-byte cell = one L2 sector), index/fraction math FP64 (bit-exact
- *           cell index), interpolation FP32, energy and force accumulation FP64 / 64-bit fixed point.
- *   DOUBLE: corners stored FP64 (64-byte cell), everything FP64. */
+ *   MIXED : grid values stored FP32, index/fraction math FP64 (bit-exact cell index), interpolation FP32,
+ *           energy and force accumulation FP64 / 64-bit fixed point.
+ *   DOUBLE: values stored FP64, everything FP64. */
 typedef enum { GFB_PRECISION_MIXED = 0, GFB_PRECISION_DOUBLE = 1 } gfb_precision;
+
+/* Device layout of a grid. Every stencil read is made of aligned 32-byte loads (LDG.E.256); a layout trades
+ * copies of the data for fewer loads per stencil. The gather rate of an SM is about one load-lane per clock
+ * whatever its width, and L2 holds whole 128-byte lines, so the best layout is the most replicated one whose
+ * TOUCHED footprint still fits L2 (DESIGN.md §3 has the measurements).
+ *   ROWS   x-major rows cut into overlapping 32-byte chunks (8 floats advancing by 7 / 4 doubles advancing by 3):
+ *          any z-pair lies inside one chunk -> 4 loads per stencil, 1.14x (1.33x) the raw grid.
+ *   PAIRS  MIXED only: 32-byte entry = 4 floats (advancing by 3) of row iy and of row iy+1 -> 2 loads, 2.67x.
+ *   CELLS  the 8 corners of every cell packed -> 1 load (2 in DOUBLE), 8x.
+ *   AUTO   CELLS while that copy is at most 1/16 of the GPU's memory (11 GB on B200), else ROWS. */
+typedef enum { GFB_LAYOUT_AUTO = 0, GFB_LAYOUT_CELLS = 1, GFB_LAYOUT_ROWS = 2, GFB_LAYOUT_PAIRS = 3 } gfb_layout;
 
 /* How execute writes forces.
  *   GFB_FORCE_F64_STORE : double [n_replicas][n_particles][3], plain stores (entries of particles this
@@ -87,20 +98,19 @@ GFB_API int gfb_device_close(gfb_device* dev);
 GFB_API int gfb_device_get_props(gfb_device* dev, gfb_device_props* props);
 GFB_API int gfb_device_synchronize(gfb_device* dev);
 
-/* Uploads one grid and repacks it on the device into cell-major form: cell (ix,iy,iz) holds its 8 corner
- * values {v000,v001,v010,v011,v100,v101,v110,v111} (last index = z) contiguously, 32 B (MIXED) or 64 B
- * (DOUBLE), so an atom's whole stencil is one aligned vector load.
+/* Uploads one grid and repacks it on the device into `layout` (gfb_layout above).
  * Replaces GridForce::getGridParameters (openmmapi/src/GridForce.cpp:355-363) + the CUDA platform's
  * float upload (CudaGridForceKernels.cpp:482-486). `vals` is a HOST pointer to counts[0]*counts[1]*counts[2]
  * doubles. counts >= 2 on every axis. */
 GFB_API int gfb_grid_create(gfb_device* dev, const int counts[3], const double spacing[3], const double origin[3],
-                            const double* vals, size_t n_vals, int precision, gfb_grid** out);
+                            const double* vals, size_t n_vals, int precision, int layout, gfb_grid** out);
 /* Same, from a DEVICE pointer to doubles (x-major); stream-ordered on the device's stream. */
 GFB_API int gfb_grid_create_from_device(gfb_device* dev, const int counts[3], const double spacing[3],
                                         const double origin[3], const double* d_vals, size_t n_vals,
-                                        int precision, gfb_grid** out);
+                                        int precision, int layout, gfb_grid** out);
 GFB_API int gfb_grid_destroy(gfb_grid* grid);
 GFB_API size_t gfb_grid_device_bytes(const gfb_grid* grid);
+GFB_API int gfb_grid_layout(const gfb_grid* grid);   /* the layout actually chosen (resolves AUTO) */
 
 /* Builds the evaluation state for n_grids GridForces that act on the same atoms — what
  * CalcGridForceKernel::initialize(System, GridForce) captures (ReferenceGridForceKernels.cpp:147-160),
@@ -113,7 +123,7 @@ GFB_API size_t gfb_grid_device_bytes(const gfb_grid* grid);
  *              ordinal, :1082 — identical when particles == NULL).
  *   inv_power  host [n_grids] or NULL (all 0 = off). > 0: v <- pow(v, n) with the chain rule (:1057-1080).
  *   oob_k      host [n_grids] out-of-grid restraint constants (GridForce::getOutOfBoundsRestraint).
- * All grids must have been created on `dev` with the same precision. */
+ * All grids must have been created on `dev` with the same precision and layout. */
 GFB_API int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int n_atoms,
                               const double* scaling, const int* particles, const double* inv_power,
                               const double* oob_k, gfb_kernel** out);

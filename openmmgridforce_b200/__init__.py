@@ -16,6 +16,11 @@ from .capi import (  # noqa: F401
     PRECISION_MIXED,
     PRECISION_DOUBLE,
     MAX_GRIDS,
+    LAYOUT_AUTO,
+    LAYOUT_CELLS,
+    LAYOUT_ROWS,
+    LAYOUT_PAIRS,
+    LAYOUT_NAMES,
     library_path,
     load_library,
     launch_count,

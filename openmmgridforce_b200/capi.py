@@ -14,6 +14,8 @@ PRECISION_DOUBLE = 1
 FORCE_F64_STORE = 0
 FORCE_F64_ADD = 1
 FORCE_FIXED_ADD = 2
+LAYOUT_AUTO, LAYOUT_CELLS, LAYOUT_ROWS, LAYOUT_PAIRS = 0, 1, 2, 3
+LAYOUT_NAMES = {0: "auto", 1: "cells", 2: "rows", 3: "pairs"}
 MAX_GRIDS = 8
 
 _LIB = None
@@ -42,8 +44,9 @@ SIGNATURES = {
     "gfb_device_close": (_i, [_vp]),
     "gfb_device_get_props": (_i, [_vp, C.POINTER(_Props)]),
     "gfb_device_synchronize": (_i, [_vp]),
-    "gfb_grid_create": (_i, [_vp, _pi, _pd, _pd, _vp, _sz, _i, C.POINTER(_vp)]),
-    "gfb_grid_create_from_device": (_i, [_vp, _pi, _pd, _pd, _vp, _sz, _i, C.POINTER(_vp)]),
+    "gfb_grid_create": (_i, [_vp, _pi, _pd, _pd, _vp, _sz, _i, _i, C.POINTER(_vp)]),
+    "gfb_grid_create_from_device": (_i, [_vp, _pi, _pd, _pd, _vp, _sz, _i, _i, C.POINTER(_vp)]),
+    "gfb_grid_layout": (_i, [_vp]),
     "gfb_grid_destroy": (_i, [_vp]),
     "gfb_grid_device_bytes": (_sz, [_vp]),
     "gfb_kernel_create": (_i, [_vp, _i, C.POINTER(_vp), _i, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
@@ -60,6 +63,8 @@ SIGNATURES = {
 
 
 def library_path():
+    if os.environ.get("GFB_LIB_PATH"):      # A/B builds of the same library (tuning experiments)
+        return os.environ["GFB_LIB_PATH"]
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgridforce_b200.so")
 
 
@@ -146,7 +151,9 @@ class Device:
 class Grid:
     """gfb_grid: counts/spacing/origin + values (x-major, z fastest), repacked cell-major on the GPU."""
 
-    def __init__(self, device, counts, spacing, origin, values, precision=PRECISION_MIXED, device_ptr=None):
+    def __init__(self, device, counts, spacing, origin, values, precision=PRECISION_MIXED, layout=None, device_ptr=None):
+        if layout is None:      # GFB_LAYOUT env var: experiment knob for the benches (auto|cells|rows|pairs)
+            layout = {v: k for k, v in LAYOUT_NAMES.items()}[os.environ.get("GFB_LAYOUT", "auto")]
         self.device = device
         self.counts = tuple(int(c) for c in counts)
         self.spacing = tuple(float(s) for s in spacing)
@@ -159,10 +166,11 @@ class Grid:
         lib = load_library()
         if device_ptr is not None:
             n = int(np.prod(self.counts))
-            _check(lib.gfb_grid_create_from_device(device._h, cn, sp, og, C.c_void_p(device_ptr), n, precision, C.byref(self._h)))
+            _check(lib.gfb_grid_create_from_device(device._h, cn, sp, og, C.c_void_p(device_ptr), n, precision, layout, C.byref(self._h)))
         else:
             v = _host_f64(values).ravel()
-            _check(lib.gfb_grid_create(device._h, cn, sp, og, _ptr(v), v.size, precision, C.byref(self._h)))
+            _check(lib.gfb_grid_create(device._h, cn, sp, og, _ptr(v), v.size, precision, layout, C.byref(self._h)))
+        self.layout = int(lib.gfb_grid_layout(self._h))
 
     @property
     def device_bytes(self):

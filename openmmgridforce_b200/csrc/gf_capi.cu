@@ -95,6 +95,8 @@ struct gfb_grid {
     int counts[3];
     double spacing[3], origin[3];
     int precision;
+    int layout;        // resolved gfb_layout (never AUTO)
+    int row_chunks;    // ROWS / PAIRS: 32-byte units per row
     void* cells;
     size_t bytes;
 };
@@ -197,11 +199,15 @@ int gfb_device_synchronize(gfb_device* dev) {
 // Grids
 // ---------------------------------------------------------------------------------------------
 static int grid_create_common(gfb_device* dev, const int counts[3], const double spacing[3], const double origin[3],
-                              const double* vals, bool vals_on_device, size_t n_vals, int precision, gfb_grid** out) {
+                              const double* vals, bool vals_on_device, size_t n_vals, int precision, int layout,
+                              gfb_grid** out) {
     if (!dev || !counts || !spacing || !origin || !vals || !out) return fail(GFB_ERR_INVALID, "gfb_grid_create: NULL argument");
     *out = nullptr;
     if (precision != GFB_PRECISION_MIXED && precision != GFB_PRECISION_DOUBLE)
         return fail(GFB_ERR_INVALID, "gfb_grid_create: unknown precision %d", precision);
+    if (layout < GFB_LAYOUT_AUTO || layout > GFB_LAYOUT_PAIRS) return fail(GFB_ERR_INVALID, "gfb_grid_create: unknown layout %d", layout);
+    if (layout == GFB_LAYOUT_PAIRS && precision == GFB_PRECISION_DOUBLE)
+        return fail(GFB_ERR_UNSUPPORTED, "gfb_grid_create: the PAIRS layout exists for MIXED precision only (use ROWS or CELLS)");
     for (int k = 0; k < 3; k++) {
         if (counts[k] < 2) return fail(GFB_ERR_INVALID, "gfb_grid_create: counts[%d]=%d, need >= 2 points per axis", k, counts[k]);
         if (!(spacing[k] > 0.0) || !std::isfinite(spacing[k]))
@@ -224,7 +230,25 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
     }
     const size_t n_cells = (size_t) (counts[0] - 1) * (counts[1] - 1) * (counts[2] - 1);
     const size_t cell_bytes = precision == GFB_PRECISION_MIXED ? 32 : 64;
-    g->bytes = n_cells * cell_bytes;
+    // AUTO: the packed-cell copy whenever it is affordable (one 128-byte line per stencil is what HBM and L2 move;
+    // measured fastest or within 7 % of fastest on every named configuration), else the 1.14x rows copy.
+    if (layout == GFB_LAYOUT_AUTO)
+        layout = n_cells * cell_bytes <= dev->prop.totalGlobalMem / 16 ? GFB_LAYOUT_CELLS : GFB_LAYOUT_ROWS;
+    g->layout = layout;
+    g->row_chunks = 0;
+    size_t n_units = n_cells;      // threads' worth of work for the repack kernel
+    if (layout == GFB_LAYOUT_CELLS) {
+        g->bytes = n_cells * cell_bytes;
+    } else if (layout == GFB_LAYOUT_ROWS) {
+        const int w = precision == GFB_PRECISION_MIXED ? 8 : 4;            // values per 32-byte chunk
+        g->row_chunks = (counts[2] - 2) / (w - 1) + 1;                     // covers every pair (iz, iz+1), iz <= nz-2
+        n_units = (size_t) counts[0] * counts[1] * g->row_chunks;
+        g->bytes = n_units * 32;
+    } else {
+        g->row_chunks = (counts[2] - 2) / 3 + 1;
+        n_units = (size_t) counts[0] * (counts[1] - 1) * g->row_chunks;
+        g->bytes = n_units * 32;
+    }
     g->cells = nullptr;
 
     const double* d_vals = vals;
@@ -236,11 +260,19 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
         d_vals = static_cast<const double*>(d_tmp);
     }
     if (err == cudaSuccess) {
-        const int blocks = (int) std::min<size_t>((n_cells + 255) / 256, (size_t) dev->prop.multiProcessorCount * 32);
-        if (precision == GFB_PRECISION_MIXED)
-            gf_repack_kernel<float><<<blocks, 256, 0, dev->stream>>>(d_vals, static_cast<float*>(g->cells), counts[0], counts[1], counts[2]);
-        else
-            gf_repack_kernel<double><<<blocks, 256, 0, dev->stream>>>(d_vals, static_cast<double*>(g->cells), counts[0], counts[1], counts[2]);
+        const int blocks = (int) std::min<size_t>((n_units + 255) / 256, (size_t) dev->prop.multiProcessorCount * 32);
+        const bool mixed = precision == GFB_PRECISION_MIXED;
+        float* cf = static_cast<float*>(g->cells);
+        double* cd = static_cast<double*>(g->cells);
+        if (layout == GFB_LAYOUT_CELLS) {
+            if (mixed) gf_repack_kernel<float><<<blocks, 256, 0, dev->stream>>>(d_vals, cf, counts[0], counts[1], counts[2]);
+            else gf_repack_kernel<double><<<blocks, 256, 0, dev->stream>>>(d_vals, cd, counts[0], counts[1], counts[2]);
+        } else if (layout == GFB_LAYOUT_ROWS) {
+            if (mixed) gf_repack_rows_kernel<float><<<blocks, 256, 0, dev->stream>>>(d_vals, cf, counts[0], counts[1], counts[2], g->row_chunks);
+            else gf_repack_rows_kernel<double><<<blocks, 256, 0, dev->stream>>>(d_vals, cd, counts[0], counts[1], counts[2], g->row_chunks);
+        } else {
+            gf_repack_pairs_kernel<<<blocks, 256, 0, dev->stream>>>(d_vals, cf, counts[0], counts[1], counts[2], g->row_chunks);
+        }
         g_launches++;
         err = cudaGetLastError();
     }
@@ -256,13 +288,13 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
 }
 
 int gfb_grid_create(gfb_device* dev, const int counts[3], const double spacing[3], const double origin[3],
-                    const double* vals, size_t n_vals, int precision, gfb_grid** out) {
-    return grid_create_common(dev, counts, spacing, origin, vals, false, n_vals, precision, out);
+                    const double* vals, size_t n_vals, int precision, int layout, gfb_grid** out) {
+    return grid_create_common(dev, counts, spacing, origin, vals, false, n_vals, precision, layout, out);
 }
 
 int gfb_grid_create_from_device(gfb_device* dev, const int counts[3], const double spacing[3], const double origin[3],
-                                const double* d_vals, size_t n_vals, int precision, gfb_grid** out) {
-    return grid_create_common(dev, counts, spacing, origin, d_vals, true, n_vals, precision, out);
+                                const double* d_vals, size_t n_vals, int precision, int layout, gfb_grid** out) {
+    return grid_create_common(dev, counts, spacing, origin, d_vals, true, n_vals, precision, layout, out);
 }
 
 int gfb_grid_destroy(gfb_grid* grid) {
@@ -274,25 +306,16 @@ int gfb_grid_destroy(gfb_grid* grid) {
 }
 
 size_t gfb_grid_device_bytes(const gfb_grid* grid) { return grid ? grid->bytes : 0; }
+int gfb_grid_layout(const gfb_grid* grid) { return grid ? grid->layout : GFB_LAYOUT_AUTO; }
 
 // ---------------------------------------------------------------------------------------------
 // Kernel state (= CalcGridForceKernel after initialize)
 // ---------------------------------------------------------------------------------------------
 static int upload_scaling(gfb_kernel* k, const double* scaling) {
+    // Scaling factors stay FP64 on the device in both precisions: the energy term s*V is formed in FP64, and the
+    // reference's branch on scale != 0.0 (:706) is then reproduced exactly.
     const size_t n = (size_t) k->n_grids * k->n_atoms;
-    if (k->precision == GFB_PRECISION_DOUBLE) {
-        CUDA_TRY(cudaMemcpyAsync(k->d_scaling, scaling, n * sizeof(double), cudaMemcpyHostToDevice, k->dev->stream));
-    } else {
-        std::vector<float> f(n);
-        for (size_t i = 0; i < n; i++) {
-            f[i] = (float) scaling[i];
-            // The reference branches on scale != 0.0 in FP64 (:706). A nonzero factor that underflows
-            // FP32 must stay nonzero or the atom would change branch.
-            if (scaling[i] != 0.0 && f[i] == 0.0f) f[i] = scaling[i] > 0.0 ? 1.4e-45f : -1.4e-45f;
-        }
-        CUDA_TRY(cudaMemcpyAsync(k->d_scaling, f.data(), n * sizeof(float), cudaMemcpyHostToDevice, k->dev->stream));
-        CUDA_TRY(cudaStreamSynchronize(k->dev->stream));  // f goes out of scope
-    }
+    CUDA_TRY(cudaMemcpyAsync(k->d_scaling, scaling, n * sizeof(double), cudaMemcpyHostToDevice, k->dev->stream));
     CUDA_TRY(cudaStreamSynchronize(k->dev->stream));
     return GFB_OK;
 }
@@ -310,6 +333,8 @@ int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int 
         if (grids[g]->dev != dev) return fail(GFB_ERR_INVALID, "gfb_kernel_create: grids[%d] lives on another device", g);
         if (grids[g]->precision != grids[0]->precision)
             return fail(GFB_ERR_INVALID, "gfb_kernel_create: grids[%d] precision differs from grids[0]", g);
+        if (grids[g]->layout != grids[0]->layout)
+            return fail(GFB_ERR_INVALID, "gfb_kernel_create: grids[%d] layout differs from grids[0]", g);
         if (inv_power && inv_power[g] < 0.0) return fail(GFB_ERR_INVALID, "gfb_kernel_create: inv_power[%d] < 0", g);
     }
     CUDA_TRY(cudaSetDevice(dev->ordinal));
@@ -332,8 +357,7 @@ int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int 
                 grids[g]->origin[a] != grids[0]->origin[a])
                 k->same_geom = false;
     }
-    const size_t elt = k->precision == GFB_PRECISION_DOUBLE ? sizeof(double) : sizeof(float);
-    cudaError_t err = cudaMalloc(&k->d_scaling, std::max<size_t>((size_t) n_grids * n_atoms * elt, 16));
+    cudaError_t err = cudaMalloc(&k->d_scaling, std::max<size_t>((size_t) n_grids * n_atoms * sizeof(double), 16));
     if (err == cudaSuccess && particles && n_atoms > 0) {
         k->max_particle = -1;
         for (int i = 0; i < n_atoms; i++) {
@@ -402,9 +426,8 @@ int gfb_kernel_update_parameters(gfb_kernel* k, const double* scaling, const dou
 // ---------------------------------------------------------------------------------------------
 static void fill_grid_view(const gfb_kernel* k, int g, GridView& v) {
     const gfb_grid* gr = k->grids[g];
-    const size_t elt = k->precision == GFB_PRECISION_DOUBLE ? sizeof(double) : sizeof(float);
     v.cells = gr->cells;
-    v.scaling = static_cast<const char*>(k->d_scaling) + (size_t) g * k->n_atoms * elt;
+    v.scaling = static_cast<const double*>(k->d_scaling) + (size_t) g * k->n_atoms;
     for (int a = 0; a < 3; a++) {
         v.origin[a] = gr->origin[a];
         v.spacing[a] = gr->spacing[a];
@@ -412,36 +435,46 @@ static void fill_grid_view(const gfb_kernel* k, int g, GridView& v) {
         v.hcorner[a] = gr->spacing[a] * (gr->counts[a] - 1);   // ReferenceGridForceKernels.cpp:654-656
         v.nc[a] = gr->counts[a] - 1;
     }
-    v.pad_ = 0;
+    v.row_chunks = gr->row_chunks;
     v.inv_power = k->inv_power[g];
     v.oob_k = k->oob_k[g];
 }
 
-template <typename S, int NG, bool SAME, int FMODE>
-static void launch_eval3(const EvalParams& p, cudaStream_t stream) {
+template <typename S, int LAYOUT, int NG, bool SAME, int FMODE>
+static void launch_eval4(const EvalParams& p, cudaStream_t stream) {
     const unsigned blocks = (unsigned) ((p.total + kBlock - 1) / kBlock);
     if (p.n_replicas == 1)
-        gf_eval_kernel<S, NG, SAME, FMODE, true><<<blocks, kBlock, 0, stream>>>(p);
+        gf_eval_kernel<S, LAYOUT, NG, SAME, FMODE, true><<<blocks, kBlock, 0, stream>>>(p);
     else
-        gf_eval_kernel<S, NG, SAME, FMODE, false><<<blocks, kBlock, 0, stream>>>(p);
+        gf_eval_kernel<S, LAYOUT, NG, SAME, FMODE, false><<<blocks, kBlock, 0, stream>>>(p);
 }
 
-template <typename S, int NG, bool SAME>
-static void launch_eval2(const EvalParams& p, int fmode, cudaStream_t stream) {
+template <typename S, int LAYOUT, int NG, bool SAME>
+static void launch_eval3(const EvalParams& p, int fmode, cudaStream_t stream) {
     switch (fmode) {
-        case GFB_FORCE_FIXED_ADD: launch_eval3<S, NG, SAME, GFB_FORCE_FIXED_ADD>(p, stream); break;
-        case GFB_FORCE_F64_ADD: launch_eval3<S, NG, SAME, GFB_FORCE_F64_ADD>(p, stream); break;
-        default: launch_eval3<S, NG, SAME, GFB_FORCE_F64_STORE>(p, stream); break;
+        case GFB_FORCE_FIXED_ADD: launch_eval4<S, LAYOUT, NG, SAME, GFB_FORCE_FIXED_ADD>(p, stream); break;
+        case GFB_FORCE_F64_ADD: launch_eval4<S, LAYOUT, NG, SAME, GFB_FORCE_F64_ADD>(p, stream); break;
+        default: launch_eval4<S, LAYOUT, NG, SAME, GFB_FORCE_F64_STORE>(p, stream); break;
     }
 }
 
-template <typename S>
-static void launch_eval1(const EvalParams& p, bool same, int fmode, cudaStream_t stream) {
-    if (p.n_grids == 1) launch_eval2<S, 1, true>(p, fmode, stream);
-    else if (p.n_grids == 2 && same) launch_eval2<S, 2, true>(p, fmode, stream);
-    else if (p.n_grids == 3 && same) launch_eval2<S, 3, true>(p, fmode, stream);
-    else if (same) launch_eval2<S, 0, true>(p, fmode, stream);
-    else launch_eval2<S, 0, false>(p, fmode, stream);
+template <typename S, int LAYOUT>
+static void launch_eval2(const EvalParams& p, bool same, int fmode, cudaStream_t stream) {
+    if (p.n_grids == 1) launch_eval3<S, LAYOUT, 1, true>(p, fmode, stream);
+    else if (p.n_grids == 3 && same) launch_eval3<S, LAYOUT, 3, true>(p, fmode, stream);
+    else if (same) launch_eval3<S, LAYOUT, 0, true>(p, fmode, stream);
+    else launch_eval3<S, LAYOUT, 0, false>(p, fmode, stream);
+}
+
+static void launch_eval1(const EvalParams& p, int precision, int layout, bool same, int fmode, cudaStream_t stream) {
+    if (precision == GFB_PRECISION_DOUBLE) {
+        if (layout == GFB_LAYOUT_CELLS) launch_eval2<double, GFB_LAYOUT_CELLS>(p, same, fmode, stream);
+        else launch_eval2<double, GFB_LAYOUT_ROWS>(p, same, fmode, stream);
+    } else {
+        if (layout == GFB_LAYOUT_CELLS) launch_eval2<float, GFB_LAYOUT_CELLS>(p, same, fmode, stream);
+        else if (layout == GFB_LAYOUT_ROWS) launch_eval2<float, GFB_LAYOUT_ROWS>(p, same, fmode, stream);
+        else launch_eval2<float, GFB_LAYOUT_PAIRS>(p, same, fmode, stream);
+    }
 }
 
 static int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos, double* d_energies,
@@ -464,8 +497,7 @@ static int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const do
     p.forces = d_forces;
     p.force_stride = force_stride;
     if (p.total == 0) return GFB_OK;
-    if (k->precision == GFB_PRECISION_DOUBLE) launch_eval1<double>(p, k->same_geom, force_mode, stream);
-    else launch_eval1<float>(p, k->same_geom, force_mode, stream);
+    launch_eval1(p, k->precision, k->grids[0]->layout, k->same_geom, force_mode, stream);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return GFB_OK;

@@ -2,9 +2,10 @@
 //
 // What is evaluated is the trilinear branch of the reference's Reference-platform kernel
 // (platforms/reference/src/ReferenceGridForceKernels.cpp:646-1121); how it is evaluated is new:
-//   * the grid is cell-major, 8 corners packed per cell, so a stencil is ONE 32-byte sector
-//     (LDG.E.256, sm_100+) instead of 8 scattered 4-byte loads over 4 rows (reference CUDA kernel,
+//   * every stencil is read with aligned 32-byte loads (LDG.E.256, sm_100+): 4 (ROWS), 2 (PAIRS) or 1 (CELLS)
+//     per stencil depending on the grid's layout, instead of 8 scattered 4-byte loads (reference CUDA kernel,
 //     platforms/cuda/src/kernels/gridForce.cu:349-417);
+//   * positions of a block are staged through shared memory with fully coalesced 16-byte loads;
 //   * all grids acting on an atom (ele/LJr/LJa) are evaluated by the same thread in one pass, so the
 //     position, the index math and the force write are paid once per atom, not once per grid;
 //   * index/fraction math is FP64 and bit-exact with the reference (:687-715); interpolation is FP32 in
@@ -81,22 +82,76 @@ __device__ __forceinline__ AtomCell classify(const GridView& g, double x, double
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stencil load: the 8 corners of one cell. FP32 cell = 32 B = one L2 sector = one LDG.E.256.
+// 32-byte aligned load = one L2 sector = one LDG.E.256: the unit every layout is built from.
 // .nc: the grid is read-only for the life of the kernel. L2::evict_last: the grid is the only data
 // with reuse across atoms/steps; positions and forces stream through.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_cell(const float* p, float v[8]) {
+__device__ __forceinline__ void load32(const float* p, float v[8]) {
     asm volatile("ld.global.nc.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                  : "l"(p));
 }
-__device__ __forceinline__ void load_cell(const double* p, double v[8]) {
+__device__ __forceinline__ void load32(const double* p, double v[4]) {
     asm volatile("ld.global.nc.L2::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];"
                  : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
                  : "l"(p));
-    asm volatile("ld.global.nc.L2::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];"
-                 : "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7])
-                 : "l"(p + 4));
+}
+__device__ __forceinline__ void load_cell(const float* p, float v[8]) { load32(p, v); }
+__device__ __forceinline__ void load_cell(const double* p, double v[8]) {
+    load32(p, v);
+    load32(p + 4, v + 4);
+}
+
+// (c[o], c[o+1]) for a per-lane offset o in [0, W-2]: compare/select chain, no local memory.
+template <typename S, int W>
+__device__ __forceinline__ void pick_pair(const S* c, int o, S& a, S& b) {
+    a = c[0];
+    b = c[1];
+#pragma unroll
+    for (int k = 1; k < W - 1; k++)
+        if (o == k) {
+            a = c[k];
+            b = c[k + 1];
+        }
+}
+
+// The 8 corners {v000,v001,v010,v011,v100,v101,v110,v111} (last index z) of cell (ix,iy,iz).
+template <typename S, int LAYOUT>
+__device__ __forceinline__ void load_stencil(const GridView& G, int ix, int iy, int iz, S v[8]) {
+    const S* base = static_cast<const S*>(G.cells);
+    if constexpr (LAYOUT == GFB_LAYOUT_CELLS) {
+        const size_t cell = ((size_t) ix * G.nc[1] + iy) * G.nc[2] + iz;
+        load_cell(base + 8 * cell, v);
+    } else if constexpr (LAYOUT == GFB_LAYOUT_ROWS) {
+        constexpr int W = 32 / (int) sizeof(S);     // values per chunk; consecutive chunks advance by W-1
+        const int j = iz / (W - 1);
+        const int o = iz - j * (W - 1);
+        const int ny = G.nc[1] + 1;
+        const size_t row = (size_t) ix * ny + iy;
+        const S* p00 = base + (row * G.row_chunks + j) * W;
+        const size_t dy = (size_t) G.row_chunks * W, dx = dy * ny;
+        S c0[W], c1[W], c2[W], c3[W];
+        load32(p00, c0);
+        load32(p00 + dy, c1);
+        load32(p00 + dx, c2);
+        load32(p00 + dx + dy, c3);
+        pick_pair<S, W>(c0, o, v[0], v[1]);
+        pick_pair<S, W>(c1, o, v[2], v[3]);
+        pick_pair<S, W>(c2, o, v[4], v[5]);
+        pick_pair<S, W>(c3, o, v[6], v[7]);
+    } else {  // PAIRS (float only): entry = {row iy: z=3j..3j+3 | row iy+1: z=3j..3j+3}
+        const int j = iz / 3;
+        const int o = iz - 3 * j;
+        const size_t ent = ((size_t) ix * G.nc[1] + iy) * G.row_chunks + j;
+        const size_t dx = (size_t) G.nc[1] * G.row_chunks * 8;
+        S e0[8], e1[8];
+        load_cell(base + ent * 8, e0);
+        load_cell(base + ent * 8 + dx, e1);
+        pick_pair<S, 4>(e0, o, v[0], v[1]);
+        pick_pair<S, 4>(e0 + 4, o, v[2], v[3]);
+        pick_pair<S, 4>(e1, o, v[4], v[5]);
+        pick_pair<S, 4>(e1 + 4, o, v[6], v[7]);
+    }
 }
 
 // Positions are read once per step: stream them (evict-first) so they do not displace grid sectors.
@@ -126,6 +181,22 @@ __device__ __forceinline__ void trilinear(const C v[8], C fx, C fy, C fz, C& val
     dz = ((v[1] - v[0]) * ay + (v[3] - v[2]) * fy) * ax + ((v[5] - v[4]) * ay + (v[7] - v[6]) * fy) * fx;
 }
 
+// MIXED mode energy path: the interpolated VALUE is formed in FP64 from the FP32-stored corners and the FP64
+// fractions (7 lerps, z -> y -> x as :1044-1053). A replica's energy is a sum of terms of both signs, so FP32
+// rounding of each term (6e-8 of |s*v|) would not meet 1e-6 of the much smaller total; in FP64 the only error left
+// is the FP32 rounding of the stored grid values. The kernel is memory-bound: the ~25 extra FP64 ops are hidden.
+__device__ __forceinline__ double trilinear_value_f64(const float v[8], double fx, double fy, double fz) {
+    const double ax = 1.0 - fx, ay = 1.0 - fy, az = 1.0 - fz;
+    const double vmm = az * (double) v[0] + fz * (double) v[1];
+    const double vmp = az * (double) v[2] + fz * (double) v[3];
+    const double vpm = az * (double) v[4] + fz * (double) v[5];
+    const double vpp = az * (double) v[6] + fz * (double) v[7];
+    const double vm = ay * vmm + fy * vmp;
+    const double vp = ay * vpm + fy * vpp;
+    return ax * vm + fx * vp;
+}
+__device__ __forceinline__ double trilinear_value_f64(const double*, double, double, double) { return 0.0; }  // unused (DOUBLE)
+
 // Sum of `e` over each run of equal `key` among the 32 lanes; the total lands in the run's first lane.
 // key < 0 marks idle lanes. Returns true in lanes that are the head of a run with key >= 0.
 __device__ __forceinline__ bool run_reduce(double& e, int key, int lane) {
@@ -149,18 +220,46 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* addr, unsigned l
 // ------------------------------------------------------------------------------------------------
 // The evaluation kernel. One thread per atom; that thread evaluates every grid.
 //   S      stored corner type (float MIXED / double DOUBLE); also the interpolation type
+//   LAYOUT gfb_layout of every grid of this launch
 //   NG     number of grids when > 0 (fully unrolled), 0 = runtime p.n_grids
 //   SAME   all grids share counts/spacing/origin: classify once
 //   FMODE  gfb_force_mode
 //   SINGLE one replica: block-level energy reduction, one atomic per block
 // ------------------------------------------------------------------------------------------------
-template <typename S, int NG, bool SAME, int FMODE, bool SINGLE>
-__global__ void __launch_bounds__(kBlock) gf_eval_kernel(const __grid_constant__ EvalParams p) {
+// Occupancy: the kernel waits on DRAM/L2 round trips, so resident warps are what hides them. ptxas fits the
+// one-grid kernel in 40 registers (6 blocks = 1536 threads per SM) and the three-grid kernel in 64 (4 blocks)
+// without meaningful spills; left alone it takes 46 / 78 registers and occupancy drops to 5 / 3 blocks.
+template <typename S, int LAYOUT, int NG, bool SAME, int FMODE, bool SINGLE>
+__global__ void __launch_bounds__(kBlock, (NG == 1 && sizeof(S) == 4) ? 6 : 4) gf_eval_kernel(const __grid_constant__ EvalParams p) {
     constexpr bool EXACT = sizeof(S) == 8;
-    const long long t = (long long) blockIdx.x * kBlock + threadIdx.x;
+    const long long t0 = (long long) blockIdx.x * kBlock;
+    const long long t = t0 + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool active = t < p.total;
     if (p.energies_clear && t < p.n_replicas) p.energies_clear[t] = 0.0;
+
+    // Positions of the block's 256 consecutive atoms are 6144 contiguous bytes when no index indirection is in
+    // play: read them as 384 16-byte vectors (4 lines per warp instruction instead of 24 sectors x 3 instructions
+    // for stride-24 scalar loads), then pick x,y,z out of shared memory (stride 3 doubles: conflict-free).
+    __shared__ double2 s_pos2[kBlock * 3 / 2];
+    const bool staged = p.order == nullptr && p.particles == nullptr && p.n_particles == p.n_atoms &&
+                        (reinterpret_cast<uintptr_t>(p.pos) & 15) == 0;
+    if (staged) {
+        const double2* src = reinterpret_cast<const double2*>(p.pos + 3 * t0);     // t0*24 bytes: 16-byte aligned
+        const long long n2 = (3 * (p.total - t0) + 1) / 2;                           // double2 left in the array
+        for (int i = threadIdx.x; i < kBlock * 3 / 2; i += kBlock)
+            if (i < n2) {
+                double2 v;
+                if (2 * (long long) i + 1 < 3 * (p.total - t0)) {
+                    asm volatile("ld.global.cs.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(src + i));
+                } else {   // odd tail: the last double of the array
+                    v.x = load_stream(reinterpret_cast<const double*>(src + i));
+                    v.y = 0.0;
+                }
+                s_pos2[i] = v;
+            }
+        __syncthreads();
+    }
 
     int rep = -1;
     long long gidx = 0;
@@ -177,10 +276,17 @@ __global__ void __launch_bounds__(kBlock) gf_eval_kernel(const __grid_constant__
         }
         const int particle = p.particles ? p.particles[ia] : ia;
         gidx = (long long) rep * p.n_particles + particle;
-        const double* pp = p.pos + 3 * gidx;
-        x = load_stream(pp);
-        y = load_stream(pp + 1);
-        z = load_stream(pp + 2);
+        if (staged) {
+            const double* sp = reinterpret_cast<const double*>(s_pos2) + 3 * threadIdx.x;
+            x = sp[0];
+            y = sp[1];
+            z = sp[2];
+        } else {
+            const double* pp = p.pos + 3 * gidx;
+            x = load_stream(pp);
+            y = load_stream(pp + 1);
+            z = load_stream(pp + 2);
+        }
     }
 
     double e_total = 0.0;
@@ -196,11 +302,10 @@ __global__ void __launch_bounds__(kBlock) gf_eval_kernel(const __grid_constant__
         double e_g = 0.0;
         if (active) {
             if (!SAME) c = classify<EXACT>(G, x, y, z);
-            const S s = static_cast<const S*>(G.scaling)[ia];
-            if (c.inside && s != (S) 0) {
-                const size_t cell = ((size_t) c.ix * G.nc[1] + c.iy) * G.nc[2] + c.iz;
+            const double sd = G.scaling[ia];
+            if (c.inside && sd != 0.0) {
                 S v[8];
-                load_cell(static_cast<const S*>(G.cells) + 8 * cell, v);
+                load_stencil<S, LAYOUT>(G, c.ix, c.iy, c.iz, v);
                 S val, dx, dy, dz;
                 trilinear<S>(v, (S) c.fx, (S) c.fy, (S) c.fz, val, dx, dy, dz);
                 double gx, gy, gz, dval;
@@ -213,7 +318,7 @@ __global__ void __launch_bounds__(kBlock) gf_eval_kernel(const __grid_constant__
                     gy = (double) (dy * (S) G.inv_spacing[1]);
                     gz = (double) (dz * (S) G.inv_spacing[2]);
                 }
-                dval = (double) val;
+                dval = EXACT ? (double) val : trilinear_value_f64(v, c.fx, c.fy, c.fz);
                 if (G.inv_power > 0.0) {  // :1057-1059, :1076-1080 (plain pow: NaN for negative base, as the oracle)
                     const double base = dval;
                     dval = pow(base, G.inv_power);
@@ -222,7 +327,6 @@ __global__ void __launch_bounds__(kBlock) gf_eval_kernel(const __grid_constant__
                     gy *= pf;
                     gz *= pf;
                 }
-                const double sd = (double) s;
                 e_g = sd * dval;      // :1061
                 Fx -= sd * gx;        // :1082
                 Fy -= sd * gy;
@@ -318,6 +422,45 @@ __global__ void __launch_bounds__(256) gf_repack_kernel(const double* __restrict
     }
 }
 
+// ROWS: one thread per (row, chunk). Chunk j of row (ix,iy) = values z = j*(W-1) .. j*(W-1)+W-1 (zero past the row).
+template <typename S>
+__global__ void __launch_bounds__(256) gf_repack_rows_kernel(const double* __restrict__ vals, S* __restrict__ out,
+                                                             int nx, int ny, int nz, int row_chunks) {
+    constexpr int W = 32 / (int) sizeof(S);
+    const size_t total = (size_t) nx * ny * row_chunks;
+    for (size_t c = (size_t) blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (size_t) gridDim.x * blockDim.x) {
+        const int j = (int) (c % row_chunks);
+        const size_t row = c / row_chunks;
+        const double* src = vals + row * nz;
+        S* o = out + c * W;
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            const int z = j * (W - 1) + k;
+            o[k] = z < nz ? (S) src[z] : (S) 0;
+        }
+    }
+}
+
+// PAIRS (float): one thread per (ix, iy < ny-1, j): {row iy: z=3j..3j+3, row iy+1: z=3j..3j+3}.
+__global__ void __launch_bounds__(256) gf_repack_pairs_kernel(const double* __restrict__ vals, float* __restrict__ out,
+                                                              int nx, int ny, int nz, int row_chunks) {
+    const size_t total = (size_t) nx * (ny - 1) * row_chunks;
+    for (size_t c = (size_t) blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (size_t) gridDim.x * blockDim.x) {
+        const int j = (int) (c % row_chunks);
+        const size_t r = c / row_chunks;
+        const int iy = (int) (r % (ny - 1));
+        const int ix = (int) (r / (ny - 1));
+        const double* src = vals + ((size_t) ix * ny + iy) * nz;
+        float* o = out + c * 8;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int z = 3 * j + k;
+            o[k] = z < nz ? (float) src[z] : 0.f;
+            o[4 + k] = z < nz ? (float) src[nz + z] : 0.f;
+        }
+    }
+}
+
 // Classification only (parity tests): same device function as the evaluation.
 template <bool EXACT>
 __global__ void __launch_bounds__(256) gf_classify_kernel(const __grid_constant__ ClassifyParams p) {
@@ -328,8 +471,7 @@ __global__ void __launch_bounds__(256) gf_classify_kernel(const __grid_constant_
     const int particle = p.particles ? p.particles[ia] : ia;
     const double* pp = p.pos + 3 * ((long long) rep * p.n_particles + particle);
     const AtomCell c = classify<EXACT>(p.grid, pp[0], pp[1], pp[2]);
-    const double s = EXACT ? static_cast<const double*>(p.grid.scaling)[ia]
-                           : (double) static_cast<const float*>(p.grid.scaling)[ia];
+    const double s = p.grid.scaling[ia];
     gfb_class out;
     out.inside = c.inside ? 1 : 0;
     const bool interp = c.inside && s != 0.0;

@@ -8,18 +8,20 @@
 
 namespace gfb {
 
-// One grid as the kernel sees it. `cells` points at the packed cell-major array
-// (8 corners per cell, 32 B in MIXED / 64 B in DOUBLE); cell (ix,iy,iz) is at
-// ((ix*nc[1] + iy)*nc[2] + iz) with nc = counts - 1.
+// One grid as the kernel sees it. `cells` points at the device copy in the grid's layout
+// (see gfb_layout in gridforce_b200.h and the repack kernels in gf_kernels.cuh):
+//   CELLS  cell (ix,iy,iz) -> 8 corners at ((ix*nc[1] + iy)*nc[2] + iz), nc = counts - 1
+//   ROWS   row (ix,iy) -> row_chunks 32-byte chunks; chunk j holds z = j*(W-1) .. j*(W-1)+W-1
+//   PAIRS  (ix,iy<ny-1) -> row_chunks 32-byte entries; entry j = {row iy: z=3j..3j+3, row iy+1: same}
 struct GridView {
     const void* cells;
-    const void* scaling;     // [n_atoms] float (MIXED) or double (DOUBLE), this grid's row
+    const double* scaling;   // [n_atoms] this grid's row of scaling factors (FP64 in both precisions)
     double origin[3];
     double spacing[3];
     double inv_spacing[3];   // fl(1/spacing): fast-path quotient, re-divided exactly near integers
     double hcorner[3];       // spacing*(counts-1), computed on the host exactly as the reference does
     int nc[3];               // cells per axis = counts - 1
-    int pad_;
+    int row_chunks;          // ROWS / PAIRS: 32-byte units per row
     double inv_power;        // 0 = off
     double oob_k;
 };

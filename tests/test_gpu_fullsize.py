@@ -18,7 +18,7 @@ def test_c3_million_atoms_mixed(gpu_device, oracle_built):
     port = oracle_built.PortOracle(w.counts, w.spacing, w.origin, w.grids, w.scaling)
     e_ref, f_ref, cls_ref = port.execute(w.pos[0], 0, classify=True)
     g = gf.Grid(gpu_device, w.counts, w.spacing, w.origin, w.grids[0], gf.PRECISION_MIXED)
-    assert g.device_bytes == 255 ** 3 * 32
+    assert g.layout == gf.LAYOUT_CELLS and g.device_bytes == 255 ** 3 * 32            # AUTO: packed cells, 506 MiB
     k = gf.Kernel(gpu_device, [g], w.scaling)
     cls = k.classify_host(w.pos, 0)
     assert np.array_equal(cls["cell"], cls_ref["cell"]) and np.array_equal(cls["inside"], cls_ref["inside"])
@@ -27,6 +27,30 @@ def test_c3_million_atoms_mixed(gpu_device, oracle_built):
     assert _rel(f[0], f_ref) <= 1e-5
     k.close()
     g.close()
+
+
+def test_c3_all_layouts_agree(gpu_device, oracle_built):
+    """A 200k-atom slice of C3 through every MIXED layout: same classification, energies/forces within tolerance of the
+    oracle, and identical forces between layouts (the layouts differ in where the 8 corners are read from, not in
+    arithmetic)."""
+    import openmmgridforce_b200 as gf
+    from openmmgridforce_b200 import workloads as W
+    w = W.c3_million_atoms(n_atoms=200_000)
+    port = oracle_built.PortOracle(w.counts, w.spacing, w.origin, w.grids, w.scaling)
+    e_ref, f_ref, _ = port.execute(w.pos[0], 0)
+    forces = {}
+    for layout in (gf.LAYOUT_CELLS, gf.LAYOUT_ROWS, gf.LAYOUT_PAIRS):
+        g = gf.Grid(gpu_device, w.counts, w.spacing, w.origin, w.grids[0], gf.PRECISION_MIXED, layout=layout)
+        k = gf.Kernel(gpu_device, [g], w.scaling)
+        en, f, _ = k.execute_host(w.pos)
+        assert abs(en[0] - e_ref) <= 1e-6 * abs(e_ref) and _rel(f[0], f_ref) <= 1e-5
+        forces[layout] = f
+        k.close()
+        g.close()
+    # same corners, same formulas; only FMA contraction may differ between the template instantiations
+    fmax = np.abs(f_ref).max()
+    assert np.abs(forces[gf.LAYOUT_CELLS] - forces[gf.LAYOUT_ROWS]).max() <= 2e-6 * fmax
+    assert np.abs(forces[gf.LAYOUT_CELLS] - forces[gf.LAYOUT_PAIRS]).max() <= 2e-6 * fmax
 
 
 def test_c4_batched_mixed_and_double(gpu_device, oracle_built):

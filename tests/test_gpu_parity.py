@@ -19,6 +19,9 @@ pytestmark = pytest.mark.gpu
 
 TOL = {0: (1e-6, 1e-5), 1: (1e-12, 1e-12)}     # precision -> (energy, force)
 GOLDEN = sorted(cases.CASES)
+# (precision, layout): every device layout of include/gridforce_b200.h's gfb_layout, in both arithmetic modes
+MODES = [(0, 1), (0, 2), (0, 3), (1, 1), (1, 2)]
+MODE_IDS = ["mixed-cells", "mixed-rows", "mixed-pairs", "double-cells", "double-rows"]
 
 
 def _rel_e(e, ref):
@@ -29,8 +32,8 @@ def _rel_f(f, ref):
     return np.abs(f - ref).max() / max(np.abs(ref).max(), 1e-300)
 
 
-def _make(gf, dev, c, precision, particles=None):
-    grids = [gf.Grid(dev, c["counts"], c["spacing"], c["origin"], g, precision) for g in c["grids"]]
+def _make(gf, dev, c, precision, particles=None, layout=None):
+    grids = [gf.Grid(dev, c["counts"], c["spacing"], c["origin"], g, precision, layout=layout) for g in c["grids"]]
     k = gf.Kernel(dev, grids, c["scaling"], particles=particles, inv_power=c["inv_power"], oob_k=c["oob_k"])
     return grids, k
 
@@ -41,12 +44,14 @@ def _close(grids, k):
         g.close()
 
 
-@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
 @pytest.mark.parametrize("name", GOLDEN)
-def test_golden_vectors(gpu_device, name, precision):
+def test_golden_vectors(gpu_device, name, mode):
     import openmmgridforce_b200 as gf
+    precision, layout = mode
     c, ref = cases.load_golden(name)
-    grids, k = _make(gf, gpu_device, c, precision)
+    grids, k = _make(gf, gpu_device, c, precision, layout=layout)
+    assert all(g.layout == layout for g in grids)
     en, forces, ge = k.execute_host(c["pos"], want_grid_energies=True)
     tol_e, tol_f = TOL[precision]
     for g in range(len(grids)):
@@ -100,11 +105,12 @@ def test_classification_adversarial_quotients(gpu_device, oracle_built):
         _close([g], k)
 
 
-@pytest.mark.parametrize("precision", [0, 1])
-def test_batched_replicas_vs_oracle(gpu_device, oracle_built, precision):
+@pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
+def test_batched_replicas_vs_oracle(gpu_device, oracle_built, mode):
     """C4's shape, shrunk: 96 replicas x 47 atoms x 3 grids, some replicas partly outside the grid."""
     import openmmgridforce_b200 as gf
     from openmmgridforce_b200 import workloads as W
+    precision, layout = mode
     w = W.c4_batched_replicas(n_replicas=96, counts=(96, 120, 104))
     # the ligand sits near the middle of the full test grid; move the small grid under it
     lig, _ = W.ligand47()
@@ -112,7 +118,7 @@ def test_batched_replicas_vs_oracle(gpu_device, oracle_built, precision):
     c = dict(counts=w.counts, spacing=w.spacing, origin=og, grids=w.grids, scaling=w.scaling, oob_k=w.oob_k, inv_power=w.inv_power)
     port = oracle_built.PortOracle(c["counts"], c["spacing"], c["origin"], c["grids"], c["scaling"], oob_k=c["oob_k"])
     ge_ref, f_ref = port.execute_batched(w.pos, n_threads=4)
-    grids, k = _make(gf, gpu_device, c, precision)
+    grids, k = _make(gf, gpu_device, c, precision, layout=layout)
     en, forces, ge = k.execute_host(w.pos, want_grid_energies=True)
     tol_e, tol_f = TOL[precision]
     outside = int((np.abs(f_ref).max(axis=(1, 2)) > 1e3).sum())
@@ -216,8 +222,8 @@ def test_upper_face_and_degenerate_inputs(gpu_device, oracle_built):
     sc = np.ones((1, 5))
     port = oracle_built.PortOracle(counts, sp, (0, 0, 0), [grid], sc)
     e_ref, f_ref, cls_ref = port.execute(pos, 0, classify=True)
-    for precision in (0, 1):
-        g = gf.Grid(gpu_device, counts, sp, (0, 0, 0), grid, precision)
+    for precision, layout in MODES:
+        g = gf.Grid(gpu_device, counts, sp, (0, 0, 0), grid, precision, layout=layout)
         k = gf.Kernel(gpu_device, [g], sc)
         cls = k.classify_host(pos, 0)
         assert np.array_equal(cls["cell"], cls_ref["cell"]) and np.array_equal(cls["inside"], cls_ref["inside"])
@@ -235,8 +241,33 @@ def test_upper_face_and_degenerate_inputs(gpu_device, oracle_built):
     _close([g], k0)
 
 
+def test_mixed_geometry_grids(gpu_device, oracle_built):
+    """Grids of different counts/spacing/origin in one kernel (the non-SAME code path): each classifies separately."""
+    import openmmgridforce_b200 as gf
+    rng = np.random.default_rng(8)
+    specs = [((9, 11, 13), (0.1, 0.09, 0.08), (0.0, 0.0, 0.0)), ((14, 8, 10), (0.07, 0.12, 0.1), (-0.1, 0.05, 0.0))]
+    vals = [rng.normal(size=s[0]) for s in specs]
+    n = 500
+    pos = rng.uniform(-0.15, 1.1, size=(n, 3))
+    sc = rng.normal(size=(2, n))
+    want_e, want_f = 0.0, np.zeros((n, 3))
+    for g, (cn, sp, og) in enumerate(specs):
+        port = oracle_built.PortOracle(cn, sp, og, [vals[g]], sc[g:g + 1])
+        e, f, _ = port.execute(pos, 0)
+        want_e += e
+        want_f += f
+    for layout in (1, 2):
+        grids = [gf.Grid(gpu_device, cn, sp, og, vals[g], 1, layout=layout) for g, (cn, sp, og) in enumerate(specs)]
+        k = gf.Kernel(gpu_device, grids, sc)
+        en, f, _ = k.execute_host(pos)
+        assert _rel_e(en[0], want_e) <= 1e-12 and _rel_f(f[0], want_f) <= 1e-12
+        _close(grids, k)
+
+
 def test_argument_errors_raise(gpu_device):
     import openmmgridforce_b200 as gf
+    with pytest.raises(gf.GridForceB200Error):      # PAIRS is a MIXED-only layout
+        gf.Grid(gpu_device, (4, 4, 4), (0.1, 0.1, 0.1), (0, 0, 0), np.zeros(64), gf.PRECISION_DOUBLE, layout=gf.LAYOUT_PAIRS)
     with pytest.raises(gf.GridForceB200Error):
         gf.Grid(gpu_device, (1, 4, 4), (0.1, 0.1, 0.1), (0, 0, 0), np.zeros(16))
     with pytest.raises(gf.GridForceB200Error):

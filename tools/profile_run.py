@@ -15,7 +15,7 @@ dev = gf.Device(0)
 tdev = torch.device("cuda:0")
 side = torch.cuda.Stream()
 torch.cuda.set_stream(side)
-w = {"c3": W.c3_million_atoms, "c5": lambda: W.c5_sharded_replicas(n_local=8192), "c4": W.c4_batched_replicas}[cfg]()
+w = {"c3": W.c3_million_atoms, "c5": lambda: W.c5_sharded_replicas(n_local=8192), "c5full": W.c5_sharded_replicas, "c4": W.c4_batched_replicas}[cfg]()
 grids = [gf.Grid(dev, w.counts, w.spacing, w.origin, v, prec) for v in w.grids]
 k = gf.Kernel(dev, grids, w.scaling)
 R, P = w.n_replicas, w.n_atoms
