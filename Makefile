@@ -8,7 +8,20 @@ NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisi
 LIBDIR    := openmmgridforce_b200/lib
 CSRC      := openmmgridforce_b200/csrc
 
-all: lib oracle
+PLUGIN    := openmmgridforce_b200/plugin
+# OPENMM_INCLUDE: point it at a real OpenMM install's include dir to build against OpenMM itself; default = the shim.
+OPENMM_INCLUDE ?= third_party/openmm_shim
+PLUGIN_SRCS := $(PLUGIN)/openmmapi/GridForce.cpp $(PLUGIN)/platform/B200GridForceKernels.cpp \
+               $(PLUGIN)/platform/B200GridForceKernelFactory.cpp $(PLUGIN)/platform/GridForceBatch.cpp $(PLUGIN)/plugin_driver.cpp
+PLUGIN_HDRS := $(wildcard $(PLUGIN)/openmmapi/*.h $(PLUGIN)/openmmapi/internal/*.h $(PLUGIN)/platform/*.h)
+
+all: lib plugin oracle
+
+plugin: $(LIBDIR)/libOpenMMGridForceB200.so
+
+$(LIBDIR)/libOpenMMGridForceB200.so: $(PLUGIN_SRCS) $(PLUGIN_HDRS) $(LIBDIR)/libgridforce_b200.so include/gridforce_b200.h
+	g++ -std=c++11 -O2 -fPIC -shared -Wall -Wno-unused-parameter -I$(OPENMM_INCLUDE) -Iinclude -I$(PLUGIN)/openmmapi -I$(PLUGIN)/platform \
+	    -o $@ $(PLUGIN_SRCS) -L$(LIBDIR) -lgridforce_b200 -Wl,-rpath,'$$ORIGIN' -Wl,-Bsymbolic -lpthread
 
 lib: $(LIBDIR)/libgridforce_b200.so
 
@@ -26,4 +39,4 @@ clean:
 	rm -f $(LIBDIR)/*.so
 	$(MAKE) -C oracle clean
 
-.PHONY: all lib oracle clean ptxas-info
+.PHONY: all lib plugin oracle clean ptxas-info

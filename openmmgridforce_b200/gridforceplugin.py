@@ -1,0 +1,254 @@
+"""Python face of the plugin path, shaped like the reference's SWIG module `gridforceplugin` plus the sliver of
+`openmm` a GridForce script touches (System, Context, Platform.getPlatformByName, State getters).
+
+    import openmmgridforce_b200.gridforceplugin as gfp
+    force = gfp.GridForce(); force.addGridCounts(nx, ny, nz); force.addGridSpacing(dx, dy, dz)
+    for v in values: force.addGridValue(v)            # or force.setGridValues(values)
+    for s in factors: force.addScalingFactor(s)
+    system = gfp.System(); [system.addParticle(m) for m in masses]; system.addForce(force)
+    context = gfp.Context(system, gfp.Platform.getPlatformByName("B200"))
+    context.setPositions(xyz_nm)
+    state = context.getState(getEnergy=True, getForces=True)
+    state.getPotentialEnergy(), state.getForces()
+
+(cf. python/tests/test_grid_force.py:40-64, 147-159 of the reference.) Everything is executed by the C++ plugin
+(libOpenMMGridForceB200.so: registerPlatforms/registerKernelFactories -> B200Platform -> GridForceImpl ->
+B200CalcGridForceKernel -> libgridforce_b200.so); this module only marshals arguments through ctypes because neither SWIG
+nor OpenMM exists in the build image. C++ OpenMMException surfaces as RuntimeError, as in gridforceplugin.i:49-59.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+InvPowerMode_NONE, InvPowerMode_RUNTIME, InvPowerMode_STORED = 0, 1, 2
+
+_LIB = None
+
+
+def plugin_library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libOpenMMGridForceB200.so")
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        path = plugin_library_path()
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: build it with `make plugin`")
+        lib = C.CDLL(path)
+        lib.b200_plugin_last_error.restype = C.c_char_p
+        lib.b200_plugin_create.restype = C.c_void_p
+        lib.b200_plugin_create.argtypes = [C.c_int]
+        lib.b200_plugin_destroy.argtypes = [C.c_void_p]
+        lib.b200_plugin_set_property.argtypes = [C.c_char_p, C.c_char_p]
+        lib.b200_plugin_add_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
+                                             C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+        lib.b200_plugin_add_particle_group.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.b200_plugin_finalize.argtypes = [C.c_void_p, C.c_char_p]
+        lib.b200_plugin_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.b200_plugin_update_scaling.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        lib.b200_plugin_group_energies.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        lib.b200_plugin_batch_evaluate.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        _LIB = lib
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(_lib().b200_plugin_last_error().decode())
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Platform:
+    """openmm.Platform look-alike: name lookup after the plugin's registerPlatforms()/registerKernelFactories()."""
+
+    def __init__(self, name):
+        self._name = name
+
+    @staticmethod
+    def getPlatformByName(name):
+        _check(_lib().b200_plugin_register())
+        if name != "B200":
+            raise RuntimeError(f'There is no registered Platform called "{name}"')
+        return Platform(name)
+
+    def getName(self):
+        return self._name
+
+    def setPropertyDefaultValue(self, prop, value):
+        _check(_lib().b200_plugin_set_property(prop.encode(), str(value).encode()))
+
+
+class GridForce:
+    """Same method names/meaning as the reference's GridForce for the evaluation path (openmmapi/include/GridForce.h)."""
+
+    def __init__(self):
+        self._counts, self._spacing, self._vals, self._scaling = [], [], [], []
+        self._origin = (0.0, 0.0, 0.0)
+        self._inv_power, self._inv_power_mode = 0.0, InvPowerMode_NONE
+        self._oob_k, self._interp, self._group = 10000.0, 0, 0
+        self._ligand_atoms, self._groups = [], []
+        self._context, self._index = None, None
+
+    def addGridCounts(self, nx, ny, nz):
+        self._counts += [int(nx), int(ny), int(nz)]
+
+    def addGridSpacing(self, dx, dy, dz):
+        self._spacing += [float(dx), float(dy), float(dz)]
+
+    def addGridValue(self, val):
+        self._vals.append(float(val))
+
+    def setGridValues(self, vals):
+        self._vals = np.ascontiguousarray(vals, dtype=np.float64).ravel()
+
+    def addScalingFactor(self, val):
+        self._scaling.append(float(val))
+
+    def setScalingFactors(self, vals):
+        self._scaling = [float(v) for v in vals]
+
+    def setGridOrigin(self, x, y, z):
+        self._origin = (float(x), float(y), float(z))
+
+    def getGridOrigin(self):
+        return self._origin
+
+    def setInvPowerMode(self, mode, inv_power):
+        if mode != InvPowerMode_NONE and inv_power == 0.0:
+            raise RuntimeError("GridForce: inv_power must be non-zero when mode != NONE")
+        if mode == InvPowerMode_NONE and inv_power != 0.0:
+            raise RuntimeError("GridForce: inv_power must be 0 when mode == NONE")
+        self._inv_power_mode, self._inv_power = mode, float(inv_power)
+
+    def getInvPower(self):
+        return self._inv_power
+
+    def setOutOfBoundsRestraint(self, k):
+        self._oob_k = float(k)
+
+    def getOutOfBoundsRestraint(self):
+        return self._oob_k
+
+    def setInterpolationMethod(self, method):
+        if method < 0 or method > 3:
+            raise RuntimeError("GridForce: Invalid interpolation method. Must be 0 (trilinear), 1 (cubic B-spline), 2 (tricubic), or 3 (quintic Hermite)")
+        self._interp = int(method)
+
+    def setLigandAtoms(self, atoms):
+        self._ligand_atoms = [int(a) for a in atoms]
+
+    def setForceGroup(self, group):
+        self._group = int(group)
+
+    def getForceGroup(self):
+        return self._group
+
+    def addParticleGroup(self, name, particle_indices, scaling_factors=()):
+        self._groups.append((name, [int(i) for i in particle_indices], [float(s) for s in scaling_factors]))
+        return len(self._groups) - 1
+
+    def getNumParticleGroups(self):
+        return len(self._groups)
+
+    def getParticleGroupEnergies(self, context):
+        out = np.zeros(max(1, len(self._groups)))
+        n = C.c_int(0)
+        _check(_lib().b200_plugin_group_energies(context._h, self._index, _p(out), out.size, C.byref(n)))
+        return list(out[:n.value])
+
+    def updateParametersInContext(self, context):
+        sc = np.ascontiguousarray(self._scaling, dtype=np.float64)
+        _check(_lib().b200_plugin_update_scaling(context._h, self._index, _p(sc), sc.size))
+
+
+class System:
+    def __init__(self):
+        self._masses, self._forces = [], []
+
+    def addParticle(self, mass):
+        self._masses.append(float(mass))
+        return len(self._masses) - 1
+
+    def getNumParticles(self):
+        return len(self._masses)
+
+    def addForce(self, force):
+        self._forces.append(force)
+        return len(self._forces) - 1
+
+    def getNumForces(self):
+        return len(self._forces)
+
+
+class State:
+    def __init__(self, energy, forces):
+        self._e, self._f = energy, forces
+
+    def getPotentialEnergy(self):
+        return self._e
+
+    def getForces(self, asNumpy=True):
+        return self._f
+
+
+class Context:
+    """Context(system, platform): creating it runs GridForceImpl::initialize -> kernel initialize() for every GridForce."""
+
+    def __init__(self, system, platform):
+        lib = _lib()
+        self._n = system.getNumParticles()
+        self._h = C.c_void_p(lib.b200_plugin_create(self._n))
+        self._pos = None
+        for index, f in enumerate(system._forces):
+            counts = np.asarray(f._counts, dtype=np.int32)
+            spacing = np.asarray(f._spacing, dtype=np.float64)
+            if counts.size != 3 or spacing.size != 3:
+                raise RuntimeError("GridForce: grid counts and spacing must each be given exactly once")
+            vals = np.ascontiguousarray(f._vals, dtype=np.float64)
+            sc = np.ascontiguousarray(f._scaling, dtype=np.float64)
+            la = np.ascontiguousarray(f._ligand_atoms, dtype=np.int32) if f._ligand_atoms else None
+            og = np.asarray(f._origin, dtype=np.float64)
+            _check(lib.b200_plugin_add_grid(self._h, _p(counts), _p(spacing), _p(og), _p(vals), vals.size, _p(sc), sc.size, _p(la),
+                                            0 if la is None else la.size, f._inv_power, f._oob_k, f._interp, f._group))
+            for name, idx, scl in f._groups:
+                ia = np.ascontiguousarray(idx, dtype=np.int32)
+                sa = np.ascontiguousarray(scl, dtype=np.float64) if scl else None
+                _check(lib.b200_plugin_add_particle_group(self._h, index, name.encode(), _p(ia), _p(sa), ia.size))
+            f._context, f._index = self, index
+        _check(lib.b200_plugin_finalize(self._h, platform.getName().encode()))
+
+    def setPositions(self, positions):
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        if pos.shape != (self._n, 3):
+            raise RuntimeError("Called setPositions() on a Context with the wrong number of positions")
+        self._pos = pos
+
+    def getState(self, getEnergy=False, getForces=False, groups=-1):
+        if self._pos is None:
+            raise RuntimeError("Particle positions have not been set")
+        e = C.c_double(0.0)
+        f = np.zeros((self._n, 3))
+        _check(_lib().b200_plugin_execute(self._h, _p(self._pos), C.c_int(groups), C.byref(e), _p(f)))
+        return State(e.value, f)
+
+    def evaluateBatch(self, positions, precision="mixed", want_forces=True):
+        """GridForceBatch over this System's GridForces: positions [R, A, 3] -> (energies [R], forces [R, A, 3] | None)."""
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        r = pos.shape[0]
+        en = np.zeros(r)
+        f = np.zeros_like(pos) if want_forces else None
+        _check(_lib().b200_plugin_batch_evaluate(self._h, precision.encode(), _p(pos), r, _p(en), _p(f)))
+        return en, f
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib().b200_plugin_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

@@ -1,0 +1,139 @@
+// See GridForce.h. Behaviour (defaults, validation messages' meaning) follows the reference's
+// openmmapi/src/GridForce.cpp for the members that exist here.
+#include "GridForce.h"
+
+#include "GridForceKernels.h"
+#include "internal/GridForceImpl.h"
+#include "openmm/OpenMMException.h"
+#include "openmm/internal/ContextImpl.h"
+
+using OpenMM::OpenMMException;
+
+namespace GridForcePlugin {
+
+// defaults: reference GridForce.cpp:52 (cap 41840 kJ/mol, restraint 10000 kJ/mol/nm^2, trilinear, no inv-power)
+GridForce::GridForce()
+    : m_origin(3, 0.0), m_invPower(0.0), m_gridCap(41840.0), m_oobK(10000.0), m_invPowerMode(InvPowerMode::NONE),
+      m_interpolation(0), m_systemPtr(0) {}
+
+void GridForce::addGridCounts(int nx, int ny, int nz) {
+    m_counts.push_back(nx);
+    m_counts.push_back(ny);
+    m_counts.push_back(nz);
+}
+void GridForce::addGridSpacing(double dx, double dy, double dz) {
+    m_spacing.push_back(dx);
+    m_spacing.push_back(dy);
+    m_spacing.push_back(dz);
+}
+void GridForce::addGridValue(double val) { m_vals.push_back(val); }
+void GridForce::setGridValues(const std::vector<double>& vals) { m_vals = vals; }
+const std::vector<double>& GridForce::getGridValues() const { return m_vals; }
+void GridForce::setGridOrigin(double x, double y, double z) {
+    m_origin[0] = x;
+    m_origin[1] = y;
+    m_origin[2] = z;
+}
+void GridForce::getGridOrigin(double& x, double& y, double& z) const {
+    x = m_origin[0];
+    y = m_origin[1];
+    z = m_origin[2];
+}
+
+void GridForce::addScalingFactor(double val) { m_scaling.push_back(val); }
+void GridForce::setScalingFactor(int index, double val) {
+    if (index < 0 || index >= (int) m_scaling.size()) throw OpenMMException("GridForce: scaling factor index out of range");
+    m_scaling[index] = val;
+}
+void GridForce::setScalingFactors(const std::vector<double>& vals) { m_scaling = vals; }
+
+void GridForce::setInvPowerMode(InvPowerMode mode, double inv_power) {
+    if (mode != InvPowerMode::NONE && inv_power == 0.0)
+        throw OpenMMException("GridForce: inv_power must be non-zero when mode != NONE");
+    if (mode == InvPowerMode::NONE && inv_power != 0.0)
+        throw OpenMMException("GridForce: inv_power must be 0 when mode == NONE");
+    m_invPowerMode = mode;
+    m_invPower = inv_power;
+}
+InvPowerMode GridForce::getInvPowerMode() const { return m_invPowerMode; }
+double GridForce::getInvPower() const { return m_invPower; }
+void GridForce::setGridCap(double uMax) { m_gridCap = uMax; }
+double GridForce::getGridCap() const { return m_gridCap; }
+void GridForce::setOutOfBoundsRestraint(double k) { m_oobK = k; }
+double GridForce::getOutOfBoundsRestraint() const { return m_oobK; }
+void GridForce::setInterpolationMethod(int method) {
+    if (method < 0 || method > 3)
+        throw OpenMMException("GridForce: Invalid interpolation method. Must be 0 (trilinear), 1 (cubic B-spline), 2 (tricubic), or 3 (quintic Hermite)");
+    m_interpolation = method;
+}
+int GridForce::getInterpolationMethod() const { return m_interpolation; }
+
+void GridForce::setLigandAtoms(const std::vector<int>& atomIndices) { m_ligandAtoms = atomIndices; }
+const std::vector<int>& GridForce::getLigandAtoms() const { return m_ligandAtoms; }
+void GridForce::setParticles(const std::vector<int>& particles) { m_particles = particles; }
+const std::vector<int>& GridForce::getParticles() const { return m_particles; }
+
+int GridForce::addParticleGroup(const std::string& name, const std::vector<int>& particleIndices,
+                                const std::vector<double>& scalingFactors) {
+    for (size_t i = 0; i < m_groups.size(); i++)
+        if (m_groups[i].name == name) throw OpenMMException("Particle group '" + name + "' already exists");
+    if (!scalingFactors.empty() && scalingFactors.size() != particleIndices.size())
+        throw OpenMMException("Particle group '" + name + "': one scaling factor per particle is required");
+    m_groups.push_back(ParticleGroup(name, particleIndices, scalingFactors));
+    return (int) m_groups.size() - 1;
+}
+int GridForce::getNumParticleGroups() const { return (int) m_groups.size(); }
+const ParticleGroup& GridForce::getParticleGroup(int index) const {
+    if (index < 0 || index >= (int) m_groups.size()) throw OpenMMException("Particle group index out of range");
+    return m_groups[index];
+}
+const ParticleGroup* GridForce::getParticleGroupByName(const std::string& name) const {
+    for (size_t i = 0; i < m_groups.size(); i++)
+        if (m_groups[i].name == name) return &m_groups[i];
+    return 0;
+}
+void GridForce::removeParticleGroup(int index) {
+    if (index < 0 || index >= (int) m_groups.size()) throw OpenMMException("Particle group index out of range");
+    m_groups.erase(m_groups.begin() + index);
+}
+void GridForce::clearParticleGroups() { m_groups.clear(); }
+
+void GridForce::getGridParameters(std::vector<int>& g_counts, std::vector<double>& g_spacing, std::vector<double>& g_vals,
+                                  std::vector<double>& g_scaling_factors) const {
+    g_counts = m_counts;
+    g_spacing = m_spacing;
+    g_vals = m_vals;
+    g_scaling_factors = m_scaling;
+}
+
+OpenMM::ForceImpl* GridForce::createImpl() const { return new GridForceImpl(*this); }
+
+void GridForce::updateParametersInContext(OpenMM::Context& context) {
+    dynamic_cast<GridForceImpl&>(getImplInContext(context)).updateParametersInContext(getContextImpl(context));
+}
+std::vector<double> GridForce::getParticleGroupEnergies(OpenMM::Context& context) const {
+    return dynamic_cast<GridForceImpl&>(getImplInContext(context)).getParticleGroupEnergies();
+}
+std::vector<double> GridForce::getParticleAtomEnergies(OpenMM::Context& context) const {
+    return dynamic_cast<GridForceImpl&>(getImplInContext(context)).getParticleAtomEnergies();
+}
+
+// ---- GridForceImpl (reference openmmapi/src/GridForceImpl.cpp:55-86) ---------------------------------------------
+void GridForceImpl::initialize(OpenMM::ContextImpl& context) {
+    const_cast<GridForce&>(owner).setSystemPointer(&context.getSystem());
+    kernel = context.getPlatform().createKernel(CalcGridForceKernel::Name(), context);
+    kernel.getAs<CalcGridForceKernel>().initialize(context.getSystem(), owner);
+}
+double GridForceImpl::calcForcesAndEnergy(OpenMM::ContextImpl& context, bool includeForces, bool includeEnergy, int groups) {
+    if ((groups & (1 << owner.getForceGroup())) != 0)
+        return kernel.getAs<CalcGridForceKernel>().execute(context, includeForces, includeEnergy);
+    return 0.0;
+}
+std::vector<std::string> GridForceImpl::getKernelNames() { return std::vector<std::string>(1, CalcGridForceKernel::Name()); }
+void GridForceImpl::updateParametersInContext(OpenMM::ContextImpl& context) {
+    kernel.getAs<CalcGridForceKernel>().copyParametersToContext(context, owner);
+}
+std::vector<double> GridForceImpl::getParticleGroupEnergies() { return kernel.getAs<CalcGridForceKernel>().getParticleGroupEnergies(); }
+std::vector<double> GridForceImpl::getParticleAtomEnergies() { return kernel.getAs<CalcGridForceKernel>().getParticleAtomEnergies(); }
+
+}  // namespace GridForcePlugin

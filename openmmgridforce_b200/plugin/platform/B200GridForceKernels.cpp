@@ -1,0 +1,173 @@
+#include "B200GridForceKernels.h"
+
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <sstream>
+
+#include "B200Platform.h"
+#include "openmm/OpenMMException.h"
+#include "openmm/internal/ContextImpl.h"
+
+using namespace OpenMM;
+
+namespace GridForcePlugin {
+
+static void check(int rc, const char* what) {
+    if (rc != GFB_OK) throw OpenMMException(std::string("GridForce[B200]: ") + what + ": " + gfb_last_error());
+}
+
+// ---- process-wide device and grid registries ---------------------------------------------------------------------
+static std::mutex registryMutex;
+
+gfb_device* b200Device(int ordinal) {
+    static std::map<int, gfb_device*> devices;
+    std::lock_guard<std::mutex> lock(registryMutex);
+    std::map<int, gfb_device*>::iterator it = devices.find(ordinal);
+    if (it != devices.end()) return it->second;
+    gfb_device* dev = 0;
+    check(gfb_device_open(ordinal, &dev), "cannot open the GPU (this platform has no CPU fallback)");
+    devices[ordinal] = dev;
+    return dev;
+}
+
+static unsigned long long fnv1a(const void* data, size_t bytes, unsigned long long h = 1469598103934665603ull) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < bytes; i++) {
+        h ^= p[i];
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+
+std::shared_ptr<SharedGrid> b200AcquireGrid(gfb_device* dev, int ordinal, int precision, const std::vector<int>& counts,
+                                            const std::vector<double>& spacing, const double origin[3],
+                                            const std::vector<double>& vals) {
+    static std::map<std::string, std::weak_ptr<SharedGrid> > cache;
+    unsigned long long h = fnv1a(vals.data(), vals.size() * sizeof(double));
+    h = fnv1a(counts.data(), 3 * sizeof(int), h);
+    h = fnv1a(spacing.data(), 3 * sizeof(double), h);
+    h = fnv1a(origin, 3 * sizeof(double), h);
+    std::ostringstream key;
+    key << ordinal << ':' << precision << ':' << vals.size() << ':' << h;
+    std::lock_guard<std::mutex> lock(registryMutex);
+    std::shared_ptr<SharedGrid> hit = cache[key.str()].lock();
+    if (hit) return hit;
+    gfb_grid* g = 0;
+    check(gfb_grid_create(dev, counts.data(), spacing.data(), origin, vals.data(), vals.size(), precision, GFB_LAYOUT_AUTO, &g),
+          "grid upload");
+    std::shared_ptr<SharedGrid> made(new SharedGrid(g));
+    cache[key.str()] = made;
+    return made;
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------------------------
+B200CalcGridForceKernel::~B200CalcGridForceKernel() { release(); }
+
+void B200CalcGridForceKernel::release() {
+    for (size_t i = 0; i < kernels.size(); i++) gfb_kernel_destroy(kernels[i]);
+    kernels.clear();
+}
+
+// What CalcGridForceKernel::initialize captures (ReferenceGridForceKernels.cpp:147-160), validated the way the CUDA
+// platform validates (CudaGridForceKernels.cpp:387-403), and refusing the reference features outside this path.
+void B200CalcGridForceKernel::build(const GridForce& force) {
+    std::vector<int> counts;
+    std::vector<double> spacing, vals, scaling;
+    force.getGridParameters(counts, spacing, vals, scaling);
+    if (force.getInterpolationMethod() != 0)
+        throw OpenMMException("GridForce[B200]: only trilinear interpolation (method 0) is implemented on this platform");
+    if (force.getTiledMode()) throw OpenMMException("GridForce[B200]: tiled grids are not supported on this platform");
+    if (force.getAutoGenerateGrid() && vals.empty())
+        throw OpenMMException("GridForce[B200]: grid auto-generation is not supported on this platform; generate the grid first");
+    if (force.getAutoCalculateScalingFactors() && scaling.empty())
+        throw OpenMMException("GridForce[B200]: automatic scaling factors are not supported on this platform; pass them explicitly");
+    if (counts.size() != 3 || spacing.size() != 3)
+        throw OpenMMException("GridForce[B200]: grid counts and spacing must each be given exactly once");
+    if (vals.size() != (size_t) counts[0] * counts[1] * counts[2])
+        throw OpenMMException("GridForce[B200]: number of grid values does not match the grid counts");
+    double origin[3];
+    force.getGridOrigin(origin[0], origin[1], origin[2]);
+    const double invPower = force.getInvPower(), oobK = force.getOutOfBoundsRestraint();
+
+    dev = b200Device(deviceIndex);
+    grid = b200AcquireGrid(dev, deviceIndex, precision, counts, spacing, origin, vals);
+    release();
+    gfb_grid* handle = grid->handle;
+    groupMode = force.getNumParticleGroups() > 0;
+    if (groupMode) {
+        // Multi-ligand mode (GridForce.h:433-508): every group is evaluated with its own particle list and scaling
+        // factors; per-group energies are kept for getParticleGroupEnergies().
+        for (int g = 0; g < force.getNumParticleGroups(); g++) {
+            const ParticleGroup& grp = force.getParticleGroup(g);
+            for (size_t i = 0; i < grp.particleIndices.size(); i++)
+                if (grp.particleIndices[i] < 0 || grp.particleIndices[i] >= numParticles)
+                    throw OpenMMException("GridForce[B200]: particle group '" + grp.name + "' has an index outside the System");
+            gfb_kernel* k = 0;
+            check(gfb_kernel_create(dev, 1, &handle, (int) grp.particleIndices.size(), grp.scalingFactors.data(),
+                                    grp.particleIndices.data(), &invPower, &oobK, &k), "kernel setup");
+            kernels.push_back(k);
+        }
+        return;
+    }
+    // Single mode: scaling factor ia belongs to particle ligandAtoms[ia] (identity when no ligand atoms are set).
+    // The loop bound is the number of scaling factors, not the particle count (reference quirk Q6).
+    const std::vector<int>& ligand = force.getLigandAtoms();
+    const int* particles = 0;
+    if (!ligand.empty()) {
+        if (ligand.size() != scaling.size())
+            throw OpenMMException("GridForce[B200]: number of ligand atoms differs from the number of scaling factors");
+        for (size_t i = 0; i < ligand.size(); i++)
+            if (ligand[i] < 0 || ligand[i] >= numParticles)
+                throw OpenMMException("GridForce[B200]: ligand atom index outside the System");
+        particles = ligand.data();
+    } else if ((int) scaling.size() > numParticles) {
+        throw OpenMMException("GridForce[B200]: more scaling factors than particles in the System");
+    }
+    gfb_kernel* k = 0;
+    check(gfb_kernel_create(dev, 1, &handle, (int) scaling.size(), scaling.data(), particles, &invPower, &oobK, &k), "kernel setup");
+    kernels.push_back(k);
+}
+
+void B200CalcGridForceKernel::initialize(const System& system, const GridForce& force) {
+    numParticles = system.getNumParticles();
+    build(force);
+}
+
+// CalcGridForceKernel::execute: positions and forces are the Reference platform's host arrays
+// (std::vector<Vec3> = contiguous double[3]); forces are accumulated (forceData[i] -= ..., :1082) and the energy is
+// returned, as the Reference kernel does (:1120) — includeForces/includeEnergy only prune work, never change values.
+double B200CalcGridForceKernel::execute(ContextImpl& context, bool includeForces, bool includeEnergy) {
+    ReferencePlatform::PlatformData* data = reinterpret_cast<ReferencePlatform::PlatformData*>(context.getPlatformData());
+    std::vector<Vec3>& pos = *data->positions;
+    std::vector<Vec3>& frc = *data->forces;
+    static_assert(sizeof(Vec3) == 3 * sizeof(double), "Vec3 must be three packed doubles");
+    if (numParticles == 0 || kernels.empty()) return 0.0;
+    const double* p = &pos[0][0];
+    double* f = includeForces ? &frc[0][0] : 0;
+    double total = 0.0;
+    lastGroupEnergies.assign(kernels.size(), 0.0);
+    for (size_t i = 0; i < kernels.size(); i++) {
+        double e = 0.0;
+        check(gfb_kernel_execute_host(kernels[i], 1, numParticles, p, &e, 0, f, GFB_FORCE_F64_ADD), "execute");
+        lastGroupEnergies[i] = e;
+        total += e;
+    }
+    (void) includeEnergy;
+    return total;
+}
+
+// Reference: re-reads grid parameters and inv_power (ReferenceGridForceKernels.cpp:1123-1127).
+void B200CalcGridForceKernel::copyParametersToContext(ContextImpl& context, const GridForce& force) {
+    build(force);
+}
+
+std::vector<double> B200CalcGridForceKernel::getParticleGroupEnergies() {
+    return groupMode ? lastGroupEnergies : std::vector<double>();
+}
+
+// Per-atom energies are a diagnostic of the reference's CUDA platform only (the Reference platform returns an empty
+// vector, ReferenceGridForceKernels.cpp:1134-1137); not produced here.
+std::vector<double> B200CalcGridForceKernel::getParticleAtomEnergies() { return std::vector<double>(); }
+
+}  // namespace GridForcePlugin

@@ -1,0 +1,165 @@
+// C entry points that drive the PLUGIN path end to end the way OpenMM would — registerPlatforms() /
+// registerKernelFactories() -> Platform::getPlatformByName("B200") -> System + GridForce -> Context -> GridForceImpl ->
+// B200CalcGridForceKernel::execute — so that tests/test_plugin.py can compare it with the oracle from Python (there is
+// no SWIG or OpenMM in the build container; with them, python/gridforceplugin_b200.i exposes the same classes).
+// Mirrors oracle/ref_driver.cpp's call shape on purpose: same inputs, two implementations.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "B200GridForceKernelFactory.h"
+#include "B200Platform.h"
+#include "GridForce.h"
+#include "GridForceBatch.h"
+#include "openmm/Context.h"
+#include "openmm/Platform.h"
+#include "openmm/System.h"
+#include "openmm/internal/windowsExport.h"
+
+using namespace OpenMM;
+using namespace GridForcePlugin;
+
+namespace {
+struct Handle {
+    System system;
+    std::vector<GridForce*> forces;   // owned by system
+    Context* context;
+    GridForceBatch* batch;
+    int numParticles;
+    Handle() : context(0), batch(0), numParticles(0) {}
+    ~Handle() {
+        delete context;
+        delete batch;
+    }
+};
+thread_local std::string lastError;
+}  // namespace
+
+#define GUARD(...)                    \
+    try {                             \
+        __VA_ARGS__;                  \
+        return 0;                     \
+    } catch (std::exception & e) {    \
+        lastError = e.what();         \
+        return 1;                     \
+    }
+
+extern "C" {
+
+OPENMM_EXPORT const char* b200_plugin_last_error() { return lastError.c_str(); }
+
+// 1 if a platform called "B200" is registered and serves the "CalcGridForce" kernel name.
+OPENMM_EXPORT int b200_plugin_register() {
+    GUARD({
+        registerPlatforms();
+        registerKernelFactories();
+        Platform& p = Platform::getPlatformByName("B200");
+        if (!p.supportsKernels(std::vector<std::string>(1, "CalcGridForce"))) throw OpenMMException("B200 platform lacks CalcGridForce");
+    })
+}
+
+OPENMM_EXPORT int b200_plugin_set_property(const char* name, const char* value) {
+    GUARD({
+        registerB200GridForceKernelFactories();
+        dynamic_cast<B200Platform&>(Platform::getPlatformByName("B200")).setPropertyDefaultValue(name, value);
+    })
+}
+
+OPENMM_EXPORT void* b200_plugin_create(int numParticles) {
+    Handle* h = new Handle();
+    h->numParticles = numParticles;
+    for (int i = 0; i < numParticles; i++) h->system.addParticle(1.0);
+    return h;
+}
+
+OPENMM_EXPORT int b200_plugin_add_grid(void* handle, const int* counts, const double* spacing, const double* origin, const double* vals,
+                                       long long nVals, const double* scaling, int nScaling, const int* ligandAtoms, int nLigandAtoms,
+                                       double invPower, double oobK, int interpolationMethod, int forceGroup) {
+    Handle* h = static_cast<Handle*>(handle);
+    GUARD({
+        GridForce* f = new GridForce();
+        h->system.addForce(f);
+        h->forces.push_back(f);
+        f->addGridCounts(counts[0], counts[1], counts[2]);
+        f->addGridSpacing(spacing[0], spacing[1], spacing[2]);
+        f->setGridOrigin(origin[0], origin[1], origin[2]);
+        f->setGridValues(std::vector<double>(vals, vals + nVals));
+        for (int i = 0; i < nScaling; i++) f->addScalingFactor(scaling[i]);
+        if (ligandAtoms && nLigandAtoms > 0) f->setLigandAtoms(std::vector<int>(ligandAtoms, ligandAtoms + nLigandAtoms));
+        if (invPower != 0.0) f->setInvPowerMode(InvPowerMode::STORED, invPower);
+        f->setOutOfBoundsRestraint(oobK);
+        f->setInterpolationMethod(interpolationMethod);
+        f->setForceGroup(forceGroup);
+    })
+}
+
+OPENMM_EXPORT int b200_plugin_add_particle_group(void* handle, int force, const char* name, const int* particles, const double* scaling, int n) {
+    Handle* h = static_cast<Handle*>(handle);
+    GUARD({
+        h->forces.at(force)->addParticleGroup(name, std::vector<int>(particles, particles + n),
+                                              scaling ? std::vector<double>(scaling, scaling + n) : std::vector<double>());
+    })
+}
+
+// Context creation on the platform named `platform` ("B200"): GridForceImpl::initialize -> kernel initialize().
+OPENMM_EXPORT int b200_plugin_finalize(void* handle, const char* platform) {
+    Handle* h = static_cast<Handle*>(handle);
+    GUARD({
+        registerB200GridForceKernelFactories();
+        h->context = new Context(h->system, Platform::getPlatformByName(platform));
+    })
+}
+
+OPENMM_EXPORT int b200_plugin_execute(void* handle, const double* positions, int groups, double* energy, double* forces) {
+    Handle* h = static_cast<Handle*>(handle);
+    GUARD({
+        if (!h->context) throw OpenMMException("finalize first");
+        std::vector<Vec3> pos(h->numParticles);
+        for (int i = 0; i < h->numParticles; i++) pos[i] = Vec3(positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]);
+        h->context->setPositions(pos);
+        *energy = h->context->computeForcesAndEnergy(true, true, groups);
+        if (forces) memcpy(forces, &h->context->getForces()[0], sizeof(double) * 3 * h->numParticles);
+    })
+}
+
+OPENMM_EXPORT int b200_plugin_update_scaling(void* handle, int force, const double* scaling, int n) {
+    Handle* h = static_cast<Handle*>(handle);
+    GUARD({
+        h->forces.at(force)->setScalingFactors(std::vector<double>(scaling, scaling + n));
+        h->forces.at(force)->updateParametersInContext(*h->context);
+    })
+}
+
+OPENMM_EXPORT int b200_plugin_group_energies(void* handle, int force, double* out, int capacity, int* count) {
+    Handle* h = static_cast<Handle*>(handle);
+    GUARD({
+        std::vector<double> e = h->forces.at(force)->getParticleGroupEnergies(*h->context);
+        *count = (int) e.size();
+        for (int i = 0; i < (int) e.size() && i < capacity; i++) out[i] = e[i];
+    })
+}
+
+// Batched entry point over the forces added so far (GridForceBatch): positions [R][A][3] -> energies [R], forces.
+OPENMM_EXPORT int b200_plugin_batch_evaluate(void* handle, const char* precision, const double* positions, int numReplicas,
+                                             double* energies, double* forces) {
+    Handle* h = static_cast<Handle*>(handle);
+    GUARD({
+        if (!h->batch) {
+            h->batch = new GridForceBatch(0, precision);
+            for (size_t i = 0; i < h->forces.size(); i++) h->batch->addForce(*h->forces[i]);
+        }
+        const size_t n = (size_t) numReplicas * h->batch->getNumAtoms() * 3;
+        std::vector<double> pos(positions, positions + n), e, f;
+        if (forces) {
+            h->batch->evaluateWithForces(pos, numReplicas, e, f);
+            memcpy(forces, f.data(), sizeof(double) * n);
+        } else {
+            e = h->batch->evaluate(pos, numReplicas);
+        }
+        memcpy(energies, e.data(), sizeof(double) * numReplicas);
+    })
+}
+
+OPENMM_EXPORT void b200_plugin_destroy(void* handle) { delete static_cast<Handle*>(handle); }
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+"""The OpenMM-plugin path (C++: registerPlatforms/registerKernelFactories -> B200Platform -> GridForceImpl ->
+B200CalcGridForceKernel), driven the way the reference's own tests drive a platform
+(python/tests/test_grid_force.py:40-64, 117-159), and compared with the golden outputs of the reference kernel."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import cases  # noqa: E402
+
+
+def test_plugin_exports_openmm_entry_points():
+    """What OpenMM's plugin loader needs from a platform library (every reference platform lib exports the same two)."""
+    import openmmgridforce_b200.gridforceplugin as gfp
+    lib = ctypes.CDLL(gfp.plugin_library_path())
+    for name in ("registerPlatforms", "registerKernelFactories", "registerB200GridForceKernelFactories"):
+        assert hasattr(lib, name)
+
+
+def test_platform_registers_and_lists_kernel():
+    import openmmgridforce_b200.gridforceplugin as gfp
+    p = gfp.Platform.getPlatformByName("B200")        # registers, then checks supportsKernels(["CalcGridForce"])
+    assert p.getName() == "B200"
+    with pytest.raises(RuntimeError):
+        gfp.Platform.getPlatformByName("CUDA")
+
+
+def test_api_validation_matches_reference_messages():
+    import openmmgridforce_b200.gridforceplugin as gfp
+    f = gfp.GridForce()
+    with pytest.raises(RuntimeError, match="Invalid interpolation method"):
+        f.setInterpolationMethod(4)
+    with pytest.raises(RuntimeError, match="inv_power must be non-zero"):
+        f.setInvPowerMode(gfp.InvPowerMode_STORED, 0.0)
+
+
+def _build_system(gfp, c, ligand_atoms=None):
+    system = gfp.System()
+    for _ in range(c["pos"].shape[0]):
+        system.addParticle(1.0)
+    forces = []
+    for g, vals in enumerate(c["grids"]):
+        force = gfp.GridForce()
+        force.addGridCounts(*c["counts"])
+        force.addGridSpacing(*c["spacing"])
+        force.setGridOrigin(*c["origin"])
+        if g == 0 and vals.size <= 5000:
+            for v in vals.ravel():                    # the reference's per-value idiom (test_grid_force.py:58-59)
+                force.addGridValue(v)
+        else:
+            force.setGridValues(vals)
+        for s in c["scaling"][g]:
+            force.addScalingFactor(s)
+        if c["inv_power"][g] > 0:
+            force.setInvPowerMode(gfp.InvPowerMode_STORED, c["inv_power"][g])
+        force.setOutOfBoundsRestraint(c["oob_k"][g])
+        force.setForceGroup(g)
+        system.addForce(force)
+        forces.append(force)
+    return system, forces
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["mixed", "double"])
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_plugin_matches_reference_kernel(name, precision):
+    import openmmgridforce_b200.gridforceplugin as gfp
+    c, ref = cases.load_golden(name)
+    platform = gfp.Platform.getPlatformByName("B200")
+    platform.setPropertyDefaultValue("Precision", precision)
+    system, forces = _build_system(gfp, c)
+    context = gfp.Context(system, platform)
+    context.setPositions(c["pos"])
+    state = context.getState(getEnergy=True, getForces=True)
+    te, tf = (1e-6, 1e-5) if precision == "mixed" else (1e-12, 1e-12)
+    assert abs(state.getPotentialEnergy() - ref["energy"]) <= te * abs(ref["energy"])
+    assert np.abs(state.getForces() - ref["forces"]).max() <= tf * np.abs(ref["forces"]).max()
+    for g in range(len(forces)):                      # force groups gate each GridForce (GridForceImpl.cpp:64-68)
+        s = context.getState(getEnergy=True, getForces=True, groups=1 << g)
+        assert abs(s.getPotentialEnergy() - ref["grid_energies"][g]) <= te * max(abs(ref["grid_energies"][g]), 1e-300)
+        assert np.abs(s.getForces() - ref["grid_forces"][g]).max() <= tf * np.abs(ref["grid_forces"][g]).max()
+    platform.setPropertyDefaultValue("Precision", "mixed")
+
+
+@pytest.mark.gpu
+def test_plugin_batch_entry_point_and_groups(oracle_built):
+    """GridForceBatch (one launch for R replicas x G forces) and particle groups, against the oracle."""
+    import openmmgridforce_b200.gridforceplugin as gfp
+    c, ref = cases.load_golden("ligand_three_grids")
+    platform = gfp.Platform.getPlatformByName("B200")
+    platform.setPropertyDefaultValue("Precision", "double")
+    system, forces = _build_system(gfp, c)
+    context = gfp.Context(system, platform)
+    rng = np.random.default_rng(0)
+    pos = np.stack([c["pos"] + rng.uniform(-0.05, 0.05, size=3) for _ in range(9)])
+    en, f = context.evaluateBatch(pos, precision="double")
+    port = oracle_built.PortOracle(c["counts"], c["spacing"], c["origin"], c["grids"], c["scaling"], oob_k=c["oob_k"])
+    ge_ref, f_ref = port.execute_batched(pos)
+    assert np.abs(en - ge_ref.sum(axis=1)).max() <= 1e-12 * np.abs(ge_ref).max()
+    assert np.abs(f - f_ref).max() <= 1e-12 * np.abs(f_ref).max()
+    # updateParametersInContext: doubled scaling factors on force 2
+    forces[2].setScalingFactors(2.0 * c["scaling"][2])
+    forces[2].updateParametersInContext(context)
+    context.setPositions(c["pos"])
+    s = context.getState(getEnergy=True, groups=1 << 2)
+    assert abs(s.getPotentialEnergy() - 2.0 * ref["grid_energies"][2]) <= 1e-12 * abs(ref["grid_energies"][2]) * 2
+    # particle groups: two groups of particles with their own scaling factors -> per-group energies
+    system2 = gfp.System()
+    for _ in range(47):
+        system2.addParticle(1.0)
+    force = gfp.GridForce()
+    force.addGridCounts(*c["counts"])
+    force.addGridSpacing(*c["spacing"])
+    force.setGridOrigin(*c["origin"])
+    force.setGridValues(c["grids"][0])
+    ga, gb = list(range(0, 20)), list(range(20, 47))
+    force.addParticleGroup("a", ga, list(c["scaling"][0][ga]))
+    force.addParticleGroup("b", gb, list(c["scaling"][0][gb]))
+    system2.addForce(force)
+    ctx2 = gfp.Context(system2, platform)
+    ctx2.setPositions(c["pos"])
+    st = ctx2.getState(getEnergy=True, getForces=True)
+    assert abs(st.getPotentialEnergy() - ref["grid_energies"][0]) <= 1e-12 * abs(ref["grid_energies"][0])
+    assert np.abs(st.getForces() - ref["grid_forces"][0]).max() <= 1e-12 * np.abs(ref["grid_forces"][0]).max()
+    eg = force.getParticleGroupEnergies(ctx2)
+    assert len(eg) == 2 and abs(sum(eg) - ref["grid_energies"][0]) <= 1e-12 * abs(ref["grid_energies"][0])
+    platform.setPropertyDefaultValue("Precision", "mixed")
+
+
+@pytest.mark.gpu
+def test_plugin_refuses_what_it_does_not_implement():
+    import openmmgridforce_b200.gridforceplugin as gfp
+    c, _ = cases.load_golden("ramp_grid")
+    platform = gfp.Platform.getPlatformByName("B200")
+    system, forces = _build_system(gfp, c)
+    forces[0].setInterpolationMethod(1)               # cubic B-spline: outside this path -> loud refusal, no fallback
+    with pytest.raises(RuntimeError, match="only trilinear"):
+        gfp.Context(system, platform)
+
+
+def test_plugin_has_no_cpu_fallback():
+    """Without a usable GPU, Context creation must raise (the product never routes through a CPU path)."""
+    import openmmgridforce_b200 as gf
+    import openmmgridforce_b200.gridforceplugin as gfp
+    try:
+        n = gf.Device.count()
+    except gf.GridForceB200Error:
+        n = 0
+    if n > 0:
+        pytest.skip("a GPU is present")
+    c, _ = cases.load_golden("ramp_grid")
+    system, _ = _build_system(gfp, c)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gfp.Context(system, gfp.Platform.getPlatformByName("B200"))
