@@ -55,7 +55,8 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks/throttle reasons sampled every 100 ms from just before the timed device loop until the last
+    GPU measurement of the run (device loop, e2e loop, and at N=1 the C3/C4 loops)."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
@@ -68,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.tmp,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.tmp,
                                          stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -339,9 +340,11 @@ def main():
 
     gathered = torch.empty(world * REPLICAS_PER_GPU, dtype=torch.float64, device=tdev) if world > 1 else None
 
+    from openmmgridforce_b200 import sharding
+
     def post_step(d_e):
         if world > 1:       # the one collective: per-replica energies of every rank, on the launching stream
-            dist.all_gather_into_tensor(gathered, d_e)
+            sharding.gather_energies(dist, d_e, out=gathered)
 
     l2_gbs = dev.bench_sector_gather(32 << 20, 1 << 24, 10) if rank == 0 else 0.0
 
@@ -353,7 +356,6 @@ def main():
     secs, launches, bufs = time_device_steps(torch, gf, kern, [d_pos], REPLICAS_PER_GPU, N_ATOMS, args.steps, args.warmup, stream,
                                              post_step=post_step)
     torch.cuda.synchronize()
-    clocks = sampler.stop()
     if world > 1:
         t = torch.tensor([secs], dtype=torch.float64, device=tdev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -376,6 +378,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_secs = float(t.item())
 
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        for name in ("C3", "C4"):
+            extras[name] = run_other_workload(torch, gf, dev, tdev, stream, name, max(20, min(args.steps, 200)), args.warmup,
+                                              peak_gbs, l2_gbs)
+    clocks = sampler.stop()
+
     evals_step_rank = REPLICAS_PER_GPU * N_ATOMS * N_GRIDS
     value = evals_step_rank * world * args.steps / secs_max
     kernel_us = secs / args.steps * 1e6        # this rank's average step (N=1: exactly the kernel's launch-to-launch time)
@@ -397,10 +406,6 @@ def main():
                         "api": "gfb_kernel_execute_host (pinned host positions in, forces + energies out)"},
                 "gpu_launches": int(launches), "clocks": clocks}
         if world == 1 and not args.no_extras:
-            extras = {}
-            for name in ("C3", "C4"):
-                extras[name] = run_other_workload(torch, gf, dev, tdev, stream, name, max(20, min(args.steps, 200)), args.warmup,
-                                                  peak_gbs, l2_gbs)
             line["other_workloads"] = extras
             line["cpu_baseline"] = cpu_baseline(w)
         print(json.dumps(line), flush=True)

@@ -148,10 +148,3 @@ def c5_sharded_replicas(n_replicas=65536, n=192, replica_offset=0, n_local=None)
         pos = np.ascontiguousarray(pos[replica_offset:replica_offset + n_local])
     return Workload(f"C5 {n_replicas} replicas x 47 atoms x 3 grids of {n}^3", counts, sp, (0.0, 0.0, 0.0), grids,
                     _ligand_scaling(3), pos, [10000.0] * 3, [0.0] * 3)
-
-
-def shard_bounds(n_units, world_size, rank):
-    """Block partition used for the multi-GPU runs: rank g owns [g*n/N, (g+1)*n/N)."""
-    lo = n_units * rank // world_size
-    hi = n_units * (rank + 1) // world_size
-    return lo, hi
