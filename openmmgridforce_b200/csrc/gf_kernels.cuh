@@ -121,7 +121,7 @@ __device__ __forceinline__ void load_stencil(const GridView& G, int ix, int iy, 
     const S* base = static_cast<const S*>(G.cells);
     if constexpr (LAYOUT == GFB_LAYOUT_CELLS) {
         const size_t cell = ((size_t) ix * G.nc[1] + iy) * G.nc[2] + iz;
-        load_cell(base + 8 * cell, v);
+        load_cell(base + (size_t) G.cell_stride * cell, v);
     } else if constexpr (LAYOUT == GFB_LAYOUT_ROWS) {
         constexpr int W = 32 / (int) sizeof(S);     // values per chunk; consecutive chunks advance by W-1
         const int j = iz / (W - 1);
@@ -229,14 +229,102 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* addr, unsigned l
 // Occupancy: the kernel waits on DRAM/L2 round trips, so resident warps are what hides them. ptxas fits the
 // one-grid kernel in 40 registers (6 blocks = 1536 threads per SM) and the three-grid kernel in 64 (4 blocks)
 // without meaningful spills; left alone it takes 46 / 78 registers and occupancy drops to 5 / 3 blocks.
+
+// One grid's contribution for an atom whose stencil v[] is already in registers (:1039-1082).
+template <typename S>
+__device__ __forceinline__ void accumulate_inside(const GridView& G, const S v[8], const AtomCell& c, double sd,
+                                                  double& e_g, double& Fx, double& Fy, double& Fz) {
+    constexpr bool EXACT = sizeof(S) == 8;
+    S val, dx, dy, dz;
+    trilinear<S>(v, (S) c.fx, (S) c.fy, (S) c.fz, val, dx, dy, dz);
+    double gx, gy, gz;
+    if (EXACT) {  // DOUBLE: divide, as the reference does (:1072)
+        gx = (double) dx / G.spacing[0];
+        gy = (double) dy / G.spacing[1];
+        gz = (double) dz / G.spacing[2];
+    } else {
+        gx = (double) (dx * (S) G.inv_spacing[0]);
+        gy = (double) (dy * (S) G.inv_spacing[1]);
+        gz = (double) (dz * (S) G.inv_spacing[2]);
+    }
+    double dval = EXACT ? (double) val : trilinear_value_f64(v, c.fx, c.fy, c.fz);
+    if (G.inv_power > 0.0) {  // :1057-1059, :1076-1080 (plain pow: NaN for a negative base, as the oracle)
+        const double base = dval;
+        dval = pow(base, G.inv_power);
+        const double pf = G.inv_power * pow(base, G.inv_power - 1.0);
+        gx *= pf;
+        gy *= pf;
+        gz *= pf;
+    }
+    e_g = sd * dval;  // :1061
+    Fx -= sd * gx;    // :1082
+    Fy -= sd * gy;
+    Fz -= sd * gz;
+}
+
+// :1093-1117 — harmonic wall outside the grid (unscaled). Inside atoms with scale == 0 land here too and contribute
+// exactly 0 (quirk Q3). Rare (1-2 % of atoms): kept out of line so its FP64 temporaries do not cost registers.
+struct Restraint {
+    double e, fx, fy, fz;
+};
+__device__ __noinline__ Restraint restraint_terms(const GridView& G, double x, double y, double z) {
+    const double px = x - G.origin[0], py = y - G.origin[1], pz = z - G.origin[2];
+    const double devx = px < 0.0 ? px : (px > G.hcorner[0] ? px - G.hcorner[0] : 0.0);
+    const double devy = py < 0.0 ? py : (py > G.hcorner[1] ? py - G.hcorner[1] : 0.0);
+    const double devz = pz < 0.0 ? pz : (pz > G.hcorner[2] ? pz - G.hcorner[2] : 0.0);
+    const double hk = 0.5 * G.oob_k;
+    Restraint r;
+    r.e = hk * devx * devx;
+    r.e += hk * devy * devy;
+    r.e += hk * devz * devz;
+    r.fx = G.oob_k * devx;
+    r.fy = G.oob_k * devy;
+    r.fz = G.oob_k * devz;
+    return r;
+}
+__device__ __forceinline__ void accumulate_restraint(const GridView& G, double x, double y, double z, double& e_g, double& Fx,
+                                                     double& Fy, double& Fz) {
+    const Restraint r = restraint_terms(G, x, y, z);
+    e_g = r.e;
+    Fx -= r.fx;
+    Fy -= r.fy;
+    Fz -= r.fz;
+}
+
 template <typename S, int LAYOUT, int NG, bool SAME, int FMODE, bool SINGLE>
 __global__ void __launch_bounds__(kBlock, (NG == 1 && sizeof(S) == 4) ? 6 : 4) gf_eval_kernel(const __grid_constant__ EvalParams p) {
     constexpr bool EXACT = sizeof(S) == 8;
-    const long long t0 = (long long) blockIdx.x * kBlock;
-    const long long t = t0 + threadIdx.x;
+    constexpr int NGC = NG > 0 ? NG : 1;
+    // With a compile-time grid count and one shared geometry, every grid's stencil load is issued before any
+    // arithmetic, so the G memory round trips overlap instead of following one another.
+    constexpr bool BATCHED = NG > 0 && SAME;
+    const unsigned t0 = blockIdx.x * kBlock;          // total <= 2e9 (checked by the launcher): 32-bit indices
+    const unsigned t = t0 + threadIdx.x;
+    const unsigned total = (unsigned) p.total;
     const int lane = threadIdx.x & 31;
-    const bool active = t < p.total;
-    if (p.energies_clear && t < p.n_replicas) p.energies_clear[t] = 0.0;
+    const bool active = t < total;
+    if (p.energies_clear && t < (unsigned) p.n_replicas) p.energies_clear[t] = 0.0;
+
+    int rep = -1;
+    unsigned ia = 0;
+    long long gidx = 0;
+    if (active) {
+        const unsigned a = p.order ? (unsigned) p.order[t] : t;
+        if (SINGLE) {
+            rep = 0;
+            ia = a;
+        } else {
+            rep = (int) (a / (unsigned) p.n_atoms);
+            ia = a - (unsigned) rep * (unsigned) p.n_atoms;
+        }
+        const int particle = p.particles ? p.particles[ia] : (int) ia;
+        gidx = (long long) rep * p.n_particles + particle;
+    }
+
+    // Scaling factors depend on the atom ordinal only: their loads go out first and overlap the position fetch.
+    double sd[NGC];
+#pragma unroll
+    for (int g = 0; g < NGC; g++) sd[g] = (NG > 0 && active) ? p.grid[g].scaling[ia] : 0.0;
 
     // Positions of the block's 256 consecutive atoms are 6144 contiguous bytes when no index indirection is in
     // play: read them as 384 16-byte vectors (4 lines per warp instruction instead of 24 sectors x 3 instructions
@@ -245,111 +333,79 @@ __global__ void __launch_bounds__(kBlock, (NG == 1 && sizeof(S) == 4) ? 6 : 4) g
     const bool staged = p.order == nullptr && p.particles == nullptr && p.n_particles == p.n_atoms &&
                         (reinterpret_cast<uintptr_t>(p.pos) & 15) == 0;
     if (staged) {
-        const double2* src = reinterpret_cast<const double2*>(p.pos + 3 * t0);     // t0*24 bytes: 16-byte aligned
-        const long long n2 = (3 * (p.total - t0) + 1) / 2;                           // double2 left in the array
-        for (int i = threadIdx.x; i < kBlock * 3 / 2; i += kBlock)
-            if (i < n2) {
-                double2 v;
-                if (2 * (long long) i + 1 < 3 * (p.total - t0)) {
-                    asm volatile("ld.global.cs.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(src + i));
-                } else {   // odd tail: the last double of the array
-                    v.x = load_stream(reinterpret_cast<const double*>(src + i));
-                    v.y = 0.0;
-                }
-                s_pos2[i] = v;
+        const double2* src = reinterpret_cast<const double2*>(p.pos + 3 * (size_t) t0);   // t0*24 bytes: 16-byte aligned
+        const unsigned left = 3u * (total - t0);                                          // doubles left in the array
+        for (unsigned i = threadIdx.x; i < kBlock * 3 / 2; i += kBlock) {
+            double2 v = make_double2(0.0, 0.0);
+            if (2 * i + 1 < left) {
+                asm volatile("ld.global.cs.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(src + i));
+            } else if (2 * i < left) {   // odd tail: the last double of the array
+                v.x = load_stream(reinterpret_cast<const double*>(src + i));
             }
+            s_pos2[i] = v;
+        }
         __syncthreads();
     }
-
-    int rep = -1;
-    long long gidx = 0;
-    int ia = 0;
+    const double* my_pos = staged ? reinterpret_cast<const double*>(s_pos2) + 3 * threadIdx.x : p.pos + 3 * gidx;
     double x = 0.0, y = 0.0, z = 0.0;
     if (active) {
-        const long long a = p.order ? (long long) p.order[t] : t;
-        if (SINGLE) {
-            rep = 0;
-            ia = (int) a;
-        } else {
-            rep = (int) (a / p.n_atoms);
-            ia = (int) (a - (long long) rep * p.n_atoms);
-        }
-        const int particle = p.particles ? p.particles[ia] : ia;
-        gidx = (long long) rep * p.n_particles + particle;
         if (staged) {
-            const double* sp = reinterpret_cast<const double*>(s_pos2) + 3 * threadIdx.x;
-            x = sp[0];
-            y = sp[1];
-            z = sp[2];
+            x = my_pos[0];
+            y = my_pos[1];
+            z = my_pos[2];
         } else {
-            const double* pp = p.pos + 3 * gidx;
-            x = load_stream(pp);
-            y = load_stream(pp + 1);
-            z = load_stream(pp + 2);
+            x = load_stream(my_pos);
+            y = load_stream(my_pos + 1);
+            z = load_stream(my_pos + 2);
         }
     }
 
     double e_total = 0.0;
     double Fx = 0.0, Fy = 0.0, Fz = 0.0;
     const int ng = NG > 0 ? NG : p.n_grids;
-    AtomCell c;
-    if (SAME) c = classify<EXACT>(p.grid[0], x, y, z);
 
+    if (BATCHED) {
+        const AtomCell c = classify<EXACT>(p.grid[0], x, y, z);
+        S v[NGC][8];
+        bool interp[NGC];
 #pragma unroll
-    for (int g = 0; g < (NG > 0 ? NG : GFB_MAX_GRIDS); g++) {
-        if (NG == 0 && g >= ng) break;
-        const GridView& G = p.grid[g];
-        double e_g = 0.0;
-        if (active) {
-            if (!SAME) c = classify<EXACT>(G, x, y, z);
-            const double sd = G.scaling[ia];
-            if (c.inside && sd != 0.0) {
-                S v[8];
-                load_stencil<S, LAYOUT>(G, c.ix, c.iy, c.iz, v);
-                S val, dx, dy, dz;
-                trilinear<S>(v, (S) c.fx, (S) c.fy, (S) c.fz, val, dx, dy, dz);
-                double gx, gy, gz, dval;
-                if (EXACT) {  // DOUBLE: divide, as the reference does (:1072)
-                    gx = (double) dx / G.spacing[0];
-                    gy = (double) dy / G.spacing[1];
-                    gz = (double) dz / G.spacing[2];
-                } else {
-                    gx = (double) (dx * (S) G.inv_spacing[0]);
-                    gy = (double) (dy * (S) G.inv_spacing[1]);
-                    gz = (double) (dz * (S) G.inv_spacing[2]);
-                }
-                dval = EXACT ? (double) val : trilinear_value_f64(v, c.fx, c.fy, c.fz);
-                if (G.inv_power > 0.0) {  // :1057-1059, :1076-1080 (plain pow: NaN for negative base, as the oracle)
-                    const double base = dval;
-                    dval = pow(base, G.inv_power);
-                    const double pf = G.inv_power * pow(base, G.inv_power - 1.0);
-                    gx *= pf;
-                    gy *= pf;
-                    gz *= pf;
-                }
-                e_g = sd * dval;      // :1061
-                Fx -= sd * gx;        // :1082
-                Fy -= sd * gy;
-                Fz -= sd * gz;
-            } else {
-                // :1093-1117 — harmonic wall outside the grid (unscaled). Inside atoms with scale == 0
-                // land here too and contribute exactly 0 (quirk Q3).
-                const double devx = c.px < 0.0 ? c.px : (c.px > G.hcorner[0] ? c.px - G.hcorner[0] : 0.0);
-                const double devy = c.py < 0.0 ? c.py : (c.py > G.hcorner[1] ? c.py - G.hcorner[1] : 0.0);
-                const double devz = c.pz < 0.0 ? c.pz : (c.pz > G.hcorner[2] ? c.pz - G.hcorner[2] : 0.0);
-                const double hk = 0.5 * G.oob_k;
-                e_g = hk * devx * devx;
-                e_g += hk * devy * devy;
-                e_g += hk * devz * devz;
-                Fx -= G.oob_k * devx;
-                Fy -= G.oob_k * devy;
-                Fz -= G.oob_k * devz;
+        for (int g = 0; g < NGC; g++) {
+            interp[g] = active && c.inside && sd[g] != 0.0;
+            if (interp[g]) load_stencil<S, LAYOUT>(p.grid[g], c.ix, c.iy, c.iz, v[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < NGC; g++) {
+            double e_g = 0.0;
+            if (interp[g]) accumulate_inside<S>(p.grid[g], v[g], c, sd[g], e_g, Fx, Fy, Fz);
+            else if (active) accumulate_restraint(p.grid[g], my_pos[0], my_pos[1], my_pos[2], e_g, Fx, Fy, Fz);
+            e_total += e_g;
+            if (p.grid_energies) {  // uniform branch
+                double eg = e_g;
+                if (run_reduce(eg, rep, lane)) red_add_f64(p.grid_energies + (size_t) rep * ng + g, eg);
             }
         }
-        e_total += e_g;
-        if (p.grid_energies) {  // uniform branch
-            double eg = e_g;
-            if (run_reduce(eg, rep, lane)) red_add_f64(p.grid_energies + (size_t) rep * ng + g, eg);
+    } else {
+        AtomCell c;
+        if (SAME) c = classify<EXACT>(p.grid[0], x, y, z);
+        for (int g = 0; g < ng; g++) {
+            const GridView& G = p.grid[g];
+            double e_g = 0.0;
+            if (active) {
+                if (!SAME) c = classify<EXACT>(G, x, y, z);
+                const double s = G.scaling[ia];
+                if (c.inside && s != 0.0) {
+                    S v[8];
+                    load_stencil<S, LAYOUT>(G, c.ix, c.iy, c.iz, v);
+                    accumulate_inside<S>(G, v, c, s, e_g, Fx, Fy, Fz);
+                } else {
+                    accumulate_restraint(G, x, y, z, e_g, Fx, Fy, Fz);
+                }
+            }
+            e_total += e_g;
+            if (p.grid_energies) {  // uniform branch
+                double eg = e_g;
+                if (run_reduce(eg, rep, lane)) red_add_f64(p.grid_energies + (size_t) rep * ng + g, eg);
+            }
         }
     }
 
@@ -419,6 +475,24 @@ __global__ void __launch_bounds__(256) gf_repack_kernel(const double* __restrict
         o[5] = (S) vals[im + nyz + 1];
         o[6] = (S) vals[im + nyz + nz];
         o[7] = (S) vals[im + nyz + nz + 1];
+    }
+}
+
+// Interleave: the packed cells of k grids that share a geometry are woven into one record per cell
+// (k*32 bytes, padded to a power of two: 64 B for 2 grids, 128 B = one L2/HBM line for 3 or 4), so that the
+// stencils one atom needs from all its grids come from ONE line instead of k lines in k arrays.
+__global__ void __launch_bounds__(256) gf_interleave_cells_kernel(const float4* __restrict__ s0, const float4* __restrict__ s1,
+                                                                  const float4* __restrict__ s2, const float4* __restrict__ s3,
+                                                                  float4* __restrict__ dst, size_t n_cells, int slots) {
+    // one thread per (cell, slot, half): 16 bytes
+    const size_t total = n_cells * slots * 2;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+        const int half = (int) (i & 1);
+        const size_t r = i >> 1;
+        const int slot = (int) (r % slots);
+        const size_t cell = r / slots;
+        const float4* src = slot == 0 ? s0 : slot == 1 ? s1 : slot == 2 ? s2 : s3;
+        dst[i] = src ? src[cell * 2 + half] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 

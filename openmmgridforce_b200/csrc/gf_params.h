@@ -22,6 +22,8 @@ struct GridView {
     double hcorner[3];       // spacing*(counts-1), computed on the host exactly as the reference does
     int nc[3];               // cells per axis = counts - 1
     int row_chunks;          // ROWS / PAIRS: 32-byte units per row
+    int cell_stride;         // CELLS: elements between consecutive cells (8, or 8*k when k grids are interleaved)
+    int pad_;
     double inv_power;        // 0 = off
     double oob_k;
 };
