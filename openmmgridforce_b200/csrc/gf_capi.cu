@@ -86,7 +86,9 @@ struct PinnedBuffer {
 struct gfb_device {
     int ordinal;
     cudaStream_t stream;
-    cudaStream_t copy_stream;   // D2H of chunk i overlaps the kernel of chunk i+1
+    cudaStream_t copy_stream;   // D2H of chunk i overlaps the kernel of chunk i+1 ...
+    cudaStream_t h2d_stream;    // ... and the H2D of chunk i+2: three streams chained by events (execute_host)
+    std::vector<cudaEvent_t> events;   // pool for the chunk pipeline (2 per chunk), created once
     cudaDeviceProp prop;
 };
 
@@ -164,6 +166,7 @@ int gfb_device_open(int ordinal, gfb_device** out) {
     d->prop = prop;
     CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->h2d_stream, cudaStreamNonBlocking));
     *out = d;
     return GFB_OK;
 }
@@ -173,6 +176,8 @@ int gfb_device_close(gfb_device* dev) {
     cudaSetDevice(dev->ordinal);
     cudaStreamDestroy(dev->stream);
     cudaStreamDestroy(dev->copy_stream);
+    cudaStreamDestroy(dev->h2d_stream);
+    for (size_t i = 0; i < dev->events.size(); i++) cudaEventDestroy(dev->events[i]);
     delete dev;
     return GFB_OK;
 }
@@ -192,6 +197,7 @@ int gfb_device_get_props(gfb_device* dev, gfb_device_props* props) {
 int gfb_device_synchronize(gfb_device* dev) {
     if (!dev) return fail(GFB_ERR_INVALID, "gfb_device_synchronize: NULL device");
     CUDA_TRY(cudaSetDevice(dev->ordinal));
+    CUDA_TRY(cudaStreamSynchronize(dev->h2d_stream));
     CUDA_TRY(cudaStreamSynchronize(dev->stream));
     CUDA_TRY(cudaStreamSynchronize(dev->copy_stream));
     return GFB_OK;
@@ -608,14 +614,25 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
     double* d_ge = d_e + n_replicas;
     CUDA_TRY(cudaMemsetAsync(d_e, 0, e_count * sizeof(double), dev->stream));
 
-    // Chunking: aim at ~4 MB of positions per chunk, at most 16 chunks; a single replica is one chunk.
+    // Chunk pipeline over three streams: H2D(c) on h2d_stream -> [up c] -> kernel(c) on stream -> [done c] -> D2H(c) on
+    // copy_stream. Uploads never wait for kernels, downloads overlap the next uploads (PCIe is full duplex: measured
+    // 55 GB/s one way, 45-49 GB/s each way when both run). ~9 MB of positions per chunk, at most 16 chunks: each
+    // chunk costs ~15 us of copy/event overhead (4/8/16/32/64 chunks of C5's 74 MB: 2.02/1.99/2.10/2.43/2.80 ms).
     int n_chunks = 1;
     if (n_replicas > 1) {
-        n_chunks = (int) std::min<size_t>(16, std::max<size_t>(1, pos_bytes / (4u << 20)));
-        n_chunks = std::min(n_chunks, n_replicas);
+        const char* env = getenv("GFB_HOST_CHUNKS");
+        n_chunks = env ? atoi(env) : (int) std::min<size_t>(16, std::max<size_t>(1, pos_bytes / (9u << 20)));
+        n_chunks = std::max(1, std::min(n_chunks, n_replicas));
     }
-    std::vector<cudaEvent_t> done(n_chunks);
-    for (int c = 0; c < n_chunks; c++) CUDA_TRY(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
+    while ((int) dev->events.size() < 2 * n_chunks) {
+        cudaEvent_t ev;
+        CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        dev->events.push_back(ev);
+    }
+    cudaEvent_t* up = dev->events.data();
+    cudaEvent_t* done = dev->events.data() + n_chunks;
+    // the energy memset (on `stream`) must precede every kernel; the first kernel waits on up[0] on the same stream
+    const bool need_f_upload = forces && (force_mode == GFB_FORCE_F64_ADD || k->d_particles || k->n_atoms < n_particles);
 
     int status = GFB_OK;
     for (int c = 0; c < n_chunks && status == GFB_OK; c++) {
@@ -628,24 +645,19 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
             memcpy(stage_pos + off * sizeof(double), src, cnt * sizeof(double));
             src = reinterpret_cast<const double*>(stage_pos) + off;
         }
-        cudaError_t err = cudaMemcpyAsync(d_pos + off, src, cnt * sizeof(double), cudaMemcpyHostToDevice, dev->stream);
-        if (err == cudaSuccess && forces && force_mode == GFB_FORCE_F64_ADD) {
-            // ADD: the caller's current forces are the accumulator's initial value
+        cudaError_t err = cudaMemcpyAsync(d_pos + off, src, cnt * sizeof(double), cudaMemcpyHostToDevice, dev->h2d_stream);
+        if (err == cudaSuccess && need_f_upload) {
+            // ADD: the caller's current forces are the accumulator's initial value.
+            // STORE with a particle subset: untouched entries must come back as they were.
             const double* fsrc = forces + off;
             if (!f_pinned) {
                 memcpy(stage_f + off * sizeof(double), fsrc, cnt * sizeof(double));
                 fsrc = reinterpret_cast<const double*>(stage_f) + off;
             }
-            err = cudaMemcpyAsync(d_f + off, fsrc, cnt * sizeof(double), cudaMemcpyHostToDevice, dev->stream);
-        } else if (err == cudaSuccess && forces && (k->d_particles || k->n_atoms < n_particles)) {
-            // STORE with a particle subset: untouched entries must come back as they were
-            const double* fsrc = forces + off;
-            if (!f_pinned) {
-                memcpy(stage_f + off * sizeof(double), fsrc, cnt * sizeof(double));
-                fsrc = reinterpret_cast<const double*>(stage_f) + off;
-            }
-            err = cudaMemcpyAsync(d_f + off, fsrc, cnt * sizeof(double), cudaMemcpyHostToDevice, dev->stream);
+            err = cudaMemcpyAsync(d_f + off, fsrc, cnt * sizeof(double), cudaMemcpyHostToDevice, dev->h2d_stream);
         }
+        if (err == cudaSuccess) err = cudaEventRecord(up[c], dev->h2d_stream);
+        if (err == cudaSuccess) err = cudaStreamWaitEvent(dev->stream, up[c], 0);
         if (err != cudaSuccess) {
             status = fail(GFB_ERR_CUDA, "gfb_kernel_execute_host: H2D: %s", cudaGetErrorString(err));
             break;
@@ -668,10 +680,10 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
         if (err == cudaSuccess) err = cudaStreamSynchronize(dev->copy_stream);
         if (err != cudaSuccess) status = fail(GFB_ERR_CUDA, "gfb_kernel_execute_host: %s", cudaGetErrorString(err));
     } else {
+        cudaStreamSynchronize(dev->h2d_stream);
         cudaStreamSynchronize(dev->stream);
         cudaStreamSynchronize(dev->copy_stream);
     }
-    for (int c = 0; c < n_chunks; c++) cudaEventDestroy(done[c]);
     if (status != GFB_OK) return status;
 
     const double* he = static_cast<const double*>(k->h_energy.ptr);
