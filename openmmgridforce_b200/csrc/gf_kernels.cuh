@@ -37,6 +37,10 @@ constexpr unsigned kFull = 0xffffffffu;
 // case the division is redone exactly. EXACT=true (DOUBLE mode) always divides, so the fraction is the
 // reference's bit for bit as well.
 // ------------------------------------------------------------------------------------------------
+// IEEE division kept out of line: ptxas otherwise if-converts the rare branch below and runs the ~12-instruction
+// FP64 division sequence for every atom on every axis.
+__device__ __noinline__ double exact_quotient(double pi, double spacing) { return pi / spacing; }
+
 template <bool EXACT>
 __device__ __forceinline__ void axis_index(double pi, double spacing, double inv_spacing, int ncell,
                                            int& idx, double& frac) {
@@ -46,7 +50,7 @@ __device__ __forceinline__ void axis_index(double pi, double spacing, double inv
     } else {
         q = pi * inv_spacing;
         const double r = rint(q);
-        if (fabs(q - r) <= 1.8e-15 * fmax(q, 1.0)) q = pi / spacing;
+        if (fabs(q - r) <= 1.8e-15 * fmax(q, 1.0)) q = exact_quotient(pi, spacing);
     }
     int i = __double2int_rz(q);
     // pi == hCorner gives i == ncell (== counts-1): the reference then reads past the grid (UB, its
@@ -59,24 +63,23 @@ __device__ __forceinline__ void axis_index(double pi, double spacing, double inv
 struct AtomCell {
     int ix, iy, iz;
     double fx, fy, fz;     // in-cell fractions
-    double px, py, pz;     // position - origin (needed by the restraint branch)
     bool inside;
 };
 
 template <bool EXACT>
 __device__ __forceinline__ AtomCell classify(const GridView& g, double x, double y, double z) {
     AtomCell c;
-    c.px = x - g.origin[0];
-    c.py = y - g.origin[1];
-    c.pz = z - g.origin[2];
-    c.inside = (c.px >= 0.0 && c.px <= g.hcorner[0]) && (c.py >= 0.0 && c.py <= g.hcorner[1]) &&
-               (c.pz >= 0.0 && c.pz <= g.hcorner[2]);
+    const double px = x - g.origin[0];
+    const double py = y - g.origin[1];
+    const double pz = z - g.origin[2];
+    c.inside = (px >= 0.0 && px <= g.hcorner[0]) && (py >= 0.0 && py <= g.hcorner[1]) &&
+               (pz >= 0.0 && pz <= g.hcorner[2]);
     c.ix = c.iy = c.iz = 0;
     c.fx = c.fy = c.fz = 0.0;
     if (c.inside) {
-        axis_index<EXACT>(c.px, g.spacing[0], g.inv_spacing[0], g.nc[0], c.ix, c.fx);
-        axis_index<EXACT>(c.py, g.spacing[1], g.inv_spacing[1], g.nc[1], c.iy, c.fy);
-        axis_index<EXACT>(c.pz, g.spacing[2], g.inv_spacing[2], g.nc[2], c.iz, c.fz);
+        axis_index<EXACT>(px, g.spacing[0], g.inv_spacing[0], g.nc[0], c.ix, c.fx);
+        axis_index<EXACT>(py, g.spacing[1], g.inv_spacing[1], g.nc[1], c.iy, c.fy);
+        axis_index<EXACT>(pz, g.spacing[2], g.inv_spacing[2], g.nc[2], c.iz, c.fz);
     }
     return c;
 }
@@ -295,9 +298,11 @@ template <typename S, int LAYOUT, int NG, bool SAME, int FMODE, bool SINGLE>
 __global__ void __launch_bounds__(kBlock, (NG == 1 && sizeof(S) == 4) ? 6 : 4) gf_eval_kernel(const __grid_constant__ EvalParams p) {
     constexpr bool EXACT = sizeof(S) == 8;
     constexpr int NGC = NG > 0 ? NG : 1;
-    // With a compile-time grid count and one shared geometry, every grid's stencil load is issued before any
-    // arithmetic, so the G memory round trips overlap instead of following one another.
-    constexpr bool BATCHED = NG > 0 && SAME;
+    // With a compile-time grid count, one shared geometry and the one-load-per-stencil layout, every grid's stencil
+    // load is issued before any arithmetic, so the G memory round trips overlap instead of following one another
+    // (C5: 157 -> 138 us). ROWS/PAIRS would need 4x/2x the registers in flight and spill (C5 ROWS: 205 -> 261 us),
+    // so they keep one grid at a time.
+    constexpr bool BATCHED = NG > 0 && SAME && LAYOUT == GFB_LAYOUT_CELLS;
     const unsigned t0 = blockIdx.x * kBlock;          // total <= 2e9 (checked by the launcher): 32-bit indices
     const unsigned t = t0 + threadIdx.x;
     const unsigned total = (unsigned) p.total;
@@ -387,12 +392,14 @@ __global__ void __launch_bounds__(kBlock, (NG == 1 && sizeof(S) == 4) ? 6 : 4) g
     } else {
         AtomCell c;
         if (SAME) c = classify<EXACT>(p.grid[0], x, y, z);
-        for (int g = 0; g < ng; g++) {
+#pragma unroll
+        for (int g = 0; g < (NG > 0 ? NG : GFB_MAX_GRIDS); g++) {
+            if (NG == 0 && g >= ng) break;
             const GridView& G = p.grid[g];
             double e_g = 0.0;
             if (active) {
                 if (!SAME) c = classify<EXACT>(G, x, y, z);
-                const double s = G.scaling[ia];
+                const double s = NG > 0 ? sd[NG > 0 ? g : 0] : G.scaling[ia];
                 if (c.inside && s != 0.0) {
                     S v[8];
                     load_stencil<S, LAYOUT>(G, c.ix, c.iy, c.iz, v);
