@@ -159,6 +159,28 @@ def time_e2e_steps(gf, kern, pos_host, forces_host, energies_host, steps, warmup
     return time.perf_counter() - t0
 
 
+def run_single_ligand(gf, dev, steps=2000):
+    """configs[1]: one 47-atom ligand in three 208x278x231 grids, one evaluation per MD step through the host API
+    (positions in, energy + forces out, synchronous). OpenMM's integrator is not available here, so the figure is the
+    grid-force-limited upper bound: steps/s x 4 fs (example/input.json:24)."""
+    from openmmgridforce_b200 import workloads as W
+    w = W.c2_single_ligand()
+    grids = [gf.Grid(dev, w.counts, w.spacing, w.origin, v, gf.PRECISION_MIXED) for v in w.grids]
+    kern = gf.Kernel(dev, grids, w.scaling, oob_k=w.oob_k)
+    pos_h, _t1 = pinned_array(w.pos.shape)
+    pos_h[...] = w.pos
+    f_h, _t2 = pinned_array(w.pos.shape)
+    e_h, _t3 = pinned_array((1,))
+    secs = time_e2e_steps(gf, kern, pos_h, f_h, e_h, steps, 50)
+    kern.close()
+    for g in grids:
+        g.close()
+    sps = steps / secs
+    return {"workload": w.name, "us_per_step": secs / steps * 1e6, "steps_per_s": sps,
+            "grid_force_limited_ns_per_day": sps * 4e-6 * 86400.0, "value": w.evals * sps, "unit": UNIT,
+            "note": "latency-bound single launch per step (H2D 1.1 KB, kernel, D2H); upper bound on MD ns/day at 4 fs"}
+
+
 def run_other_workload(torch, gf, dev, tdev, stream, name, steps, warmup, peak_gbs, l2_gbs):
     from openmmgridforce_b200 import workloads as W
     if name == "C3":
@@ -332,9 +354,8 @@ def main():
     stream = torch.cuda.Stream(device=tdev)
     peak_gbs, peak_src = measured_peaks()
 
-    # this rank's batch: replicas [rank*R, (rank+1)*R) of an N*R-replica job
-    lo = rank * REPLICAS_PER_GPU
-    w = W.c5_sharded_replicas(n_replicas=REPLICAS_PER_GPU * world, n=GRID_N, replica_offset=lo, n_local=REPLICAS_PER_GPU)
+    # this rank's batch: its own 65,536 replica poses (same grids and scaling factors on every rank)
+    w = W.c5_sharded_replicas(n_replicas=REPLICAS_PER_GPU, n=GRID_N, pose_seed=W.SEED + rank)
     grids = [gf.Grid(dev, w.counts, w.spacing, w.origin, v, gf.PRECISION_MIXED) for v in w.grids]
     kern = gf.Kernel(dev, grids, w.scaling, oob_k=w.oob_k)
     d_pos = torch.from_numpy(w.pos).to(tdev)
@@ -384,6 +405,7 @@ def main():
         for name in ("C3", "C4"):
             extras[name] = run_other_workload(torch, gf, dev, tdev, stream, name, max(20, min(args.steps, 200)), args.warmup,
                                               peak_gbs, l2_gbs)
+        extras["C2"] = run_single_ligand(gf, dev)
     clocks = sampler.stop()
 
     evals_step_rank = REPLICAS_PER_GPU * N_ATOMS * N_GRIDS

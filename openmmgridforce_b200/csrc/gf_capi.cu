@@ -645,7 +645,10 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
             memcpy(stage_pos + off * sizeof(double), src, cnt * sizeof(double));
             src = reinterpret_cast<const double*>(stage_pos) + off;
         }
-        cudaError_t err = cudaMemcpyAsync(d_pos + off, src, cnt * sizeof(double), cudaMemcpyHostToDevice, dev->h2d_stream);
+        // One chunk (a single ligand per MD step, configs[1]) is pure latency: everything goes on one stream, no events.
+        cudaStream_t up_stream = n_chunks == 1 ? dev->stream : dev->h2d_stream;
+        cudaStream_t down_stream = n_chunks == 1 ? dev->stream : dev->copy_stream;
+        cudaError_t err = cudaMemcpyAsync(d_pos + off, src, cnt * sizeof(double), cudaMemcpyHostToDevice, up_stream);
         if (err == cudaSuccess && need_f_upload) {
             // ADD: the caller's current forces are the accumulator's initial value.
             // STORE with a particle subset: untouched entries must come back as they were.
@@ -654,10 +657,12 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
                 memcpy(stage_f + off * sizeof(double), fsrc, cnt * sizeof(double));
                 fsrc = reinterpret_cast<const double*>(stage_f) + off;
             }
-            err = cudaMemcpyAsync(d_f + off, fsrc, cnt * sizeof(double), cudaMemcpyHostToDevice, dev->h2d_stream);
+            err = cudaMemcpyAsync(d_f + off, fsrc, cnt * sizeof(double), cudaMemcpyHostToDevice, up_stream);
         }
-        if (err == cudaSuccess) err = cudaEventRecord(up[c], dev->h2d_stream);
-        if (err == cudaSuccess) err = cudaStreamWaitEvent(dev->stream, up[c], 0);
+        if (n_chunks > 1) {
+            if (err == cudaSuccess) err = cudaEventRecord(up[c], dev->h2d_stream);
+            if (err == cudaSuccess) err = cudaStreamWaitEvent(dev->stream, up[c], 0);
+        }
         if (err != cudaSuccess) {
             status = fail(GFB_ERR_CUDA, "gfb_kernel_execute_host: H2D: %s", cudaGetErrorString(err));
             break;
@@ -665,19 +670,22 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
         status = enqueue_eval(k, r1 - r0, n_particles, d_pos + off, d_e + r0, grid_energies ? d_ge + (size_t) r0 * ng : nullptr,
                               d_f ? d_f + off : nullptr, force_mode, 0, nullptr, nullptr, dev->stream);
         if (status != GFB_OK) break;
-        err = cudaEventRecord(done[c], dev->stream);
-        if (err == cudaSuccess && forces) {
-            err = cudaStreamWaitEvent(dev->copy_stream, done[c], 0);
+        err = cudaSuccess;
+        if (forces) {
+            if (n_chunks > 1) {
+                err = cudaEventRecord(done[c], dev->stream);
+                if (err == cudaSuccess) err = cudaStreamWaitEvent(dev->copy_stream, done[c], 0);
+            }
             double* dst = f_pinned ? forces + off : reinterpret_cast<double*>(stage_f) + off;
             if (err == cudaSuccess)
-                err = cudaMemcpyAsync(dst, d_f + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, dev->copy_stream);
+                err = cudaMemcpyAsync(dst, d_f + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, down_stream);
         }
         if (err != cudaSuccess) status = fail(GFB_ERR_CUDA, "gfb_kernel_execute_host: D2H: %s", cudaGetErrorString(err));
     }
     if (status == GFB_OK) {
         cudaError_t err = cudaMemcpyAsync(k->h_energy.ptr, d_e, e_count * sizeof(double), cudaMemcpyDeviceToHost, dev->stream);
         if (err == cudaSuccess) err = cudaStreamSynchronize(dev->stream);
-        if (err == cudaSuccess) err = cudaStreamSynchronize(dev->copy_stream);
+        if (err == cudaSuccess && n_chunks > 1) err = cudaStreamSynchronize(dev->copy_stream);
         if (err != cudaSuccess) status = fail(GFB_ERR_CUDA, "gfb_kernel_execute_host: %s", cudaGetErrorString(err));
     } else {
         cudaStreamSynchronize(dev->h2d_stream);

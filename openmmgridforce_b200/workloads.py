@@ -137,13 +137,15 @@ def c4_batched_replicas(n_replicas=4096, counts=TEST_GRID_COUNTS):
                     _ligand_scaling(3), pos, [10000.0] * 3, [0.0] * 3)
 
 
-def c5_sharded_replicas(n_replicas=65536, n=192, replica_offset=0, n_local=None):
+def c5_sharded_replicas(n_replicas=65536, n=192, replica_offset=0, n_local=None, pose_seed=SEED):
     """Replicas [replica_offset, replica_offset + n_local) of the 65,536-replica batch (a rank's shard).
-    The whole batch is generated from one seed and sliced, so shards are identical however they are cut."""
+    The whole batch is generated from one seed and sliced, so shards are identical however they are cut.
+    `pose_seed` changes the replica poses only (grids and scaling factors stay): bench.py's weak-scaling runs give
+    every rank its own 65,536 poses with pose_seed = SEED + rank instead of generating N x 65,536 and slicing."""
     counts, sp = (n, n, n), (TEST_GRID_SPACING,) * 3
     grids = [synthetic_grid(counts, sp, seed=SEED + g) for g in range(3)]
     half = 0.5 * sp[0] * (n - 1)
-    pos = ligand_replicas(n_replicas, (half, half, half), escape_shift=(0.9, 0.0, 0.0))
+    pos = ligand_replicas(n_replicas, (half, half, half), seed=pose_seed, escape_shift=(0.9, 0.0, 0.0))
     if n_local is not None:
         pos = np.ascontiguousarray(pos[replica_offset:replica_offset + n_local])
     return Workload(f"C5 {n_replicas} replicas x 47 atoms x 3 grids of {n}^3", counts, sp, (0.0, 0.0, 0.0), grids,
