@@ -132,9 +132,17 @@ GFB_API int gfb_kernel_destroy(gfb_kernel* k);
  * factors [n_grids][n_atoms] and inv_power [n_grids] (NULL = keep). */
 GFB_API int gfb_kernel_update_parameters(gfb_kernel* k, const double* scaling, const double* inv_power);
 
+/* Particle groups (GridForce::addParticleGroup / getParticleGroupEnergies, openmmapi/include/GridForce.h:433-508;
+ * CUDA platform: flattened groups + particle->group map, CudaGridForceKernels.cpp:607-675, 985-1005): gives every
+ * evaluated atom an energy slot. Afterwards every energy array of execute has n_replicas * n_slots entries, entry
+ * [r * n_slots + s] being the energy of the atoms of replica r whose slot is s (and [.. ][n_grids] for grid_energies).
+ * slots: host [n_atoms] with values in [0, n_slots); NULL restores the default (one slot). Atoms of a group should be
+ * contiguous in the atom list (one atomic per run of equal slot per warp). */
+GFB_API int gfb_kernel_set_energy_slots(gfb_kernel* k, const int* slots, int n_slots);
+
 /* CalcGridForceKernel::execute for host-resident data (Reference-platform style), batched over replicas.
  *   pos       host [n_replicas][n_particles][3] doubles (std::vector<Vec3> layout)
- *   energies  host out [n_replicas] (sum over grids) or NULL
+ *   energies  host out [n_replicas] (sum over grids) or NULL   ([n_replicas][n_slots] with energy slots)
  *   grid_energies host out [n_replicas][n_grids] or NULL
  *   forces    host [n_replicas][n_particles][3]; force_mode STORE overwrites the evaluated particles'
  *             entries with the total grid force, ADD adds to what is there. NULL = energy only.

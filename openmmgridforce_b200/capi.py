@@ -52,6 +52,7 @@ SIGNATURES = {
     "gfb_kernel_create": (_i, [_vp, _i, C.POINTER(_vp), _i, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "gfb_kernel_destroy": (_i, [_vp]),
     "gfb_kernel_update_parameters": (_i, [_vp, _vp, _vp]),
+    "gfb_kernel_set_energy_slots": (_i, [_vp, _vp, _i]),
     "gfb_kernel_execute_host": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i]),
     "gfb_kernel_execute_device": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp]),
     "gfb_kernel_sort_atoms": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
@@ -196,6 +197,7 @@ class Kernel:
             raise GridForceB200Error(f"scaling has {sc.shape[0]} rows for {g} grids")
         self.n_grids = g
         self.n_atoms = sc.shape[1]
+        self.n_slots = 1
         self._scaling = sc
         ok = _host_f64(oob_k if oob_k is not None else [10000.0] * g).ravel()  # GridForce.cpp:52 default
         ip = _host_f64(inv_power).ravel() if inv_power is not None else None
@@ -204,6 +206,18 @@ class Kernel:
         self._h = C.c_void_p()
         _check(load_library().gfb_kernel_create(device._h, g, handles, self.n_atoms, _ptr(sc), _ptr(pa), _ptr(ip), _ptr(ok),
                                                 C.byref(self._h)))
+
+    def set_energy_slots(self, slots, n_slots):
+        """Particle groups: slots[ia] in [0, n_slots); energies then come back as [R, n_slots]."""
+        if slots is None:
+            _check(load_library().gfb_kernel_set_energy_slots(self._h, None, 1))
+            self.n_slots = 1
+            return
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        if sl.size != self.n_atoms:
+            raise GridForceB200Error(f"{sl.size} slots for {self.n_atoms} atoms")
+        _check(load_library().gfb_kernel_set_energy_slots(self._h, _ptr(sl), int(n_slots)))
+        self.n_slots = int(n_slots)
 
     def update_parameters(self, scaling=None, inv_power=None):
         sc = _host_f64(scaling).reshape(self.n_grids, self.n_atoms) if scaling is not None else None
@@ -219,8 +233,9 @@ class Kernel:
         if pos.ndim == 2:
             pos = pos.reshape(1, *pos.shape)
         r, p, _ = pos.shape
-        en = energies_out if energies_out is not None else np.empty(r, dtype=np.float64)
-        ge = np.empty((r, self.n_grids), dtype=np.float64) if want_grid_energies else None
+        ne = r * self.n_slots
+        en = energies_out if energies_out is not None else np.empty(ne, dtype=np.float64)
+        ge = np.empty((ne, self.n_grids), dtype=np.float64) if want_grid_energies else None
         if forces is None and want_forces:
             forces = np.zeros((r, p, 3), dtype=np.float64)
         _check(load_library().gfb_kernel_execute_host(self._h, r, p, _ptr(pos), _ptr(en), _ptr(ge), _ptr(forces), force_mode))

@@ -112,6 +112,8 @@ struct gfb_kernel {
     void* d_scaling;      // [n_grids][n_atoms] float|double
     int* d_particles;     // [n_atoms] or null
     int max_particle;     // largest particle index referenced (+1 = minimum n_particles)
+    int* d_slots;         // [n_atoms] energy slot per atom (particle groups) or null
+    int n_slots;          // energy slots per replica
     float* d_interleaved; // MIXED + CELLS + shared geometry + 2..4 grids: one record per cell holding every grid's corners
     int il_slots;         // grids per record incl. padding (2 or 4); 0 = not interleaved
     // host-path scratch
@@ -357,6 +359,8 @@ int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int 
     k->d_particles = nullptr;
     k->d_interleaved = nullptr;
     k->il_slots = 0;
+    k->d_slots = nullptr;
+    k->n_slots = 1;
     k->max_particle = n_atoms - 1;
     for (int g = 0; g < n_grids; g++) {
         k->grids[g] = grids[g];
@@ -435,6 +439,7 @@ int gfb_kernel_destroy(gfb_kernel* k) {
     if (k->d_scaling) cudaFree(k->d_scaling);
     if (k->d_particles) cudaFree(k->d_particles);
     if (k->d_interleaved) cudaFree(k->d_interleaved);
+    if (k->d_slots) cudaFree(k->d_slots);
     k->d_pos.release();
     k->d_forces.release();
     k->d_energy.release();
@@ -443,6 +448,25 @@ int gfb_kernel_destroy(gfb_kernel* k) {
     k->h_stage.release();
     k->h_energy.release();
     delete k;
+    return GFB_OK;
+}
+
+int gfb_kernel_set_energy_slots(gfb_kernel* k, const int* slots, int n_slots) {
+    if (!k) return fail(GFB_ERR_INVALID, "gfb_kernel_set_energy_slots: NULL kernel");
+    CUDA_TRY(cudaSetDevice(k->dev->ordinal));
+    if (!slots) {
+        if (k->d_slots) cudaFree(k->d_slots);
+        k->d_slots = nullptr;
+        k->n_slots = 1;
+        return GFB_OK;
+    }
+    if (n_slots < 1) return fail(GFB_ERR_INVALID, "gfb_kernel_set_energy_slots: n_slots=%d", n_slots);
+    for (int i = 0; i < k->n_atoms; i++)
+        if (slots[i] < 0 || slots[i] >= n_slots)
+            return fail(GFB_ERR_INVALID, "gfb_kernel_set_energy_slots: slots[%d]=%d outside [0,%d)", i, slots[i], n_slots);
+    if (!k->d_slots) CUDA_TRY(cudaMalloc((void**) &k->d_slots, std::max<size_t>((size_t) k->n_atoms * sizeof(int), 16)));
+    CUDA_TRY(cudaMemcpy(k->d_slots, slots, (size_t) k->n_atoms * sizeof(int), cudaMemcpyHostToDevice));
+    k->n_slots = n_slots;
     return GFB_OK;
 }
 
@@ -488,7 +512,7 @@ static void fill_grid_view(const gfb_kernel* k, int g, GridView& v) {
 template <typename S, int LAYOUT, int NG, bool SAME, int FMODE>
 static void launch_eval4(const EvalParams& p, cudaStream_t stream) {
     const unsigned blocks = (unsigned) ((p.total + kBlock - 1) / kBlock);
-    if (p.n_replicas == 1)
+    if (p.n_replicas == 1 && p.slots == nullptr)
         gf_eval_kernel<S, LAYOUT, NG, SAME, FMODE, true><<<blocks, kBlock, 0, stream>>>(p);
     else
         gf_eval_kernel<S, LAYOUT, NG, SAME, FMODE, false><<<blocks, kBlock, 0, stream>>>(p);
@@ -536,6 +560,8 @@ static int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const do
     p.pos = d_pos;
     p.particles = k->d_particles;
     p.order = d_order;
+    p.slots = k->d_slots;
+    p.n_slots = k->n_slots;
     p.energies = d_energies;
     p.grid_energies = d_grid_energies;
     p.energies_clear = d_energies_clear;
@@ -594,7 +620,8 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
     const size_t np = (size_t) n_replicas * n_particles;
     const size_t pos_bytes = np * 3 * sizeof(double);
     const int ng = k->n_grids;
-    const size_t e_count = (size_t) n_replicas * (1 + ng);
+    const size_t n_e = (size_t) n_replicas * k->n_slots;          // energy entries: [replica][slot]
+    const size_t e_count = n_e * (1 + ng);
     if ((rc = k->d_pos.ensure(pos_bytes)) != GFB_OK) return rc;
     if (forces && (rc = k->d_forces.ensure(pos_bytes)) != GFB_OK) return rc;
     if ((rc = k->d_energy.ensure(e_count * sizeof(double))) != GFB_OK) return rc;
@@ -611,7 +638,7 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
     double* d_pos = static_cast<double*>(k->d_pos.ptr);
     double* d_f = forces ? static_cast<double*>(k->d_forces.ptr) : nullptr;
     double* d_e = static_cast<double*>(k->d_energy.ptr);
-    double* d_ge = d_e + n_replicas;
+    double* d_ge = d_e + n_e;
     CUDA_TRY(cudaMemsetAsync(d_e, 0, e_count * sizeof(double), dev->stream));
 
     // Chunk pipeline over three streams: H2D(c) on h2d_stream -> [up c] -> kernel(c) on stream -> [done c] -> D2H(c) on
@@ -667,7 +694,8 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
             status = fail(GFB_ERR_CUDA, "gfb_kernel_execute_host: H2D: %s", cudaGetErrorString(err));
             break;
         }
-        status = enqueue_eval(k, r1 - r0, n_particles, d_pos + off, d_e + r0, grid_energies ? d_ge + (size_t) r0 * ng : nullptr,
+        status = enqueue_eval(k, r1 - r0, n_particles, d_pos + off, d_e + (size_t) r0 * k->n_slots,
+                              grid_energies ? d_ge + (size_t) r0 * k->n_slots * ng : nullptr,
                               d_f ? d_f + off : nullptr, force_mode, 0, nullptr, nullptr, dev->stream);
         if (status != GFB_OK) break;
         err = cudaSuccess;
@@ -695,8 +723,8 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
     if (status != GFB_OK) return status;
 
     const double* he = static_cast<const double*>(k->h_energy.ptr);
-    if (energies) memcpy(energies, he, (size_t) n_replicas * sizeof(double));
-    if (grid_energies) memcpy(grid_energies, he + n_replicas, (size_t) n_replicas * ng * sizeof(double));
+    if (energies) memcpy(energies, he, n_e * sizeof(double));
+    if (grid_energies) memcpy(grid_energies, he + n_e, n_e * ng * sizeof(double));
     if (forces && !f_pinned) memcpy(forces, stage_f, pos_bytes);
     return GFB_OK;
 }

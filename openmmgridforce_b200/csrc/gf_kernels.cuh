@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kBlock, (NG == 1 && sizeof(S) == 4) ? 6 : 4) g
     const unsigned total = (unsigned) p.total;
     const int lane = threadIdx.x & 31;
     const bool active = t < total;
-    if (p.energies_clear && t < (unsigned) p.n_replicas) p.energies_clear[t] = 0.0;
+    if (p.energies_clear && t < (unsigned) (p.n_replicas * p.n_slots)) p.energies_clear[t] = 0.0;
 
     int rep = -1;
     unsigned ia = 0;
@@ -324,6 +324,9 @@ __global__ void __launch_bounds__(kBlock, (NG == 1 && sizeof(S) == 4) ? 6 : 4) g
         }
         const int particle = p.particles ? p.particles[ia] : (int) ia;
         gidx = (long long) rep * p.n_particles + particle;
+        // Particle groups (GridForce::addParticleGroup): every atom carries the energy slot of its group, and the
+        // energy of replica r, group s accumulates at [r * n_slots + s]. Runs of equal key reduce together.
+        if (p.slots) rep = rep * p.n_slots + p.slots[ia];
     }
 
     // Scaling factors depend on the atom ordinal only: their loads go out first and overlap the position fetch.

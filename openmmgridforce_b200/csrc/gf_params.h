@@ -38,6 +38,9 @@ struct EvalParams {
     const double* pos;       // [n_replicas][n_particles][3]
     const int* particles;    // [n_atoms] or null
     const int* order;        // [total] or null
+    const int* slots;        // [n_atoms] energy slot of each atom inside a replica (particle groups), or null
+    int n_slots;             // energy slots per replica (1 without groups)
+    int pad2_;
     double* energies;        // [n_replicas] or null, accumulated
     double* grid_energies;   // [n_replicas][n_grids] or null, accumulated
     double* energies_clear;  // [n_replicas] or null: zero-filled by this launch (next step's accumulator)

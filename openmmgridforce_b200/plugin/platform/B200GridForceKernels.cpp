@@ -96,20 +96,31 @@ void B200CalcGridForceKernel::build(const GridForce& force) {
     gfb_grid* handle = grid->handle;
     groupMode = force.getNumParticleGroups() > 0;
     if (groupMode) {
-        // Multi-ligand mode (GridForce.h:433-508): every group is evaluated with its own particle list and scaling
-        // factors; per-group energies are kept for getParticleGroupEnergies().
-        for (int g = 0; g < force.getNumParticleGroups(); g++) {
+        // Multi-ligand mode (GridForce.h:433-508): all groups are flattened into ONE atom list (particle index +
+        // scaling factor + the group's energy slot per atom) and evaluated by one launch; the kernel reduces energies
+        // per slot, which is what getParticleGroupEnergies() returns. Same flattening as the reference CUDA platform
+        // (CudaGridForceKernels.cpp:607-675), minus its per-step host round trips (:840-853, 987-996).
+        std::vector<int> particlesFlat, slots;
+        std::vector<double> scalingFlat;
+        numGroups = force.getNumParticleGroups();
+        for (int g = 0; g < numGroups; g++) {
             const ParticleGroup& grp = force.getParticleGroup(g);
-            for (size_t i = 0; i < grp.particleIndices.size(); i++)
+            for (size_t i = 0; i < grp.particleIndices.size(); i++) {
                 if (grp.particleIndices[i] < 0 || grp.particleIndices[i] >= numParticles)
                     throw OpenMMException("GridForce[B200]: particle group '" + grp.name + "' has an index outside the System");
-            gfb_kernel* k = 0;
-            check(gfb_kernel_create(dev, 1, &handle, (int) grp.particleIndices.size(), grp.scalingFactors.data(),
-                                    grp.particleIndices.data(), &invPower, &oobK, &k), "kernel setup");
-            kernels.push_back(k);
+                particlesFlat.push_back(grp.particleIndices[i]);
+                scalingFlat.push_back(grp.scalingFactors[i]);
+                slots.push_back(g);
+            }
         }
+        gfb_kernel* k = 0;
+        check(gfb_kernel_create(dev, 1, &handle, (int) particlesFlat.size(), scalingFlat.data(), particlesFlat.data(), &invPower,
+                                &oobK, &k), "kernel setup");
+        kernels.push_back(k);
+        check(gfb_kernel_set_energy_slots(k, slots.data(), numGroups), "particle group slots");
         return;
     }
+    numGroups = 0;
     // Single mode: scaling factor ia belongs to particle ligandAtoms[ia] (identity when no ligand atoms are set).
     // The loop bound is the number of scaling factors, not the particle count (reference quirk Q6).
     const std::vector<int>& ligand = force.getLigandAtoms();
@@ -146,13 +157,9 @@ double B200CalcGridForceKernel::execute(ContextImpl& context, bool includeForces
     const double* p = &pos[0][0];
     double* f = includeForces ? &frc[0][0] : 0;
     double total = 0.0;
-    lastGroupEnergies.assign(kernels.size(), 0.0);
-    for (size_t i = 0; i < kernels.size(); i++) {
-        double e = 0.0;
-        check(gfb_kernel_execute_host(kernels[i], 1, numParticles, p, &e, 0, f, GFB_FORCE_F64_ADD), "execute");
-        lastGroupEnergies[i] = e;
-        total += e;
-    }
+    lastGroupEnergies.assign(groupMode ? numGroups : 1, 0.0);      // one energy per group slot (or the single total)
+    check(gfb_kernel_execute_host(kernels[0], 1, numParticles, p, lastGroupEnergies.data(), 0, f, GFB_FORCE_F64_ADD), "execute");
+    for (size_t i = 0; i < lastGroupEnergies.size(); i++) total += lastGroupEnergies[i];
     (void) includeEnergy;
     return total;
 }

@@ -44,7 +44,8 @@ private:
     int deviceIndex, precision;
     gfb_device* dev;
     std::shared_ptr<SharedGrid> grid;
-    std::vector<gfb_kernel*> kernels;       // one, or one per particle group
+    std::vector<gfb_kernel*> kernels;       // the one evaluation state of this force
+    int numGroups = 0;
     std::vector<double> lastGroupEnergies;
     int numParticles;
     bool groupMode = false;

@@ -293,3 +293,36 @@ def test_update_parameters(gpu_device, oracle_built):
     e2, f2, _ = port.execute(c["pos"], 0)
     assert _rel_e(en[0], e2) <= 1e-12 and _rel_f(f[0], f2) <= 1e-12
     _close(grids, k)
+
+
+def test_energy_slots_particle_groups(gpu_device, oracle_built):
+    """gfb_kernel_set_energy_slots: three particle groups flattened into one atom list, two replicas; energies come
+    back per (replica, group) and equal the oracle evaluated group by group; forces accumulate per particle, including
+    a particle that belongs to two groups."""
+    import openmmgridforce_b200 as gf
+    c = cases.case_random_aniso()
+    rng = np.random.default_rng(12)
+    groups = [list(range(0, 40)), list(range(40, 75)), [5, 80, 81, 82]]          # particle 5 is in groups 0 and 2
+    particles = np.array(sum(groups, []), dtype=np.int32)
+    slots = np.concatenate([np.full(len(g), i) for i, g in enumerate(groups)]).astype(np.int32)
+    scaling = rng.normal(size=(1, particles.size))
+    pos = np.ascontiguousarray(np.stack([c["pos"][:100], c["pos"][100:200]]))
+    g = gf.Grid(gpu_device, c["counts"], c["spacing"], c["origin"], c["grids"][0], gf.PRECISION_DOUBLE)
+    k = gf.Kernel(gpu_device, [g], scaling, particles=particles, oob_k=c["oob_k"][:1])
+    k.set_energy_slots(slots, 3)
+    forces = np.zeros_like(pos)
+    en, _, ge = k.execute_host(pos, forces=forces, force_mode=gf.FORCE_F64_ADD, want_grid_energies=True)
+    en = en.reshape(2, 3)
+    for r in range(2):
+        want_f = np.zeros((100, 3))
+        lo = 0
+        for s, grp in enumerate(groups):
+            port = oracle_built.PortOracle(c["counts"], c["spacing"], c["origin"], c["grids"][:1], scaling[:, lo:lo + len(grp)],
+                                           oob_k=c["oob_k"][:1])
+            e, f, _ = port.execute(pos[r][grp], 0)
+            np.add.at(want_f, grp, f)
+            assert _rel_e(en[r, s], e) <= 1e-12, (r, s)
+            lo += len(grp)
+        assert _rel_f(forces[r], want_f) <= 1e-12
+    assert np.allclose(ge.reshape(2, 3), en, rtol=1e-13)
+    _close([g], k)
