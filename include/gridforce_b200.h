@@ -108,6 +108,32 @@ GFB_API int gfb_grid_create(gfb_device* dev, const int counts[3], const double s
 GFB_API int gfb_grid_create_from_device(gfb_device* dev, const int counts[3], const double spacing[3],
                                         const double origin[3], const double* d_vals, size_t n_vals,
                                         int precision, int layout, gfb_grid** out);
+/* ---- V3 "OMGRID" grid files: the reference's binary format (GridForce::loadFromFile / saveToFile,
+ * openmmapi/src/GridForce.cpp:495-799; GridData::saveToFile, openmmapi/src/GridData.cpp:181-267). Bulk ingest: a
+ * 16.8 M-point grid costs 16.8 M addGridValue() calls through SWIG in the reference's own tests
+ * (python/tests/test_grid_force.py:58-59); here a file goes disk -> pinned staging -> HBM -> on-device repack. */
+typedef struct {
+    int counts[3];
+    double spacing[3];
+    double origin[3];
+    int grid_type;                  /* 0 none, 1 charge, 2 ljr, 3 lja */
+    double inv_power;
+    int inv_power_mode;             /* InvPowerMode: 0 NONE, 1 RUNTIME, 2 STORED */
+    unsigned int deriv_count;       /* 0, or 27 when the file carries derivative grids (function values come first) */
+    unsigned long long data_offset; /* 128 */
+} gfb_gridfile_header;
+
+GFB_API int gfb_gridfile_read_header(const char* path, gfb_gridfile_header* header);
+/* Reads the nx*ny*nz function values into a HOST buffer (n_vals must equal the header's point count). */
+GFB_API int gfb_gridfile_read_values(const char* path, double* vals, size_t n_vals);
+/* Writes a V3 file byte-identical to the reference's: with_trailer = 0 -> GridForce::saveToFile (header + values),
+ * with_trailer = 1 -> GridData::saveToFile (adds i32 0 and the origin again). deriv_count is written as 0. */
+GFB_API int gfb_gridfile_write(const char* path, const gfb_gridfile_header* header, const double* vals, size_t n_vals,
+                               int with_trailer);
+/* File -> device grid in one call, streamed through pinned staging in 32 MB pieces (no full host copy). */
+GFB_API int gfb_grid_create_from_file(gfb_device* dev, const char* path, int precision, int layout, gfb_grid** out,
+                                      gfb_gridfile_header* header_out);
+
 GFB_API int gfb_grid_destroy(gfb_grid* grid);
 GFB_API size_t gfb_grid_device_bytes(const gfb_grid* grid);
 GFB_API int gfb_grid_layout(const gfb_grid* grid);   /* the layout actually chosen (resolves AUTO) */

@@ -24,6 +24,8 @@ from .capi import (  # noqa: F401
     library_path,
     load_library,
     launch_count,
+    read_grid_file,
+    write_grid_file,
 )
 
 __version__ = "0.1.0"

@@ -26,6 +26,12 @@ class GridForceB200Error(RuntimeError):
     the same way, python/gridforceplugin.i:49-59)."""
 
 
+class GridFileHeader(C.Structure):
+    _fields_ = [("counts", C.c_int * 3), ("spacing", C.c_double * 3), ("origin", C.c_double * 3), ("grid_type", C.c_int),
+                ("inv_power", C.c_double), ("inv_power_mode", C.c_int), ("deriv_count", C.c_uint),
+                ("data_offset", C.c_ulonglong)]
+
+
 class _Props(C.Structure):
     _fields_ = [("name", C.c_char * 128), ("cc_major", C.c_int), ("cc_minor", C.c_int), ("sm_count", C.c_int),
                 ("l2_bytes", C.c_int), ("total_mem_bytes", C.c_size_t)]
@@ -47,6 +53,10 @@ SIGNATURES = {
     "gfb_grid_create": (_i, [_vp, _pi, _pd, _pd, _vp, _sz, _i, _i, C.POINTER(_vp)]),
     "gfb_grid_create_from_device": (_i, [_vp, _pi, _pd, _pd, _vp, _sz, _i, _i, C.POINTER(_vp)]),
     "gfb_grid_layout": (_i, [_vp]),
+    "gfb_gridfile_read_header": (_i, [C.c_char_p, C.POINTER(GridFileHeader)]),
+    "gfb_gridfile_read_values": (_i, [C.c_char_p, _vp, _sz]),
+    "gfb_gridfile_write": (_i, [C.c_char_p, C.POINTER(GridFileHeader), _vp, _sz, _i]),
+    "gfb_grid_create_from_file": (_i, [_vp, C.c_char_p, _i, _i, C.POINTER(_vp), C.POINTER(GridFileHeader)]),
     "gfb_grid_destroy": (_i, [_vp]),
     "gfb_grid_device_bytes": (_sz, [_vp]),
     "gfb_kernel_create": (_i, [_vp, _i, C.POINTER(_vp), _i, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
@@ -112,6 +122,33 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def read_grid_file(path):
+    """V3 OMGRID file -> (header dict, values [nx, ny, nz] float64). Host only."""
+    lib = load_library()
+    h = GridFileHeader()
+    _check(lib.gfb_gridfile_read_header(os.fsencode(path), C.byref(h)))
+    vals = np.empty(tuple(h.counts), dtype=np.float64)
+    _check(lib.gfb_gridfile_read_values(os.fsencode(path), _ptr(vals), vals.size))
+    return _header_dict(h), vals
+
+
+def write_grid_file(path, counts, spacing, origin, values, grid_type=0, inv_power=0.0, inv_power_mode=0, with_trailer=False):
+    """Writes the reference's V3 format: GridForce::saveToFile bytes, or GridData::saveToFile bytes with_trailer."""
+    h = GridFileHeader()
+    h.counts = (C.c_int * 3)(*[int(c) for c in counts])
+    h.spacing = (C.c_double * 3)(*[float(c) for c in spacing])
+    h.origin = (C.c_double * 3)(*[float(c) for c in origin])
+    h.grid_type, h.inv_power, h.inv_power_mode = int(grid_type), float(inv_power), int(inv_power_mode)
+    v = _host_f64(values).ravel()
+    _check(load_library().gfb_gridfile_write(os.fsencode(path), C.byref(h), _ptr(v), v.size, 1 if with_trailer else 0))
+
+
+def _header_dict(h):
+    return {"counts": tuple(h.counts), "spacing": tuple(h.spacing), "origin": tuple(h.origin), "grid_type": h.grid_type,
+            "inv_power": h.inv_power, "inv_power_mode": h.inv_power_mode, "deriv_count": h.deriv_count,
+            "data_offset": h.data_offset}
+
+
 class Device:
     """gfb_device: one GPU."""
 
@@ -172,6 +209,19 @@ class Grid:
             v = _host_f64(values).ravel()
             _check(lib.gfb_grid_create(device._h, cn, sp, og, _ptr(v), v.size, precision, layout, C.byref(self._h)))
         self.layout = int(lib.gfb_grid_layout(self._h))
+
+    @classmethod
+    def from_file(cls, device, path, precision=PRECISION_MIXED, layout=LAYOUT_AUTO):
+        """gfb_grid_create_from_file: V3 OMGRID file -> pinned staging -> HBM -> on-device repack."""
+        self = cls.__new__(cls)
+        self.device, self.precision, self._h = device, precision, C.c_void_p()
+        h = GridFileHeader()
+        lib = load_library()
+        _check(lib.gfb_grid_create_from_file(device._h, os.fsencode(path), precision, layout, C.byref(self._h), C.byref(h)))
+        self.header = _header_dict(h)
+        self.counts, self.spacing, self.origin = self.header["counts"], self.header["spacing"], self.header["origin"]
+        self.layout = int(lib.gfb_grid_layout(self._h))
+        return self
 
     @property
     def device_bytes(self):

@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "gf_gridfile.h"
 #include "gf_kernels.cuh"
 #include "gridforce_b200.h"
 
@@ -305,6 +306,108 @@ int gfb_grid_create(gfb_device* dev, const int counts[3], const double spacing[3
 int gfb_grid_create_from_device(gfb_device* dev, const int counts[3], const double spacing[3], const double origin[3],
                                 const double* d_vals, size_t n_vals, int precision, int layout, gfb_grid** out) {
     return grid_create_common(dev, counts, spacing, origin, d_vals, true, n_vals, precision, layout, out);
+}
+
+// ---- V3 grid files -------------------------------------------------------------------------------------------
+int gfb_gridfile_read_header(const char* path, gfb_gridfile_header* header) {
+    if (!path || !header) return fail(GFB_ERR_INVALID, "gfb_gridfile_read_header: NULL argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(GFB_ERR_INVALID, "GridForce: Cannot open file '%s'", path);
+    const std::string err = gridfile_read_header(f, header);
+    fclose(f);
+    if (!err.empty()) return fail(GFB_ERR_INVALID, "GridForce: %s (%s)", err.c_str(), path);
+    return GFB_OK;
+}
+
+int gfb_gridfile_read_values(const char* path, double* vals, size_t n_vals) {
+    if (!path || !vals) return fail(GFB_ERR_INVALID, "gfb_gridfile_read_values: NULL argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(GFB_ERR_INVALID, "GridForce: Cannot open file '%s'", path);
+    gfb_gridfile_header h;
+    std::string err = gridfile_read_header(f, &h);
+    const size_t n = (size_t) h.counts[0] * h.counts[1] * h.counts[2];
+    if (err.empty() && n != n_vals) err = "buffer holds " + std::to_string(n_vals) + " values, file has " + std::to_string(n);
+    if (err.empty() && fseek(f, (long) h.data_offset, SEEK_SET) != 0) err = "cannot seek to the data offset";
+    if (err.empty() && fread(vals, sizeof(double), n, f) != n) err = "file ends before the last grid value";
+    fclose(f);
+    if (!err.empty()) return fail(GFB_ERR_INVALID, "GridForce: %s (%s)", err.c_str(), path);
+    return GFB_OK;
+}
+
+int gfb_gridfile_write(const char* path, const gfb_gridfile_header* header, const double* vals, size_t n_vals, int with_trailer) {
+    if (!path || !header || !vals) return fail(GFB_ERR_INVALID, "gfb_gridfile_write: NULL argument");
+    const size_t n = (size_t) header->counts[0] * header->counts[1] * header->counts[2];
+    if (n != n_vals) return fail(GFB_ERR_INVALID, "GridForce: Number of grid values doesn't match dimensions");
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(GFB_ERR_INVALID, "GridForce: Cannot create file '%s'", path);
+    PackedHeader h;
+    gridfile_fill_header(*header, h);
+    bool ok = fwrite(&h, 1, sizeof h, f) == sizeof h && fwrite(vals, sizeof(double), n, f) == n;
+    if (ok && with_trailer) {   // GridData::saveToFile trailer (GridData.cpp:250-256)
+        const int32_t n_scaling = 0;
+        ok = fwrite(&n_scaling, sizeof n_scaling, 1, f) == 1 && fwrite(header->origin, sizeof(double), 3, f) == 3;
+    }
+    ok = fclose(f) == 0 && ok;
+    if (!ok) return fail(GFB_ERR_INVALID, "GridForce: write to '%s' failed", path);
+    return GFB_OK;
+}
+
+int gfb_grid_create_from_file(gfb_device* dev, const char* path, int precision, int layout, gfb_grid** out,
+                              gfb_gridfile_header* header_out) {
+    if (!dev || !path || !out) return fail(GFB_ERR_INVALID, "gfb_grid_create_from_file: NULL argument");
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(GFB_ERR_INVALID, "GridForce: Cannot open file '%s'", path);
+    gfb_gridfile_header h;
+    std::string err = gridfile_read_header(f, &h);
+    if (err.empty() && fseek(f, (long) h.data_offset, SEEK_SET) != 0) err = "cannot seek to the data offset";
+    if (!err.empty()) {
+        fclose(f);
+        return fail(GFB_ERR_INVALID, "GridForce: %s (%s)", err.c_str(), path);
+    }
+    if (cudaSetDevice(dev->ordinal) != cudaSuccess) {
+        fclose(f);
+        return fail(GFB_ERR_CUDA, "gfb_grid_create_from_file: cudaSetDevice failed");
+    }
+    const size_t n = (size_t) h.counts[0] * h.counts[1] * h.counts[2];
+    // disk -> two pinned 32 MB buffers (alternating) -> device doubles; then the normal on-device repack
+    const size_t piece = (size_t) 4 << 20;   // doubles per piece (32 MB)
+    double* d_vals = nullptr;
+    double* stage[2] = {nullptr, nullptr};
+    cudaEvent_t used[2] = {nullptr, nullptr};
+    cudaError_t ce = cudaMalloc((void**) &d_vals, n * sizeof(double));
+    for (int b = 0; b < 2 && ce == cudaSuccess; b++) {
+        ce = cudaHostAlloc((void**) &stage[b], std::min(piece, n) * sizeof(double), cudaHostAllocDefault);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&used[b], cudaEventDisableTiming);
+    }
+    size_t done = 0;
+    int b = 0;
+    while (ce == cudaSuccess && err.empty() && done < n) {
+        const size_t cnt = std::min(piece, n - done);
+        ce = cudaEventSynchronize(used[b]);      // the copy that last read this buffer has finished
+        if (ce != cudaSuccess) break;
+        if (fread(stage[b], sizeof(double), cnt, f) != cnt) {
+            err = "file ends before the last grid value";
+            break;
+        }
+        ce = cudaMemcpyAsync(d_vals + done, stage[b], cnt * sizeof(double), cudaMemcpyHostToDevice, dev->stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(used[b], dev->stream);
+        done += cnt;
+        b ^= 1;
+    }
+    fclose(f);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(dev->stream);
+    int rc = GFB_OK;
+    if (ce != cudaSuccess) rc = fail(GFB_ERR_CUDA, "gfb_grid_create_from_file: %s", cudaGetErrorString(ce));
+    else if (!err.empty()) rc = fail(GFB_ERR_INVALID, "GridForce: %s (%s)", err.c_str(), path);
+    else rc = grid_create_common(dev, h.counts, h.spacing, h.origin, d_vals, true, n, precision, layout, out);
+    for (int i = 0; i < 2; i++) {
+        if (stage[i]) cudaFreeHost(stage[i]);
+        if (used[i]) cudaEventDestroy(used[i]);
+    }
+    if (d_vals) cudaFree(d_vals);
+    if (rc == GFB_OK && header_out) *header_out = h;
+    return rc;
 }
 
 int gfb_grid_destroy(gfb_grid* grid) {

@@ -106,6 +106,24 @@ class GridForce:
     def setGridValues(self, vals):
         self._vals = np.ascontiguousarray(vals, dtype=np.float64).ravel()
 
+    def loadFromFile(self, filename):
+        """V3 OMGRID file (reference GridForce::loadFromFile): geometry, origin, values and inv-power state."""
+        from . import capi
+        try:
+            h, vals = capi.read_grid_file(filename)
+        except capi.GridForceB200Error as e:
+            raise RuntimeError(str(e))
+        self._counts, self._spacing, self._origin = list(h["counts"]), list(h["spacing"]), tuple(h["origin"])
+        self._vals = vals.ravel()
+        self._inv_power, self._inv_power_mode = h["inv_power"], h["inv_power_mode"]
+
+    def saveToFile(self, filename):
+        from . import capi
+        if len(self._counts) != 3 or len(self._spacing) != 3:
+            raise RuntimeError("GridForce: Grid dimensions must be set before saving")
+        capi.write_grid_file(filename, self._counts, self._spacing, self._origin, np.asarray(self._vals, dtype=np.float64),
+                             inv_power=self._inv_power, inv_power_mode=self._inv_power_mode)
+
     def addScalingFactor(self, val):
         self._scaling.append(float(val))
 

@@ -3,6 +3,7 @@
 #include "GridForce.h"
 
 #include "GridForceKernels.h"
+#include "gridforce_b200.h"
 #include "internal/GridForceImpl.h"
 #include "openmm/OpenMMException.h"
 #include "openmm/internal/ContextImpl.h"
@@ -38,6 +39,39 @@ void GridForce::getGridOrigin(double& x, double& y, double& z) const {
     x = m_origin[0];
     y = m_origin[1];
     z = m_origin[2];
+}
+
+// V3 files go through the C ABI's reader/writer (gf_gridfile.h), which is byte-compatible with the reference's
+// GridForce::saveToFile / loadFromFile (tests/test_gridfile.py).
+void GridForce::loadFromFile(const std::string& filename) {
+    gfb_gridfile_header h;
+    if (gfb_gridfile_read_header(filename.c_str(), &h) != GFB_OK) throw OpenMMException(gfb_last_error());
+    std::vector<double> vals((size_t) h.counts[0] * h.counts[1] * h.counts[2]);
+    if (gfb_gridfile_read_values(filename.c_str(), vals.data(), vals.size()) != GFB_OK) throw OpenMMException(gfb_last_error());
+    m_counts.assign(h.counts, h.counts + 3);
+    m_spacing.assign(h.spacing, h.spacing + 3);
+    m_origin.assign(h.origin, h.origin + 3);
+    m_vals.swap(vals);
+    m_invPower = h.inv_power;                                  // restored without transforming (GridForce.cpp:646-662)
+    m_invPowerMode = static_cast<InvPowerMode>(h.inv_power_mode);
+    static const char* names[] = {"", "charge", "ljr", "lja"};
+    m_gridType = h.grid_type >= 1 && h.grid_type <= 3 ? names[h.grid_type] : "";
+}
+
+void GridForce::saveToFile(const std::string& filename) const {
+    if (m_counts.size() != 3 || m_spacing.size() != 3) throw OpenMMException("GridForce: Grid dimensions must be set before saving");
+    gfb_gridfile_header h;
+    for (int k = 0; k < 3; k++) {
+        h.counts[k] = m_counts[k];
+        h.spacing[k] = m_spacing[k];
+        h.origin[k] = m_origin[k];
+    }
+    h.grid_type = m_gridType == "charge" ? 1 : m_gridType == "ljr" ? 2 : m_gridType == "lja" ? 3 : 0;
+    h.inv_power = m_invPower;
+    h.inv_power_mode = static_cast<int>(m_invPowerMode);
+    h.deriv_count = 0;
+    h.data_offset = 128;
+    if (gfb_gridfile_write(filename.c_str(), &h, m_vals.data(), m_vals.size(), 0) != GFB_OK) throw OpenMMException(gfb_last_error());
 }
 
 void GridForce::addScalingFactor(double val) { m_scaling.push_back(val); }

@@ -43,6 +43,12 @@ public:
     void setGridOrigin(double x, double y, double z);
     void getGridOrigin(double& x, double& y, double& z) const;
 
+    // ---- V3 "OMGRID" files (reference GridForce.cpp:495-799): values, geometry, origin, type, inv-power state ----
+    void loadFromFile(const std::string& filename);
+    void saveToFile(const std::string& filename) const;
+    void setGridType(const std::string& type) { m_gridType = type; }        // "", "charge", "ljr", "lja"
+    const std::string& getGridType() const { return m_gridType; }
+
     // ---- per-atom scaling factors ------------------------------------------------------------------------------
     void addScalingFactor(double val);
     void setScalingFactor(int index, double val);
@@ -100,6 +106,7 @@ private:
     InvPowerMode m_invPowerMode;
     int m_interpolation;
     const void* m_systemPtr;
+    std::string m_gridType;
 };
 
 }  // namespace GridForcePlugin

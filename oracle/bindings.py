@@ -90,6 +90,33 @@ def ref_available():
     return os.path.exists(REF_PATH)
 
 
+def ref_save_file(mode, path, counts, spacing, origin, values, grid_type="", inv_power=0.0, inv_power_mode=0):
+    """mode 0: the reference's GridForce::saveToFile; mode 1: its GridData::saveToFile."""
+    lib = C.CDLL(REF_PATH)
+    lib.oracle_ref_last_error.restype = C.c_char_p
+    v = _f64(values).ravel()
+    rc = lib.oracle_ref_save_file(mode, os.fsencode(path), (C.c_int * 3)(*counts), (C.c_double * 3)(*spacing),
+                                  (C.c_double * 3)(*origin), _dp(v), C.c_longlong(v.size), grid_type.encode(),
+                                  C.c_double(inv_power), inv_power_mode)
+    if rc:
+        raise RuntimeError(lib.oracle_ref_last_error().decode())
+
+
+def ref_load_file(path, capacity):
+    """The reference's GridForce::loadFromFile -> (counts, spacing, origin, values, inv_power, inv_power_mode)."""
+    lib = C.CDLL(REF_PATH)
+    lib.oracle_ref_last_error.restype = C.c_char_p
+    counts, spacing, origin = (C.c_int * 3)(), (C.c_double * 3)(), (C.c_double * 3)()
+    vals = np.empty(capacity)
+    ip, mode = C.c_double(0), C.c_int(0)
+    rc = lib.oracle_ref_load_file(os.fsencode(path), counts, spacing, origin, _dp(vals), C.c_longlong(capacity), C.byref(ip),
+                                  C.byref(mode))
+    if rc:
+        raise RuntimeError(lib.oracle_ref_last_error().decode())
+    n = counts[0] * counts[1] * counts[2]
+    return tuple(counts), tuple(spacing), tuple(origin), vals[:n].reshape(tuple(counts)), ip.value, mode.value
+
+
 class RefOracle:
     """The reference's own ReferenceCalcGridForceKernel: one System with P particles and G GridForces."""
 

@@ -12,9 +12,11 @@
 #include <sstream>
 #include <vector>
 
+#include "GridData.h"
 #include "GridForce.h"
 #include "GridForceKernels.h"
 #include "openmm/Context.h"
+#include "openmm/OpenMMException.h"
 #include "openmm/Platform.h"
 #include "openmm/System.h"
 #include "openmm/reference/ReferencePlatform.h"
@@ -160,5 +162,61 @@ int oracle_ref_execute_repeat(void* handle, const double* positions, int reps, d
 }
 
 void oracle_ref_destroy(void* handle) { delete static_cast<Handle*>(handle); }
+
+// ---- V3 grid files through the reference's own reader/writers (for tests/test_gridfile.py) -----------------------
+// mode 0: GridForce::saveToFile (openmmapi/src/GridForce.cpp:694-799); mode 1: GridData::saveToFile (GridData.cpp:181-267).
+int oracle_ref_save_file(int mode, const char* path, const int* counts, const double* spacing, const double* origin,
+                         const double* vals, long long nVals, const char* gridType, double invPower, int invPowerMode) {
+    try {
+        std::vector<double> v(vals, vals + nVals);
+        if (mode == 0) {
+            GridForce f;
+            f.addGridCounts(counts[0], counts[1], counts[2]);
+            f.addGridSpacing(spacing[0], spacing[1], spacing[2]);
+            f.setGridOrigin(origin[0], origin[1], origin[2]);
+            f.setGridValues(v);
+            f.setGridType(gridType);
+            if (invPowerMode != 0) f.setInvPowerMode(static_cast<InvPowerMode>(invPowerMode), invPower);
+            f.saveToFile(path);
+        } else {
+            GridForcePlugin::GridData d(counts[0], counts[1], counts[2], spacing[0], spacing[1], spacing[2]);
+            d.setOrigin(origin[0], origin[1], origin[2]);
+            d.setValues(v);
+            d.setGridType(gridType);
+            d.setInvPower(invPower);
+            d.setInvPowerMode(static_cast<InvPowerMode>(invPowerMode));
+            d.saveToFile(path);
+        }
+        return 0;
+    } catch (std::exception& e) {
+        lastError = e.what();
+        return 1;
+    }
+}
+
+// GridForce::loadFromFile (GridForce.cpp:495-692) -> what the kernel would then pull with getGridParameters.
+int oracle_ref_load_file(const char* path, int* counts, double* spacing, double* origin, double* vals, long long capacity,
+                         double* invPower, int* invPowerMode) {
+    try {
+        GridForce f;
+        f.loadFromFile(path);
+        std::vector<int> c;
+        std::vector<double> sp, v, sc;
+        f.getGridParameters(c, sp, v, sc);
+        if ((long long) v.size() > capacity) throw OpenMMException("buffer too small");
+        for (int k = 0; k < 3; k++) {
+            counts[k] = c[k];
+            spacing[k] = sp[k];
+        }
+        f.getGridOrigin(origin[0], origin[1], origin[2]);
+        memcpy(vals, v.data(), v.size() * sizeof(double));
+        *invPower = f.getInvPower();
+        *invPowerMode = static_cast<int>(f.getInvPowerMode());
+        return 0;
+    } catch (std::exception& e) {
+        lastError = e.what();
+        return 1;
+    }
+}
 
 }  // extern "C"

@@ -155,3 +155,23 @@ def test_plugin_has_no_cpu_fallback():
     system, _ = _build_system(gfp, c)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         gfp.Context(system, gfp.Platform.getPlatformByName("B200"))
+
+
+def test_gridforce_file_round_trip(tmp_path):
+    """GridForce.saveToFile / loadFromFile round trip, as python/tests/test_auto_grid.py:54-102 does it."""
+    import openmmgridforce_b200.gridforceplugin as gfp
+    c = cases.case_ramp_grid()
+    f = gfp.GridForce()
+    f.addGridCounts(*c["counts"])
+    f.addGridSpacing(*c["spacing"])
+    f.setGridOrigin(0.25, -1.5, 3.0)
+    f.setGridValues(c["grids"][0])
+    f.setInvPowerMode(gfp.InvPowerMode_STORED, 4.0)
+    path = str(tmp_path / "ramp.grid")
+    f.saveToFile(path)
+    g = gfp.GridForce()
+    g.loadFromFile(path)
+    assert g._counts == list(c["counts"]) and g._spacing == list(c["spacing"]) and g.getGridOrigin() == (0.25, -1.5, 3.0)
+    assert np.array_equal(np.asarray(g._vals), c["grids"][0].ravel()) and g.getInvPower() == 4.0
+    with pytest.raises(RuntimeError, match="Cannot open"):
+        gfp.GridForce().loadFromFile(str(tmp_path / "nope.grid"))
