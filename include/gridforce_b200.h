@@ -134,6 +134,18 @@ GFB_API int gfb_gridfile_write(const char* path, const gfb_gridfile_header* head
 GFB_API int gfb_grid_create_from_file(gfb_device* dev, const char* path, int precision, int layout, gfb_grid** out,
                                       gfb_gridfile_header* header_out);
 
+/* Grid generation from receptor atoms — ReferenceCalcGridForceKernel::generateGrid
+ * (platforms/reference/src/ReferenceGridForceKernels.cpp:465-544; the auto-generate switch of GridForce,
+ * openmmapi/include/GridForce.h:342). grid_type: 1 charge, 2 ljr, 3 lja. Host inputs: pos [n_atoms][3] nm and the
+ * NonbondedForce parameters (charge e, sigma nm, epsilon kJ/mol) of the same atoms; grid_cap = GridForce::getGridCap().
+ * Outputs (either may be NULL): vals_out, host nx*ny*nz doubles (x-major, z fastest); grid_out, the grid already
+ * repacked on the device in `precision`/`layout`, ready for gfb_kernel_create. FP64 on the GPU; matches the reference
+ * to ~1e-13 relative (different libm for pow/tanh), tests assert 1e-10. */
+GFB_API int gfb_grid_generate(gfb_device* dev, const int counts[3], const double spacing[3], const double origin[3],
+                              int grid_type, int n_atoms, const double* pos, const double* charges, const double* sigmas,
+                              const double* epsilons, double grid_cap, double* vals_out, int precision, int layout,
+                              gfb_grid** grid_out);
+
 GFB_API int gfb_grid_destroy(gfb_grid* grid);
 GFB_API size_t gfb_grid_device_bytes(const gfb_grid* grid);
 GFB_API int gfb_grid_layout(const gfb_grid* grid);   /* the layout actually chosen (resolves AUTO) */

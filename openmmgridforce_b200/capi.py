@@ -56,6 +56,7 @@ SIGNATURES = {
     "gfb_gridfile_read_header": (_i, [C.c_char_p, C.POINTER(GridFileHeader)]),
     "gfb_gridfile_read_values": (_i, [C.c_char_p, _vp, _sz]),
     "gfb_gridfile_write": (_i, [C.c_char_p, C.POINTER(GridFileHeader), _vp, _sz, _i]),
+    "gfb_grid_generate": (_i, [_vp, _pi, _pd, _pd, _i, _i, _vp, _vp, _vp, _vp, C.c_double, _vp, _i, _i, C.POINTER(_vp)]),
     "gfb_grid_create_from_file": (_i, [_vp, C.c_char_p, _i, _i, C.POINTER(_vp), C.POINTER(GridFileHeader)]),
     "gfb_grid_destroy": (_i, [_vp]),
     "gfb_grid_device_bytes": (_sz, [_vp]),
@@ -222,6 +223,31 @@ class Grid:
         self.counts, self.spacing, self.origin = self.header["counts"], self.header["spacing"], self.header["origin"]
         self.layout = int(lib.gfb_grid_layout(self._h))
         return self
+
+    @classmethod
+    def generate(cls, device, counts, spacing, origin, grid_type, pos, charges=None, sigmas=None, epsilons=None,
+                 grid_cap=41840.0, precision=PRECISION_MIXED, layout=LAYOUT_AUTO, want_values=True, want_grid=True):
+        """gfb_grid_generate: grid from receptor atoms ("charge" | "ljr" | "lja"). Returns (Grid or None, values or None)."""
+        code = {"charge": 1, "ljr": 2, "lja": 3}.get(grid_type)
+        if code is None:
+            raise GridForceB200Error(f"GridForce: Invalid grid type '{grid_type}'. Must be 'charge', 'ljr', or 'lja'")
+        pos = _host_f64(pos)
+        q = _host_f64(charges) if charges is not None else None
+        sg = _host_f64(sigmas) if sigmas is not None else None
+        ep = _host_f64(epsilons) if epsilons is not None else None
+        vals = np.empty(tuple(int(c) for c in counts), dtype=np.float64) if want_values else None
+        handle = C.c_void_p()
+        lib = load_library()
+        _check(lib.gfb_grid_generate(device._h, (C.c_int * 3)(*[int(c) for c in counts]), (C.c_double * 3)(*spacing),
+                                     (C.c_double * 3)(*origin), code, pos.shape[0], _ptr(pos), _ptr(q), _ptr(sg), _ptr(ep),
+                                     float(grid_cap), _ptr(vals), precision, layout, C.byref(handle) if want_grid else None))
+        grid = None
+        if want_grid:
+            grid = cls.__new__(cls)
+            grid.device, grid.precision, grid._h = device, precision, handle
+            grid.counts, grid.spacing, grid.origin = tuple(counts), tuple(spacing), tuple(origin)
+            grid.layout = int(lib.gfb_grid_layout(handle))
+        return grid, vals
 
     @property
     def device_bytes(self):

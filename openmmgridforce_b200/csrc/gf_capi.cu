@@ -410,6 +410,59 @@ int gfb_grid_create_from_file(gfb_device* dev, const char* path, int precision, 
     return rc;
 }
 
+int gfb_grid_generate(gfb_device* dev, const int counts[3], const double spacing[3], const double origin[3], int grid_type,
+                      int n_atoms, const double* pos, const double* charges, const double* sigmas, const double* epsilons,
+                      double grid_cap, double* vals_out, int precision, int layout, gfb_grid** grid_out) {
+    if (!dev || !counts || !spacing || !origin || (n_atoms > 0 && !pos)) return fail(GFB_ERR_INVALID, "gfb_grid_generate: NULL argument");
+    if (grid_out) *grid_out = nullptr;
+    if (grid_type < 1 || grid_type > 3)
+        return fail(GFB_ERR_INVALID, "GridForce: Invalid grid type code %d. Must be 1 (charge), 2 (ljr) or 3 (lja)", grid_type);
+    if ((grid_type == 1 && !charges) || (grid_type != 1 && (!sigmas || !epsilons)))
+        return fail(GFB_ERR_INVALID, "gfb_grid_generate: the parameter array this grid type needs is NULL");
+    if (n_atoms < 0 || !(grid_cap > 0.0)) return fail(GFB_ERR_INVALID, "gfb_grid_generate: n_atoms=%d grid_cap=%g", n_atoms, grid_cap);
+    for (int k = 0; k < 3; k++)
+        if (counts[k] < 1) return fail(GFB_ERR_INVALID, "gfb_grid_generate: counts[%d]=%d", k, counts[k]);
+    CUDA_TRY(cudaSetDevice(dev->ordinal));
+    const size_t n_points = (size_t) counts[0] * counts[1] * counts[2];
+    // fold the per-atom parameters into one coefficient, associating exactly as the reference's expressions do
+    std::vector<double> packed((size_t) std::max(n_atoms, 1) * 4, 0.0);
+    for (int a = 0; a < n_atoms; a++) {
+        packed[4 * (size_t) a] = pos[3 * a];
+        packed[4 * (size_t) a + 1] = pos[3 * a + 1];
+        packed[4 * (size_t) a + 2] = pos[3 * a + 2];
+        double c;
+        if (grid_type == 1) c = 138.935456 * charges[a];                                     // :527
+        else if (grid_type == 2) c = std::sqrt(epsilons[a]) * std::pow(2.0 * sigmas[a], 6.0);   // :530-531
+        else c = -2.0 * std::sqrt(epsilons[a]) * std::pow(2.0 * sigmas[a], 3.0);                // :534-535
+        packed[4 * (size_t) a + 3] = c;
+    }
+    double4* d_atoms = nullptr;
+    double* d_vals = nullptr;
+    cudaError_t ce = cudaMalloc((void**) &d_atoms, packed.size() * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**) &d_vals, n_points * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_atoms, packed.data(), packed.size() * sizeof(double), cudaMemcpyHostToDevice, dev->stream);
+    if (ce == cudaSuccess) {
+        const unsigned blocks = (unsigned) ((n_points + 255) / 256);
+        const double ox = origin[0], oy = origin[1], oz = origin[2], sx = spacing[0], sy = spacing[1], sz = spacing[2];
+        if (grid_type == 1)
+            gf_generate_grid_kernel<1><<<blocks, 256, 0, dev->stream>>>(d_atoms, n_atoms, counts[0], counts[1], counts[2], ox, oy, oz, sx, sy, sz, grid_cap, d_vals);
+        else if (grid_type == 2)
+            gf_generate_grid_kernel<12><<<blocks, 256, 0, dev->stream>>>(d_atoms, n_atoms, counts[0], counts[1], counts[2], ox, oy, oz, sx, sy, sz, grid_cap, d_vals);
+        else
+            gf_generate_grid_kernel<6><<<blocks, 256, 0, dev->stream>>>(d_atoms, n_atoms, counts[0], counts[1], counts[2], ox, oy, oz, sx, sy, sz, grid_cap, d_vals);
+        g_launches++;
+        ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess && vals_out) ce = cudaMemcpyAsync(vals_out, d_vals, n_points * sizeof(double), cudaMemcpyDeviceToHost, dev->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(dev->stream);
+    int rc = GFB_OK;
+    if (ce != cudaSuccess) rc = fail(GFB_ERR_CUDA, "gfb_grid_generate: %s", cudaGetErrorString(ce));
+    else if (grid_out) rc = grid_create_common(dev, counts, spacing, origin, d_vals, true, n_points, precision, layout, grid_out);
+    if (d_atoms) cudaFree(d_atoms);
+    if (d_vals) cudaFree(d_vals);
+    return rc;
+}
+
 int gfb_grid_destroy(gfb_grid* grid) {
     if (!grid) return GFB_OK;
     cudaSetDevice(grid->dev->ordinal);

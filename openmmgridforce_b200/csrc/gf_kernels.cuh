@@ -545,6 +545,56 @@ __global__ void __launch_bounds__(256) gf_repack_pairs_kernel(const double* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Grid generation from receptor atoms (reference: ReferenceGridForceKernels.cpp:465-544; the reference's own GPU
+// version, platforms/cuda/src/kernels/gridGeneration.cu:198-371, is FP32). One thread per grid point, FP64 throughout,
+// atoms streamed through shared memory in tiles of 256 {x, y, z, coefficient} (the N-body pattern: every atom is read
+// once per block, from smem, by all 256 threads). Per atom the host has folded the parameters into one coefficient c
+// exactly as the reference's expression associates: charge c = 138.935456*q, ljr c = sqrt(eps)*(2 sigma)^6,
+// lja c = -2*sqrt(eps)*(2 sigma)^3; the term is c / r^P (P = 1, 12, 6) with r clamped to >= 1e-6 nm (:520-522),
+// formed from rsqrt(r2) and multiplications (no FP64 division or pow in the inner loop). Atoms are summed in index
+// order, like the reference; the result is capped with U*tanh(v/U) (:540).
+// Compute-bound: ~20 FP64 instructions per (point, atom) pair.
+// ------------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(256) gf_generate_grid_kernel(const double4* __restrict__ atoms, int n_atoms, int nx, int ny, int nz,
+                                                               double ox, double oy, double oz, double sx, double sy, double sz,
+                                                               double cap, double* __restrict__ out) {
+    __shared__ double4 tile[256];
+    const size_t n_points = (size_t) nx * ny * nz;
+    const size_t idx = (size_t) blockIdx.x * 256 + threadIdx.x;
+    const bool live = idx < n_points;
+    const size_t pt = live ? idx : n_points - 1;
+    const int k = (int) (pt % nz);
+    const size_t r = pt / nz;
+    const int j = (int) (r % ny);
+    const int i = (int) (r / ny);
+    const double gx = ox + i * sx, gy = oy + j * sy, gz = oz + k * sz;      // :502-504
+    double v = 0.0;
+    for (int base = 0; base < n_atoms; base += 256) {
+        const int m = min(256, n_atoms - base);
+        if ((int) threadIdx.x < m) tile[threadIdx.x] = atoms[base + threadIdx.x];
+        __syncthreads();
+#pragma unroll 4
+        for (int a = 0; a < m; a++) {
+            const double4 at = tile[a];
+            const double dx = gx - at.x, dy = gy - at.y, dz = gz - at.z;
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            const double rinv = fmin(rsqrt(r2), 1.0e6);                     // r = max(sqrt(r2), 1e-6)
+            double t;
+            if (P == 1) {
+                t = rinv;
+            } else {
+                const double i2 = rinv * rinv, i6 = i2 * i2 * i2;
+                t = P == 6 ? i6 : i6 * i6;
+            }
+            v += at.w * t;
+        }
+        __syncthreads();
+    }
+    if (live) out[idx] = cap * tanh(v / cap);
+}
+
 // Classification only (parity tests): same device function as the evaluation.
 template <bool EXACT>
 __global__ void __launch_bounds__(256) gf_classify_kernel(const __grid_constant__ ClassifyParams p) {

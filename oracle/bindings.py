@@ -184,3 +184,34 @@ class RefOracle:
             self.close()
         except Exception:
             pass
+
+
+GRID_TYPE_CODES = {"charge": 1, "ljr": 2, "lja": 3}
+
+
+def port_generate_grid(counts, spacing, origin, grid_type, pos, charges, sigmas, epsilons, grid_cap=41840.0, n_threads=1):
+    """C restatement of the reference's generateGrid -> [nx, ny, nz] float64."""
+    if not os.path.exists(PORT_PATH):
+        build()
+    lib = C.CDLL(PORT_PATH)
+    pos, q, sg, ep = _f64(pos), _f64(charges), _f64(sigmas), _f64(epsilons)
+    out = np.empty(tuple(counts))
+    lib.gfo_generate_grid.restype = None
+    lib.gfo_generate_grid((C.c_int * 3)(*counts), (C.c_double * 3)(*spacing), (C.c_double * 3)(*origin),
+                          GRID_TYPE_CODES[grid_type], pos.shape[0], _dp(pos), _dp(q), _dp(sg), _dp(ep), C.c_double(grid_cap),
+                          _dp(out), n_threads)
+    return out
+
+
+def ref_generate_grid(counts, spacing, origin, grid_type, pos, charges, sigmas, epsilons, grid_cap=41840.0):
+    """The reference's own auto-generation path (Context creation on a System with a NonbondedForce)."""
+    lib = C.CDLL(REF_PATH)
+    lib.oracle_ref_last_error.restype = C.c_char_p
+    pos, q, sg, ep = _f64(pos), _f64(charges), _f64(sigmas), _f64(epsilons)
+    out = np.empty(tuple(counts))
+    rc = lib.oracle_ref_generate_grid((C.c_int * 3)(*counts), (C.c_double * 3)(*spacing), (C.c_double * 3)(*origin),
+                                      grid_type.encode(), pos.shape[0], _dp(pos), _dp(q), _dp(sg), _dp(ep),
+                                      C.c_double(grid_cap), _dp(out))
+    if rc:
+        raise RuntimeError(lib.oracle_ref_last_error().decode())
+    return out

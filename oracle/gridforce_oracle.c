@@ -145,3 +145,71 @@ void gfo_execute_batched(const gfo_grid* grids, int n_grids, const double* scali
         free(jobs);
     }
 }
+
+/* ---- grid generation (ReferenceGridForceKernels.cpp:465-544) ------------------------------------------------- */
+typedef struct {
+    const int* counts;
+    const double *spacing, *origin, *pos, *charges, *sigmas, *epsilons;
+    int grid_type, n_atoms, i0, i1;
+    double grid_cap;
+    double* out;
+} gfo_gen_job;
+
+static void* gfo_gen_worker(void* arg) {
+    gfo_gen_job* j = (gfo_gen_job*)arg;
+    const int ny = j->counts[1], nz = j->counts[2];
+    const double COULOMB_CONST = 138.935456;                                                  /* :493 */
+    const double U_MAX = j->grid_cap;                                                         /* :494 */
+    int i, jj, k, a;
+    for (i = j->i0; i < j->i1; i++)
+        for (jj = 0; jj < ny; jj++)
+            for (k = 0; k < nz; k++) {
+                const double gx = j->origin[0] + i * j->spacing[0];                           /* :502-504 */
+                const double gy = j->origin[1] + jj * j->spacing[1];
+                const double gz = j->origin[2] + k * j->spacing[2];
+                double v = 0.0;
+                for (a = 0; a < j->n_atoms; a++) {                                            /* :508 */
+                    const double dx = gx - j->pos[3 * a], dy = gy - j->pos[3 * a + 1], dz = gz - j->pos[3 * a + 2];
+                    const double r2 = dx * dx + dy * dy + dz * dz;                            /* :516 */
+                    double r = sqrt(r2);
+                    if (r < 1e-6) r = 1e-6;                                                   /* :520-522 */
+                    if (j->grid_type == 1) {
+                        v += COULOMB_CONST * j->charges[a] / r;                               /* :527 */
+                    } else if (j->grid_type == 2) {
+                        const double diameter = 2.0 * j->sigmas[a];
+                        v += sqrt(j->epsilons[a]) * pow(diameter, 6.0) / pow(r, 12.0);        /* :531 */
+                    } else if (j->grid_type == 3) {
+                        const double diameter = 2.0 * j->sigmas[a];
+                        v += -2.0 * sqrt(j->epsilons[a]) * pow(diameter, 3.0) / pow(r, 6.0);  /* :535 */
+                    }
+                }
+                j->out[((size_t)i * ny + jj) * nz + k] = U_MAX * tanh(v / U_MAX);             /* :540-541 */
+            }
+    return 0;
+}
+
+void gfo_generate_grid(const int counts[3], const double spacing[3], const double origin[3], int grid_type, int n_atoms,
+                       const double* pos, const double* charges, const double* sigmas, const double* epsilons,
+                       double grid_cap, double* out, int n_threads) {
+    int t;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > counts[0]) n_threads = counts[0];
+    {
+        pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * n_threads);
+        gfo_gen_job* jobs = (gfo_gen_job*)malloc(sizeof(gfo_gen_job) * n_threads);
+        for (t = 0; t < n_threads; t++) {
+            gfo_gen_job j;
+            j.counts = counts; j.spacing = spacing; j.origin = origin; j.pos = pos;
+            j.charges = charges; j.sigmas = sigmas; j.epsilons = epsilons;
+            j.grid_type = grid_type; j.n_atoms = n_atoms; j.grid_cap = grid_cap; j.out = out;
+            j.i0 = (int)((long long)counts[0] * t / n_threads);
+            j.i1 = (int)((long long)counts[0] * (t + 1) / n_threads);
+            jobs[t] = j;
+            if (t > 0) pthread_create(&th[t], 0, gfo_gen_worker, &jobs[t]);
+        }
+        gfo_gen_worker(&jobs[0]);
+        for (t = 1; t < n_threads; t++) pthread_join(th[t], 0);
+        free(th);
+        free(jobs);
+    }
+}

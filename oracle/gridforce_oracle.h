@@ -54,6 +54,15 @@ double gfo_execute(const gfo_grid* grid, const double* scaling, int n_scaling, c
 void gfo_execute_batched(const gfo_grid* grids, int n_grids, const double* scaling, int n_replicas, int n_atoms,
                          const double* pos, double* forces, double* energies, int n_threads);
 
+/* Grid generation from receptor atoms (ReferenceGridForceKernels.cpp:465-544): for every grid point the sum over
+ * atoms of   charge: 138.935456*q/r   ljr: sqrt(eps)*(2 sigma)^6/r^12   lja: -2 sqrt(eps)*(2 sigma)^3/r^6
+ * with r clamped to >= 1e-6 nm, then capped with U*tanh(v/U) (U = grid cap, GridForce.cpp:52 default 41840).
+ * grid_type: 1 charge, 2 ljr, 3 lja (the V3 file codes). pos [n_atoms][3] nm. out: nx*ny*nz, x-major, z fastest.
+ * n_threads >= 1 splits the x planes over pthreads (the reference is single-threaded). */
+void gfo_generate_grid(const int counts[3], const double spacing[3], const double origin[3], int grid_type, int n_atoms,
+                       const double* pos, const double* charges, const double* sigmas, const double* epsilons,
+                       double grid_cap, double* out, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@
 #include "GridForce.h"
 #include "GridForceKernels.h"
 #include "openmm/Context.h"
+#include "openmm/NonbondedForce.h"
 #include "openmm/OpenMMException.h"
 #include "openmm/Platform.h"
 #include "openmm/System.h"
@@ -187,6 +188,48 @@ int oracle_ref_save_file(int mode, const char* path, const int* counts, const do
             d.setInvPowerMode(static_cast<InvPowerMode>(invPowerMode));
             d.saveToFile(path);
         }
+        return 0;
+    } catch (std::exception& e) {
+        lastError = e.what();
+        return 1;
+    }
+}
+
+// Grid generation through the reference's own auto-generate path: a System with a NonbondedForce carrying the
+// receptor parameters and a GridForce with setAutoGenerateGrid(true); creating the Context runs
+// ReferenceCalcGridForceKernel::initialize -> generateGrid (:213-278, :465-544), which copies the values back into the
+// GridForce (:272). gridType: "charge" | "ljr" | "lja".
+int oracle_ref_generate_grid(const int* counts, const double* spacing, const double* origin, const char* gridType, int nAtoms,
+                             const double* pos, const double* charges, const double* sigmas, const double* epsilons,
+                             double gridCap, double* out) {
+    try {
+        System system;
+        NonbondedForce* nb = new NonbondedForce();
+        std::vector<double> xs(nAtoms), ys(nAtoms), zs(nAtoms);
+        for (int i = 0; i < nAtoms; i++) {
+            system.addParticle(1.0);
+            nb->addParticle(charges[i], sigmas[i], epsilons[i]);
+            xs[i] = pos[3 * i];
+            ys[i] = pos[3 * i + 1];
+            zs[i] = pos[3 * i + 2];
+        }
+        system.addForce(nb);
+        GridForce* f = new GridForce();
+        system.addForce(f);
+        f->addGridCounts(counts[0], counts[1], counts[2]);
+        f->addGridSpacing(spacing[0], spacing[1], spacing[2]);
+        f->setGridOrigin(origin[0], origin[1], origin[2]);
+        f->setGridCap(gridCap);
+        f->setAutoGenerateGrid(true);
+        f->setGridType(gridType);
+        f->setReceptorPositionsFromArrays(xs, ys, zs);
+        {
+            CoutSilencer quiet;
+            Context context(system, referencePlatform());
+        }
+        const std::vector<double>& v = f->getGridValues();
+        if (v.size() != (size_t) counts[0] * counts[1] * counts[2]) throw OpenMMException("generation produced no values");
+        memcpy(out, v.data(), v.size() * sizeof(double));
         return 0;
     } catch (std::exception& e) {
         lastError = e.what();
