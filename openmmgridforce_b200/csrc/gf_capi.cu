@@ -3,6 +3,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <atomic>
+#include <mutex>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -90,6 +91,7 @@ struct gfb_device {
     cudaStream_t copy_stream;   // D2H of chunk i overlaps the kernel of chunk i+1 ...
     cudaStream_t h2d_stream;    // ... and the H2D of chunk i+2: three streams chained by events (execute_host)
     std::vector<cudaEvent_t> events;   // pool for the chunk pipeline (2 per chunk), created once
+    std::mutex host_mutex;             // host-path calls share the three streams and the event pool: one at a time per GPU
     cudaDeviceProp prop;
 };
 
@@ -771,6 +773,7 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
         return fail(GFB_ERR_INVALID, "gfb_kernel_execute_host: FIXED_ADD is a device-buffer format; use F64_STORE or F64_ADD");
     if (n_replicas == 0) return GFB_OK;
     gfb_device* dev = k->dev;
+    std::lock_guard<std::mutex> host_lock(dev->host_mutex);   // several Contexts/threads may drive one GPU
     CUDA_TRY(cudaSetDevice(dev->ordinal));
 
     const size_t np = (size_t) n_replicas * n_particles;
@@ -893,6 +896,7 @@ int gfb_kernel_classify_host(gfb_kernel* k, int grid_index, int n_replicas, int 
     const long long total = (long long) n_replicas * k->n_atoms;
     if (total == 0) return GFB_OK;
     gfb_device* dev = k->dev;
+    std::lock_guard<std::mutex> host_lock(dev->host_mutex);
     CUDA_TRY(cudaSetDevice(dev->ordinal));
     const size_t pos_bytes = (size_t) n_replicas * n_particles * 3 * sizeof(double);
     if ((rc = k->d_pos.ensure(pos_bytes)) != GFB_OK) return rc;

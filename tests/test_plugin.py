@@ -175,3 +175,38 @@ def test_gridforce_file_round_trip(tmp_path):
     assert np.array_equal(np.asarray(g._vals), c["grids"][0].ravel()) and g.getInvPower() == 4.0
     with pytest.raises(RuntimeError, match="Cannot open"):
         gfp.GridForce().loadFromFile(str(tmp_path / "nope.grid"))
+
+
+@pytest.mark.gpu
+def test_many_contexts_share_grids_and_run_from_threads():
+    """The sampler pattern (example/sampler.py:130-151): several Contexts over Systems with the same three grids. Device
+    grids are shared through the plugin's cache, and Contexts may be driven from different threads."""
+    import threading
+    import openmmgridforce_b200.gridforceplugin as gfp
+    c, ref = cases.load_golden("ligand_three_grids")
+    platform = gfp.Platform.getPlatformByName("B200")
+    platform.setPropertyDefaultValue("Precision", "double")
+    contexts = []
+    for _ in range(4):
+        system, _forces = _build_system(gfp, c)
+        contexts.append(gfp.Context(system, platform))
+    results = [None] * 4
+
+    def run(i):
+        ctx = contexts[i]
+        for _ in range(20):
+            ctx.setPositions(c["pos"] + 1e-3 * i)
+            s = ctx.getState(getEnergy=True, getForces=True)
+        ctx.setPositions(c["pos"])
+        s = ctx.getState(getEnergy=True, getForces=True)
+        results[i] = (s.getPotentialEnergy(), s.getForces())
+
+    threads = [threading.Thread(target=run, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e, f in results:
+        assert abs(e - ref["energy"]) <= 1e-12 * abs(ref["energy"])
+        assert np.abs(f - ref["forces"]).max() <= 1e-12 * np.abs(ref["forces"]).max()
+    platform.setPropertyDefaultValue("Precision", "mixed")
