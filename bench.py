@@ -122,27 +122,40 @@ def time_device_steps(torch, gf, kern, pos_sets, n_replicas, n_atoms, steps, war
     for _ in pos_sets:
         d_f = torch.zeros(3 * stride, dtype=torch.int64, device=dev)
         bufs.append(d_f)
-    # two per-replica energy accumulators: step i adds into e[i % 2] and zero-fills e[(i + 1) % 2] in the same launch
-    d_e2 = [torch.zeros(n_replicas, dtype=torch.float64, device=dev) for _ in range(2)]
+    # three per-replica energy accumulators: step i adds into e[i % 3] and zero-fills e[(i + 1) % 3] in the same launch;
+    # the energy gather of step i (N > 1) reads e[i % 3] on NCCL's stream while step i+1 runs, and is waited for before
+    # step i+2 (whose launch clears e[i % 3] again).
+    d_e3 = [torch.zeros(n_replicas, dtype=torch.float64, device=dev) for _ in range(3)]
+    pending = {}
     torch.cuda.synchronize()
 
     def step(i):
         s = i % len(pos_sets)
-        d_f, d_e, d_next = bufs[s], d_e2[i % 2], d_e2[(i + 1) % 2]
+        d_f, d_e, d_next = bufs[s], d_e3[i % 3], d_e3[(i + 1) % 3]
+        if i - 2 in pending:
+            pending.pop(i - 2).wait()
         kern.execute_device(n_replicas, n_atoms, pos_sets[s].data_ptr(), d_e.data_ptr(), None, d_f.data_ptr(), force_mode,
                             stride, None, stream.cuda_stream, d_energies_clear=d_next.data_ptr())
         if post_step is not None:
-            post_step(d_e)
+            work = post_step(d_e)
+            if work is not None:
+                pending[i] = work
+
+    def drain():
+        for key in sorted(pending):
+            pending.pop(key).wait()
 
     with torch.cuda.stream(stream):
         for i in range(warmup):
             step(i)
+        drain()
         stream.synchronize()
         l0 = gf.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for i in range(steps):
             step(warmup + i)
+        drain()                  # the last gathers are inside the timed region
         e1.record(stream)
         stream.synchronize()
         launches = gf.launch_count() - l0
@@ -316,7 +329,8 @@ def workload_config(n_gpus):
             "grids": N_GRIDS, "grid_points": [GRID_N] * 3, "precision": "mixed", "parallelism": f"replica-sharded x{n_gpus}",
             "l2": "inputs larger than L2: each step streams 74 MB of positions + 74 MB of forces per GPU and gathers from "
                   "3 grids; no L2 flush between steps",
-            "energy_gather": "torch.distributed all_gather_into_tensor (NCCL) of per-replica energies every step (N>1)"}
+            "energy_gather": "torch.distributed all_gather_into_tensor (NCCL) of per-replica energies every step (N>1), "
+                             "asynchronous: the gather of step i overlaps the kernel of step i+1 and is waited for before i+2"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -364,9 +378,14 @@ def main():
 
     from openmmgridforce_b200 import sharding
 
+    gathered2 = [torch.empty_like(gathered) for _ in range(2)] if world > 1 else None
+    counter = [0]
+
     def post_step(d_e):
-        if world > 1:       # the one collective: per-replica energies of every rank, on the launching stream
-            sharding.gather_energies(dist, d_e, out=gathered)
+        if world > 1:       # the one collective: per-replica energies of every rank; overlaps the next step's kernel
+            counter[0] += 1
+            return dist.all_gather_into_tensor(gathered2[counter[0] % 2], d_e, async_op=True)
+        return None
 
     l2_gbs = dev.bench_sector_gather(32 << 20, 1 << 24, 10) if rank == 0 else 0.0
 
