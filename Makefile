@@ -25,7 +25,7 @@ $(LIBDIR)/libOpenMMGridForceB200.so: $(PLUGIN_SRCS) $(PLUGIN_HDRS) $(LIBDIR)/lib
 
 lib: $(LIBDIR)/libgridforce_b200.so
 
-$(LIBDIR)/libgridforce_b200.so: $(CSRC)/gf_capi.cu $(CSRC)/gf_kernels.cuh $(CSRC)/gf_params.h include/gridforce_b200.h
+$(LIBDIR)/libgridforce_b200.so: $(CSRC)/gf_capi.cu $(CSRC)/gf_kernels.cuh $(CSRC)/gf_eval_lines.cuh $(CSRC)/gf_gridfile.h $(CSRC)/gf_params.h include/gridforce_b200.h
 	mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/gf_capi.cu
 

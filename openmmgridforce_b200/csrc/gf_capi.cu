@@ -2,6 +2,7 @@
 // Host logic only — every number is produced by the kernels in gf_kernels.cuh. No CPU fallback.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <cmath>
@@ -15,6 +16,7 @@
 
 #include "gf_gridfile.h"
 #include "gf_kernels.cuh"
+#include "gf_eval_lines.cuh"
 #include "gridforce_b200.h"
 
 using namespace gfb;
@@ -115,6 +117,7 @@ struct gfb_kernel {
     void* d_scaling;      // [n_grids][n_atoms] float|double
     int* d_particles;     // [n_atoms] or null
     int max_particle;     // largest particle index referenced (+1 = minimum n_particles)
+    bool unique_particles; // no particle index appears twice in `particles` (plain read-modify-write of forces is legal)
     int* d_slots;         // [n_atoms] energy slot per atom (particle groups) or null
     int n_slots;          // energy slots per replica
     float* d_interleaved; // MIXED + CELLS + shared geometry + 2..4 grids: one record per cell holding every grid's corners
@@ -520,6 +523,7 @@ int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int 
     k->d_slots = nullptr;
     k->n_slots = 1;
     k->max_particle = n_atoms - 1;
+    k->unique_particles = true;
     for (int g = 0; g < n_grids; g++) {
         k->grids[g] = grids[g];
         k->inv_power[g] = inv_power ? inv_power[g] : 0.0;
@@ -540,6 +544,9 @@ int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int 
             }
             k->max_particle = std::max(k->max_particle, particles[i]);
         }
+        std::vector<int> sorted(particles, particles + n_atoms);
+        std::sort(sorted.begin(), sorted.end());
+        k->unique_particles = std::adjacent_find(sorted.begin(), sorted.end()) == sorted.end();
         err = cudaMalloc((void**) &k->d_particles, (size_t) n_atoms * sizeof(int));
         if (err == cudaSuccess)
             err = cudaMemcpy(k->d_particles, particles, (size_t) n_atoms * sizeof(int), cudaMemcpyHostToDevice);
@@ -557,15 +564,17 @@ int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int 
             return rc;
         }
     }
-    // Optional (GFB_INTERLEAVE=1): weave the packed cells of 2-4 same-geometry grids into one record per cell, so an
-    // atom's stencils come from one 128-byte line instead of one line per grid. Measured on C5 it cuts DRAM reads from
-    // 712 MB to 395 MB per launch and is still 14 % SLOWER (157 vs 138 us: three sector requests queue on one in-flight
-    // line instead of three lines fetched in parallel), so it is off by default and kept as an experiment.
-    const char* il = getenv("GFB_INTERLEAVE");
-    if (il && il[0] == '1' && k->same_geom && n_grids >= 2 && n_grids <= 4 && k->precision == GFB_PRECISION_MIXED &&
-        grids[0]->layout == GFB_LAYOUT_CELLS) {
-        const size_t n_cells = grids[0]->bytes / 32;
-        const int slots = n_grids == 2 ? 2 : 4;
+    // 2-4 MIXED packed-cell grids of one geometry: weave them into one 128-byte record per cell (4 slots of 32 bytes),
+    // so that everything an atom needs is ONE line of HBM/L2 (gf_eval_lines.cuh reads it with quad-coalesced loads).
+    // Costs a second copy of the grids (4 x 32 bytes per cell); GFB_LINES=0 keeps the per-grid arrays only.
+    const char* il = getenv("GFB_LINES");
+    const bool want_lines = !(il && il[0] == '0');
+    const size_t n_cells0 = grids[0]->bytes / 32;
+    if (want_lines && k->same_geom && n_grids >= 2 && n_grids <= 4 && k->precision == GFB_PRECISION_MIXED &&
+        grids[0]->layout == GFB_LAYOUT_CELLS && n_cells0 < 0xffffffffull &&
+        n_cells0 * 128 <= dev->prop.totalGlobalMem / 8) {
+        const size_t n_cells = n_cells0;
+        const int slots = 4;
         cudaError_t e = cudaMalloc((void**) &k->d_interleaved, n_cells * slots * 32);
         if (e == cudaSuccess) {
             const float4* src[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -577,7 +586,7 @@ int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int 
             e = cudaGetLastError();
             if (e == cudaSuccess) e = cudaStreamSynchronize(dev->stream);
         }
-        if (e != cudaSuccess) {      // not fatal: fall back to the per-grid arrays
+        if (e != cudaSuccess) {      // not fatal: the general kernel reads the per-grid arrays
             cudaGetLastError();
             if (k->d_interleaved) cudaFree(k->d_interleaved);
             k->d_interleaved = nullptr;
@@ -650,10 +659,6 @@ static void fill_grid_view(const gfb_kernel* k, int g, GridView& v) {
     v.cells = gr->cells;
     v.cell_stride = 8;
     v.pad_ = 0;
-    if (k->il_slots) {
-        v.cells = k->d_interleaved + 8 * g;
-        v.cell_stride = 8 * k->il_slots;
-    }
     v.scaling = static_cast<const double*>(k->d_scaling) + (size_t) g * k->n_atoms;
     for (int a = 0; a < 3; a++) {
         v.origin[a] = gr->origin[a];
@@ -704,6 +709,58 @@ static void launch_eval1(const EvalParams& p, int precision, int layout, bool sa
     }
 }
 
+// ---- gf_eval_lines_kernel dispatch (gf_eval_lines.cuh) ---------------------------------------------------------
+// How the ADD force modes reach memory: 0 RED atomics, 1 RED + early L2 prefetch of the force lines, 2 plain
+// read-modify-write with the read issued at kernel start. 2 is only legal when no two atoms of a launch share a particle
+// (checked at gfb_kernel_create) — nothing else writes the buffer while the kernel runs (stream order).
+// Measured (B200): the prefetch takes C3 (one grid: the force lines are a third of the traffic) from 45.5
+// to 35.1 us and changes nothing for three grids; read-modify-write is never better. Default: prefetch for one grid, RED
+// alone otherwise. GFB_FORCE_PATH=0|1|2 overrides (tuning probe).
+static int force_path_default(int n_grids) {
+    static const int v = [] {
+        const char* e = getenv("GFB_FORCE_PATH");
+        return e ? std::max(0, std::min(2, atoi(e))) : -1;
+    }();
+    return v >= 0 ? v : (n_grids == 1 ? kForcePrefetch : kForceRed);
+}
+
+template <int NG, int FMODE, int FPATH>
+static void launch_lines3(const EvalParams& p, cudaStream_t stream) {
+    const unsigned blocks = (unsigned) ((p.total + kBlock - 1) / kBlock);
+    if (p.n_replicas == 1 && p.slots == nullptr) gf_eval_lines_kernel<NG, FMODE, FPATH, true><<<blocks, kBlock, 0, stream>>>(p);
+    else gf_eval_lines_kernel<NG, FMODE, FPATH, false><<<blocks, kBlock, 0, stream>>>(p);
+}
+
+template <int NG>
+static void launch_lines2(const EvalParams& p, int fmode, int fpath, cudaStream_t stream) {
+    if (fmode == GFB_FORCE_F64_STORE || !p.forces) {
+        launch_lines3<NG, GFB_FORCE_F64_STORE, kForceRed>(p, stream);
+    } else if (fmode == GFB_FORCE_FIXED_ADD) {
+        if (fpath == kForceRmw) launch_lines3<NG, GFB_FORCE_FIXED_ADD, kForceRmw>(p, stream);
+        else if (fpath == kForcePrefetch) launch_lines3<NG, GFB_FORCE_FIXED_ADD, kForcePrefetch>(p, stream);
+        else launch_lines3<NG, GFB_FORCE_FIXED_ADD, kForceRed>(p, stream);
+    } else {
+        if (fpath == kForceRmw) launch_lines3<NG, GFB_FORCE_F64_ADD, kForceRmw>(p, stream);
+        else if (fpath == kForcePrefetch) launch_lines3<NG, GFB_FORCE_F64_ADD, kForcePrefetch>(p, stream);
+        else launch_lines3<NG, GFB_FORCE_F64_ADD, kForceRed>(p, stream);
+    }
+}
+
+// The lines kernel serves MIXED packed cells of one geometry without inv-power and without an evaluation order.
+static bool lines_eligible(const gfb_kernel* k, const EvalParams& p) {
+    static const bool off = [] {
+        const char* e = getenv("GFB_LINES");
+        return e && e[0] == '0';
+    }();
+    if (off || k->precision != GFB_PRECISION_MIXED || k->grids[0]->layout != GFB_LAYOUT_CELLS || !k->same_geom) return false;
+    if (p.order != nullptr || k->n_grids > 4) return false;
+    if (k->n_grids > 1 && !k->il_slots) return false;
+    if (k->grids[0]->bytes / 32 >= 0xffffffffull) return false;
+    for (int g = 0; g < k->n_grids; g++)
+        if (k->inv_power[g] > 0.0) return false;
+    return true;
+}
+
 static int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos, double* d_energies,
                         double* d_grid_energies, void* d_forces, int force_mode, long long force_stride,
                         const int* d_order, double* d_energies_clear, cudaStream_t stream) {
@@ -726,7 +783,21 @@ static int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const do
     p.forces = d_forces;
     p.force_stride = force_stride;
     if (p.total == 0) return GFB_OK;
-    launch_eval1(p, k->precision, k->grids[0]->layout, k->same_geom, force_mode, stream);
+    if (lines_eligible(k, p)) {
+        p.lines = k->d_interleaved;
+        p.div_magic = (unsigned) std::min<unsigned long long>(0x100000000ull / (unsigned long long) k->n_atoms, 0xffffffffull);
+        for (int a = 0; a < 3; a++) p.near_int[a] = 1.8e-15 * (double) std::max(1, p.grid[0].nc[a]);
+        const int fp = force_path_default(k->n_grids);
+        const int fpath = k->unique_particles ? fp : std::min(fp, (int) kForcePrefetch);
+        switch (k->n_grids) {
+            case 1: launch_lines2<1>(p, force_mode, fpath, stream); break;
+            case 2: launch_lines2<2>(p, force_mode, fpath, stream); break;
+            case 3: launch_lines2<3>(p, force_mode, fpath, stream); break;
+            default: launch_lines2<4>(p, force_mode, fpath, stream); break;
+        }
+    } else {
+        launch_eval1(p, k->precision, k->grids[0]->layout, k->same_geom, force_mode, stream);
+    }
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return GFB_OK;
