@@ -724,11 +724,31 @@ static int force_path_default(int n_grids) {
     return v >= 0 ? v : (n_grids == 1 ? kForcePrefetch : kForceRed);
 }
 
+static bool lines_async() {
+    static const bool v = [] {
+        const char* e = getenv("GFB_LINES_ASYNC");
+        return !(e && e[0] == '0');
+    }();
+    return v;
+}
+
+template <int NG, int FMODE, int FPATH, bool SINGLE, bool GE>
+static void launch_lines5(const EvalParams& p, cudaStream_t stream) {
+    const unsigned blocks = (unsigned) ((p.total + kBlock - 1) / kBlock);
+    if (NG > 1 && lines_async()) gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, GE, (NG > 1)><<<blocks, kBlock, 0, stream>>>(p);
+    else gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, GE, false><<<blocks, kBlock, 0, stream>>>(p);
+}
+
 template <int NG, int FMODE, int FPATH>
 static void launch_lines3(const EvalParams& p, cudaStream_t stream) {
-    const unsigned blocks = (unsigned) ((p.total + kBlock - 1) / kBlock);
-    if (p.n_replicas == 1 && p.slots == nullptr) gf_eval_lines_kernel<NG, FMODE, FPATH, true><<<blocks, kBlock, 0, stream>>>(p);
-    else gf_eval_lines_kernel<NG, FMODE, FPATH, false><<<blocks, kBlock, 0, stream>>>(p);
+    const bool single = p.n_replicas == 1 && p.slots == nullptr;
+    if (single) {
+        if (p.grid_energies) launch_lines5<NG, FMODE, FPATH, true, true>(p, stream);
+        else launch_lines5<NG, FMODE, FPATH, true, false>(p, stream);
+    } else {
+        if (p.grid_energies) launch_lines5<NG, FMODE, FPATH, false, true>(p, stream);
+        else launch_lines5<NG, FMODE, FPATH, false, false>(p, stream);
+    }
 }
 
 template <int NG>

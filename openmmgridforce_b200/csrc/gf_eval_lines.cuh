@@ -104,12 +104,28 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 constexpr int kForceRed = 0, kForcePrefetch = 1, kForceRmw = 2;
 
+#ifndef GF_LINES_ASYNC_BLOCKS
+#define GF_LINES_ASYNC_BLOCKS 5
+#endif
+
+__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 //   NG     grids evaluated per atom, 1..4 (1: the grid's own packed cells; 2..4: 128-byte records of 4 slots)
 //   FMODE  gfb_force_mode
 //   FPATH  kForceRed | kForcePrefetch | kForceRmw (ADD modes only)
 //   SINGLE one replica and no energy slots: block-level energy reduction, one atomic per block
-template <int NG, int FMODE, int FPATH, bool SINGLE>
-__global__ void __launch_bounds__(kBlock, NG == 1 ? 6 : 4) gf_eval_lines_kernel(const __grid_constant__ EvalParams p) {
+//   GE     per-grid energies wanted (p.grid_energies): a template flag so that the per-grid terms cost no registers
+//          in the common case
+//   ASYNC  NG > 1: records go global -> shared with cp.async (no register staging) and each grid's corners are read from
+//          shared memory right before they are used, which is what lets 5-6 blocks share an SM
+template <int NG, int FMODE, int FPATH, bool SINGLE, bool GE, bool ASYNC>
+__global__ void __launch_bounds__(kBlock, NG == 1 ? 6 : (ASYNC ? GF_LINES_ASYNC_BLOCKS : 4))
+    gf_eval_lines_kernel(const __grid_constant__ EvalParams p) {
     __shared__ __align__(16) double2 s_pos2[kBlock * 3 / 2];
     __shared__ __align__(128) float4 s_rec[NG == 1 ? 1 : kBlock * 8];   // 128 bytes per atom of the block
 
@@ -141,7 +157,7 @@ __global__ void __launch_bounds__(kBlock, NG == 1 ? 6 : 4) gf_eval_lines_kernel(
     // ---- loads that depend on the atom ordinal only go out first -------------------------------------------------
     double sd[NG];
 #pragma unroll
-    for (int g = 0; g < NG; g++) sd[g] = active ? p.grid[g].scaling[ia] : 0.0;
+    for (int g = 0; g < NG; g++) sd[g] = (active && !(ASYNC && NG > 1)) ? p.grid[g].scaling[ia] : 0.0;
 
     unsigned long long* const ffix = static_cast<unsigned long long*>(p.forces);
     double* const fdbl = static_cast<double*>(p.forces);
@@ -237,10 +253,59 @@ __global__ void __launch_bounds__(kBlock, NG == 1 ? 6 : 4) gf_eval_lines_kernel(
         fz = (float) dfz;
     }
 
-    // ---- stencils ------------------------------------------------------------------------------------------------------
-    float v[NG][8];
+    // ---- stencils + interpolation: gradient FP32, value FP64 (see trilinear_value_f64) -----------------------------------
+    double e_g[GE ? NG : 1];
+    double e_total = 0.0;
+    float sx = 0.f, sy = 0.f, sz = 0.f;   // sum over grids of scaling * (corner-difference gradient), before 1/spacing
+    if (GE) {
+#pragma unroll
+        for (int g = 0; g < (GE ? NG : 1); g++) e_g[g] = 0.0;
+    }
+    auto one_grid = [&](int g, const float* v, double s) {
+        float val, dx, dy, dz;
+        trilinear<float>(v, fx, fy, fz, val, dx, dy, dz);
+        const float sf = (float) s;
+        sx = fmaf(sf, dx, sx);
+        sy = fmaf(sf, dy, sy);
+        sz = fmaf(sf, dz, sz);
+        const double e = s * trilinear_value_f64(v, dfx, dfy, dfz);   // :1061
+        e_total += e;
+        if (GE) e_g[GE ? g : 0] = e;
+    };
     if (NG == 1) {
-        if (inside && sd[0] != 0.0) load32(static_cast<const float*>(G.cells) + 8 * (size_t) cell, v[0]);
+        if (inside && sd[0] != 0.0) {   // :706
+            float v[8];
+            load32(static_cast<const float*>(G.cells) + 8 * (size_t) cell, v);
+            one_grid(0, v, sd[0]);
+        }
+    } else if (ASYNC) {
+        // The record of atom A (lane A of this warp) lives at warp_base + 128*A, its 16-byte granule c (slot c/2, half
+        // c%2) at position c ^ (A & 7). Round i: the eight lanes of an octet copy the eight granules of the record of the
+        // atom owned by lane 4i + octet -> 4 full lines per instruction, each written to one 128-byte smem row.
+        const unsigned warp_base = (unsigned) __cvta_generic_to_shared(s_rec) + (tid >> 5) * 4096u;
+        const unsigned gran = lane & 7u, octet = lane >> 3;
+        const char* lane_base = static_cast<const char*>(p.lines) + 16u * gran;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const unsigned A = 4u * i + octet;
+            const unsigned c = __shfl_sync(kFull, cell, (int) A);
+            if (c != 0xffffffffu && gran < 2u * NG) cp_async16(warp_base + A * 128u + ((gran ^ (A & 7u)) << 4), lane_base + 128ull * c);
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        const unsigned rbase = (warp_base + lane * 128u) ^ ((lane & 7u) << 4);   // 128-byte aligned base: xor == or
+        if (inside) {
+#pragma unroll
+            for (int g = 0; g < NG; g++) {
+                const double s = p.grid[g].scaling[ia];   // 47 x NG doubles: L1-resident
+                if (s != 0.0) {                           // :706
+                    float v[8];
+                    lds128(rbase ^ (32u * g), v);
+                    lds128(rbase ^ (32u * g + 16u), v + 4);
+                    one_grid(g, v, s);
+                }
+            }
+        }
     } else {
         const unsigned sub = lane & 3u, quad = lane >> 2;
         const char* lane_base = static_cast<const char*>(p.lines) + 32u * sub;
@@ -252,8 +317,7 @@ __global__ void __launch_bounds__(kBlock, NG == 1 ? 6 : 4) gf_eval_lines_kernel(
             ok[j] = c != 0xffffffffu && sub < (unsigned) NG;
             if (ok[j]) load_sector(lane_base + 128ull * c, r[j]);
         }
-        // smem transpose: the record of atom A (lane A of this warp) lives at warp_base + 128*A, its 16-byte granule c
-        // (sector c/2, half c%2) at position c ^ (A & 7): both the quad-wise writes and the per-owner reads touch
+        // smem transpose, same record placement as above: both the quad-wise writes and the per-owner reads touch
         // 8 different granule positions per quarter-warp -> no bank conflicts.
         const unsigned warp_base = (unsigned) __cvta_generic_to_shared(s_rec) + (tid >> 5) * 4096u;
         const unsigned wbase = warp_base + quad * 128u;
@@ -265,30 +329,17 @@ __global__ void __launch_bounds__(kBlock, NG == 1 ? 6 : 4) gf_eval_lines_kernel(
                 sts128(w1 + 1024u * j, r[j] + 4);
             }
         __syncwarp();
-        const unsigned rbase = (warp_base + lane * 128u) ^ ((lane & 7u) << 4);   // 128-byte aligned base: xor == or
+        const unsigned rbase = (warp_base + lane * 128u) ^ ((lane & 7u) << 4);
         if (inside) {
+            float v[NG][8];
 #pragma unroll
             for (int g = 0; g < NG; g++) {
                 lds128(rbase ^ (32u * g), v[g]);
                 lds128(rbase ^ (32u * g + 16u), v[g] + 4);
             }
-        }
-    }
-
-    // ---- interpolation: gradient FP32, value FP64 (see trilinear_value_f64) ----------------------------------------------
-    double e_g[NG];
-    float sx = 0.f, sy = 0.f, sz = 0.f;   // sum over grids of scaling * (corner-difference gradient), before 1/spacing
 #pragma unroll
-    for (int g = 0; g < NG; g++) {
-        e_g[g] = 0.0;
-        if (inside && sd[g] != 0.0) {   // :706
-            float val, dx, dy, dz;
-            trilinear<float>(v[g], fx, fy, fz, val, dx, dy, dz);
-            const float s = (float) sd[g];
-            sx = fmaf(s, dx, sx);
-            sy = fmaf(s, dy, sy);
-            sz = fmaf(s, dz, sz);
-            e_g[g] = sd[g] * trilinear_value_f64(v[g], dfx, dfy, dfz);   // :1061
+            for (int g = 0; g < NG; g++)
+                if (sd[g] != 0.0) one_grid(g, v[g], sd[g]);   // :706
         }
     }
     float Fx = -sx * (float) G.inv_spacing[0];   // :1072, :1082
@@ -297,7 +348,10 @@ __global__ void __launch_bounds__(kBlock, NG == 1 ? 6 : 4) gf_eval_lines_kernel(
     if (active && !inside) {   // :1093-1117 (inside atoms with scale 0 take that branch too and add exactly 0)
         const RestraintAll<NG> r = restraint_all<NG>(p, x, y, z);
 #pragma unroll
-        for (int g = 0; g < NG; g++) e_g[g] = r.e[g];
+        for (int g = 0; g < NG; g++) {
+            e_total += r.e[g];
+            if (GE) e_g[GE ? g : 0] = r.e[g];
+        }
         Fx -= r.fx;
         Fy -= r.fy;
         Fz -= r.fz;
@@ -337,14 +391,11 @@ __global__ void __launch_bounds__(kBlock, NG == 1 ? 6 : 4) gf_eval_lines_kernel(
     }
 
     // ---- energies ------------------------------------------------------------------------------------------------------
-    double e_total = e_g[0];
-#pragma unroll
-    for (int g = 1; g < NG; g++) e_total += e_g[g];
     if (SINGLE) {
         __shared__ double warp_sum[kBlock / 32];
-        if (p.grid_energies) {   // uniform branch
+        if (GE) {
 #pragma unroll
-            for (int g = 0; g < NG; g++) {
+            for (int g = 0; g < (GE ? NG : 1); g++) {
                 double eg = e_g[g];
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) eg += __shfl_xor_sync(kFull, eg, off);
@@ -363,13 +414,13 @@ __global__ void __launch_bounds__(kBlock, NG == 1 ? 6 : 4) gf_eval_lines_kernel(
                 if (tid == 0) red_add_f64(p.energies, b);
             }
         }
-    } else if (p.energies || p.grid_energies) {
+    } else if (p.energies || GE) {
         unsigned heads;
         const unsigned span = run_span(key, lane, heads);
         const bool head = key >= 0 && ((heads >> lane) & 1u);
-        if (p.grid_energies) {   // uniform branch
+        if (GE) {
 #pragma unroll
-            for (int g = 0; g < NG; g++) {
+            for (int g = 0; g < (GE ? NG : 1); g++) {
                 double eg = e_g[g];
                 run_sum(eg, span);
                 if (head) red_add_f64(p.grid_energies + (size_t) key * NG + g, eg);
