@@ -170,6 +170,11 @@ GFB_API int gfb_kernel_destroy(gfb_kernel* k);
  * factors [n_grids][n_atoms] and inv_power [n_grids] (NULL = keep). */
 GFB_API int gfb_kernel_update_parameters(gfb_kernel* k, const double* scaling, const double* inv_power);
 
+/* Which evaluation kernel a launch of this state (without an evaluation order) uses: 1 = gf_eval_lines_kernel (MIXED,
+ * packed cells, one geometry, 1-4 grids, no inv-power: the 2-4 grid case reads one 128-byte record per atom), 0 = the
+ * general gf_eval_kernel. Introspection for tests and bench.py; no reference counterpart. */
+GFB_API int gfb_kernel_eval_path(const gfb_kernel* k);
+
 /* Particle groups (GridForce::addParticleGroup / getParticleGroupEnergies, openmmapi/include/GridForce.h:433-508;
  * CUDA platform: flattened groups + particle->group map, CudaGridForceKernels.cpp:607-675, 985-1005): gives every
  * evaluated atom an energy slot. Afterwards every energy array of execute has n_replicas * n_slots entries, entry

@@ -64,6 +64,7 @@ SIGNATURES = {
     "gfb_kernel_destroy": (_i, [_vp]),
     "gfb_kernel_update_parameters": (_i, [_vp, _vp, _vp]),
     "gfb_kernel_set_energy_slots": (_i, [_vp, _vp, _i]),
+    "gfb_kernel_eval_path": (_i, [_vp]),
     "gfb_kernel_execute_host": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i]),
     "gfb_kernel_execute_device": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp]),
     "gfb_kernel_sort_atoms": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
@@ -294,6 +295,10 @@ class Kernel:
             raise GridForceB200Error(f"{sl.size} slots for {self.n_atoms} atoms")
         _check(load_library().gfb_kernel_set_energy_slots(self._h, _ptr(sl), int(n_slots)))
         self.n_slots = int(n_slots)
+
+    def uses_lines_kernel(self):
+        """True when launches of this state go to gf_eval_lines_kernel (see gfb_kernel_eval_path)."""
+        return bool(load_library().gfb_kernel_eval_path(self._h))
 
     def update_parameters(self, scaling=None, inv_power=None):
         sc = _host_f64(scaling).reshape(self.n_grids, self.n_atoms) if scaling is not None else None

@@ -117,7 +117,6 @@ struct gfb_kernel {
     void* d_scaling;      // [n_grids][n_atoms] float|double
     int* d_particles;     // [n_atoms] or null
     int max_particle;     // largest particle index referenced (+1 = minimum n_particles)
-    bool unique_particles; // no particle index appears twice in `particles` (plain read-modify-write of forces is legal)
     int* d_slots;         // [n_atoms] energy slot per atom (particle groups) or null
     int n_slots;          // energy slots per replica
     float* d_interleaved; // MIXED + CELLS + shared geometry + 2..4 grids: one record per cell holding every grid's corners
@@ -523,7 +522,6 @@ int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int 
     k->d_slots = nullptr;
     k->n_slots = 1;
     k->max_particle = n_atoms - 1;
-    k->unique_particles = true;
     for (int g = 0; g < n_grids; g++) {
         k->grids[g] = grids[g];
         k->inv_power[g] = inv_power ? inv_power[g] : 0.0;
@@ -544,9 +542,6 @@ int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int 
             }
             k->max_particle = std::max(k->max_particle, particles[i]);
         }
-        std::vector<int> sorted(particles, particles + n_atoms);
-        std::sort(sorted.begin(), sorted.end());
-        k->unique_particles = std::adjacent_find(sorted.begin(), sorted.end()) == sorted.end();
         err = cudaMalloc((void**) &k->d_particles, (size_t) n_atoms * sizeof(int));
         if (err == cudaSuccess)
             err = cudaMemcpy(k->d_particles, particles, (size_t) n_atoms * sizeof(int), cudaMemcpyHostToDevice);
@@ -710,45 +705,29 @@ static void launch_eval1(const EvalParams& p, int precision, int layout, bool sa
 }
 
 // ---- gf_eval_lines_kernel dispatch (gf_eval_lines.cuh) ---------------------------------------------------------
-// How the ADD force modes reach memory: 0 RED atomics, 1 RED + early L2 prefetch of the force lines, 2 plain
-// read-modify-write with the read issued at kernel start. 2 is only legal when no two atoms of a launch share a particle
-// (checked at gfb_kernel_create) — nothing else writes the buffer while the kernel runs (stream order).
+// How the ADD force modes reach memory: 0 RED atomics alone, 1 RED + L2 prefetch of the force lines at kernel start.
 // Measured (B200): the prefetch takes C3 (one grid: the force lines are a third of the traffic) from 45.5
-// to 35.1 us and changes nothing for three grids; read-modify-write is never better. Default: prefetch for one grid, RED
-// alone otherwise. GFB_FORCE_PATH=0|1|2 overrides (tuning probe).
+// to 35.1 us and changes nothing for three grids. Default: prefetch for one grid. GFB_FORCE_PATH=0|1 overrides (probe).
 static int force_path_default(int n_grids) {
     static const int v = [] {
         const char* e = getenv("GFB_FORCE_PATH");
-        return e ? std::max(0, std::min(2, atoi(e))) : -1;
+        return e ? std::max(0, std::min(1, atoi(e))) : -1;
     }();
     return v >= 0 ? v : (n_grids == 1 ? kForcePrefetch : kForceRed);
 }
 
-static bool lines_async() {
-    static const bool v = [] {
-        const char* e = getenv("GFB_LINES_ASYNC");
-        return !(e && e[0] == '0');
-    }();
-    return v;
-}
-
-template <int NG, int FMODE, int FPATH, bool SINGLE, bool GE>
-static void launch_lines5(const EvalParams& p, cudaStream_t stream) {
-    const unsigned blocks = (unsigned) ((p.total + kBlock - 1) / kBlock);
-    if (NG > 1 && lines_async()) gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, GE, (NG > 1)><<<blocks, kBlock, 0, stream>>>(p);
-    else gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, GE, false><<<blocks, kBlock, 0, stream>>>(p);
+template <int NG, int FMODE, int FPATH, bool SINGLE>
+static void launch_lines4(const EvalParams& p, cudaStream_t stream) {
+    constexpr int block = lines_block(NG);
+    const unsigned blocks = (unsigned) ((p.total + block - 1) / block);
+    if (p.grid_energies) gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, true><<<blocks, block, 0, stream>>>(p);
+    else gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, false><<<blocks, block, 0, stream>>>(p);
 }
 
 template <int NG, int FMODE, int FPATH>
 static void launch_lines3(const EvalParams& p, cudaStream_t stream) {
-    const bool single = p.n_replicas == 1 && p.slots == nullptr;
-    if (single) {
-        if (p.grid_energies) launch_lines5<NG, FMODE, FPATH, true, true>(p, stream);
-        else launch_lines5<NG, FMODE, FPATH, true, false>(p, stream);
-    } else {
-        if (p.grid_energies) launch_lines5<NG, FMODE, FPATH, false, true>(p, stream);
-        else launch_lines5<NG, FMODE, FPATH, false, false>(p, stream);
-    }
+    if (p.n_replicas == 1 && p.slots == nullptr) launch_lines4<NG, FMODE, FPATH, true>(p, stream);
+    else launch_lines4<NG, FMODE, FPATH, false>(p, stream);
 }
 
 template <int NG>
@@ -756,12 +735,10 @@ static void launch_lines2(const EvalParams& p, int fmode, int fpath, cudaStream_
     if (fmode == GFB_FORCE_F64_STORE || !p.forces) {
         launch_lines3<NG, GFB_FORCE_F64_STORE, kForceRed>(p, stream);
     } else if (fmode == GFB_FORCE_FIXED_ADD) {
-        if (fpath == kForceRmw) launch_lines3<NG, GFB_FORCE_FIXED_ADD, kForceRmw>(p, stream);
-        else if (fpath == kForcePrefetch) launch_lines3<NG, GFB_FORCE_FIXED_ADD, kForcePrefetch>(p, stream);
+        if (fpath == kForcePrefetch) launch_lines3<NG, GFB_FORCE_FIXED_ADD, kForcePrefetch>(p, stream);
         else launch_lines3<NG, GFB_FORCE_FIXED_ADD, kForceRed>(p, stream);
     } else {
-        if (fpath == kForceRmw) launch_lines3<NG, GFB_FORCE_F64_ADD, kForceRmw>(p, stream);
-        else if (fpath == kForcePrefetch) launch_lines3<NG, GFB_FORCE_F64_ADD, kForcePrefetch>(p, stream);
+        if (fpath == kForcePrefetch) launch_lines3<NG, GFB_FORCE_F64_ADD, kForcePrefetch>(p, stream);
         else launch_lines3<NG, GFB_FORCE_F64_ADD, kForceRed>(p, stream);
     }
 }
@@ -807,8 +784,7 @@ static int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const do
         p.lines = k->d_interleaved;
         p.div_magic = (unsigned) std::min<unsigned long long>(0x100000000ull / (unsigned long long) k->n_atoms, 0xffffffffull);
         for (int a = 0; a < 3; a++) p.near_int[a] = 1.8e-15 * (double) std::max(1, p.grid[0].nc[a]);
-        const int fp = force_path_default(k->n_grids);
-        const int fpath = k->unique_particles ? fp : std::min(fp, (int) kForcePrefetch);
+        const int fpath = force_path_default(k->n_grids);
         switch (k->n_grids) {
             case 1: launch_lines2<1>(p, force_mode, fpath, stream); break;
             case 2: launch_lines2<2>(p, force_mode, fpath, stream); break;
@@ -838,6 +814,13 @@ static int check_exec_args(const char* fn, gfb_kernel* k, int n_replicas, int n_
 }
 
 extern "C" {
+
+int gfb_kernel_eval_path(const gfb_kernel* k) {
+    if (!k) return 0;
+    EvalParams probe;
+    memset(&probe, 0, sizeof probe);
+    return lines_eligible(k, probe) ? 1 : 0;
+}
 
 int gfb_kernel_execute_device(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos, double* d_energies,
                               double* d_grid_energies, void* d_forces, int force_mode, long long force_stride,
@@ -1003,8 +986,18 @@ int gfb_kernel_classify_host(gfb_kernel* k, int grid_index, int n_replicas, int 
     p.particles = k->d_particles;
     p.out = static_cast<gfb_class*>(k->d_cls.ptr);
     const unsigned blocks = (unsigned) ((total + 255) / 256);
-    if (k->precision == GFB_PRECISION_DOUBLE) gf_classify_kernel<true><<<blocks, 256, 0, dev->stream>>>(p);
-    else gf_classify_kernel<false><<<blocks, 256, 0, dev->stream>>>(p);
+    // the classification code of the kernel that would evaluate this state: lines kernel (MIXED packed cells of one
+    // geometry) or the general one
+    EvalParams probe;
+    memset(&probe, 0, sizeof probe);
+    if (lines_eligible(k, probe)) {
+        for (int a = 0; a < 3; a++) p.near_int[a] = 1.8e-15 * (double) std::max(1, p.grid.nc[a]);
+        gf_classify_lines_kernel<<<blocks, 256, 0, dev->stream>>>(p);
+    } else if (k->precision == GFB_PRECISION_DOUBLE) {
+        gf_classify_kernel<true><<<blocks, 256, 0, dev->stream>>>(p);
+    } else {
+        gf_classify_kernel<false><<<blocks, 256, 0, dev->stream>>>(p);
+    }
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(cls, k->d_cls.ptr, (size_t) total * sizeof(gfb_class), cudaMemcpyDeviceToHost, dev->stream));

@@ -200,17 +200,23 @@ __device__ __forceinline__ double trilinear_value_f64(const float v[8], double f
 }
 __device__ __forceinline__ double trilinear_value_f64(const double*, double, double, double) { return 0.0; }  // unused (DOUBLE)
 
-// Sum of `e` over each run of equal `key` among the 32 lanes; the total lands in the run's first lane.
-// key < 0 marks idle lanes. Returns true in lanes that are the head of a run with key >= 0.
-__device__ __forceinline__ bool run_reduce(double& e, int key, int lane) {
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const double ev = __shfl_down_sync(kFull, e, off);
-        const int kv = __shfl_down_sync(kFull, key, off);
-        if (lane + off < 32 && kv == key) e += ev;
-    }
+// Number of lanes that follow `lane` inside its run of equal keys (runs = maximal stretches of consecutive lanes with
+// the same key). `heads` gets the ballot of run heads. Equal keys that are not adjacent form separate runs, which is
+// still correct: each run issues its own atomic.
+__device__ __forceinline__ unsigned run_span(int key, unsigned lane, unsigned& heads) {
     const int kprev = __shfl_up_sync(kFull, key, 1);
-    return key >= 0 && (lane == 0 || kprev != key);
+    heads = __ballot_sync(kFull, lane == 0 || kprev != key);
+    const unsigned above = (heads >> 1) >> lane;   // bit i: lane+1+i starts a new run
+    return above ? (unsigned) __ffs((int) above) - 1u : 31u - lane;
+}
+
+// Segmented sum over a run; the total lands in the run's first lane.
+__device__ __forceinline__ void run_sum(double& e, unsigned span) {
+#pragma unroll
+    for (unsigned off = 1; off < 32; off <<= 1) {
+        const double ev = __shfl_down_sync(kFull, e, off);
+        if (off <= span) e += ev;
+    }
 }
 
 __device__ __forceinline__ void red_add_f64(double* addr, double v) {
@@ -371,6 +377,9 @@ __global__ void __launch_bounds__(kBlock, (NG == 1 && sizeof(S) == 4) ? 6 : 4) g
     double e_total = 0.0;
     double Fx = 0.0, Fy = 0.0, Fz = 0.0;
     const int ng = NG > 0 ? NG : p.n_grids;
+    unsigned heads;
+    const unsigned span = run_span(rep, (unsigned) lane, heads);   // runs of equal energy key inside the warp
+    const bool head = rep >= 0 && ((heads >> lane) & 1u);
 
     if (BATCHED) {
         const AtomCell c = classify<EXACT>(p.grid[0], x, y, z);
@@ -389,7 +398,8 @@ __global__ void __launch_bounds__(kBlock, (NG == 1 && sizeof(S) == 4) ? 6 : 4) g
             e_total += e_g;
             if (p.grid_energies) {  // uniform branch
                 double eg = e_g;
-                if (run_reduce(eg, rep, lane)) red_add_f64(p.grid_energies + (size_t) rep * ng + g, eg);
+                run_sum(eg, span);
+                if (head) red_add_f64(p.grid_energies + (size_t) rep * ng + g, eg);
             }
         }
     } else {
@@ -414,7 +424,8 @@ __global__ void __launch_bounds__(kBlock, (NG == 1 && sizeof(S) == 4) ? 6 : 4) g
             e_total += e_g;
             if (p.grid_energies) {  // uniform branch
                 double eg = e_g;
-                if (run_reduce(eg, rep, lane)) red_add_f64(p.grid_energies + (size_t) rep * ng + g, eg);
+                run_sum(eg, span);
+                if (head) red_add_f64(p.grid_energies + (size_t) rep * ng + g, eg);
             }
         }
     }
@@ -455,7 +466,8 @@ __global__ void __launch_bounds__(kBlock, (NG == 1 && sizeof(S) == 4) ? 6 : 4) g
                 if (threadIdx.x == 0) red_add_f64(p.energies, b);
             }
         } else {
-            if (run_reduce(e_total, rep, lane)) red_add_f64(p.energies + rep, e_total);
+            run_sum(e_total, span);
+            if (head) red_add_f64(p.energies + rep, e_total);
         }
     }
 }

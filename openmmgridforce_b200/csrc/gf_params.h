@@ -61,6 +61,7 @@ struct ClassifyParams {
     const int* particles;
     gfb_class* out;
     int exact_div;
+    double near_int[3];      // as EvalParams::near_int (gf_classify_lines_kernel)
 };
 
 }  // namespace gfb

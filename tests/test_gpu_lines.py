@@ -1,0 +1,235 @@
+"""GPU parity tests (-m gpu) of gf_eval_lines_kernel — the kernel that serves MIXED packed cells of one geometry
+(openmmgridforce_b200/csrc/gf_eval_lines.cuh): 1 grid read directly, 2-4 grids through 128-byte records, cp.async +
+swizzled shared memory. Every case is compared with the C oracle (oracle/gridforce_oracle.c, bit-exact with the
+reference's ReferenceCalcGridForceKernel) on the same inputs.
+
+Tolerances (BASELINE.json north_star): classification bit-exact; energies 1e-6 relative; forces 1e-5 relative, max-norm.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+
+pytestmark = pytest.mark.gpu
+
+TOL_E, TOL_F = 1e-6, 1e-5
+
+
+def _case(n_grids, n_replicas, n_atoms, seed, counts=(23, 19, 31), frac_outside=0.08):
+    """Random anisotropic grids (FP32-representable values, so the test measures arithmetic and not storage rounding),
+    replicas of n_atoms atoms scattered over the box with a few outside, zero scaling factors sprinkled in."""
+    rng = np.random.default_rng(seed)
+    sp, og = (0.05, 0.07, 0.04), (0.3, -0.2, 1.0)
+    grids = [(rng.normal(size=counts) * 4).astype(np.float32).astype(np.float64) for _ in range(n_grids)]
+    length = np.array(sp) * (np.array(counts) - 1)
+    pos = np.array(og) + rng.uniform(0.0, 1.0, size=(n_replicas, n_atoms, 3)) * length
+    out = rng.uniform(size=(n_replicas, n_atoms)) < frac_outside
+    pos[out] += rng.choice([-1.0, 1.0], size=(int(out.sum()), 3)) * rng.uniform(0.0, 0.3, size=(int(out.sum()), 3)) * length
+    sc = rng.normal(size=(n_grids, n_atoms))
+    sc[:, ::7] = 0.0
+    if n_grids > 1 and n_atoms > 3:
+        sc[1, 3] = 0.0                    # zero on one grid only: that grid skips, the others interpolate
+    oob = [10000.0, 1234.0, 777.0, 5000.0][:n_grids]
+    return dict(counts=counts, spacing=sp, origin=og, grids=grids, scaling=sc, pos=pos, oob_k=oob)
+
+
+def _oracle(bindings, c):
+    port = bindings.PortOracle(c["counts"], c["spacing"], c["origin"], c["grids"], c["scaling"], oob_k=c["oob_k"])
+    return port.execute_batched(c["pos"], n_threads=4)           # ([R][G] energies, [R][A][3] forces)
+
+
+def _make(gf, dev, c, particles=None):
+    grids = [gf.Grid(dev, c["counts"], c["spacing"], c["origin"], g, gf.PRECISION_MIXED, layout=gf.LAYOUT_CELLS) for g in c["grids"]]
+    k = gf.Kernel(dev, grids, c["scaling"], particles=particles, oob_k=c["oob_k"])
+    return grids, k
+
+
+def _close(grids, k):
+    k.close()
+    for g in grids:
+        g.close()
+
+
+def _check(en, ge, forces, ge_ref, f_ref):
+    scale_e = np.abs(ge_ref).max()
+    assert np.abs(ge - ge_ref).max() <= TOL_E * scale_e
+    e_ref = ge_ref.sum(axis=1)
+    assert np.abs(en - e_ref).max() <= TOL_E * max(np.abs(e_ref).max(), scale_e)
+    assert np.abs(forces - f_ref).max() <= TOL_F * np.abs(f_ref).max()
+
+
+# ragged totals on purpose: 1x1, fewer atoms than a warp, totals that are not multiples of 32 / 128 / 256
+SHAPES = [(1, 1), (1, 5), (1, 300), (3, 47), (37, 47), (130, 9), (1, 4099)]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=[f"{r}x{a}" for r, a in SHAPES])
+@pytest.mark.parametrize("n_grids", [1, 2, 3, 4])
+def test_lines_kernel_vs_oracle(gpu_device, oracle_built, n_grids, shape):
+    import openmmgridforce_b200 as gf
+    r, a = shape
+    c = _case(n_grids, r, a, seed=100 * n_grids + r + a)
+    ge_ref, f_ref = _oracle(oracle_built, c)
+    grids, k = _make(gf, gpu_device, c)
+    assert k.uses_lines_kernel()
+    en, forces, ge = k.execute_host(c["pos"], want_grid_energies=True)
+    _check(en, ge, forces, ge_ref, f_ref)
+    # without per-grid energies (the other template instantiation), accumulating onto existing forces
+    f0 = np.random.default_rng(1).normal(size=c["pos"].shape)
+    facc = f0.copy()
+    en2, _, _ = k.execute_host(c["pos"], forces=facc, force_mode=gf.FORCE_F64_ADD)
+    assert np.abs(en2 - ge_ref.sum(axis=1)).max() <= TOL_E * max(np.abs(ge_ref.sum(axis=1)).max(), np.abs(ge_ref).max())
+    assert np.abs(facc - f0 - f_ref).max() <= TOL_F * np.abs(f_ref).max()
+    # classification through the same device function the kernel uses: bit-exact
+    port = oracle_built.PortOracle(c["counts"], c["spacing"], c["origin"], c["grids"], c["scaling"], oob_k=c["oob_k"])
+    for g in range(n_grids):
+        got = k.classify_host(c["pos"], g)
+        for rep in range(min(r, 3)):
+            _, _, want = port.execute(c["pos"][rep], g, classify=True)
+            sl = slice(rep * a, (rep + 1) * a)
+            assert np.array_equal(got["inside"][sl], want["inside"]) and np.array_equal(got["cell"][sl], want["cell"])
+    _close(grids, k)
+
+
+@pytest.mark.parametrize("n_grids", [1, 3])
+def test_lines_kernel_device_fixed_point(gpu_device, oracle_built, n_grids):
+    """CUDA-platform style: device positions, OpenMM fixed-point planar forces accumulated over two launches (with the L2
+    prefetch of the force lines for one grid), energies accumulated, next step's accumulator cleared by the launch."""
+    import torch
+    import openmmgridforce_b200 as gf
+    r, a = 41, 47
+    c = _case(n_grids, r, a, seed=7)
+    ge_ref, f_ref = _oracle(oracle_built, c)
+    grids, k = _make(gf, gpu_device, c)
+    dev = torch.device("cuda:0")
+    n = r * a
+    stride = ((n + 31) // 32) * 32
+    d_pos = torch.from_numpy(c["pos"]).to(dev)
+    d_f = torch.zeros(3 * stride, dtype=torch.int64, device=dev)
+    d_e = torch.zeros(r, dtype=torch.float64, device=dev)
+    d_next = torch.full((r,), 123.0, dtype=torch.float64, device=dev)
+    d_out = torch.empty(n, 3, dtype=torch.float64, device=dev)
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for _ in range(2):
+        k.execute_device(r, a, d_pos.data_ptr(), d_e.data_ptr(), None, d_f.data_ptr(), gf.FORCE_FIXED_ADD, stride, None,
+                         side.cuda_stream, d_energies_clear=d_next.data_ptr())
+    gpu_device.fixed_to_f64(d_f.data_ptr(), stride, n, d_out.data_ptr(), side.cuda_stream)
+    torch.cuda.synchronize()
+    e_ref = ge_ref.sum(axis=1)
+    assert np.abs(d_e.cpu().numpy() - 2 * e_ref).max() <= TOL_E * 2 * max(np.abs(e_ref).max(), np.abs(ge_ref).max())
+    assert np.abs(d_out.cpu().numpy().reshape(r, a, 3) - 2 * f_ref).max() <= TOL_F * 2 * np.abs(f_ref).max()
+    assert not d_next.cpu().numpy().any()
+    _close(grids, k)
+
+
+def test_lines_kernel_particle_subset_and_slots(gpu_device, oracle_built):
+    """setParticles-style subset (the non-contiguous position path) plus energy slots whose atoms INTERLEAVE
+    (slot pattern 0,1,2,0,1,2,...): every run of equal keys inside a warp has length 1, and equal keys that are not
+    adjacent must not be merged twice."""
+    import openmmgridforce_b200 as gf
+    rng = np.random.default_rng(3)
+    r, n_particles, a = 5, 90, 60
+    c = _case(3, r, n_particles, seed=11)
+    particles = np.sort(rng.choice(n_particles, size=a, replace=False)).astype(np.int32)
+    sc = rng.normal(size=(3, a))
+    slots = (np.arange(a) % 3).astype(np.int32)
+    grids = [gf.Grid(gpu_device, c["counts"], c["spacing"], c["origin"], g, gf.PRECISION_MIXED) for g in c["grids"]]
+    k = gf.Kernel(gpu_device, grids, sc, particles=particles, oob_k=c["oob_k"])
+    k.set_energy_slots(slots, 3)
+    assert k.uses_lines_kernel()
+    forces = np.zeros_like(c["pos"])
+    en, _, ge = k.execute_host(c["pos"], forces=forces, force_mode=gf.FORCE_F64_ADD, want_grid_energies=True)
+    en = en.reshape(r, 3)
+    ge = ge.reshape(r, 3, 3)
+    want_f = np.zeros_like(forces)
+    for s in range(3):
+        sel = np.nonzero(slots == s)[0]
+        port = oracle_built.PortOracle(c["counts"], c["spacing"], c["origin"], c["grids"], sc[:, sel], oob_k=c["oob_k"])
+        ge_ref, f_ref = port.execute_batched(np.ascontiguousarray(c["pos"][:, particles[sel]]), n_threads=2)
+        scale = np.abs(ge_ref).max()
+        assert np.abs(ge[:, s, :] - ge_ref).max() <= TOL_E * scale, s
+        assert np.abs(en[:, s] - ge_ref.sum(axis=1)).max() <= TOL_E * scale * 3, s
+        want_f[:, particles[sel]] += f_ref
+    assert np.abs(forces - want_f).max() <= TOL_F * np.abs(want_f).max()
+    untouched = np.setdiff1d(np.arange(n_particles), particles)
+    assert not forces[:, untouched].any()
+    _close(grids, k)
+
+
+def test_general_kernel_interleaved_slots_double(gpu_device, oracle_built):
+    """The same interleaved-slot pattern through the general kernel (DOUBLE precision): 1e-12."""
+    import openmmgridforce_b200 as gf
+    r, a = 2, 70
+    c = _case(1, r, a, seed=21)
+    slots = (np.arange(a) % 2).astype(np.int32)
+    g = gf.Grid(gpu_device, c["counts"], c["spacing"], c["origin"], c["grids"][0], gf.PRECISION_DOUBLE)
+    k = gf.Kernel(gpu_device, [g], c["scaling"], oob_k=c["oob_k"])
+    k.set_energy_slots(slots, 2)
+    assert not k.uses_lines_kernel()
+    en, _, _ = k.execute_host(c["pos"])
+    en = en.reshape(r, 2)
+    for s in range(2):
+        sel = np.nonzero(slots == s)[0]
+        port = oracle_built.PortOracle(c["counts"], c["spacing"], c["origin"], c["grids"], c["scaling"][:, sel], oob_k=c["oob_k"])
+        ge_ref, _ = port.execute_batched(np.ascontiguousarray(c["pos"][:, sel]), n_threads=2)
+        assert np.abs(en[:, s] - ge_ref[:, 0]).max() <= 1e-12 * np.abs(ge_ref).max()
+    _close([g], k)
+
+
+def test_lines_kernel_adversarial_quotients_three_grids(gpu_device, oracle_built):
+    """Positions a few ulps either side of grid nodes, evaluated (not only classified) by the 3-grid lines kernel: a wrong
+    cell would show up as a wrong energy only when the field is discontinuous, so the check is on the classification the
+    kernel's own device function reports, plus energies/forces against the oracle."""
+    import openmmgridforce_b200 as gf
+    rng = np.random.default_rng(17)
+    counts, sp, og = (120, 41, 57), (0.0125, 0.1 / 3, 0.07), (1.00175115, -0.3, 0.0)
+    grids = [rng.normal(size=counts).astype(np.float32).astype(np.float64) for _ in range(3)]
+    n = 20000
+    node = np.stack([rng.integers(1, cc - 1, size=n) for cc in counts], 1).astype(np.float64)
+    pos = np.array(og) + node * np.array(sp)
+    for _ in range(3):
+        step = rng.integers(-3, 4, size=pos.shape)
+        pos = np.where(step > 0, np.nextafter(pos, np.inf), np.where(step < 0, np.nextafter(pos, -np.inf), pos))
+    sc = rng.uniform(0.5, 1.5, size=(3, n))
+    port = oracle_built.PortOracle(counts, sp, og, grids, sc)
+    g3 = [gf.Grid(gpu_device, counts, sp, og, g, gf.PRECISION_MIXED) for g in grids]
+    k = gf.Kernel(gpu_device, g3, sc)
+    assert k.uses_lines_kernel()
+    _, _, want = port.execute(pos, 0, classify=True)
+    got = k.classify_host(pos, 0)
+    assert np.array_equal(got["inside"], want["inside"])
+    assert np.array_equal(got["cell"], want["cell"]), int((got["cell"] != want["cell"]).any(axis=1).sum())
+    ge_ref, f_ref = port.execute_batched(pos[None], n_threads=4)
+    en, f, ge = k.execute_host(pos, want_grid_energies=True)
+    _check(en, ge, f, ge_ref, f_ref)
+    _close(g3, k)
+
+
+def test_lines_off_switch_matches(gpu_device):
+    """The general kernel (reached with an evaluation order) and the lines kernel agree on the same state."""
+    import torch
+    import openmmgridforce_b200 as gf
+    r, a = 64, 47
+    c = _case(3, r, a, seed=5)
+    grids, k = _make(gf, gpu_device, c)
+    dev = torch.device("cuda:0")
+    n = r * a
+    d_pos = torch.from_numpy(c["pos"]).to(dev)
+    side = torch.cuda.Stream()
+    res = []
+    for use_order in (False, True):
+        d_f = torch.zeros(n, 3, dtype=torch.float64, device=dev)
+        d_e = torch.zeros(r, dtype=torch.float64, device=dev)
+        d_order = torch.arange(n, dtype=torch.int32, device=dev) if use_order else None
+        torch.cuda.synchronize()
+        k.execute_device(r, a, d_pos.data_ptr(), d_e.data_ptr(), None, d_f.data_ptr(), gf.FORCE_F64_STORE, 0,
+                         d_order.data_ptr() if use_order else None, side.cuda_stream)
+        torch.cuda.synchronize()
+        res.append((d_e.cpu().numpy(), d_f.cpu().numpy()))
+    (e0, f0), (e1, f1) = res
+    assert np.abs(e0 - e1).max() <= 1e-9 * np.abs(e1).max()
+    assert np.abs(f0 - f1).max() <= 2e-6 * np.abs(f1).max()
+    _close(grids, k)
