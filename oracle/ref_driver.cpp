@@ -9,6 +9,7 @@
 // is replaced by third_party/openmm_shim.
 #include <cstring>
 #include <iostream>
+#include <mutex>
 #include <sstream>
 #include <vector>
 
@@ -30,12 +31,26 @@ using GridForcePlugin::InvPowerMode;
 
 namespace {
 
-// The reference prints debug text from execute() on its first calls (:662-704); swallow it.
+// The reference prints debug text from execute() on its first calls (:662-704); swallow it. std::cout's buffer is
+// process-wide and bench.py --impl reference drives one Context per thread, so the swap is reference-counted under a
+// mutex: the first caller installs a discarding buffer that lives for the whole process, the last one restores.
+struct DiscardBuf : std::streambuf {
+    int_type overflow(int_type c) { return traits_type::not_eof(c); }
+    std::streamsize xsputn(const char*, std::streamsize n) { return n; }
+};
 struct CoutSilencer {
-    std::ostringstream sink;
-    std::streambuf* saved;
-    CoutSilencer() : saved(std::cout.rdbuf(sink.rdbuf())) {}
-    ~CoutSilencer() { std::cout.rdbuf(saved); }
+    static std::mutex& lock() { static std::mutex m; return m; }
+    static int& users() { static int n = 0; return n; }
+    static std::streambuf*& saved() { static std::streambuf* b = 0; return b; }
+    CoutSilencer() {
+        static DiscardBuf* discard = new DiscardBuf();   // never destroyed: threads may still be printing at exit
+        std::lock_guard<std::mutex> g(lock());
+        if (users()++ == 0) saved() = std::cout.rdbuf(discard);
+    }
+    ~CoutSilencer() {
+        std::lock_guard<std::mutex> g(lock());
+        if (--users() == 0) std::cout.rdbuf(saved());
+    }
 };
 
 Platform& referencePlatform() {

@@ -115,3 +115,32 @@ def test_batched_threads_agree(oracle_built):
     assert np.array_equal(e1, e4) and np.array_equal(f1, f4)
     e0, f0, _ = port.execute(pos[3], 1)
     assert e1[3, 1] == e0
+
+
+def test_reference_contexts_on_threads(oracle_built):
+    """bench.py --impl reference drives one reference Context per host thread; the driver's stdout silencer is shared
+    process state and must survive concurrent entry/exit (a crash here took the reference arm down on a 16-core box)."""
+    if not oracle_built.ref_available():
+        pytest.skip("needs oracle/_ref")
+    import threading
+    c = cases.case_random_aniso()
+    n = c["pos"].shape[0]
+    want = None
+    oracles = [oracle_built.RefOracle(n, c["counts"], c["spacing"], c["origin"], c["grids"], c["scaling"],
+                                      oob_k=c["oob_k"]) for _ in range(16)]
+    want = oracles[0].execute_repeat(c["pos"], 3)
+    got = [None] * len(oracles)
+
+    def work(i):
+        for _ in range(200):
+            got[i] = oracles[i].execute_repeat(c["pos"], 1)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(oracles))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert all(g == want for g in got)
+    for o in oracles:
+        o.close()
+    print("stdout still works", flush=True)
