@@ -39,7 +39,7 @@ REPLICAS_PER_GPU = 65536
 N_ATOMS = 47
 N_GRIDS = 3
 GRID_N = 192
-C5_DRAM_BYTES_PER_LAUNCH = 842.1e6     # measured once per change with ncu --set full (profiles/README.md)
+C5_DRAM_BYTES_PER_LAUNCH = 494.7e6     # measured once per change with ncu --set full (profiles/README.md, r1b)
 
 
 def b_alg(n_grids, precision=0):
@@ -439,9 +439,9 @@ def main():
                 "config": workload_config(world),
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
                              "traffic": C5_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch",
-                             "traffic_source": "profiles/r1_c5_warm_raw.csv: dram__bytes_read.sum 728.1 MB + "
-                                               "dram__bytes_write.sum 113.9 MB (ncu --set full, this kernel, this workload)",
-                             "peak_source": peak_src, "kernel": "gf_eval_kernel<float, CELLS, 3 grids, FIXED_ADD>",
+                             "traffic_source": "profiles/r1b_c5_lines_warm_raw.csv: dram__bytes_read.sum 397.0 MB + "
+                                               "dram__bytes_write.sum 97.7 MB (ncu --set full, this kernel, this workload)",
+                             "peak_source": peak_src, "kernel": "gf_eval_lines_kernel<3 grids, FIXED_ADD> (one 128-byte record per cell)",
                              "bytes_per_eval": b_alg(N_GRIDS), "evals_per_launch": evals_step_rank,
                              "launch_us": kernel_us},
                 "roofline_l2_gather": {"achieved": ach, "peak": l2_gbs, "unit": "GB/s", "frac": ach / l2_gbs if l2_gbs else None,

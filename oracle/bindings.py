@@ -22,7 +22,8 @@ def build(quiet=True):
 
 class _Grid(C.Structure):
     _fields_ = [("counts", C.c_int * 3), ("spacing", C.c_double * 3), ("origin", C.c_double * 3),
-                ("vals", C.POINTER(C.c_double)), ("inv_power", C.c_double), ("oob_k", C.c_double)]
+                ("vals", C.POINTER(C.c_double)), ("inv_power", C.c_double), ("oob_k", C.c_double),
+                ("interp_method", C.c_int)]
 
 
 CLASS_DTYPE = np.dtype([("inside", np.int32), ("cell", np.int32, (3,))])
@@ -39,7 +40,7 @@ def _dp(a):
 class PortOracle:
     """G grids acting on the same A atoms (C restatement)."""
 
-    def __init__(self, counts, spacing, origin, grids, scaling, oob_k=None, inv_power=None):
+    def __init__(self, counts, spacing, origin, grids, scaling, oob_k=None, inv_power=None, interpolation_method=0):
         if not os.path.exists(PORT_PATH):
             build()
         self.lib = C.CDLL(PORT_PATH)
@@ -63,6 +64,7 @@ class PortOracle:
             self.grids[g].vals = _dp(self._vals[g])
             self.grids[g].inv_power = inv_power[g]
             self.grids[g].oob_k = oob_k[g]
+            self.grids[g].interp_method = interpolation_method
 
     def execute(self, pos, grid=0, ligand_atoms=None, classify=False):
         """One GridForce, one Context. pos [P,3]. Returns (E, forces[A,3], cls or None)."""

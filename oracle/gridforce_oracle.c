@@ -1,5 +1,6 @@
 /* TEST INFRASTRUCTURE — see gridforce_oracle.h. Plain C99 restatement of
- * /root/reference/platforms/reference/src/ReferenceGridForceKernels.cpp:646-1121 (trilinear branch).
+ * /root/reference/platforms/reference/src/ReferenceGridForceKernels.cpp:646-1121 (trilinear branch, and the cubic
+ * B-spline branch :727-795 when gfo_grid.interp_method == 1).
  * Build with -ffp-contract=off so a*b+c stays two roundings, as in the reference build. */
 #include "gridforce_oracle.h"
 
@@ -8,6 +9,59 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* Cubic B-spline basis and derivative (:54-63), same expressions. */
+static double bs_b0(double t) { return (1.0 - t) * (1.0 - t) * (1.0 - t) / 6.0; }
+static double bs_b1(double t) { return (3.0 * t * t * t - 6.0 * t * t + 4.0) / 6.0; }
+static double bs_b2(double t) { return (-3.0 * t * t * t + 3.0 * t * t + 3.0 * t + 1.0) / 6.0; }
+static double bs_b3(double t) { return t * t * t / 6.0; }
+static double bs_d0(double t) { return -(1.0 - t) * (1.0 - t) / 2.0; }
+static double bs_d1(double t) { return (3.0 * t * t - 4.0 * t) / 2.0; }
+static double bs_d2(double t) { return (-3.0 * t * t + 2.0 * t + 1.0) / 2.0; }
+static double bs_d3(double t) { return t * t / 2.0; }
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* interpolation method 1 (:727-795): 4x4x4 points ix-1..ix+2 with indices clamped into the grid, weights
+ * bx[i]*by[j]*bz[k], summed in i, j, k order. Unlike the trilinear branch the clamping makes the upper face
+ * (idx == n-1, fraction 0) well defined, so it is evaluated exactly as the reference does. */
+static double gfo_interp_bspline(const gfo_grid* g, double scale, const double* pi, double* f, gfo_class* cls) {
+    const int nz = g->counts[2];
+    const int nyz = g->counts[1] * nz;
+    int i, j, k, idx[3];
+    double fr[3], b[3][4], d[3][4];
+    double interpolated = 0.0, dvdx = 0.0, dvdy = 0.0, dvdz = 0.0, grd[3];
+    for (k = 0; k < 3; k++) {
+        idx[k] = (int)(pi[k] / g->spacing[k]);                   /* :708-710 */
+        fr[k] = (pi[k] / g->spacing[k]) - idx[k];                /* :713-715 */
+        b[k][0] = bs_b0(fr[k]); b[k][1] = bs_b1(fr[k]); b[k][2] = bs_b2(fr[k]); b[k][3] = bs_b3(fr[k]);   /* :741-743 */
+        d[k][0] = bs_d0(fr[k]); d[k][1] = bs_d1(fr[k]); d[k][2] = bs_d2(fr[k]); d[k][3] = bs_d3(fr[k]);   /* :746-748 */
+    }
+    if (cls) { cls->cell[0] = idx[0]; cls->cell[1] = idx[1]; cls->cell[2] = idx[2]; }
+    for (i = 0; i < 4; i++) {                                                                /* :754-775 */
+        const int gx = clampi(idx[0] - 1 + i, 0, g->counts[0] - 1);
+        for (j = 0; j < 4; j++) {
+            const int gy = clampi(idx[1] - 1 + j, 0, g->counts[1] - 1);
+            for (k = 0; k < 4; k++) {
+                const int gz = clampi(idx[2] - 1 + k, 0, nz - 1);
+                const double val = g->vals[gx * nyz + gy * nz + gz];
+                const double weight = b[0][i] * b[1][j] * b[2][k];
+                interpolated += weight * val;
+                dvdx += d[0][i] * b[1][j] * b[2][k] * val;
+                dvdy += b[0][i] * d[1][j] * b[2][k] * val;
+                dvdz += b[0][i] * b[1][j] * d[2][k] * val;
+            }
+        }
+    }
+    if (g->inv_power > 0.0) {                                                                /* :778-787 */
+        const double base = interpolated;
+        const double pf = g->inv_power * pow(base, g->inv_power - 1.0);
+        interpolated = pow(interpolated, g->inv_power);
+        dvdx *= pf; dvdy *= pf; dvdz *= pf;
+    }
+    grd[0] = dvdx / g->spacing[0]; grd[1] = dvdy / g->spacing[1]; grd[2] = dvdz / g->spacing[2];   /* :790 */
+    if (f) for (k = 0; k < 3; k++) f[k] -= scale * grd[k];                                   /* :794 */
+    return scale * interpolated;                                                             /* :793 */
+}
+
 /* The inside branch for one atom (:706-1084). pi = position - origin. Returns scale * V and
  * subtracts scale * grad V from f[3]. */
 static double gfo_interp(const gfo_grid* g, double scale, const double* pi, double* f, gfo_class* cls) {
@@ -15,6 +69,7 @@ static double gfo_interp(const gfo_grid* g, double scale, const double* pi, doub
     const int nyz = g->counts[1] * nz;                           /* :653 */
     int k, idx[3];
     double fr[3];
+    if (g->interp_method == 1) return gfo_interp_bspline(g, scale, pi, f, cls);               /* :727 */
     for (k = 0; k < 3; k++) {
         idx[k] = (int)(pi[k] / g->spacing[k]);                   /* :708-710 */
         fr[k] = (pi[k] / g->spacing[k]) - idx[k];                /* :713-715 */
