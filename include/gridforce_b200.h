@@ -53,8 +53,15 @@ typedef enum { GFB_PRECISION_MIXED = 0, GFB_PRECISION_DOUBLE = 1 } gfb_precision
  *          any z-pair lies inside one chunk -> 4 loads per stencil, 1.14x (1.33x) the raw grid.
  *   PAIRS  MIXED only: 32-byte entry = 4 floats (advancing by 3) of row iy and of row iy+1 -> 2 loads, 2.67x.
  *   CELLS  the 8 corners of every cell packed -> 1 load (2 in DOUBLE), 8x.
- *   AUTO   CELLS while that copy is at most 1/16 of the GPU's memory (11 GB on B200), else ROWS. */
-typedef enum { GFB_LAYOUT_AUTO = 0, GFB_LAYOUT_CELLS = 1, GFB_LAYOUT_ROWS = 2, GFB_LAYOUT_PAIRS = 3 } gfb_layout;
+ *   AUTO   CELLS while that copy is at most 1/16 of the GPU's memory (11 GB on B200), else ROWS.
+ * The layout also fixes the INTERPOLATION METHOD (GridForce::setInterpolationMethod, openmmapi/include/GridForce.h:296):
+ * the four above are trilinear (method 0, ReferenceGridForceKernels.cpp:1016-1084);
+ *   BSPLINE cubic B-spline (method 1, :727-795): the index clamping of the 4x4x4 stencil is baked into a padded copy cut
+ *          into tiles of 4 y-rows x 8 z-values (one 128-byte line in MIXED) advancing by 1 row / 5 values, so a stencil is
+ *          4 lines read with 16 aligned 32-byte loads; 6.4x the raw grid. Never chosen by AUTO. */
+typedef enum {
+    GFB_LAYOUT_AUTO = 0, GFB_LAYOUT_CELLS = 1, GFB_LAYOUT_ROWS = 2, GFB_LAYOUT_PAIRS = 3, GFB_LAYOUT_BSPLINE = 4
+} gfb_layout;
 
 /* How execute writes forces.
  *   GFB_FORCE_F64_STORE : double [n_replicas][n_particles][3], plain stores (entries of particles this
@@ -145,6 +152,13 @@ GFB_API int gfb_grid_generate(gfb_device* dev, const int counts[3], const double
                               int grid_type, int n_atoms, const double* pos, const double* charges, const double* sigmas,
                               const double* epsilons, double grid_cap, double* vals_out, int precision, int layout,
                               gfb_grid** grid_out);
+
+/* GridForce::applyInvPowerTransformation (openmmapi/src/GridForce.cpp:221-272; CachedGridData::transformValues,
+ * openmmapi/src/CachedGridData.cpp:50-57): G -> sign(G) * |G|^(1/inv_power) for every non-zero value, in place, computed
+ * on the GPU in FP64. `vals` is a HOST pointer (uploaded, transformed, downloaded) or, with vals_on_device != 0, a DEVICE
+ * pointer (stream-ordered on the device's stream, then synchronised). inv_power must be non-zero. CUDA's pow differs
+ * from libm's by at most 2 ulp; tests assert 1e-14 relative against the reference's own method. */
+GFB_API int gfb_inv_power_transform(gfb_device* dev, double* vals, size_t n_vals, double inv_power, int vals_on_device);
 
 GFB_API int gfb_grid_destroy(gfb_grid* grid);
 GFB_API size_t gfb_grid_device_bytes(const gfb_grid* grid);

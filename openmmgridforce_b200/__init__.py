@@ -20,6 +20,7 @@ from .capi import (  # noqa: F401
     LAYOUT_CELLS,
     LAYOUT_ROWS,
     LAYOUT_PAIRS,
+    LAYOUT_BSPLINE,
     LAYOUT_NAMES,
     library_path,
     load_library,

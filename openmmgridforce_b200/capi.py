@@ -14,8 +14,8 @@ PRECISION_DOUBLE = 1
 FORCE_F64_STORE = 0
 FORCE_F64_ADD = 1
 FORCE_FIXED_ADD = 2
-LAYOUT_AUTO, LAYOUT_CELLS, LAYOUT_ROWS, LAYOUT_PAIRS = 0, 1, 2, 3
-LAYOUT_NAMES = {0: "auto", 1: "cells", 2: "rows", 3: "pairs"}
+LAYOUT_AUTO, LAYOUT_CELLS, LAYOUT_ROWS, LAYOUT_PAIRS, LAYOUT_BSPLINE = 0, 1, 2, 3, 4
+LAYOUT_NAMES = {0: "auto", 1: "cells", 2: "rows", 3: "pairs", 4: "bspline"}
 MAX_GRIDS = 8
 
 _LIB = None
@@ -58,6 +58,7 @@ SIGNATURES = {
     "gfb_gridfile_write": (_i, [C.c_char_p, C.POINTER(GridFileHeader), _vp, _sz, _i]),
     "gfb_grid_generate": (_i, [_vp, _pi, _pd, _pd, _i, _i, _vp, _vp, _vp, _vp, C.c_double, _vp, _i, _i, C.POINTER(_vp)]),
     "gfb_grid_create_from_file": (_i, [_vp, C.c_char_p, _i, _i, C.POINTER(_vp), C.POINTER(GridFileHeader)]),
+    "gfb_inv_power_transform": (_i, [_vp, _vp, _sz, C.c_double, _i]),
     "gfb_grid_destroy": (_i, [_vp]),
     "gfb_grid_device_bytes": (_sz, [_vp]),
     "gfb_kernel_create": (_i, [_vp, _i, C.POINTER(_vp), _i, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
@@ -178,6 +179,16 @@ class Device:
         out = C.c_double(0.0)
         _check(load_library().gfb_bench_sector_gather(self._h, nbytes, n_loads, reps, C.byref(out)))
         return out.value
+
+    def inv_power_transform(self, values, inv_power, device_ptr=None, n=None):
+        """GridForce::applyInvPowerTransformation on the GPU: G -> sign(G)|G|^(1/inv_power). Host array in -> new host
+        array out; or, with device_ptr and n, in place on device doubles."""
+        if device_ptr is not None:
+            _check(load_library().gfb_inv_power_transform(self._h, _ptr(int(device_ptr)), n, float(inv_power), 1))
+            return None
+        out = np.array(values, dtype=np.float64, order="C", copy=True)
+        _check(load_library().gfb_inv_power_transform(self._h, _ptr(out), out.size, float(inv_power), 0))
+        return out
 
     def fixed_to_f64(self, d_fixed, stride, n, d_out, stream=0):
         _check(load_library().gfb_forces_fixed_to_f64(self._h, _ptr(d_fixed), stride, n, _ptr(d_out), _ptr(stream or None)))

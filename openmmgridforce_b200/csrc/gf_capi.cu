@@ -220,7 +220,7 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
     *out = nullptr;
     if (precision != GFB_PRECISION_MIXED && precision != GFB_PRECISION_DOUBLE)
         return fail(GFB_ERR_INVALID, "gfb_grid_create: unknown precision %d", precision);
-    if (layout < GFB_LAYOUT_AUTO || layout > GFB_LAYOUT_PAIRS) return fail(GFB_ERR_INVALID, "gfb_grid_create: unknown layout %d", layout);
+    if (layout < GFB_LAYOUT_AUTO || layout > GFB_LAYOUT_BSPLINE) return fail(GFB_ERR_INVALID, "gfb_grid_create: unknown layout %d", layout);
     if (layout == GFB_LAYOUT_PAIRS && precision == GFB_PRECISION_DOUBLE)
         return fail(GFB_ERR_UNSUPPORTED, "gfb_grid_create: the PAIRS layout exists for MIXED precision only (use ROWS or CELLS)");
     for (int k = 0; k < 3; k++) {
@@ -259,10 +259,14 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
         g->row_chunks = (counts[2] - 2) / (w - 1) + 1;                     // covers every pair (iz, iz+1), iz <= nz-2
         n_units = (size_t) counts[0] * counts[1] * g->row_chunks;
         g->bytes = n_units * 32;
-    } else {
+    } else if (layout == GFB_LAYOUT_PAIRS) {
         g->row_chunks = (counts[2] - 2) / 3 + 1;
         n_units = (size_t) counts[0] * (counts[1] - 1) * g->row_chunks;
         g->bytes = n_units * 32;
+    } else {   // BSPLINE: tiles (a < nx+2, ty < ny-1, tc) of 4 rows x 8 values, one thread per tile row
+        g->row_chunks = (counts[2] - 2) / 5 + 1;
+        n_units = (size_t) (counts[0] + 2) * (counts[1] - 1) * g->row_chunks * 4;
+        g->bytes = n_units * 8 * (precision == GFB_PRECISION_MIXED ? sizeof(float) : sizeof(double));
     }
     g->cells = nullptr;
 
@@ -285,8 +289,11 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
         } else if (layout == GFB_LAYOUT_ROWS) {
             if (mixed) gf_repack_rows_kernel<float><<<blocks, 256, 0, dev->stream>>>(d_vals, cf, counts[0], counts[1], counts[2], g->row_chunks);
             else gf_repack_rows_kernel<double><<<blocks, 256, 0, dev->stream>>>(d_vals, cd, counts[0], counts[1], counts[2], g->row_chunks);
-        } else {
+        } else if (layout == GFB_LAYOUT_PAIRS) {
             gf_repack_pairs_kernel<<<blocks, 256, 0, dev->stream>>>(d_vals, cf, counts[0], counts[1], counts[2], g->row_chunks);
+        } else {
+            if (mixed) gf_repack_bspline_kernel<float><<<blocks, 256, 0, dev->stream>>>(d_vals, cf, counts[0], counts[1], counts[2], g->row_chunks);
+            else gf_repack_bspline_kernel<double><<<blocks, 256, 0, dev->stream>>>(d_vals, cd, counts[0], counts[1], counts[2], g->row_chunks);
         }
         g_launches++;
         err = cudaGetLastError();
@@ -465,6 +472,31 @@ int gfb_grid_generate(gfb_device* dev, const int counts[3], const double spacing
     if (d_atoms) cudaFree(d_atoms);
     if (d_vals) cudaFree(d_vals);
     return rc;
+}
+
+int gfb_inv_power_transform(gfb_device* dev, double* vals, size_t n_vals, double inv_power, int vals_on_device) {
+    if (!dev || (!vals && n_vals)) return fail(GFB_ERR_INVALID, "gfb_inv_power_transform: NULL argument");
+    if (inv_power == 0.0) return fail(GFB_ERR_INVALID, "GridForce: inv_power must be non-zero");
+    if (n_vals == 0) return GFB_OK;
+    CUDA_TRY(cudaSetDevice(dev->ordinal));
+    double* d = vals;
+    if (!vals_on_device) {
+        CUDA_TRY(cudaMalloc((void**) &d, n_vals * sizeof(double)));
+        cudaError_t e = cudaMemcpyAsync(d, vals, n_vals * sizeof(double), cudaMemcpyHostToDevice, dev->stream);
+        if (e != cudaSuccess) {
+            cudaFree(d);
+            return fail(GFB_ERR_CUDA, "gfb_inv_power_transform: H2D: %s", cudaGetErrorString(e));
+        }
+    }
+    const int blocks = (int) std::min<size_t>((n_vals + 255) / 256, (size_t) dev->prop.multiProcessorCount * 32);
+    gf_inv_power_transform_kernel<<<blocks, 256, 0, dev->stream>>>(d, n_vals, 1.0 / inv_power);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && !vals_on_device) e = cudaMemcpyAsync(vals, d, n_vals * sizeof(double), cudaMemcpyDeviceToHost, dev->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(dev->stream);
+    if (!vals_on_device) cudaFree(d);
+    if (e != cudaSuccess) return fail(GFB_ERR_CUDA, "gfb_inv_power_transform: %s", cudaGetErrorString(e));
+    return GFB_OK;
 }
 
 int gfb_grid_destroy(gfb_grid* grid) {
@@ -694,7 +726,10 @@ static void launch_eval2(const EvalParams& p, bool same, int fmode, cudaStream_t
 }
 
 static void launch_eval1(const EvalParams& p, int precision, int layout, bool same, int fmode, cudaStream_t stream) {
-    if (precision == GFB_PRECISION_DOUBLE) {
+    if (layout == GFB_LAYOUT_BSPLINE) {   // cubic B-spline: run-time grid count, each grid classified on its own geometry
+        if (precision == GFB_PRECISION_DOUBLE) launch_eval3<double, GFB_LAYOUT_BSPLINE, 0, false>(p, fmode, stream);
+        else launch_eval3<float, GFB_LAYOUT_BSPLINE, 0, false>(p, fmode, stream);
+    } else if (precision == GFB_PRECISION_DOUBLE) {
         if (layout == GFB_LAYOUT_CELLS) launch_eval2<double, GFB_LAYOUT_CELLS>(p, same, fmode, stream);
         else launch_eval2<double, GFB_LAYOUT_ROWS>(p, same, fmode, stream);
     } else {

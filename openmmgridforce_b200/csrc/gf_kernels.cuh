@@ -271,6 +271,126 @@ __device__ __forceinline__ void accumulate_inside(const GridView& G, const S v[8
     Fz -= sd * gz;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cubic B-spline interpolation (GridForce::setInterpolationMethod(1); ReferenceGridForceKernels.cpp:727-795):
+// 4x4x4 points ix-1..ix+2 (indices clamped into the grid), separable weights bx[i]*by[j]*bz[k].
+//
+// Layout GFB_LAYOUT_BSPLINE (gf_repack_bspline_kernel): the clamping is baked into a padded copy
+// P[a][b][c] = V[clamp(a-1)][clamp(b-1)][clamp(c-1)], so the stencil of cell (ix,iy,iz) is P[ix..ix+3][iy..iy+3][iz..iz+3],
+// and the copy is cut into TILES of 4 y-rows x 8 z-values (128 bytes of floats = one L2/HBM line; 256 bytes of doubles):
+// tile (a, ty, tc) holds P[a][ty..ty+3][5tc..5tc+7]. Consecutive tiles advance by ONE row in y and by FIVE values in z,
+// so every 4x4 (y,z) window lies inside a single tile: a stencil is 4 lines (one per x-plane), read with 16 aligned
+// 32-byte loads, instead of 64 scattered 4-byte loads to 16 lines (reference CUDA kernel, gridForce.cu:103-147).
+// The per-lane z offset inside the tile (0..4) is folded into the WEIGHTS (8 weights, zero outside the window), so
+// no value has to be selected at a run-time register index. Copy size: 6.4x the raw grid.
+//
+// Arithmetic: S = double -> everything FP64. S = float -> gradient FP32, interpolated VALUE FP64 from the FP32-stored
+// points and FP64 weights (same reasoning as trilinear_value_f64).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bspline_basis(double t, double b[4], double d[4]) {   // :54-63
+    const double u = 1.0 - t, t2 = t * t, t3 = t2 * t;
+    const double sixth = 1.0 / 6.0;
+    b[0] = u * u * u * sixth;
+    b[1] = (3.0 * t3 - 6.0 * t2 + 4.0) * sixth;
+    b[2] = (-3.0 * t3 + 3.0 * t2 + 3.0 * t + 1.0) * sixth;
+    b[3] = t3 * sixth;
+    d[0] = -u * u * 0.5;
+    d[1] = (3.0 * t2 - 4.0 * t) * 0.5;
+    d[2] = (-3.0 * t2 + 2.0 * t + 1.0) * 0.5;
+    d[3] = t2 * 0.5;
+}
+
+__device__ __forceinline__ void load_row8(const float* p, float v[8]) { load32(p, v); }
+__device__ __forceinline__ void load_row8(const double* p, double v[8]) {
+    load32(p, v);
+    load32(p + 4, v + 4);
+}
+
+template <typename S>
+__device__ __forceinline__ void bspline_interpolate(const GridView& G, int ix, int iy, int iz, double fx, double fy, double fz,
+                                                    double& val, S& gx, S& gy, S& gz) {
+    constexpr bool F64 = sizeof(S) == 8;
+    double bx[4], dbx[4], by[4], dby[4], bz[4], dbz[4];
+    bspline_basis(fx, bx, dbx);   // :741-748
+    bspline_basis(fy, by, dby);
+    bspline_basis(fz, bz, dbz);
+    const int tc = iz / 5, off = iz - 5 * tc;
+    double wz[8];        // value weights over the tile's 8 z-values
+    S wzs[8], dwz[8];    // gradient path (S); wzs aliases wz when S = double
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int m = k - off;
+        const double w = m == 0 ? bz[0] : m == 1 ? bz[1] : m == 2 ? bz[2] : m == 3 ? bz[3] : 0.0;
+        const double dw = m == 0 ? dbz[0] : m == 1 ? dbz[1] : m == 2 ? dbz[2] : m == 3 ? dbz[3] : 0.0;
+        wz[k] = w;
+        wzs[k] = (S) w;
+        dwz[k] = (S) dw;
+    }
+    const S* tile = static_cast<const S*>(G.cells) + (((size_t) ix * G.nc[1] + iy) * G.row_chunks + tc) * 32;
+    const size_t plane = (size_t) G.nc[1] * G.row_chunks * 32;    // tiles of the next x-plane
+    val = 0.0;
+    gx = gy = gz = (S) 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        S v[4][8];
+#pragma unroll
+        for (int r = 0; r < 4; r++) load_row8(tile + i * plane + 8 * r, v[r]);   // one line (two in FP64)
+        double pv = 0.0;          // sum over (j,k) of by*bz*V in this x-plane
+        S pdy = (S) 0, pdz = (S) 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            double rz = 0.0;
+            S rzs = (S) 0, drz = (S) 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                rz = fma(wz[k], (double) v[r][k], rz);
+                if (!F64) rzs = fma(wzs[k], v[r][k], rzs);
+                drz = fma(dwz[k], v[r][k], drz);
+            }
+            if (F64) rzs = (S) rz;
+            pv = fma(by[r], rz, pv);
+            pdy = fma((S) dby[r], rzs, pdy);
+            pdz = fma((S) by[r], drz, pdz);
+        }
+        val = fma(bx[i], pv, val);
+        gx = fma((S) dbx[i], (S) pv, gx);
+        gy = fma((S) bx[i], pdy, gy);
+        gz = fma((S) bx[i], pdz, gz);
+    }
+}
+
+// One grid's B-spline contribution for an inside atom (:727-795), same epilogue as accumulate_inside.
+template <typename S>
+__device__ __forceinline__ void accumulate_bspline(const GridView& G, const AtomCell& c, double sd, double& e_g, double& Fx,
+                                                   double& Fy, double& Fz) {
+    constexpr bool EXACT = sizeof(S) == 8;
+    double dval;
+    S dx, dy, dz;
+    bspline_interpolate<S>(G, c.ix, c.iy, c.iz, c.fx, c.fy, c.fz, dval, dx, dy, dz);
+    double gx, gy, gz;
+    if (EXACT) {  // :790
+        gx = (double) dx / G.spacing[0];
+        gy = (double) dy / G.spacing[1];
+        gz = (double) dz / G.spacing[2];
+    } else {
+        gx = (double) (dx * (S) G.inv_spacing[0]);
+        gy = (double) (dy * (S) G.inv_spacing[1]);
+        gz = (double) (dz * (S) G.inv_spacing[2]);
+    }
+    if (G.inv_power > 0.0) {  // :778-787
+        const double base = dval;
+        dval = pow(base, G.inv_power);
+        const double pf = G.inv_power * pow(base, G.inv_power - 1.0);
+        gx *= pf;
+        gy *= pf;
+        gz *= pf;
+    }
+    e_g = sd * dval;  // :793
+    Fx -= sd * gx;    // :794
+    Fy -= sd * gy;
+    Fz -= sd * gz;
+}
+
 // :1093-1117 — harmonic wall outside the grid (unscaled). Inside atoms with scale == 0 land here too and contribute
 // exactly 0 (quirk Q3). Rare (1-2 % of atoms): kept out of line so its FP64 temporaries do not cost registers.
 struct Restraint {
@@ -300,8 +420,13 @@ __device__ __forceinline__ void accumulate_restraint(const GridView& G, double x
     Fz -= r.fz;
 }
 
+template <typename S, int LAYOUT, int NG>
+__host__ __device__ constexpr int eval_min_blocks() {
+    return LAYOUT == GFB_LAYOUT_BSPLINE ? (sizeof(S) == 4 ? 2 : 1) : ((NG == 1 && sizeof(S) == 4) ? 6 : 4);
+}
+
 template <typename S, int LAYOUT, int NG, bool SAME, int FMODE, bool SINGLE>
-__global__ void __launch_bounds__(kBlock, (NG == 1 && sizeof(S) == 4) ? 6 : 4) gf_eval_kernel(const __grid_constant__ EvalParams p) {
+__global__ void __launch_bounds__(kBlock, eval_min_blocks<S, LAYOUT, NG>()) gf_eval_kernel(const __grid_constant__ EvalParams p) {
     constexpr bool EXACT = sizeof(S) == 8;
     constexpr int NGC = NG > 0 ? NG : 1;
     // With a compile-time grid count, one shared geometry and the one-load-per-stencil layout, every grid's stencil
@@ -381,7 +506,7 @@ __global__ void __launch_bounds__(kBlock, (NG == 1 && sizeof(S) == 4) ? 6 : 4) g
     const unsigned span = run_span(rep, (unsigned) lane, heads);   // runs of equal energy key inside the warp
     const bool head = rep >= 0 && ((heads >> lane) & 1u);
 
-    if (BATCHED) {
+    if constexpr (BATCHED) {
         const AtomCell c = classify<EXACT>(p.grid[0], x, y, z);
         S v[NGC][8];
         bool interp[NGC];
@@ -414,9 +539,13 @@ __global__ void __launch_bounds__(kBlock, (NG == 1 && sizeof(S) == 4) ? 6 : 4) g
                 if (!SAME) c = classify<EXACT>(G, x, y, z);
                 const double s = NG > 0 ? sd[NG > 0 ? g : 0] : G.scaling[ia];
                 if (c.inside && s != 0.0) {
-                    S v[8];
-                    load_stencil<S, LAYOUT>(G, c.ix, c.iy, c.iz, v);
-                    accumulate_inside<S>(G, v, c, s, e_g, Fx, Fy, Fz);
+                    if constexpr (LAYOUT == GFB_LAYOUT_BSPLINE) {
+                        accumulate_bspline<S>(G, c, s, e_g, Fx, Fy, Fz);
+                    } else {
+                        S v[8];
+                        load_stencil<S, LAYOUT>(G, c.ix, c.iy, c.iz, v);
+                        accumulate_inside<S>(G, v, c, s, e_g, Fx, Fy, Fz);
+                    }
                 } else {
                     accumulate_restraint(G, x, y, z, e_g, Fx, Fy, Fz);
                 }
@@ -554,6 +683,37 @@ __global__ void __launch_bounds__(256) gf_repack_pairs_kernel(const double* __re
             o[k] = z < nz ? (float) src[z] : 0.f;
             o[4 + k] = z < nz ? (float) src[nz + z] : 0.f;
         }
+    }
+}
+
+// BSPLINE tiles (see bspline_interpolate): one thread per (tile, row r): 8 values
+// P[a][ty+r][5tc+k] = V[clamp(a-1)][clamp(ty+r-1)][clamp(5tc+k-1)], k = 0..7. a < nx+2, ty < ny-1, tc < row_chunks.
+template <typename S>
+__global__ void __launch_bounds__(256) gf_repack_bspline_kernel(const double* __restrict__ vals, S* __restrict__ out,
+                                                                int nx, int ny, int nz, int row_chunks) {
+    const size_t total = (size_t) (nx + 2) * (ny - 1) * row_chunks * 4;
+    for (size_t c = (size_t) blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (size_t) gridDim.x * blockDim.x) {
+        const int r = (int) (c & 3);
+        size_t t = c >> 2;
+        const int tc = (int) (t % row_chunks);
+        t /= row_chunks;
+        const int ty = (int) (t % (ny - 1));
+        const int a = (int) (t / (ny - 1));
+        const int gx = min(max(a - 1, 0), nx - 1);
+        const int gy = min(max(ty + r - 1, 0), ny - 1);
+        const double* src = vals + ((size_t) gx * ny + gy) * nz;
+        S* o = out + c * 8;
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = (S) src[min(max(5 * tc + k - 1, 0), nz - 1)];
+    }
+}
+
+// GridForce::applyInvPowerTransformation (openmmapi/src/GridForce.cpp:262-268; CachedGridData.cpp:50-57): the RUNTIME
+// inv-power mode stores G -> sign(G) * |G|^(1/n) once, and the evaluation applies ^n. In place, FP64.
+__global__ void __launch_bounds__(256) gf_inv_power_transform_kernel(double* __restrict__ vals, size_t n, double inv_n) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        const double v = vals[i];
+        if (v != 0.0) vals[i] = (v >= 0.0 ? 1.0 : -1.0) * pow(fabs(v), inv_n);
     }
 }
 

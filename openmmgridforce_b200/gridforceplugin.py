@@ -44,6 +44,7 @@ def _lib():
         lib.b200_plugin_set_property.argtypes = [C.c_char_p, C.c_char_p]
         lib.b200_plugin_add_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
                                              C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+        lib.b200_plugin_apply_inv_power.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_double, C.c_void_p]
         lib.b200_plugin_add_particle_group.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.b200_plugin_finalize.argtypes = [C.c_void_p, C.c_char_p]
         lib.b200_plugin_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -145,6 +146,20 @@ class GridForce:
 
     def getInvPower(self):
         return self._inv_power
+
+    def getInvPowerMode(self):
+        return self._inv_power_mode
+
+    def getGridValues(self):
+        return np.asarray(self._vals, dtype=np.float64)
+
+    def applyInvPowerTransformation(self):
+        """RUNTIME mode: G -> sign(G)|G|^(1/n) once (on the GPU), then the mode is STORED (gridforceplugin.i:181)."""
+        vals = np.array(self._vals, dtype=np.float64, order="C", copy=True).ravel()
+        mode = C.c_int(-1)
+        _check(_lib().b200_plugin_apply_inv_power(_p(vals), vals.size, int(self._inv_power_mode), float(self._inv_power),
+                                                  C.byref(mode)))
+        self._vals, self._inv_power_mode = vals, mode.value
 
     def setOutOfBoundsRestraint(self, k):
         self._oob_k = float(k)

@@ -2,6 +2,8 @@
 // openmmapi/src/GridForce.cpp for the members that exist here.
 #include "GridForce.h"
 
+#include <string>
+
 #include "GridForceKernels.h"
 #include "gridforce_b200.h"
 #include "internal/GridForceImpl.h"
@@ -86,8 +88,32 @@ void GridForce::setInvPowerMode(InvPowerMode mode, double inv_power) {
         throw OpenMMException("GridForce: inv_power must be non-zero when mode != NONE");
     if (mode == InvPowerMode::NONE && inv_power != 0.0)
         throw OpenMMException("GridForce: inv_power must be 0 when mode == NONE");
+    if (!m_vals.empty()) {   // conflicting mode changes once a grid is loaded (reference GridForce.cpp:199-211)
+        if (m_invPowerMode == InvPowerMode::STORED && mode == InvPowerMode::RUNTIME)
+            throw OpenMMException("GridForce: Cannot set RUNTIME mode on grid that already has STORED transformation. "
+                                  "This would apply transformation twice!");
+        if (m_invPowerMode == InvPowerMode::RUNTIME && mode == InvPowerMode::STORED)
+            throw OpenMMException("GridForce: Cannot set STORED mode on untransformed grid loaded with RUNTIME mode. "
+                                  "Call applyInvPowerTransformation() first.");
+    }
     m_invPowerMode = mode;
     m_invPower = inv_power;
+}
+
+// Reference GridForce.cpp:241-271 (the direct path; this stand-in has no CachedGridData), with the pow loop moved to the GPU.
+void GridForce::applyInvPowerTransformation(int deviceIndex) {
+    if (m_invPowerMode != InvPowerMode::RUNTIME)
+        throw OpenMMException("GridForce: Can only call applyInvPowerTransformation() when mode == RUNTIME. Current mode: " +
+                              std::to_string(static_cast<int>(m_invPowerMode)));
+    if (m_invPower == 0.0) throw OpenMMException("GridForce: inv_power must be non-zero");
+    if (m_vals.empty()) throw OpenMMException("GridForce: No grid values to transform. Load grid first.");
+    gfb_device* dev = 0;
+    if (gfb_device_open(deviceIndex, &dev) != GFB_OK) throw OpenMMException(gfb_last_error());
+    const int rc = gfb_inv_power_transform(dev, m_vals.data(), m_vals.size(), m_invPower, 0);
+    const std::string err = rc == GFB_OK ? "" : gfb_last_error();
+    gfb_device_close(dev);
+    if (rc != GFB_OK) throw OpenMMException(err);
+    m_invPowerMode = InvPowerMode::STORED;
 }
 InvPowerMode GridForce::getInvPowerMode() const { return m_invPowerMode; }
 double GridForce::getInvPower() const { return m_invPower; }

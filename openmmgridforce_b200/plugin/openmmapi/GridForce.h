@@ -57,12 +57,15 @@ public:
     // ---- evaluation options --------------------------------------------------------------------------------------
     void setInvPowerMode(InvPowerMode mode, double inv_power);
     InvPowerMode getInvPowerMode() const;
+    // RUNTIME mode: G -> sign(G)|G|^(1/n) once, after which the mode is STORED (reference GridForce.cpp:221-272).
+    // Computed on the GPU (gfb_inv_power_transform); `deviceIndex` picks which one.
+    void applyInvPowerTransformation(int deviceIndex = 0);
     double getInvPower() const;
     void setGridCap(double uMax);
     double getGridCap() const;
     void setOutOfBoundsRestraint(double k);                 // kJ/mol/nm^2, default 10000
     double getOutOfBoundsRestraint() const;
-    void setInterpolationMethod(int method);                // 0 trilinear .. 3 quintic; only 0 runs on this platform
+    void setInterpolationMethod(int method);                // 0 trilinear, 1 cubic B-spline run on this platform; 2, 3 throw at Context creation
     int getInterpolationMethod() const;
 
     // ---- which particles ------------------------------------------------------------------------------------------

@@ -48,7 +48,14 @@ static unsigned long long hashWords(const void* data, size_t bytes, unsigned lon
     return h ^ (h >> 32);
 }
 
-std::shared_ptr<SharedGrid> b200AcquireGrid(gfb_device* dev, int ordinal, int precision, const std::vector<int>& counts,
+int b200LayoutForMethod(int interpolationMethod, const char* who) {
+    if (interpolationMethod == 0) return GFB_LAYOUT_AUTO;        // trilinear
+    if (interpolationMethod == 1) return GFB_LAYOUT_BSPLINE;     // cubic B-spline
+    throw OpenMMException(std::string(who) + ": interpolation methods 2 (tricubic) and 3 (quintic Hermite) need derivative "
+                          "grids and are not implemented on this platform; use 0 (trilinear) or 1 (cubic B-spline)");
+}
+
+std::shared_ptr<SharedGrid> b200AcquireGrid(gfb_device* dev, int ordinal, int precision, int layout, const std::vector<int>& counts,
                                             const std::vector<double>& spacing, const double origin[3],
                                             const std::vector<double>& vals) {
     static std::map<std::string, std::weak_ptr<SharedGrid> > cache;
@@ -57,12 +64,12 @@ std::shared_ptr<SharedGrid> b200AcquireGrid(gfb_device* dev, int ordinal, int pr
     h = hashWords(spacing.data(), 3 * sizeof(double), h);
     h = hashWords(origin, 3 * sizeof(double), h);
     std::ostringstream key;
-    key << ordinal << ':' << precision << ':' << vals.size() << ':' << h;
+    key << ordinal << ':' << precision << ':' << layout << ':' << vals.size() << ':' << h;
     std::lock_guard<std::mutex> lock(registryMutex);
     std::shared_ptr<SharedGrid> hit = cache[key.str()].lock();
     if (hit) return hit;
     gfb_grid* g = 0;
-    check(gfb_grid_create(dev, counts.data(), spacing.data(), origin, vals.data(), vals.size(), precision, GFB_LAYOUT_AUTO, &g),
+    check(gfb_grid_create(dev, counts.data(), spacing.data(), origin, vals.data(), vals.size(), precision, layout, &g),
           "grid upload");
     std::shared_ptr<SharedGrid> made(new SharedGrid(g));
     cache[key.str()] = made;
@@ -83,8 +90,7 @@ void B200CalcGridForceKernel::build(const GridForce& force) {
     std::vector<int> counts;
     std::vector<double> spacing, vals, scaling;
     force.getGridParameters(counts, spacing, vals, scaling);
-    if (force.getInterpolationMethod() != 0)
-        throw OpenMMException("GridForce[B200]: only trilinear interpolation (method 0) is implemented on this platform");
+    const int layout = b200LayoutForMethod(force.getInterpolationMethod(), "GridForce[B200]");
     if (force.getTiledMode()) throw OpenMMException("GridForce[B200]: tiled grids are not supported on this platform");
     if (force.getAutoGenerateGrid() && vals.empty())
         throw OpenMMException("GridForce[B200]: grid auto-generation is not supported on this platform; generate the grid first");
@@ -99,7 +105,7 @@ void B200CalcGridForceKernel::build(const GridForce& force) {
     const double invPower = force.getInvPower(), oobK = force.getOutOfBoundsRestraint();
 
     dev = b200Device(deviceIndex);
-    grid = b200AcquireGrid(dev, deviceIndex, precision, counts, spacing, origin, vals);
+    grid = b200AcquireGrid(dev, deviceIndex, precision, layout, counts, spacing, origin, vals);
     release();
     gfb_grid* handle = grid->handle;
     groupMode = force.getNumParticleGroups() > 0;

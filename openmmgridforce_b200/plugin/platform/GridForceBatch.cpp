@@ -44,8 +44,9 @@ void GridForceBatch::build() {
     size_t nAtoms = 0;
     for (size_t g = 0; g < forces.size(); g++) {
         const GridForce& f = *forces[g];
-        if (f.getInterpolationMethod() != 0)
-            throw OpenMMException("GridForceBatch: only trilinear interpolation (method 0) is implemented");
+        const int layout = b200LayoutForMethod(f.getInterpolationMethod(), "GridForceBatch");
+        if (f.getInterpolationMethod() != forces[0]->getInterpolationMethod())
+            throw OpenMMException("GridForceBatch: all forces must use the same interpolation method");
         std::vector<int> counts;
         std::vector<double> spacing, vals, scaling;
         f.getGridParameters(counts, spacing, vals, scaling);
@@ -56,7 +57,7 @@ void GridForceBatch::build() {
             throw OpenMMException("GridForceBatch: all forces must have the same number of scaling factors");
         double origin[3];
         f.getGridOrigin(origin[0], origin[1], origin[2]);
-        grids.push_back(b200AcquireGrid(dev, deviceIndex, precision, counts, spacing, origin, vals));
+        grids.push_back(b200AcquireGrid(dev, deviceIndex, precision, layout, counts, spacing, origin, vals));
         handles.push_back(grids.back()->handle);
         scalingAll.insert(scalingAll.end(), scaling.begin(), scaling.end());
         invPower.push_back(f.getInvPower());

@@ -93,6 +93,20 @@ OPENMM_EXPORT int b200_plugin_add_grid(void* handle, const int* counts, const do
     })
 }
 
+// GridForce::setInvPowerMode(RUNTIME, n) + applyInvPowerTransformation() on `vals` (in place); *modeAfter = the mode the
+// force is left in. Errors (wrong mode, empty grid, n == 0) surface exactly as the C++ class raises them.
+OPENMM_EXPORT int b200_plugin_apply_inv_power(double* vals, long long nVals, int mode, double invPower, int* modeAfter) {
+    GUARD({
+        GridForce f;
+        f.setGridValues(std::vector<double>(vals, vals + nVals));
+        f.setInvPowerMode(static_cast<InvPowerMode>(mode), invPower);
+        f.applyInvPowerTransformation();
+        const std::vector<double>& v = f.getGridValues();
+        memcpy(vals, v.data(), v.size() * sizeof(double));
+        *modeAfter = static_cast<int>(f.getInvPowerMode());
+    })
+}
+
 OPENMM_EXPORT int b200_plugin_add_particle_group(void* handle, int force, const char* name, const int* particles, const double* scaling, int n) {
     Handle* h = static_cast<Handle*>(handle);
     GUARD({

@@ -217,3 +217,27 @@ def ref_generate_grid(counts, spacing, origin, grid_type, pos, charges, sigmas, 
     if rc:
         raise RuntimeError(lib.oracle_ref_last_error().decode())
     return out
+
+
+def port_inv_power_transform(values, inv_power):
+    """C restatement of GridForce::applyInvPowerTransformation -> new array."""
+    if not os.path.exists(PORT_PATH):
+        build()
+    lib = C.CDLL(PORT_PATH)
+    out = np.array(values, dtype=np.float64, order="C", copy=True)
+    lib.gfo_inv_power_transform.restype = None
+    lib.gfo_inv_power_transform(_dp(out), C.c_size_t(out.size), C.c_double(inv_power))
+    return out
+
+
+def ref_inv_power_transform(values, inv_power):
+    """The reference's own GridForce::applyInvPowerTransformation on a RUNTIME-mode grid -> (new array, mode after)."""
+    lib = C.CDLL(REF_PATH)
+    lib.oracle_ref_last_error.restype = C.c_char_p
+    out = np.array(values, dtype=np.float64, order="C", copy=True)
+    counts = (C.c_int * 3)(*out.shape) if out.ndim == 3 else (C.c_int * 3)(out.size, 1, 1)
+    mode = C.c_int(-1)
+    rc = lib.oracle_ref_apply_inv_power(counts, _dp(out), C.c_longlong(out.size), C.c_double(inv_power), C.byref(mode))
+    if rc:
+        raise RuntimeError(lib.oracle_ref_last_error().decode())
+    return out, mode.value

@@ -268,3 +268,14 @@ void gfo_generate_grid(const int counts[3], const double spacing[3], const doubl
         free(jobs);
     }
 }
+
+/* GridForce::applyInvPowerTransformation (openmmapi/src/GridForce.cpp:262-268): G -> sign(G) * |G|^(1/n), zeros kept. */
+void gfo_inv_power_transform(double* vals, size_t n, double inv_power) {
+    size_t i;
+    for (i = 0; i < n; i++) {
+        if (vals[i] != 0.0) {
+            const double sign = (vals[i] >= 0.0) ? 1.0 : -1.0;
+            vals[i] = sign * pow(fabs(vals[i]), 1.0 / inv_power);
+        }
+    }
+}

@@ -15,6 +15,7 @@
  */
 #ifndef GRIDFORCE_ORACLE_H_
 #define GRIDFORCE_ORACLE_H_
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -64,6 +65,10 @@ void gfo_execute_batched(const gfo_grid* grids, int n_grids, const double* scali
 void gfo_generate_grid(const int counts[3], const double spacing[3], const double origin[3], int grid_type, int n_atoms,
                        const double* pos, const double* charges, const double* sigmas, const double* epsilons,
                        double grid_cap, double* out, int n_threads);
+
+/* GridForce::applyInvPowerTransformation (openmmapi/src/GridForce.cpp:262-268), the RUNTIME inv-power mode's one-off
+ * transformation of the stored values, in place. */
+void gfo_inv_power_transform(double* vals, size_t n, double inv_power);
 
 #ifdef __cplusplus
 }

@@ -277,4 +277,25 @@ int oracle_ref_load_file(const char* path, int* counts, double* spacing, double*
     }
 }
 
+// GridForce::applyInvPowerTransformation (GridForce.cpp:221-272) on a grid in RUNTIME mode: vals are transformed in
+// place; *modeAfter receives the mode the reference leaves the force in (STORED).
+int oracle_ref_apply_inv_power(const int* counts, double* vals, long long nVals, double invPower, int* modeAfter) {
+    try {
+        GridForce f;
+        f.addGridCounts(counts[0], counts[1], counts[2]);
+        f.addGridSpacing(0.1, 0.1, 0.1);
+        f.setGridValues(std::vector<double>(vals, vals + nVals));
+        f.setInvPowerMode(InvPowerMode::RUNTIME, invPower);
+        f.applyInvPowerTransformation();
+        const std::vector<double>& v = f.getGridValues();
+        if ((long long) v.size() != nVals) throw OpenMMException("value count changed");
+        memcpy(vals, v.data(), v.size() * sizeof(double));
+        *modeAfter = static_cast<int>(f.getInvPowerMode());
+        return 0;
+    } catch (std::exception& e) {
+        lastError = e.what();
+        return 1;
+    }
+}
+
 }  // extern "C"

@@ -88,6 +88,46 @@ def case_inv_power():
                 pos=pos, oob_k=[10000.0], inv_power=[4.0])
 
 
+def case_bspline_random_aniso():
+    """Cubic B-spline (interpolation method 1, ReferenceGridForceKernels.cpp:727-795) on the random_aniso inputs plus
+    atoms in the first/last cells of every axis (clamped stencil) and on the upper faces (index n-1, fraction 0)."""
+    c = case_random_aniso()
+    counts, sp, og = np.array(c["counts"]), np.array(c["spacing"]), np.array(c["origin"])
+    rng = np.random.default_rng(21)
+    pos = c["pos"]
+    length = sp * (counts - 1)
+    pos[100:130] = og + rng.uniform(0.0, 1.0, size=(30, 3)) * sp                      # first cells
+    pos[130:160] = og + length - rng.uniform(0.0, 1.0, size=(30, 3)) * sp             # last cells
+    pos[160:165, 0] = (og + length)[0]                                                 # upper faces
+    pos[165:170, 1] = (og + length)[1]
+    pos[170:175, 2] = (og + length)[2]
+    pos[175] = og + length
+    c["interp"] = 1
+    return c
+
+
+def case_bspline_ligand_three_grids():
+    c = case_ligand_three_grids()
+    c["interp"] = 1
+    return c
+
+
+def case_bspline_inv_power():
+    c = case_inv_power()
+    c["interp"] = 1
+    return c
+
+
+def case_bspline_thin_grid():
+    """Smallest legal grids (2 and 3 points on an axis): every stencil index is clamped."""
+    rng = np.random.default_rng(33)
+    counts, sp = (2, 3, 7), (0.2, 0.15, 0.1)
+    length = np.array(sp) * (np.array(counts) - 1)
+    pos = rng.uniform(-0.05, 1.05, size=(200, 3)) * length
+    return dict(counts=counts, spacing=sp, origin=(0.0, 0.0, 0.0), grids=[rng.normal(size=counts)],
+                scaling=rng.uniform(0.5, 1.5, size=(1, 200)), pos=pos, oob_k=[10000.0], inv_power=[0.0], interp=1)
+
+
 CASES = {
     "ones_grid": case_ones_grid,
     "ramp_grid": case_ramp_grid,
@@ -95,6 +135,10 @@ CASES = {
     "random_aniso": case_random_aniso,
     "ligand_three_grids": case_ligand_three_grids,
     "inv_power": case_inv_power,
+    "bspline_random_aniso": case_bspline_random_aniso,
+    "bspline_ligand_three_grids": case_bspline_ligand_three_grids,
+    "bspline_inv_power": case_bspline_inv_power,
+    "bspline_thin_grid": case_bspline_thin_grid,
 }
 
 
@@ -104,7 +148,7 @@ def load_golden(name):
     n_grids = int(z["n_grids"])
     inp = dict(counts=tuple(int(c) for c in z["counts"]), spacing=tuple(z["spacing"]), origin=tuple(z["origin"]),
                grids=[z[f"grid{g}"].astype(np.float64) for g in range(n_grids)], scaling=z["scaling"], pos=z["pos"],
-               oob_k=list(z["oob_k"]), inv_power=list(z["inv_power"]))
+               oob_k=list(z["oob_k"]), inv_power=list(z["inv_power"]), interp=int(z["interp"]) if "interp" in z else 0)
     out = dict(grid_energies=z["ref_grid_energies"], energy=float(z["ref_energy"]), forces=z["ref_forces"],
                grid_forces=z["ref_grid_forces"])
     return inp, out

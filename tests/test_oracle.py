@@ -18,7 +18,7 @@ GOLDEN = sorted(cases.CASES)
 
 def _port(bindings, c):
     return bindings.PortOracle(c["counts"], c["spacing"], c["origin"], c["grids"], c["scaling"], oob_k=c["oob_k"],
-                               inv_power=c["inv_power"])
+                               inv_power=c["inv_power"], interpolation_method=c.get("interp", 0))
 
 
 @pytest.mark.parametrize("name", GOLDEN)
@@ -144,3 +144,43 @@ def test_reference_contexts_on_threads(oracle_built):
     for o in oracles:
         o.close()
     print("stdout still works", flush=True)
+
+
+def test_port_bspline_matches_reference_build_random(oracle_built):
+    """Interpolation method 1 (cubic B-spline, :727-795) incl. atoms on the faces and in edge cells, bit for bit."""
+    if not oracle_built.ref_available():
+        pytest.skip("oracle/_ref not built; golden vectors bspline_* cover it")
+    rng = np.random.default_rng(7)
+    for trial in range(8):
+        counts = tuple(int(v) for v in rng.integers(2, 14, size=3))
+        sp = tuple(rng.uniform(0.01, 0.3, size=3))
+        og = tuple(rng.uniform(-2, 2, size=3))
+        n = int(rng.integers(2, 300))
+        grid = rng.normal(size=counts) * 10
+        length = np.array(sp) * (np.array(counts) - 1)
+        pos = np.array(og) + rng.uniform(-0.1, 1.1, size=(n, 3)) * length
+        pos[0] = np.array(og) + length
+        pos[1] = np.array(og)
+        sc = rng.normal(size=(1, n))
+        ref = oracle_built.RefOracle(n, counts, sp, og, [grid], sc, interpolation_method=1)
+        port = oracle_built.PortOracle(counts, sp, og, [grid], sc, interpolation_method=1)
+        er, fr = ref.execute(pos)
+        ep, fp, _ = port.execute(pos, 0)
+        assert er == ep and np.array_equal(fr, fp), trial
+        ref.close()
+
+
+def test_inv_power_transform_matches_reference(oracle_built):
+    """RUNTIME inv-power mode: the restatement of GridForce::applyInvPowerTransformation against the reference's own
+    method (where built) and against the committed fixture it produced."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inv_power_transform.npz"))
+    got = oracle_built.port_inv_power_transform(z["values"], float(z["inv_power"]))
+    assert np.array_equal(got, z["ref_transformed"])
+    assert int(z["mode_after"]) == 2        # STORED
+    if oracle_built.ref_available():
+        rng = np.random.default_rng(3)
+        v = rng.normal(size=(7, 5, 9)) * 10 ** rng.uniform(-3, 4, size=(7, 5, 9))
+        v[rng.integers(0, 7, 10), rng.integers(0, 5, 10), rng.integers(0, 9, 10)] = 0.0
+        for n in (2.0, 4.0, 3.5):
+            ref, mode = oracle_built.ref_inv_power_transform(v, n)
+            assert mode == 2 and np.array_equal(ref, oracle_built.port_inv_power_transform(v, n))

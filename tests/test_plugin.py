@@ -57,6 +57,7 @@ def _build_system(gfp, c, ligand_atoms=None):
         if c["inv_power"][g] > 0:
             force.setInvPowerMode(gfp.InvPowerMode_STORED, c["inv_power"][g])
         force.setOutOfBoundsRestraint(c["oob_k"][g])
+        force.setInterpolationMethod(c.get("interp", 0))
         force.setForceGroup(g)
         system.addForce(force)
         forces.append(force)
@@ -136,9 +137,46 @@ def test_plugin_refuses_what_it_does_not_implement():
     c, _ = cases.load_golden("ramp_grid")
     platform = gfp.Platform.getPlatformByName("B200")
     system, forces = _build_system(gfp, c)
-    forces[0].setInterpolationMethod(1)               # cubic B-spline: outside this path -> loud refusal, no fallback
-    with pytest.raises(RuntimeError, match="only trilinear"):
+    forces[0].setInterpolationMethod(2)               # tricubic needs derivative grids: loud refusal, no fallback
+    with pytest.raises(RuntimeError, match="not implemented on this platform"):
         gfp.Context(system, platform)
+
+
+@pytest.mark.gpu
+def test_plugin_runtime_inv_power_mode(oracle_built):
+    """RUNTIME mode through the GridForce API: applyInvPowerTransformation() stores G^(1/n) (on the GPU), flips the mode to
+    STORED, and the evaluation then recovers the untransformed field (python/gridforceplugin.i:181, GridForce.cpp:221-272)."""
+    import openmmgridforce_b200.gridforceplugin as gfp
+    c, _ = cases.load_golden("inv_power")
+    raw = c["grids"][0] ** 4                              # an untransformed, strictly positive field
+    force = gfp.GridForce()
+    force.addGridCounts(*c["counts"])
+    force.addGridSpacing(*c["spacing"])
+    force.setGridValues(raw)
+    with pytest.raises(RuntimeError, match="when mode == RUNTIME"):
+        force.applyInvPowerTransformation()
+    force.setInvPowerMode(gfp.InvPowerMode_RUNTIME, 4.0)
+    force.applyInvPowerTransformation()
+    assert force.getInvPowerMode() == gfp.InvPowerMode_STORED
+    want = oracle_built.port_inv_power_transform(raw, 4.0)
+    got = force.getGridValues().reshape(raw.shape)
+    assert np.abs(got - want).max() <= 1e-14 * np.abs(want).max()
+    for s in c["scaling"][0]:
+        force.addScalingFactor(s)
+    system = gfp.System()
+    for _ in range(c["pos"].shape[0]):
+        system.addParticle(1.0)
+    system.addForce(force)
+    platform = gfp.Platform.getPlatformByName("B200")
+    platform.setPropertyDefaultValue("Precision", "double")
+    ctx = gfp.Context(system, platform)
+    ctx.setPositions(c["pos"])
+    st = ctx.getState(getEnergy=True, getForces=True)
+    port = oracle_built.PortOracle(c["counts"], c["spacing"], c["origin"], [want], c["scaling"], inv_power=[4.0])
+    e, f, _ = port.execute(c["pos"], 0)
+    assert abs(st.getPotentialEnergy() - e) <= 1e-11 * abs(e)
+    assert np.abs(st.getForces() - f).max() <= 1e-11 * np.abs(f).max()
+    platform.setPropertyDefaultValue("Precision", "mixed")
 
 
 def test_plugin_has_no_cpu_fallback():
