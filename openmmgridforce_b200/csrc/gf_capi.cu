@@ -124,6 +124,9 @@ struct gfb_kernel {
     // host-path scratch
     DeviceBuffer d_pos, d_forces, d_energy, d_cls, d_sort;
     PinnedBuffer h_stage, h_energy;
+    // one-ligand-per-step path (execute_host_small): host-mapped staging the kernel reads and writes over PCIe
+    PinnedBuffer h_small;
+    bool unique_particles;   // no particle index occurs twice: a plain store per evaluated particle is the whole force
 };
 
 static bool is_pinned(const void* p) {
@@ -554,6 +557,7 @@ int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int 
     k->d_slots = nullptr;
     k->n_slots = 1;
     k->max_particle = n_atoms - 1;
+    k->unique_particles = true;
     for (int g = 0; g < n_grids; g++) {
         k->grids[g] = grids[g];
         k->inv_power[g] = inv_power ? inv_power[g] : 0.0;
@@ -574,6 +578,9 @@ int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int 
             }
             k->max_particle = std::max(k->max_particle, particles[i]);
         }
+        std::vector<int> sorted(particles, particles + n_atoms);
+        std::sort(sorted.begin(), sorted.end());
+        k->unique_particles = std::adjacent_find(sorted.begin(), sorted.end()) == sorted.end();
         err = cudaMalloc((void**) &k->d_particles, (size_t) n_atoms * sizeof(int));
         if (err == cudaSuccess)
             err = cudaMemcpy(k->d_particles, particles, (size_t) n_atoms * sizeof(int), cudaMemcpyHostToDevice);
@@ -641,6 +648,7 @@ int gfb_kernel_destroy(gfb_kernel* k) {
     k->d_sort.release();
     k->h_stage.release();
     k->h_energy.release();
+    k->h_small.release();
     delete k;
     return GFB_OK;
 }
@@ -795,9 +803,10 @@ static bool lines_eligible(const gfb_kernel* k, const EvalParams& p) {
 
 static int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos, double* d_energies,
                         double* d_grid_energies, void* d_forces, int force_mode, long long force_stride,
-                        const int* d_order, double* d_energies_clear, cudaStream_t stream) {
+                        const int* d_order, double* d_energies_clear, cudaStream_t stream, bool energy_store = false) {
     EvalParams p;
     memset(&p, 0, sizeof p);
+    p.energy_store = energy_store ? 1 : 0;
     for (int g = 0; g < k->n_grids; g++) fill_grid_view(k, g, p.grid[g]);
     p.n_grids = k->n_grids;
     p.n_atoms = k->n_atoms;
@@ -848,6 +857,62 @@ static int check_exec_args(const char* fn, gfb_kernel* k, int n_replicas, int n_
     return GFB_OK;
 }
 
+
+// Threads per block of the kernel enqueue_eval would launch for this state without an evaluation order.
+static int eval_block_threads(const gfb_kernel* k) {
+    EvalParams probe;
+    memset(&probe, 0, sizeof probe);
+    return lines_eligible(k, probe) ? lines_block(k->n_grids) : kBlock;
+}
+
+// One replica of at most a few thousand particles — a ligand evaluated once per MD step (BASELINE configs[1]; what
+// B200CalcGridForceKernel::execute issues). Such a call is pure latency, so instead of H2D copy -> kernel -> D2H copies
+// (6-7 driver calls, 3 trips through the copy engines) the kernel works on HOST-MAPPED pinned memory directly: it reads
+// the positions over PCIe, stores the forces over PCIe and — when one block covers the ligand — stores the energy too.
+// One launch + one synchronize per call. The caller's forces are combined on the host from the kernel's stores
+// (STORE: staged copy of the caller's array with the evaluated entries overwritten; ADD: caller's value + kernel's).
+static int execute_host_small(gfb_kernel* k, int n_particles, const double* pos, double* energies, double* grid_energies,
+                              double* forces, int force_mode) {
+    gfb_device* dev = k->dev;
+    const size_t np3 = (size_t) n_particles * 3;
+    const int ng = k->n_grids;
+    const size_t e_count = 1 + (size_t) ng;
+    const size_t e_off = (2 * np3 + 15) & ~(size_t) 15;                    // doubles: [pos | forces | pad | energies]
+    int rc = k->h_small.ensure((e_off + e_count) * sizeof(double));
+    if (rc != GFB_OK) return rc;
+    double* h_pos = static_cast<double*>(k->h_small.ptr);
+    double* h_f = h_pos + np3;
+    double* h_e = h_pos + e_off;
+    memcpy(h_pos, pos, np3 * sizeof(double));
+    if (forces) {
+        if (force_mode == GFB_FORCE_F64_ADD) memset(h_f, 0, np3 * sizeof(double));
+        else memcpy(h_f, forces, np3 * sizeof(double));
+    }
+    const bool one_block = k->n_atoms <= eval_block_threads(k) && !grid_energies;
+    double* d_e = nullptr;
+    if (!one_block) {   // several blocks (or per-grid energies): device accumulators, cleared here, fetched below
+        if ((rc = k->d_energy.ensure(e_count * sizeof(double))) != GFB_OK) return rc;
+        d_e = static_cast<double*>(k->d_energy.ptr);
+        CUDA_TRY(cudaMemsetAsync(d_e, 0, e_count * sizeof(double), dev->stream));
+    }
+    // cudaHostAlloc memory is mapped into the device's address space at the same address (unified addressing)
+    rc = enqueue_eval(k, 1, n_particles, h_pos, one_block ? h_e : d_e, (grid_energies && d_e) ? d_e + 1 : nullptr,
+                      forces ? h_f : nullptr, GFB_FORCE_F64_STORE, 0, nullptr, nullptr, dev->stream, one_block);
+    if (rc != GFB_OK) return rc;
+    if (!one_block) CUDA_TRY(cudaMemcpyAsync(h_e, d_e, e_count * sizeof(double), cudaMemcpyDeviceToHost, dev->stream));
+    CUDA_TRY(cudaStreamSynchronize(dev->stream));
+    if (energies) energies[0] = h_e[0];
+    if (grid_energies) memcpy(grid_energies, h_e + 1, ng * sizeof(double));
+    if (forces) {
+        if (force_mode == GFB_FORCE_F64_ADD) {
+            for (size_t i = 0; i < np3; i++) forces[i] += h_f[i];
+        } else {
+            memcpy(forces, h_f, np3 * sizeof(double));
+        }
+    }
+    return GFB_OK;
+}
+
 extern "C" {
 
 int gfb_kernel_eval_path(const gfb_kernel* k) {
@@ -884,6 +949,13 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
     gfb_device* dev = k->dev;
     std::lock_guard<std::mutex> host_lock(dev->host_mutex);   // several Contexts/threads may drive one GPU
     CUDA_TRY(cudaSetDevice(dev->ordinal));
+
+    static const bool small_off = [] {
+        const char* e = getenv("GFB_SMALL_PATH");   // 0: always take the copy pipeline (A/B measurements)
+        return e && e[0] == '0';
+    }();
+    if (!small_off && n_replicas == 1 && k->d_slots == nullptr && k->unique_particles && n_particles <= 4096 && k->n_atoms > 0)
+        return execute_host_small(k, n_particles, pos, energies, grid_energies, forces, force_mode);
 
     const size_t np = (size_t) n_replicas * n_particles;
     const size_t pos_bytes = np * 3 * sizeof(double);

@@ -368,7 +368,10 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 10) gf_eval_lin
                 double b = tid < kBlock / 32 ? warp_sum[tid] : 0.0;
 #pragma unroll
                 for (int off = kBlock / 64; off > 0; off >>= 1) b += __shfl_xor_sync(kFull, b, off);
-                if (tid == 0) red_add_f64(p.energies, b);
+                if (tid == 0) {
+                    if (p.energy_store) *p.energies = b;
+                    else red_add_f64(p.energies, b);
+                }
             }
         }
     } else if (p.energies || GE) {

@@ -592,7 +592,10 @@ __global__ void __launch_bounds__(kBlock, eval_min_blocks<S, LAYOUT, NG>()) gf_e
                 double b = threadIdx.x < kBlock / 32 ? warp_sum[threadIdx.x] : 0.0;
 #pragma unroll
                 for (int off = kBlock / 64; off > 0; off >>= 1) b += __shfl_xor_sync(kFull, b, off);
-                if (threadIdx.x == 0) red_add_f64(p.energies, b);
+                if (threadIdx.x == 0) {
+                    if (p.energy_store) *p.energies = b;
+                    else red_add_f64(p.energies, b);
+                }
             }
         } else {
             run_sum(e_total, span);

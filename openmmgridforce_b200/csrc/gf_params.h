@@ -40,7 +40,8 @@ struct EvalParams {
     const int* order;        // [total] or null
     const int* slots;        // [n_atoms] energy slot of each atom inside a replica (particle groups), or null
     int n_slots;             // energy slots per replica (1 without groups)
-    int pad2_;
+    int energy_store;        // single replica, single block: the block's energy is STORED to *energies (which may then be
+                             // host-mapped memory) instead of accumulated with an atomic
     double* energies;        // [n_replicas] or null, accumulated
     double* grid_energies;   // [n_replicas][n_grids] or null, accumulated
     double* energies_clear;  // [n_replicas] or null: zero-filled by this launch (next step's accumulator)
