@@ -803,16 +803,23 @@ static bool lines_eligible(const gfb_kernel* k, const EvalParams& p) {
 
 static int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos, double* d_energies,
                         double* d_grid_energies, void* d_forces, int force_mode, long long force_stride,
-                        const int* d_order, double* d_energies_clear, cudaStream_t stream, bool energy_store = false) {
+                        const int* d_order, double* d_energies_clear, cudaStream_t stream, bool energy_store = false,
+                        int atom_begin = 0, int atom_count = -1) {
+    // atom_begin/atom_count: evaluate only atoms [atom_begin, atom_begin + atom_count) of a state without particle
+    // indirection (the host path cuts one large replica into atom ranges); d_pos/d_forces then point at the range.
+    const int n_atoms = atom_count >= 0 ? atom_count : k->n_atoms;
     EvalParams p;
     memset(&p, 0, sizeof p);
     p.energy_store = energy_store ? 1 : 0;
-    for (int g = 0; g < k->n_grids; g++) fill_grid_view(k, g, p.grid[g]);
+    for (int g = 0; g < k->n_grids; g++) {
+        fill_grid_view(k, g, p.grid[g]);
+        p.grid[g].scaling += atom_begin;
+    }
     p.n_grids = k->n_grids;
-    p.n_atoms = k->n_atoms;
+    p.n_atoms = n_atoms;
     p.n_particles = n_particles;
     p.n_replicas = n_replicas;
-    p.total = (long long) n_replicas * k->n_atoms;
+    p.total = (long long) n_replicas * n_atoms;
     p.pos = d_pos;
     p.particles = k->d_particles;
     p.order = d_order;
@@ -826,7 +833,7 @@ static int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const do
     if (p.total == 0) return GFB_OK;
     if (lines_eligible(k, p)) {
         p.lines = k->d_interleaved;
-        p.div_magic = (unsigned) std::min<unsigned long long>(0x100000000ull / (unsigned long long) k->n_atoms, 0xffffffffull);
+        p.div_magic = (unsigned) std::min<unsigned long long>(0x100000000ull / (unsigned long long) n_atoms, 0xffffffffull);
         for (int a = 0; a < 3; a++) p.near_int[a] = 1.8e-15 * (double) std::max(1, p.grid[0].nc[a]);
         const int fpath = force_path_default(k->n_grids);
         switch (k->n_grids) {
@@ -985,11 +992,15 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
     // copy_stream. Uploads never wait for kernels, downloads overlap the next uploads (PCIe is full duplex: measured
     // 55 GB/s one way, 45-49 GB/s each way when both run). ~9 MB of positions per chunk, at most 16 chunks: each
     // chunk costs ~15 us of copy/event overhead (4/8/16/32/64 chunks of C5's 74 MB: 2.02/1.99/2.10/2.43/2.80 ms).
+    // What a chunk is made of: replicas, or — one large replica without particle indirection (C3: 1 M atoms) — atoms.
+    const bool by_atoms = n_replicas == 1 && !k->d_particles && !k->d_slots && k->n_atoms == n_particles;
+    const int n_units = by_atoms ? n_particles : n_replicas;
+    const size_t unit_doubles = by_atoms ? 3 : (size_t) n_particles * 3;
     int n_chunks = 1;
-    if (n_replicas > 1) {
+    if (n_units > 1) {
         const char* env = getenv("GFB_HOST_CHUNKS");
         n_chunks = env ? atoi(env) : (int) std::min<size_t>(16, std::max<size_t>(1, pos_bytes / (9u << 20)));
-        n_chunks = std::max(1, std::min(n_chunks, n_replicas));
+        n_chunks = std::max(1, std::min(n_chunks, n_units));
     }
     while ((int) dev->events.size() < 2 * n_chunks) {
         cudaEvent_t ev;
@@ -1003,10 +1014,14 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
 
     int status = GFB_OK;
     for (int c = 0; c < n_chunks && status == GFB_OK; c++) {
-        const int r0 = (int) ((long long) n_replicas * c / n_chunks);
-        const int r1 = (int) ((long long) n_replicas * (c + 1) / n_chunks);
-        const size_t off = (size_t) r0 * n_particles * 3;            // doubles
-        const size_t cnt = (size_t) (r1 - r0) * n_particles * 3;
+        int r0 = (int) ((long long) n_units * c / n_chunks);         // first unit (replica or atom) of the chunk
+        int r1 = (int) ((long long) n_units * (c + 1) / n_chunks);
+        if (by_atoms) {   // whole warps per range: keeps every range's positions 16-byte aligned (warp-staged loads)
+            r0 &= ~31;
+            if (c + 1 < n_chunks) r1 &= ~31;
+        }
+        const size_t off = (size_t) r0 * unit_doubles;               // doubles
+        const size_t cnt = (size_t) (r1 - r0) * unit_doubles;
         const double* src = pos + off;
         if (!pos_pinned) {
             memcpy(stage_pos + off * sizeof(double), src, cnt * sizeof(double));
@@ -1034,9 +1049,13 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
             status = fail(GFB_ERR_CUDA, "gfb_kernel_execute_host: H2D: %s", cudaGetErrorString(err));
             break;
         }
-        status = enqueue_eval(k, r1 - r0, n_particles, d_pos + off, d_e + (size_t) r0 * k->n_slots,
-                              grid_energies ? d_ge + (size_t) r0 * k->n_slots * ng : nullptr,
-                              d_f ? d_f + off : nullptr, force_mode, 0, nullptr, nullptr, dev->stream);
+        if (by_atoms)   // every range accumulates into the one replica's energy entries
+            status = enqueue_eval(k, 1, r1 - r0, d_pos + off, d_e, grid_energies ? d_ge : nullptr, d_f ? d_f + off : nullptr,
+                                  force_mode, 0, nullptr, nullptr, dev->stream, false, r0, r1 - r0);
+        else
+            status = enqueue_eval(k, r1 - r0, n_particles, d_pos + off, d_e + (size_t) r0 * k->n_slots,
+                                  grid_energies ? d_ge + (size_t) r0 * k->n_slots * ng : nullptr,
+                                  d_f ? d_f + off : nullptr, force_mode, 0, nullptr, nullptr, dev->stream);
         if (status != GFB_OK) break;
         err = cudaSuccess;
         if (forces) {

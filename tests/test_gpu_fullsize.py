@@ -109,3 +109,32 @@ def test_c5_shard_properties(gpu_device):
     assert np.allclose(np.concatenate([en_a, en_b]), en, rtol=1e-12, atol=1e-9)
     k.close()
     grid.close()
+
+
+@pytest.mark.parametrize("precision", [0, 1], ids=["mixed", "double"])
+def test_single_replica_atom_range_chunks(gpu_device, oracle_built, precision, monkeypatch):
+    """One large replica goes through the host pipeline in ATOM ranges (C3's e2e path). Forced to 7 uneven chunks here:
+    energies of all ranges accumulate into the one replica entry, per-grid energies too, ADD keeps the caller's forces."""
+    import openmmgridforce_b200 as gf
+    rng = np.random.default_rng(12)
+    counts, sp, og = (40, 36, 44), (0.05, 0.06, 0.045), (-0.3, 0.2, 1.0)
+    n = 100_003
+    grids = [(rng.normal(size=counts) * 4).astype(np.float32).astype(np.float64) for _ in range(2)]
+    length = np.array(sp) * (np.array(counts) - 1)
+    pos = np.array(og) + rng.uniform(-0.02, 1.02, size=(n, 3)) * length
+    sc = rng.uniform(0.5, 1.5, size=(2, n))
+    port = oracle_built.PortOracle(counts, sp, og, grids, sc)
+    ge_ref, f_ref = port.execute_batched(pos[None], n_threads=4)
+    monkeypatch.setenv("GFB_HOST_CHUNKS", "7")
+    gs = [gf.Grid(gpu_device, counts, sp, og, g, precision) for g in grids]
+    k = gf.Kernel(gpu_device, gs, sc)
+    base = rng.normal(size=(1, n, 3))
+    forces = base.copy()
+    en, _, ge = k.execute_host(pos, forces=forces, force_mode=gf.FORCE_F64_ADD, want_grid_energies=True)
+    te, tf = ((1e-6, 1e-5), (1e-12, 1e-12))[precision]
+    assert np.abs(ge[0] - ge_ref[0]).max() <= te * np.abs(ge_ref).max()
+    assert abs(en[0] - ge_ref.sum()) <= te * abs(ge_ref.sum())
+    assert _rel(forces - base, f_ref) <= tf + 1e-15
+    k.close()
+    for g in gs:
+        g.close()
