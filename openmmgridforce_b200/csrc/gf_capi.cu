@@ -969,8 +969,23 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
     const int ng = k->n_grids;
     const size_t n_e = (size_t) n_replicas * k->n_slots;          // energy entries: [replica][slot]
     const size_t e_count = n_e * (1 + ng);
+    // Forces straight into host memory: when every particle is an evaluated atom (no indirection), the mode is STORE
+    // and the lines kernel runs, its warps emit their forces as full contiguous 768-byte runs (16-byte stores), which
+    // the GPU writes over PCIe at copy-engine speed (51 GB/s measured) — so the D2H copies and the device force buffer
+    // drop out of the pipeline, and the downloads overlap the uploads inside the kernels themselves. C5 (74 MB each
+    // way): 2.11 -> 1.86 ms per step; the two directions together top out at ~80 GB/s on this box.
+    static const bool zc_off = [] {
+        const char* e = getenv("GFB_ZEROCOPY_FORCES");   // 0: always download with the copy engine (A/B measurements)
+        return e && e[0] == '0';
+    }();
+    bool zc_forces = false;
+    if (forces && force_mode == GFB_FORCE_F64_STORE && !zc_off && !k->d_particles && k->n_atoms == n_particles) {
+        EvalParams probe;
+        memset(&probe, 0, sizeof probe);
+        zc_forces = lines_eligible(k, probe);
+    }
     if ((rc = k->d_pos.ensure(pos_bytes)) != GFB_OK) return rc;
-    if (forces && (rc = k->d_forces.ensure(pos_bytes)) != GFB_OK) return rc;
+    if (forces && !zc_forces && (rc = k->d_forces.ensure(pos_bytes)) != GFB_OK) return rc;
     if ((rc = k->d_energy.ensure(e_count * sizeof(double))) != GFB_OK) return rc;
     if ((rc = k->h_energy.ensure(e_count * sizeof(double))) != GFB_OK) return rc;
 
@@ -983,14 +998,16 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
     char* stage_f = stage_pos + (pos_pinned ? 0 : pos_bytes);
 
     double* d_pos = static_cast<double*>(k->d_pos.ptr);
-    double* d_f = forces ? static_cast<double*>(k->d_forces.ptr) : nullptr;
+    // where the kernels write forces: the device buffer, or (zero-copy) the pinned host destination itself
+    double* d_f = nullptr;
+    if (forces) d_f = !zc_forces ? static_cast<double*>(k->d_forces.ptr) : (f_pinned ? forces : reinterpret_cast<double*>(stage_f));
     double* d_e = static_cast<double*>(k->d_energy.ptr);
     double* d_ge = d_e + n_e;
     CUDA_TRY(cudaMemsetAsync(d_e, 0, e_count * sizeof(double), dev->stream));
 
     // Chunk pipeline over three streams: H2D(c) on h2d_stream -> [up c] -> kernel(c) on stream -> [done c] -> D2H(c) on
     // copy_stream. Uploads never wait for kernels, downloads overlap the next uploads (PCIe is full duplex: measured
-    // 55 GB/s one way, 45-49 GB/s each way when both run). ~9 MB of positions per chunk, at most 16 chunks: each
+    // 55 GB/s one way, 45-49 GB/s each way when both run). >= 2 MB of positions per chunk, at most 8 chunks: each
     // chunk costs ~15 us of copy/event overhead (4/8/16/32/64 chunks of C5's 74 MB: 2.02/1.99/2.10/2.43/2.80 ms).
     // What a chunk is made of: replicas, or — one large replica without particle indirection (C3: 1 M atoms) — atoms.
     const bool by_atoms = n_replicas == 1 && !k->d_particles && !k->d_slots && k->n_atoms == n_particles;
@@ -999,7 +1016,7 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
     int n_chunks = 1;
     if (n_units > 1) {
         const char* env = getenv("GFB_HOST_CHUNKS");
-        n_chunks = env ? atoi(env) : (int) std::min<size_t>(16, std::max<size_t>(1, pos_bytes / (9u << 20)));
+        n_chunks = env ? atoi(env) : (int) std::min<size_t>(8, std::max<size_t>(1, pos_bytes / (2u << 20)));
         n_chunks = std::max(1, std::min(n_chunks, n_units));
     }
     while ((int) dev->events.size() < 2 * n_chunks) {
@@ -1019,6 +1036,9 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
         if (by_atoms) {   // whole warps per range: keeps every range's positions 16-byte aligned (warp-staged loads)
             r0 &= ~31;
             if (c + 1 < n_chunks) r1 &= ~31;
+        } else if (n_units >= 2 * n_chunks) {   // even replica boundaries: an odd particle count leaves odd replicas 8 mod 16
+            r0 &= ~1;
+            if (c + 1 < n_chunks) r1 &= ~1;
         }
         const size_t off = (size_t) r0 * unit_doubles;               // doubles
         const size_t cnt = (size_t) (r1 - r0) * unit_doubles;
@@ -1058,7 +1078,7 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
                                   d_f ? d_f + off : nullptr, force_mode, 0, nullptr, nullptr, dev->stream);
         if (status != GFB_OK) break;
         err = cudaSuccess;
-        if (forces) {
+        if (forces && !zc_forces) {
             if (n_chunks > 1) {
                 err = cudaEventRecord(done[c], dev->stream);
                 if (err == cudaSuccess) err = cudaStreamWaitEvent(dev->copy_stream, done[c], 0);

@@ -325,6 +325,24 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 10) gf_eval_lin
     }
 
     // ---- forces --------------------------------------------------------------------------------------------------------
+    // F64_STORE without indirection: a full warp's 32 forces are 768 contiguous bytes. They go through the warp's smem
+    // slice and leave as 48 coalesced 16-byte stores (the mirror image of the position staging) instead of 96 scalar
+    // stores at stride 24 — which matters most when `forces` is host-mapped memory (PCIe write TLPs of 128 bytes
+    // instead of 8): gfb_kernel_execute_host's zero-copy path.
+    const bool stage_f = FMODE == GFB_FORCE_F64_STORE && p.forces != nullptr && plain && (t - lane) + 32u <= total &&
+                         (reinterpret_cast<uintptr_t>(p.forces) & 15) == 0;   // warp-uniform
+    if (stage_f) {
+        double* const s_f = reinterpret_cast<double*>(s_pos2 + (tid >> 5) * kWarpSlice16);
+        __syncwarp();   // every lane has consumed its record from this slice
+        s_f[3 * lane] = (double) Fx;
+        s_f[3 * lane + 1] = (double) Fy;
+        s_f[3 * lane + 2] = (double) Fz;
+        __syncwarp();
+        const double2* const s_f2 = reinterpret_cast<const double2*>(s_f);
+        double2* const dst = reinterpret_cast<double2*>(static_cast<double*>(p.forces) + 3 * (size_t) (t - lane));
+        dst[lane] = s_f2[lane];
+        if (lane < 16) dst[32 + lane] = s_f2[32 + lane];
+    }
     if (active && p.forces) {
         if (FMODE == GFB_FORCE_FIXED_ADD) {   // OpenMM's 2^32 fixed point, gridForce.cu:487-499
             const unsigned long long ax = (unsigned long long) __float2ll_rz(Fx * 4294967296.f);
@@ -336,9 +354,11 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 10) gf_eval_lin
         } else {
             double* f = fdbl + 3 * (size_t) gidx;
             if (FMODE == GFB_FORCE_F64_STORE) {
-                f[0] = (double) Fx;
-                f[1] = (double) Fy;
-                f[2] = (double) Fz;
+                if (!stage_f) {
+                    f[0] = (double) Fx;
+                    f[1] = (double) Fy;
+                    f[2] = (double) Fz;
+                }
             } else {
                 red_add_f64(f, (double) Fx);
                 red_add_f64(f + 1, (double) Fy);
