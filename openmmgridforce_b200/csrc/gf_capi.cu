@@ -17,6 +17,7 @@
 #include "gf_gridfile.h"
 #include "gf_kernels.cuh"
 #include "gf_eval_lines.cuh"
+#include "gf_eval_bspline.cuh"
 #include "gridforce_b200.h"
 
 using namespace gfb;
@@ -801,6 +802,30 @@ static bool lines_eligible(const gfb_kernel* k, const EvalParams& p) {
     return true;
 }
 
+// gf_eval_bspline_kernel (gf_eval_bspline.cuh): MIXED B-spline tiles of one geometry, no evaluation order.
+static bool bspline_tiles_eligible(const gfb_kernel* k, const EvalParams& p) {
+    static const bool off = [] {
+        const char* e = getenv("GFB_BSPLINE_TILES");   // 0: always the general kernel (A/B measurements)
+        return e && e[0] == '0';
+    }();
+    if (off || k->precision != GFB_PRECISION_MIXED || k->grids[0]->layout != GFB_LAYOUT_BSPLINE || !k->same_geom) return false;
+    if (p.order != nullptr) return false;
+    return k->grids[0]->bytes / 128 < 0x7fffffffull;
+}
+
+template <int FMODE>
+static void launch_bspline2(const EvalParams& p, cudaStream_t stream) {
+    const unsigned blocks = (unsigned) ((p.total + kBsBlock - 1) / kBsBlock);
+    if (p.n_replicas == 1 && p.slots == nullptr) gf_eval_bspline_kernel<FMODE, true><<<blocks, kBsBlock, 0, stream>>>(p);
+    else gf_eval_bspline_kernel<FMODE, false><<<blocks, kBsBlock, 0, stream>>>(p);
+}
+
+static void launch_bspline(const EvalParams& p, int fmode, cudaStream_t stream) {
+    if (fmode == GFB_FORCE_FIXED_ADD) launch_bspline2<GFB_FORCE_FIXED_ADD>(p, stream);
+    else if (fmode == GFB_FORCE_F64_ADD) launch_bspline2<GFB_FORCE_F64_ADD>(p, stream);
+    else launch_bspline2<GFB_FORCE_F64_STORE>(p, stream);
+}
+
 static int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos, double* d_energies,
                         double* d_grid_energies, void* d_forces, int force_mode, long long force_stride,
                         const int* d_order, double* d_energies_clear, cudaStream_t stream, bool energy_store = false,
@@ -831,10 +856,12 @@ static int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const do
     p.forces = d_forces;
     p.force_stride = force_stride;
     if (p.total == 0) return GFB_OK;
-    if (lines_eligible(k, p)) {
+    p.div_magic = (unsigned) std::min<unsigned long long>(0x100000000ull / (unsigned long long) n_atoms, 0xffffffffull);
+    for (int a = 0; a < 3; a++) p.near_int[a] = 1.8e-15 * (double) std::max(1, p.grid[0].nc[a]);
+    if (bspline_tiles_eligible(k, p)) {
+        launch_bspline(p, force_mode, stream);
+    } else if (lines_eligible(k, p)) {
         p.lines = k->d_interleaved;
-        p.div_magic = (unsigned) std::min<unsigned long long>(0x100000000ull / (unsigned long long) n_atoms, 0xffffffffull);
-        for (int a = 0; a < 3; a++) p.near_int[a] = 1.8e-15 * (double) std::max(1, p.grid[0].nc[a]);
         const int fpath = force_path_default(k->n_grids);
         switch (k->n_grids) {
             case 1: launch_lines2<1>(p, force_mode, fpath, stream); break;
@@ -869,6 +896,7 @@ static int check_exec_args(const char* fn, gfb_kernel* k, int n_replicas, int n_
 static int eval_block_threads(const gfb_kernel* k) {
     EvalParams probe;
     memset(&probe, 0, sizeof probe);
+    if (bspline_tiles_eligible(k, probe)) return kBsBlock;
     return lines_eligible(k, probe) ? lines_block(k->n_grids) : kBlock;
 }
 
