@@ -45,6 +45,10 @@ def _lib():
         lib.b200_plugin_add_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
                                              C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
         lib.b200_plugin_apply_inv_power.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_double, C.c_void_p]
+        lib.b200_plugin_add_nonbonded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.b200_plugin_set_auto.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_double, C.c_void_p, C.c_int,
+                                             C.c_void_p, C.c_int]
+        lib.b200_plugin_get_force_data.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]
         lib.b200_plugin_add_particle_group.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.b200_plugin_finalize.argtypes = [C.c_void_p, C.c_char_p]
         lib.b200_plugin_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -94,6 +98,9 @@ class GridForce:
         self._oob_k, self._interp, self._group = 10000.0, 0, 0
         self._ligand_atoms, self._groups = [], []
         self._context, self._index = None, None
+        self._auto_scaling, self._scaling_property = False, ""
+        self._auto_generate, self._grid_type, self._grid_cap = False, "", 41840.0
+        self._receptor_atoms, self._receptor_positions = [], np.zeros((0, 3))
 
     def addGridCounts(self, nx, ny, nz):
         self._counts += [int(nx), int(ny), int(nz)]
@@ -151,6 +158,8 @@ class GridForce:
         return self._inv_power_mode
 
     def getGridValues(self):
+        if self._context is not None and self._auto_generate and len(self._vals) == 0:
+            self._vals = self._pull(0)          # the kernel copies a generated grid back into the force
         return np.asarray(self._vals, dtype=np.float64)
 
     def applyInvPowerTransformation(self):
@@ -171,6 +180,45 @@ class GridForce:
         if method < 0 or method > 3:
             raise RuntimeError("GridForce: Invalid interpolation method. Must be 0 (trilinear), 1 (cubic B-spline), 2 (tricubic), or 3 (quintic Hermite)")
         self._interp = int(method)
+
+    # ---- inputs derived from the System's NonbondedForce at Context creation (reference GridForce.h:171-198, 335-342,
+    #      523-573); the grid is generated on the GPU ------------------------------------------------------------------
+    def setAutoCalculateScalingFactors(self, enable):
+        self._auto_scaling = bool(enable)
+
+    def setScalingProperty(self, prop):
+        self._scaling_property = str(prop)
+
+    def setAutoGenerateGrid(self, enable):
+        self._auto_generate = bool(enable)
+
+    def setGridType(self, grid_type):
+        self._grid_type = str(grid_type)
+
+    def setGridCap(self, u_max):
+        self._grid_cap = float(u_max)
+
+    def setReceptorAtoms(self, atoms):
+        self._receptor_atoms = [int(a) for a in atoms]
+
+    def setReceptorPositions(self, positions):
+        self._receptor_positions = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
+
+    def setReceptorPositionsFromLists(self, x, y, z):
+        if not (len(x) == len(y) == len(z)):
+            raise RuntimeError("GridForce: x, y, z arrays must have the same size")
+        self.setReceptorPositions(np.stack([x, y, z], axis=1))
+
+    def _pull(self, which):
+        """Grid values / scaling factors as the kernel left them in the C++ force (generated or auto-calculated)."""
+        n = C.c_longlong(0)
+        _check(_lib().b200_plugin_get_force_data(self._context._h, self._index, which, None, 0, C.byref(n)))
+        out = np.zeros(n.value)
+        _check(_lib().b200_plugin_get_force_data(self._context._h, self._index, which, _p(out), out.size, C.byref(n)))
+        return out
+
+    def getScalingFactors(self):
+        return self._pull(1) if self._context is not None else np.asarray(self._scaling, dtype=np.float64)
 
     def setLigandAtoms(self, atoms):
         self._ligand_atoms = [int(a) for a in atoms]
@@ -197,6 +245,20 @@ class GridForce:
     def updateParametersInContext(self, context):
         sc = np.ascontiguousarray(self._scaling, dtype=np.float64)
         _check(_lib().b200_plugin_update_scaling(context._h, self._index, _p(sc), sc.size))
+
+
+class NonbondedForce:
+    """Parameter container (charge e, sigma nm, epsilon kJ/mol per particle): what the auto-derived GridForce inputs read."""
+
+    def __init__(self):
+        self._params = []
+
+    def addParticle(self, charge, sigma, epsilon):
+        self._params.append((float(charge), float(sigma), float(epsilon)))
+        return len(self._params) - 1
+
+    def getNumParticles(self):
+        return len(self._params)
 
 
 class System:
@@ -237,7 +299,12 @@ class Context:
         self._n = system.getNumParticles()
         self._h = C.c_void_p(lib.b200_plugin_create(self._n))
         self._pos = None
-        for index, f in enumerate(system._forces):
+        grid_forces = [f for f in system._forces if isinstance(f, GridForce)]
+        for nb in (f for f in system._forces if isinstance(f, NonbondedForce)):
+            prm = np.ascontiguousarray(nb._params, dtype=np.float64).reshape(-1, 3)
+            q, sg, ep = (np.ascontiguousarray(prm[:, k]) for k in range(3))
+            _check(lib.b200_plugin_add_nonbonded(self._h, _p(q), _p(sg), _p(ep), prm.shape[0]))
+        for index, f in enumerate(grid_forces):
             counts = np.asarray(f._counts, dtype=np.int32)
             spacing = np.asarray(f._spacing, dtype=np.float64)
             if counts.size != 3 or spacing.size != 3:
@@ -248,6 +315,12 @@ class Context:
             og = np.asarray(f._origin, dtype=np.float64)
             _check(lib.b200_plugin_add_grid(self._h, _p(counts), _p(spacing), _p(og), _p(vals), vals.size, _p(sc), sc.size, _p(la),
                                             0 if la is None else la.size, f._inv_power, f._oob_k, f._interp, f._group))
+            if f._auto_scaling or f._auto_generate:
+                ra = np.ascontiguousarray(f._receptor_atoms, dtype=np.int32) if f._receptor_atoms else None
+                rp = np.ascontiguousarray(f._receptor_positions, dtype=np.float64)
+                _check(lib.b200_plugin_set_auto(self._h, index, int(f._auto_scaling), f._scaling_property.encode(),
+                                                int(f._auto_generate), f._grid_type.encode(), f._grid_cap, _p(ra),
+                                                0 if ra is None else ra.size, _p(rp), rp.shape[0]))
             for name, idx, scl in f._groups:
                 ia = np.ascontiguousarray(idx, dtype=np.int32)
                 sa = np.ascontiguousarray(scl, dtype=np.float64) if scl else None

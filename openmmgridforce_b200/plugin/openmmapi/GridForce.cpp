@@ -76,6 +76,14 @@ void GridForce::saveToFile(const std::string& filename) const {
     if (gfb_gridfile_write(filename.c_str(), &h, m_vals.data(), m_vals.size(), 0) != GFB_OK) throw OpenMMException(gfb_last_error());
 }
 
+void GridForce::setReceptorPositionsFromArrays(const std::vector<double>& x, const std::vector<double>& y,
+                                               const std::vector<double>& z) {
+    if (x.size() != y.size() || y.size() != z.size()) throw OpenMMException("GridForce: x, y, z arrays must have the same size");
+    m_receptorPositions.clear();
+    m_receptorPositions.reserve(x.size());
+    for (size_t i = 0; i < x.size(); i++) m_receptorPositions.push_back(OpenMM::Vec3(x[i], y[i], z[i]));
+}
+
 void GridForce::addScalingFactor(double val) { m_scaling.push_back(val); }
 void GridForce::setScalingFactor(int index, double val) {
     if (index < 0 || index >= (int) m_scaling.size()) throw OpenMMException("GridForce: scaling factor index out of range");

@@ -3,7 +3,7 @@
 // (a) a script written against the reference API runs unchanged for this path, and
 // (b) platform/B200GridForceKernels.cpp compiles against either this header or the reference's own.
 // Members of the reference API that feed other subsystems (GridData/CachedGridData sharing, tiled streaming,
-// receptor-based auto-generation, derivative grids, file I/O) are declared only as far as the kernel must be
+// derivative grids) are declared only as far as the kernel must be
 // able to ask "is this on?" and refuse; they are out of scope of this repository.
 #ifndef B200_GRIDFORCE_H_
 #define B200_GRIDFORCE_H_
@@ -83,9 +83,21 @@ public:
     std::vector<double> getParticleGroupEnergies(OpenMM::Context& context) const;
     std::vector<double> getParticleAtomEnergies(OpenMM::Context& context) const;
 
+    // ---- derive inputs from the System's NonbondedForce at Context creation (reference GridForce.h:171-198, 335-342,
+    //      523-573; ReferenceGridForceKernels.cpp:163-278). The grid is generated on the GPU (gfb_grid_generate). -----
+    void setAutoCalculateScalingFactors(bool enable) { m_autoScaling = enable; }
+    bool getAutoCalculateScalingFactors() const { return m_autoScaling; }
+    void setScalingProperty(const std::string& property) { m_scalingProperty = property; }   // validated by the kernel
+    const std::string& getScalingProperty() const { return m_scalingProperty; }
+    void setAutoGenerateGrid(bool enable) { m_autoGenerate = enable; }
+    bool getAutoGenerateGrid() const { return m_autoGenerate; }
+    void setReceptorAtoms(const std::vector<int>& atomIndices) { m_receptorAtoms = atomIndices; }
+    const std::vector<int>& getReceptorAtoms() const { return m_receptorAtoms; }
+    void setReceptorPositions(const std::vector<OpenMM::Vec3>& positions) { m_receptorPositions = positions; }
+    void setReceptorPositionsFromArrays(const std::vector<double>& x, const std::vector<double>& y, const std::vector<double>& z);
+    const std::vector<OpenMM::Vec3>& getReceptorPositions() const { return m_receptorPositions; }
+
     // ---- switches of subsystems outside this path: always off here; the kernel checks them -------------------------
-    bool getAutoCalculateScalingFactors() const { return false; }
-    bool getAutoGenerateGrid() const { return false; }
     bool getTiledMode() const { return false; }
     bool hasDerivatives() const { return false; }
 
@@ -109,7 +121,10 @@ private:
     InvPowerMode m_invPowerMode;
     int m_interpolation;
     const void* m_systemPtr;
-    std::string m_gridType;
+    std::string m_gridType, m_scalingProperty;
+    bool m_autoScaling = false, m_autoGenerate = false;
+    std::vector<int> m_receptorAtoms;
+    std::vector<OpenMM::Vec3> m_receptorPositions;
 };
 
 }  // namespace GridForcePlugin

@@ -1,11 +1,14 @@
 #include "B200GridForceKernels.h"
 
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <sstream>
 
 #include "B200Platform.h"
+#include "openmm/NonbondedForce.h"
 #include "openmm/OpenMMException.h"
 #include "openmm/internal/ContextImpl.h"
 
@@ -92,20 +95,74 @@ void B200CalcGridForceKernel::build(const GridForce& force) {
     force.getGridParameters(counts, spacing, vals, scaling);
     const int layout = b200LayoutForMethod(force.getInterpolationMethod(), "GridForce[B200]");
     if (force.getTiledMode()) throw OpenMMException("GridForce[B200]: tiled grids are not supported on this platform");
-    if (force.getAutoGenerateGrid() && vals.empty())
-        throw OpenMMException("GridForce[B200]: grid auto-generation is not supported on this platform; generate the grid first");
-    if (force.getAutoCalculateScalingFactors() && scaling.empty())
-        throw OpenMMException("GridForce[B200]: automatic scaling factors are not supported on this platform; pass them explicitly");
+    double origin[3];
+    force.getGridOrigin(origin[0], origin[1], origin[2]);
+    const double invPower = force.getInvPower(), oobK = force.getOutOfBoundsRestraint();
+    dev = b200Device(deviceIndex);
+
+    const NonbondedForce* nonbonded = 0;
+    if (system)
+        for (int i = 0; i < system->getNumForces() && !nonbonded; i++)
+            nonbonded = dynamic_cast<const NonbondedForce*>(&system->getForce(i));
+
+    // Scaling factors from the NonbondedForce (ReferenceGridForceKernels.cpp:163-209; the Reference platform's formulas,
+    // SURVEY.md quirk Q9), written back to the force as the reference does (:209).
+    if (force.getAutoCalculateScalingFactors() && scaling.empty()) {
+        const std::string prop = force.getScalingProperty();
+        if (prop.empty()) throw OpenMMException("GridForce: Auto-calculate scaling factors enabled but no scaling property specified");
+        if (prop != "charge" && prop != "ljr" && prop != "lja")
+            throw OpenMMException("GridForce: Invalid scaling property '" + prop + "'. Must be 'charge', 'ljr', or 'lja'");
+        if (!nonbonded) throw OpenMMException("GridForce: Auto-calculate scaling factors requires a NonbondedForce in the system");
+        scaling.resize(numParticles);
+        for (int i = 0; i < numParticles; i++) {
+            double q, sigma, eps;
+            nonbonded->getParticleParameters(i, q, sigma, eps);
+            if (prop == "charge") scaling[i] = q;
+            else scaling[i] = std::sqrt(eps) * std::pow(2.0 * sigma, prop == "ljr" ? 6.0 : 3.0);
+        }
+        const_cast<GridForce&>(force).setScalingFactors(scaling);
+    }
+
+    // Grid from the receptor atoms (ReferenceGridForceKernels.cpp:213-278 + generateGrid :465-544): generated on the GPU,
+    // left there ready for evaluation, and copied back into the force (:272) so that saveToFile()/getGridParameters() see it.
+    std::shared_ptr<SharedGrid> generated;
+    if (force.getAutoGenerateGrid() && vals.empty()) {
+        const std::string type = force.getGridType();
+        if (type != "charge" && type != "ljr" && type != "lja")
+            throw OpenMMException("GridForce: Invalid grid type '" + type + "'. Must be 'charge', 'ljr', or 'lja'");
+        if (counts.size() != 3 || spacing.size() != 3)
+            throw OpenMMException("GridForce: Grid counts and spacing must be set before auto-generation");
+        if (!nonbonded) throw OpenMMException("GridForce: Auto-grid generation requires a NonbondedForce in the system");
+        std::vector<int> receptor = force.getReceptorAtoms();
+        const std::vector<int>& ligand = force.getLigandAtoms();
+        const std::vector<Vec3>& rpos = force.getReceptorPositions();
+        if (receptor.empty())
+            for (int i = 0; i < numParticles; i++)
+                if (std::find(ligand.begin(), ligand.end(), i) == ligand.end()) receptor.push_back(i);
+        if (rpos.empty()) throw OpenMMException("GridForce: Receptor positions must be set for auto-grid generation");
+        if (rpos.size() < receptor.size()) throw OpenMMException("GridForce: Not enough receptor positions provided");
+        const size_t n = receptor.size();
+        std::vector<double> q(n), sig(n), eps(n), xyz(3 * n);
+        for (size_t i = 0; i < n; i++) {
+            nonbonded->getParticleParameters(receptor[i], q[i], sig[i], eps[i]);
+            xyz[3 * i] = rpos[i][0];
+            xyz[3 * i + 1] = rpos[i][1];
+            xyz[3 * i + 2] = rpos[i][2];
+        }
+        vals.resize((size_t) counts[0] * counts[1] * counts[2]);
+        gfb_grid* g = 0;
+        check(gfb_grid_generate(dev, counts.data(), spacing.data(), origin, type == "charge" ? 1 : type == "ljr" ? 2 : 3, (int) n,
+                                xyz.data(), q.data(), sig.data(), eps.data(), force.getGridCap(), vals.data(), precision, layout, &g),
+              "grid generation");
+        generated.reset(new SharedGrid(g));
+        const_cast<GridForce&>(force).setGridValues(vals);
+    }
     if (counts.size() != 3 || spacing.size() != 3)
         throw OpenMMException("GridForce[B200]: grid counts and spacing must each be given exactly once");
     if (vals.size() != (size_t) counts[0] * counts[1] * counts[2])
         throw OpenMMException("GridForce[B200]: number of grid values does not match the grid counts");
-    double origin[3];
-    force.getGridOrigin(origin[0], origin[1], origin[2]);
-    const double invPower = force.getInvPower(), oobK = force.getOutOfBoundsRestraint();
 
-    dev = b200Device(deviceIndex);
-    grid = b200AcquireGrid(dev, deviceIndex, precision, layout, counts, spacing, origin, vals);
+    grid = generated ? generated : b200AcquireGrid(dev, deviceIndex, precision, layout, counts, spacing, origin, vals);
     release();
     gfb_grid* handle = grid->handle;
     groupMode = force.getNumParticleGroups() > 0;
@@ -155,6 +212,7 @@ void B200CalcGridForceKernel::build(const GridForce& force) {
 }
 
 void B200CalcGridForceKernel::initialize(const System& system, const GridForce& force) {
+    this->system = &system;
     numParticles = system.getNumParticles();
     build(force);
 }

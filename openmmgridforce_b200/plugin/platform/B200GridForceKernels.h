@@ -43,6 +43,7 @@ public:
 private:
     void release();
     void build(const GridForce& force);
+    const OpenMM::System* system = 0;       // for the auto-derived inputs (NonbondedForce parameters)
     int deviceIndex, precision;
     gfb_device* dev;
     std::shared_ptr<SharedGrid> grid;

@@ -12,6 +12,7 @@
 #include "GridForce.h"
 #include "GridForceBatch.h"
 #include "openmm/Context.h"
+#include "openmm/NonbondedForce.h"
 #include "openmm/Platform.h"
 #include "openmm/System.h"
 #include "openmm/internal/windowsExport.h"
@@ -104,6 +105,50 @@ OPENMM_EXPORT int b200_plugin_apply_inv_power(double* vals, long long nVals, int
         const std::vector<double>& v = f.getGridValues();
         memcpy(vals, v.data(), v.size() * sizeof(double));
         *modeAfter = static_cast<int>(f.getInvPowerMode());
+    })
+}
+
+// System.addForce(NonbondedForce): the parameter source of the auto-derived inputs (charge e, sigma nm, epsilon kJ/mol).
+OPENMM_EXPORT int b200_plugin_add_nonbonded(void* handle, const double* charges, const double* sigmas, const double* epsilons, int n) {
+    Handle* h = static_cast<Handle*>(handle);
+    GUARD({
+        NonbondedForce* nb = new NonbondedForce();
+        for (int i = 0; i < n; i++) nb->addParticle(charges[i], sigmas[i], epsilons[i]);
+        h->system.addForce(nb);
+    })
+}
+
+// GridForce::setAutoCalculateScalingFactors / setScalingProperty / setAutoGenerateGrid / setGridType / setGridCap /
+// setReceptorAtoms / setReceptorPositions on force `force` (reference GridForce.h:171-198, 335-342, 523-573).
+OPENMM_EXPORT int b200_plugin_set_auto(void* handle, int force, int autoScaling, const char* scalingProperty, int autoGenerate,
+                                       const char* gridType, double gridCap, const int* receptorAtoms, int nReceptorAtoms,
+                                       const double* receptorPositions, int nReceptorPositions) {
+    Handle* h = static_cast<Handle*>(handle);
+    GUARD({
+        GridForce* f = h->forces.at(force);
+        f->setAutoCalculateScalingFactors(autoScaling != 0);
+        f->setScalingProperty(scalingProperty ? scalingProperty : "");
+        f->setAutoGenerateGrid(autoGenerate != 0);
+        f->setGridType(gridType ? gridType : "");
+        f->setGridCap(gridCap);
+        if (receptorAtoms && nReceptorAtoms > 0) f->setReceptorAtoms(std::vector<int>(receptorAtoms, receptorAtoms + nReceptorAtoms));
+        std::vector<Vec3> pos(nReceptorPositions);
+        for (int i = 0; i < nReceptorPositions; i++)
+            pos[i] = Vec3(receptorPositions[3 * i], receptorPositions[3 * i + 1], receptorPositions[3 * i + 2]);
+        f->setReceptorPositions(pos);
+    })
+}
+
+// What the kernel wrote back into the force at Context creation: which = 0 grid values, 1 scaling factors.
+OPENMM_EXPORT int b200_plugin_get_force_data(void* handle, int force, int which, double* out, long long capacity, long long* count) {
+    Handle* h = static_cast<Handle*>(handle);
+    GUARD({
+        std::vector<int> c;
+        std::vector<double> sp, v, sc;
+        h->forces.at(force)->getGridParameters(c, sp, v, sc);
+        const std::vector<double>& src = which == 0 ? v : sc;
+        *count = (long long) src.size();
+        for (long long i = 0; i < (long long) src.size() && i < capacity; i++) out[i] = src[i];
     })
 }
 

@@ -248,3 +248,82 @@ def test_many_contexts_share_grids_and_run_from_threads():
         assert abs(e - ref["energy"]) <= 1e-12 * abs(ref["energy"])
         assert np.abs(f - ref["forces"]).max() <= 1e-12 * np.abs(ref["forces"]).max()
     platform.setPropertyDefaultValue("Precision", "mixed")
+
+
+def _auto_system(gfp, grid_type, with_nonbonded=True):
+    """20 ligand particles + 280 receptor particles with NonbondedForce parameters; a GridForce that derives its grid
+    (setAutoGenerateGrid) and its scaling factors (setAutoCalculateScalingFactors) from them, as
+    python/tests/test_auto_grid.py:135-202 and test_auto_scaling.py do in the reference."""
+    rng = np.random.default_rng(5)
+    n_lig, n_rec = 20, 280
+    counts, sp, og = (15, 14, 13), (0.12, 0.13, 0.14), (0.2, 0.1, 0.0)
+    length = np.array(sp) * (np.array(counts) - 1)
+    rec_pos = rng.uniform(-0.4, 2.2, size=(n_rec, 3))
+    lig_pos = np.array(og) + rng.uniform(0.1, 0.9, size=(n_lig, 3)) * length
+    q = rng.normal(size=n_lig + n_rec) * 0.4
+    sg = rng.uniform(0.1, 0.2, size=n_lig + n_rec)
+    ep = rng.uniform(0.1, 1.0, size=n_lig + n_rec)
+    system = gfp.System()
+    for _ in range(n_lig + n_rec):
+        system.addParticle(1.0)
+    if with_nonbonded:
+        nb = gfp.NonbondedForce()
+        for i in range(n_lig + n_rec):
+            nb.addParticle(q[i], sg[i], ep[i])
+        system.addForce(nb)
+    force = gfp.GridForce()
+    force.addGridCounts(*counts)
+    force.addGridSpacing(*sp)
+    force.setGridOrigin(*og)
+    force.setAutoGenerateGrid(True)
+    force.setGridType(grid_type)
+    force.setReceptorAtoms(range(n_lig, n_lig + n_rec))
+    force.setReceptorPositionsFromLists(rec_pos[:, 0], rec_pos[:, 1], rec_pos[:, 2])
+    force.setAutoCalculateScalingFactors(True)
+    force.setScalingProperty(grid_type)
+    system.addForce(force)
+    pos = np.concatenate([lig_pos, rec_pos])
+    return system, force, dict(counts=counts, spacing=sp, origin=og, rec_pos=rec_pos, pos=pos, q=q, sg=sg, ep=ep, n_lig=n_lig)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grid_type", ["charge", "ljr", "lja"])
+def test_plugin_auto_generated_grid_and_scaling(oracle_built, grid_type):
+    import openmmgridforce_b200.gridforceplugin as gfp
+    system, force, d = _auto_system(gfp, grid_type)
+    platform = gfp.Platform.getPlatformByName("B200")
+    platform.setPropertyDefaultValue("Precision", "double")
+    ctx = gfp.Context(system, platform)
+    n_lig = d["n_lig"]
+    # the kernel wrote both derived inputs back into the force (ReferenceGridForceKernels.cpp:209, :272)
+    want_grid = oracle_built.port_generate_grid(d["counts"], d["spacing"], d["origin"], grid_type, d["rec_pos"], d["q"][n_lig:],
+                                                d["sg"][n_lig:], d["ep"][n_lig:], grid_cap=41840.0, n_threads=4)
+    got_grid = force.getGridValues().reshape(d["counts"])
+    assert np.abs(got_grid - want_grid).max() <= 1e-10 * np.abs(want_grid).max()
+    want_sc = {"charge": d["q"], "ljr": np.sqrt(d["ep"]) * (2 * d["sg"]) ** 6, "lja": np.sqrt(d["ep"]) * (2 * d["sg"]) ** 3}[grid_type]
+    got_sc = force.getScalingFactors()
+    assert got_sc.shape == want_sc.shape and np.abs(got_sc - want_sc).max() <= 1e-14 * np.abs(want_sc).max()
+    # evaluation: every particle has a scaling factor now, so every particle is evaluated (as in the reference's tests)
+    ctx.setPositions(d["pos"])
+    st = ctx.getState(getEnergy=True, getForces=True)
+    port = oracle_built.PortOracle(d["counts"], d["spacing"], d["origin"], [want_grid], want_sc[None, :])
+    e, f, _ = port.execute(d["pos"], 0)
+    assert abs(st.getPotentialEnergy() - e) <= 1e-9 * abs(e)
+    assert np.abs(st.getForces() - f).max() <= 1e-9 * np.abs(f).max()
+    platform.setPropertyDefaultValue("Precision", "mixed")
+
+
+@pytest.mark.gpu
+def test_plugin_auto_inputs_errors():
+    import openmmgridforce_b200.gridforceplugin as gfp
+    platform = gfp.Platform.getPlatformByName("B200")
+    system, force, _ = _auto_system(gfp, "charge", with_nonbonded=False)
+    with pytest.raises(RuntimeError, match="requires a NonbondedForce"):
+        gfp.Context(system, platform)
+    system, force, _ = _auto_system(gfp, "dipole")
+    with pytest.raises(RuntimeError, match="Invalid scaling property|Invalid grid type"):
+        gfp.Context(system, platform)
+    system, force, _ = _auto_system(gfp, "ljr")
+    force.setReceptorPositions(np.zeros((0, 3)))
+    with pytest.raises(RuntimeError, match="Receptor positions must be set"):
+        gfp.Context(system, platform)
