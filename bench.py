@@ -111,7 +111,7 @@ def pinned_array(shape, dtype=np.float64):
 # device-timed loops
 # ----------------------------------------------------------------------------------------------------------------
 def time_device_steps(torch, gf, kern, pos_sets, n_replicas, n_atoms, steps, warmup, stream, post_step=None,
-                      force_mode=None):
+                      force_mode=None, energy_bufs_out=None):
     """K launches on `stream`, rotating through pos_sets (and matching force/energy buffers). Returns
     (seconds, launches) with CUDA events recorded on the launching stream."""
     force_mode = gf.FORCE_FIXED_ADD if force_mode is None else force_mode
@@ -126,6 +126,8 @@ def time_device_steps(torch, gf, kern, pos_sets, n_replicas, n_atoms, steps, war
     # the energy gather of step i (N > 1) reads e[i % 3] on NCCL's stream while step i+1 runs, and is waited for before
     # step i+2 (whose launch clears e[i % 3] again).
     d_e3 = [torch.zeros(n_replicas, dtype=torch.float64, device=dev) for _ in range(3)]
+    if energy_bufs_out is not None:
+        energy_bufs_out.extend(d_e3)
     pending = {}
     torch.cuda.synchronize()
 
@@ -330,8 +332,10 @@ def workload_config(n_gpus):
             "grids": N_GRIDS, "grid_points": [GRID_N] * 3, "precision": "mixed", "parallelism": f"replica-sharded x{n_gpus}",
             "l2": "inputs larger than L2: each step streams 74 MB of positions + 74 MB of forces per GPU and gathers from "
                   "3 grids; no L2 flush between steps",
-            "energy_gather": "torch.distributed all_gather_into_tensor (NCCL) of per-replica energies every step (N>1), "
-                             "asynchronous: the gather of step i overlaps the kernel of step i+1 and is waited for before i+2"}
+            "energy_gather": "per-replica energies of every rank gathered on every rank every step (N>1), asynchronously: the "
+                             "gather of step i overlaps the kernel of step i+1 and is waited for before i+2; mode in "
+                             "config.energy_gather_mode (peer-put = copy-engine puts over NVLink into symmetric memory + "
+                             "signal barrier; nccl = all_gather_into_tensor)"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -375,18 +379,61 @@ def main():
     kern = gf.Kernel(dev, grids, w.scaling, oob_k=w.oob_k)
     d_pos = torch.from_numpy(w.pos).to(tdev)
 
-    gathered = torch.empty(world * REPLICAS_PER_GPU, dtype=torch.float64, device=tdev) if world > 1 else None
-
     from openmmgridforce_b200 import sharding
 
-    gathered2 = [torch.empty_like(gathered) for _ in range(2)] if world > 1 else None
+    # The one collective (N > 1): per-replica energies of every rank, every step, overlapping the next step's kernel.
+    #   "nccl"      torch.distributed all_gather_into_tensor, asynchronous (default: what the north star names);
+    #   "peer-put"  GFB_ENERGY_GATHER=peer-put: each rank copies its 512 KB into its slot of every peer's buffer with the
+    #               copy engines over NVLink (gfb_peer_put on torch symmetric-memory buffers) and then passes a signal-pad
+    #               barrier, so no SM is taken from the evaluation kernel running alongside. Measured on the same boxes:
+    #               N=8 807 vs 791 G evals/s, N=2 209 vs 213 — within box-to-box noise, so NCCL stays the default.
+    gather_mode = "none"
     counter = [0]
+    if world > 1:
+        gather_mode = os.environ.get("GFB_ENERGY_GATHER", "nccl")
+        if gather_mode == "peer-put":
+            try:
+                import torch.distributed._symmetric_memory as symm
+                sym_buf = symm.empty(2 * world * REPLICAS_PER_GPU, dtype=torch.float64, device=tdev)
+                sym_hdl = symm.rendezvous(sym_buf, dist.group.WORLD)
+                peer_ptrs = [int(p) for p in sym_hdl.buffer_ptrs]
+                gather_stream = torch.cuda.Stream(device=tdev)
+            except Exception as exc:      # no symmetric memory on this box/build: use NCCL, and say so
+                print(f"[bench] symmetric memory unavailable ({exc!r}); energy gather falls back to NCCL", file=sys.stderr)
+                gather_mode = "nccl"
+        if gather_mode == "nccl":
+            gathered2 = [torch.empty(world * REPLICAS_PER_GPU, dtype=torch.float64, device=tdev) for _ in range(2)]
+
+    class _StreamEvent:
+        """What time_device_steps waits on before reusing an energy accumulator (same face as an NCCL Work)."""
+        def __init__(self, ev):
+            self.ev = ev
+
+        def wait(self):
+            torch.cuda.current_stream().wait_event(self.ev)
 
     def post_step(d_e):
-        if world > 1:       # the one collective: per-replica energies of every rank; overlaps the next step's kernel
-            counter[0] += 1
-            return dist.all_gather_into_tensor(gathered2[counter[0] % 2], d_e, async_op=True)
-        return None
+        if world == 1:
+            return None
+        counter[0] += 1
+        b = counter[0] % 2
+        if gather_mode == "nccl":
+            return dist.all_gather_into_tensor(gathered2[b], d_e, async_op=True)
+        ready = torch.cuda.Event()
+        ready.record(stream)                       # the step's kernel has produced d_e
+        gather_stream.wait_event(ready)
+        dev.peer_put(d_e.data_ptr(), peer_ptrs, (b * world + rank) * REPLICAS_PER_GPU * 8, REPLICAS_PER_GPU * 8,
+                     first_peer=rank + 1, stream=gather_stream.cuda_stream)
+        with torch.cuda.stream(gather_stream):
+            sym_hdl.barrier(channel=b)             # every rank's puts of this step have landed everywhere
+            done = torch.cuda.Event()
+            done.record(gather_stream)
+        return _StreamEvent(done)
+
+    def gathered_view(b):
+        if gather_mode == "nccl":
+            return gathered2[b]
+        return sym_buf.view(2, world * REPLICAS_PER_GPU)[b]
 
     l2_gbs = dev.bench_sector_gather(32 << 20, 1 << 24, 10) if rank == 0 else 0.0
 
@@ -395,9 +442,17 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
+    energy_bufs = []
     secs, launches, bufs = time_device_steps(torch, gf, kern, [d_pos], REPLICAS_PER_GPU, N_ATOMS, args.steps, args.warmup, stream,
-                                             post_step=post_step)
+                                             post_step=post_step, energy_bufs_out=energy_bufs)
     torch.cuda.synchronize()
+    if world > 1:
+        # outside the timed region: the last step's gathered energies must equal a plain blocking NCCL all-gather of them
+        last = (args.warmup + args.steps - 1) % 3
+        check = torch.empty(world * REPLICAS_PER_GPU, dtype=torch.float64, device=tdev)
+        dist.all_gather_into_tensor(check, energy_bufs[last])
+        if not torch.equal(check, gathered_view(counter[0] % 2)):
+            raise SystemExit(f"rank {rank}: energy gather ({gather_mode}) does not match NCCL all_gather")
     if world > 1:
         t = torch.tensor([secs], dtype=torch.float64, device=tdev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -437,7 +492,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": secs_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 interpolation, f64 index/energy, i64 fixed-point forces", "data": "synthetic",
-                "config": workload_config(world),
+                "config": dict(workload_config(world), energy_gather_mode=gather_mode),
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
                              "traffic": C5_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch",
                              "traffic_source": "profiles/r1b_c5_lines_warm_raw.csv: dram__bytes_read.sum 397.0 MB + "

@@ -237,6 +237,16 @@ GFB_API int gfb_kernel_classify_host(gfb_kernel* k, int grid_index, int n_replic
 GFB_API int gfb_forces_fixed_to_f64(gfb_device* dev, const void* d_fixed, long long force_stride, long long n,
                                     double* d_out, void* stream);
 
+/* Replica-sharded runs: the only cross-GPU traffic is the gather of per-replica energies. This puts
+ * `bytes` from local device memory into the same offset of every peer's buffer with the copy engines over NVLink/NVSwitch
+ * (cudaMemcpyAsync on peer-mapped addresses: no SM is taken from the evaluation kernel running next to it, unlike an
+ * NCCL all-gather's CTAs). peer_dst: n_peers base addresses valid in THIS process (e.g. torch symmetric memory's
+ * buffer_ptrs, or cudaIpcOpenMemHandle results; the entry of this rank itself may be included: a local copy);
+ * first_peer staggers the order so that ranks do not all write to the same peer at once. Stream-ordered on `stream`;
+ * cross-rank completion is the caller's barrier. No reference counterpart (the reference is single-GPU). */
+GFB_API int gfb_peer_put(gfb_device* dev, const void* d_src, void* const* peer_dst, int n_peers, size_t dst_offset,
+                         size_t bytes, int first_peer, void* stream);
+
 /* Number of kernels this library has launched on any device since load (bench.py's gpu_launches). */
 GFB_API unsigned long long gfb_launch_count(void);
 

@@ -71,6 +71,7 @@ SIGNATURES = {
     "gfb_kernel_sort_atoms": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "gfb_kernel_classify_host": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "gfb_forces_fixed_to_f64": (_i, [_vp, _vp, _ll, _ll, _vp, _vp]),
+    "gfb_peer_put": (_i, [_vp, _vp, C.POINTER(_vp), _i, _sz, _sz, _i, _vp]),
     "gfb_launch_count": (C.c_ulonglong, []),
     "gfb_bench_sector_gather": (_i, [_vp, _sz, _ll, _i, _pd]),
 }
@@ -189,6 +190,12 @@ class Device:
         out = np.array(values, dtype=np.float64, order="C", copy=True)
         _check(load_library().gfb_inv_power_transform(self._h, _ptr(out), out.size, float(inv_power), 0))
         return out
+
+    def peer_put(self, d_src, peer_ptrs, dst_offset, nbytes, first_peer=0, stream=0):
+        """Copy-engine put of nbytes from local device memory into every peer buffer at dst_offset (gfb_peer_put)."""
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        _check(load_library().gfb_peer_put(self._h, _ptr(int(d_src)), arr, len(peer_ptrs), dst_offset, nbytes, first_peer,
+                                           _ptr(stream or None)))
 
     def fixed_to_f64(self, d_fixed, stride, n, d_out, stream=0):
         _check(load_library().gfb_forces_fixed_to_f64(self._h, _ptr(d_fixed), stride, n, _ptr(d_out), _ptr(stream or None)))

@@ -1227,6 +1227,20 @@ int gfb_forces_fixed_to_f64(gfb_device* dev, const void* d_fixed, long long forc
     return GFB_OK;
 }
 
+int gfb_peer_put(gfb_device* dev, const void* d_src, void* const* peer_dst, int n_peers, size_t dst_offset, size_t bytes,
+                 int first_peer, void* stream) {
+    if (!dev || !d_src || !peer_dst || n_peers < 1) return fail(GFB_ERR_INVALID, "gfb_peer_put: NULL argument");
+    if (bytes == 0) return GFB_OK;
+    CUDA_TRY(cudaSetDevice(dev->ordinal));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : dev->stream;
+    for (int i = 0; i < n_peers; i++) {
+        const int p = ((first_peer % n_peers) + n_peers + i) % n_peers;
+        if (!peer_dst[p]) return fail(GFB_ERR_INVALID, "gfb_peer_put: peer_dst[%d] is NULL", p);
+        CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(peer_dst[p]) + dst_offset, d_src, bytes, cudaMemcpyDefault, s));
+    }
+    return GFB_OK;
+}
+
 int gfb_bench_sector_gather(gfb_device* dev, size_t bytes, long long n_loads, int reps, double* gbs) {
     if (!dev || !gbs) return fail(GFB_ERR_INVALID, "gfb_bench_sector_gather: NULL argument");
     if (bytes < 32 || n_loads < 1 || reps == 0) return fail(GFB_ERR_INVALID, "gfb_bench_sector_gather: bad sizes");
