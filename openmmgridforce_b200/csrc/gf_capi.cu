@@ -923,7 +923,10 @@ static int execute_host_small(gfb_kernel* k, int n_particles, const double* pos,
         if (force_mode == GFB_FORCE_F64_ADD) memset(h_f, 0, np3 * sizeof(double));
         else memcpy(h_f, forces, np3 * sizeof(double));
     }
-    const bool one_block = k->n_atoms <= eval_block_threads(k) && !grid_energies;
+    EvalParams probe;
+    memset(&probe, 0, sizeof probe);
+    // one block covers the ligand: its energy (and, in the lines kernel, its per-grid energies) are plain stores
+    const bool one_block = k->n_atoms <= eval_block_threads(k) && (!grid_energies || !bspline_tiles_eligible(k, probe));
     double* d_e = nullptr;
     if (!one_block) {   // several blocks (or per-grid energies): device accumulators, cleared here, fetched below
         if ((rc = k->d_energy.ensure(e_count * sizeof(double))) != GFB_OK) return rc;
@@ -931,7 +934,8 @@ static int execute_host_small(gfb_kernel* k, int n_particles, const double* pos,
         CUDA_TRY(cudaMemsetAsync(d_e, 0, e_count * sizeof(double), dev->stream));
     }
     // cudaHostAlloc memory is mapped into the device's address space at the same address (unified addressing)
-    rc = enqueue_eval(k, 1, n_particles, h_pos, one_block ? h_e : d_e, (grid_energies && d_e) ? d_e + 1 : nullptr,
+    double* e_dst = one_block ? h_e : d_e;
+    rc = enqueue_eval(k, 1, n_particles, h_pos, e_dst, grid_energies ? e_dst + 1 : nullptr,
                       forces ? h_f : nullptr, GFB_FORCE_F64_STORE, 0, nullptr, nullptr, dev->stream, one_block);
     if (rc != GFB_OK) return rc;
     if (!one_block) CUDA_TRY(cudaMemcpyAsync(h_e, d_e, e_count * sizeof(double), cudaMemcpyDeviceToHost, dev->stream));

@@ -370,13 +370,22 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 10) gf_eval_lin
     // ---- energies ------------------------------------------------------------------------------------------------------
     if (SINGLE) {
         __shared__ double warp_sum[kBlock / 32];
-        if (GE) {
+        if (GE) {   // per-grid energies: warp sums -> one atomic per block and grid (a plain store when one block is the call)
+            __shared__ double warp_ge[kBlock / 32][GE ? NG : 1];
 #pragma unroll
             for (int g = 0; g < (GE ? NG : 1); g++) {
                 double eg = e_g[g];
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) eg += __shfl_xor_sync(kFull, eg, off);
-                if (lane == 0) red_add_f64(p.grid_energies + g, eg);
+                if (lane == 0) warp_ge[tid >> 5][g] = eg;
+            }
+            __syncthreads();
+            if (tid < (GE ? NG : 1)) {
+                double b = 0.0;
+#pragma unroll
+                for (int w = 0; w < kBlock / 32; w++) b += warp_ge[w][tid];
+                if (p.energy_store) p.grid_energies[tid] = b;
+                else red_add_f64(p.grid_energies + tid, b);
             }
         }
         if (p.energies) {

@@ -502,6 +502,7 @@ __global__ void __launch_bounds__(kBlock, eval_min_blocks<S, LAYOUT, NG>()) gf_e
     double e_total = 0.0;
     double Fx = 0.0, Fy = 0.0, Fz = 0.0;
     const int ng = NG > 0 ? NG : p.n_grids;
+    __shared__ double s_warp_ge[SINGLE ? kBlock / 32 : 1][SINGLE ? GFB_MAX_GRIDS : 1];
     unsigned heads;
     const unsigned span = run_span(rep, (unsigned) lane, heads);   // runs of equal energy key inside the warp
     const bool head = rep >= 0 && ((heads >> lane) & 1u);
@@ -523,8 +524,14 @@ __global__ void __launch_bounds__(kBlock, eval_min_blocks<S, LAYOUT, NG>()) gf_e
             e_total += e_g;
             if (p.grid_energies) {  // uniform branch
                 double eg = e_g;
-                run_sum(eg, span);
-                if (head) red_add_f64(p.grid_energies + (size_t) rep * ng + g, eg);
+                if (SINGLE) {   // warp sums now, one atomic (or plain store) per block and grid after the loop
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) eg += __shfl_xor_sync(kFull, eg, off);
+                    if (lane == 0) s_warp_ge[threadIdx.x >> 5][g] = eg;
+                } else {
+                    run_sum(eg, span);
+                    if (head) red_add_f64(p.grid_energies + (size_t) rep * ng + g, eg);
+                }
             }
         }
     } else {
@@ -553,9 +560,26 @@ __global__ void __launch_bounds__(kBlock, eval_min_blocks<S, LAYOUT, NG>()) gf_e
             e_total += e_g;
             if (p.grid_energies) {  // uniform branch
                 double eg = e_g;
-                run_sum(eg, span);
-                if (head) red_add_f64(p.grid_energies + (size_t) rep * ng + g, eg);
+                if (SINGLE) {   // warp sums now, one atomic (or plain store) per block and grid after the loop
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) eg += __shfl_xor_sync(kFull, eg, off);
+                    if (lane == 0) s_warp_ge[threadIdx.x >> 5][g] = eg;
+                } else {
+                    run_sum(eg, span);
+                    if (head) red_add_f64(p.grid_energies + (size_t) rep * ng + g, eg);
+                }
             }
+        }
+    }
+
+    if (SINGLE && p.grid_energies) {  // uniform branch
+        __syncthreads();
+        if ((int) threadIdx.x < ng) {
+            double b = 0.0;
+#pragma unroll
+            for (int w = 0; w < kBlock / 32; w++) b += s_warp_ge[SINGLE ? w : 0][SINGLE ? threadIdx.x : 0];
+            if (p.energy_store) p.grid_energies[threadIdx.x] = b;
+            else red_add_f64(p.grid_energies + threadIdx.x, b);
         }
     }
 

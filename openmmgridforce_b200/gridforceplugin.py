@@ -52,6 +52,7 @@ def _lib():
         lib.b200_plugin_add_particle_group.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.b200_plugin_finalize.argtypes = [C.c_void_p, C.c_char_p]
         lib.b200_plugin_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.b200_plugin_time_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.b200_plugin_update_scaling.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         lib.b200_plugin_group_energies.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         lib.b200_plugin_batch_evaluate.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -341,6 +342,15 @@ class Context:
         f = np.zeros((self._n, 3))
         _check(_lib().b200_plugin_execute(self._h, _p(self._pos), C.c_int(groups), C.byref(e), _p(f)))
         return State(e.value, f)
+
+    def timeEvaluations(self, reps, groups=-1):
+        """`reps` energy+force evaluations issued back to back from C++ (what an integrator's step loop does):
+        returns (seconds per evaluation, last energy)."""
+        if self._pos is None:
+            raise RuntimeError("Particle positions have not been set")
+        secs, e = C.c_double(0.0), C.c_double(0.0)
+        _check(_lib().b200_plugin_time_execute(self._h, _p(self._pos), C.c_int(groups), int(reps), C.byref(secs), C.byref(e)))
+        return secs.value, e.value
 
     def evaluateBatch(self, positions, precision="mixed", want_forces=True):
         """GridForceBatch over this System's GridForces: positions [R, A, 3] -> (energies [R], forces [R, A, 3] | None)."""

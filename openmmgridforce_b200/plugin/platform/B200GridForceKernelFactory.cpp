@@ -30,7 +30,7 @@ KernelImpl* B200GridForceKernelFactory::createKernelImpl(std::string name, const
     if (prec != "mixed" && prec != "double")
         throw OpenMMException("B200 platform: Precision must be 'mixed' or 'double', got '" + prec + "'");
     const int device = atoi(b200.getPropertyDefaultValue(B200Platform::DeviceIndex()).c_str());
-    return new B200CalcGridForceKernel(name, platform, device, prec == "double" ? GFB_PRECISION_DOUBLE : GFB_PRECISION_MIXED);
+    return new B200CalcGridForceKernel(name, platform, device, prec == "double" ? GFB_PRECISION_DOUBLE : GFB_PRECISION_MIXED, &context);
 }
 
 }  // namespace GridForcePlugin

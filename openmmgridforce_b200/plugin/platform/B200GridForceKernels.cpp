@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -79,8 +80,60 @@ std::shared_ptr<SharedGrid> b200AcquireGrid(gfb_device* dev, int ordinal, int pr
     return made;
 }
 
+// ---- step fusion ---------------------------------------------------------------------------------------------------
+// An OpenMM System for docking-style MD carries one GridForce per receptor grid (electrostatic, LJ repulsive, LJ
+// attractive: python/tests/test_grid_force.py:117-159, example/sampler.py), and ContextImpl::calcForcesAndEnergy calls
+// their kernels one after the other. Each call is pure latency (one launch + one synchronize, ~16 us), so three forces
+// cost three of them per step. The kernels of one Context that evaluate the same atoms on grids of one geometry
+// therefore share a launch: the first member called in an evaluation looks at ContextImpl::getLastForceGroups(),
+// evaluates every member whose force group is part of this evaluation in ONE launch (per-grid energies, summed
+// forces), and the other members return their cached energy when OpenMM calls them moments later.
+// B200_FUSE_FORCES=0 switches it off.
+struct B200StepFusion {
+    std::mutex lock;
+    std::vector<B200CalcGridForceKernel*> members;
+    std::map<unsigned, gfb_kernel*> fused;     // by member mask
+    std::vector<double> cachedEnergy;
+    unsigned pendingMask = 0;
+    int pendingGroups = 0;
+    void dropFused() {
+        for (std::map<unsigned, gfb_kernel*>::iterator it = fused.begin(); it != fused.end(); ++it) gfb_kernel_destroy(it->second);
+        fused.clear();
+        pendingMask = 0;
+    }
+};
+
+static std::map<ContextImpl*, B200StepFusion*>& fusionRegistry() {
+    static std::map<ContextImpl*, B200StepFusion*> reg;
+    return reg;
+}
+
+static bool fusionEnabled() {
+    static const bool on = [] {
+        const char* e = getenv("B200_FUSE_FORCES");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------------------------
-B200CalcGridForceKernel::~B200CalcGridForceKernel() { release(); }
+B200CalcGridForceKernel::~B200CalcGridForceKernel() {
+    if (fusion) {
+        std::lock_guard<std::mutex> reg(registryMutex);
+        {
+            std::lock_guard<std::mutex> g(fusion->lock);
+            fusion->dropFused();
+            std::vector<B200CalcGridForceKernel*>& m = fusion->members;
+            m.erase(std::remove(m.begin(), m.end(), this), m.end());
+        }
+        if (fusion->members.empty()) {
+            fusionRegistry().erase(owner);
+            delete fusion;
+        }
+        fusion = 0;
+    }
+    release();
+}
 
 void B200CalcGridForceKernel::release() {
     for (size_t i = 0; i < kernels.size(); i++) gfb_kernel_destroy(kernels[i]);
@@ -189,6 +242,7 @@ void B200CalcGridForceKernel::build(const GridForce& force) {
                                 &oobK, &k), "kernel setup");
         kernels.push_back(k);
         check(gfb_kernel_set_energy_slots(k, slots.data(), numGroups), "particle group slots");
+        fusionKey.clear();
         return;
     }
     numGroups = 0;
@@ -209,6 +263,34 @@ void B200CalcGridForceKernel::build(const GridForce& force) {
     gfb_kernel* k = 0;
     check(gfb_kernel_create(dev, 1, &handle, (int) scaling.size(), scaling.data(), particles, &invPower, &oobK, &k), "kernel setup");
     kernels.push_back(k);
+
+    // what a fused launch needs from this member, and which other kernels may share one with it
+    scalingCopy = scaling;
+    ligandCopy = ligand;
+    invPowerCopy = invPower;
+    oobKCopy = oobK;
+    forceGroup = force.getForceGroup();
+    std::ostringstream key;
+    key.precision(17);
+    key << deviceIndex << '|' << precision << '|' << layout << '|' << counts[0] << 'x' << counts[1] << 'x' << counts[2] << '|'
+        << spacing[0] << ',' << spacing[1] << ',' << spacing[2] << '|' << origin[0] << ',' << origin[1] << ',' << origin[2] << '|'
+        << scaling.size() << '|' << hashWords(ligand.data(), ligand.size() * sizeof(int));
+    fusionKey = key.str();
+    if (owner && fusionEnabled()) {
+        std::lock_guard<std::mutex> reg(registryMutex);
+        if (!fusion) {
+            B200StepFusion*& slot = fusionRegistry()[owner];
+            if (!slot) slot = new B200StepFusion();
+            fusion = slot;
+            std::lock_guard<std::mutex> g(fusion->lock);
+            if (fusion->members.size() < 32) fusion->members.push_back(this);
+            else fusion = 0;
+        }
+        if (fusion) {   // (re)built parameters invalidate every fused state of this Context
+            std::lock_guard<std::mutex> g(fusion->lock);
+            fusion->dropFused();
+        }
+    }
 }
 
 void B200CalcGridForceKernel::initialize(const System& system, const GridForce& force) {
@@ -228,12 +310,87 @@ double B200CalcGridForceKernel::execute(ContextImpl& context, bool includeForces
     if (numParticles == 0 || kernels.empty()) return 0.0;
     const double* p = &pos[0][0];
     double* f = includeForces ? &frc[0][0] : 0;
+    if (fusion && !groupMode && !fusionKey.empty()) {
+        bool done = false;
+        const double e = executeFused(context, p, f, done);
+        if (done) return e;
+    }
     double total = 0.0;
     lastGroupEnergies.assign(groupMode ? numGroups : 1, 0.0);      // one energy per group slot (or the single total)
     check(gfb_kernel_execute_host(kernels[0], 1, numParticles, p, lastGroupEnergies.data(), 0, f, GFB_FORCE_F64_ADD), "execute");
     for (size_t i = 0; i < lastGroupEnergies.size(); i++) total += lastGroupEnergies[i];
     (void) includeEnergy;
     return total;
+}
+
+// See B200StepFusion. Returns with done = false when this call has to run on its own (no partner in this evaluation).
+double B200CalcGridForceKernel::executeFused(ContextImpl& context, const double* pos, double* frc, bool& done) {
+    B200StepFusion& fu = *fusion;
+    std::lock_guard<std::mutex> g(fu.lock);
+    const size_t n = fu.members.size();
+    size_t me = n;
+    for (size_t i = 0; i < n; i++)
+        if (fu.members[i] == this) me = i;
+    if (me == n || n < 2) return 0.0;
+    const int groups = context.getLastForceGroups();
+    if (fu.cachedEnergy.size() != n) {
+        fu.cachedEnergy.assign(n, 0.0);
+        fu.pendingMask = 0;
+    }
+    if ((fu.pendingMask >> me) & 1u) {
+        if (fu.pendingGroups == groups) {   // evaluated moments ago by the member OpenMM called first
+            fu.pendingMask &= ~(1u << me);
+            done = true;
+            return fu.cachedEnergy[me];
+        }
+        fu.pendingMask = 0;                 // left over from an evaluation that did not finish
+    }
+    fu.pendingMask = 0;
+    // members that OpenMM will call in this evaluation and that can share a launch with this one
+    unsigned mask = 0;
+    int count = 0;
+    for (size_t i = 0; i < n; i++) {
+        const B200CalcGridForceKernel* k = fu.members[i];
+        if (k->fusionKey == fusionKey && !k->groupMode && k->numParticles == numParticles &&
+            ((groups >> k->forceGroup) & 1) != 0 && count < GFB_MAX_GRIDS) {
+            mask |= 1u << i;
+            count++;
+        }
+    }
+    if (count < 2 || !((mask >> me) & 1u)) return 0.0;
+    gfb_kernel*& fk = fu.fused[mask];
+    if (!fk) {
+        std::vector<gfb_grid*> grids;
+        std::vector<double> scalingAll, invPower, oobK;
+        for (size_t i = 0; i < n; i++) {
+            if (!((mask >> i) & 1u)) continue;
+            const B200CalcGridForceKernel* k = fu.members[i];
+            grids.push_back(k->grid->handle);
+            scalingAll.insert(scalingAll.end(), k->scalingCopy.begin(), k->scalingCopy.end());
+            invPower.push_back(k->invPowerCopy);
+            oobK.push_back(k->oobKCopy);
+        }
+        check(gfb_kernel_create(dev, count, grids.data(), (int) scalingCopy.size(), scalingAll.data(),
+                                ligandCopy.empty() ? 0 : ligandCopy.data(), invPower.data(), oobK.data(), &fk), "fused kernel setup");
+    }
+    double total = 0.0;
+    std::vector<double> perGrid(count, 0.0);
+    check(gfb_kernel_execute_host(fk, 1, numParticles, pos, &total, perGrid.data(), frc, GFB_FORCE_F64_ADD), "fused execute");
+    int slot = 0;
+    double mine = 0.0;
+    for (size_t i = 0; i < n; i++) {
+        if (!((mask >> i) & 1u)) continue;
+        if (i == me) mine = perGrid[slot];
+        else {
+            fu.cachedEnergy[i] = perGrid[slot];
+            fu.pendingMask |= 1u << i;
+        }
+        fu.members[i]->lastGroupEnergies.assign(1, perGrid[slot]);
+        slot++;
+    }
+    fu.pendingGroups = groups;
+    done = true;
+    return mine;
 }
 
 // Reference: re-reads grid parameters and inv_power (ReferenceGridForceKernels.cpp:1123-1127).

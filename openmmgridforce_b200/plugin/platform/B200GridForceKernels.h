@@ -29,10 +29,13 @@ std::shared_ptr<SharedGrid> b200AcquireGrid(gfb_device* dev, int ordinal, int pr
                                             const std::vector<double>& spacing, const double origin[3],
                                             const std::vector<double>& vals);
 
+struct B200StepFusion;   // the GridForces of one Context that can be evaluated by ONE launch per step (B200GridForceKernels.cpp)
+
 class B200CalcGridForceKernel : public CalcGridForceKernel {
 public:
-    B200CalcGridForceKernel(std::string name, const OpenMM::Platform& platform, int deviceIndex, int precision)
-        : CalcGridForceKernel(name, platform), deviceIndex(deviceIndex), precision(precision), dev(0), numParticles(0) {}
+    B200CalcGridForceKernel(std::string name, const OpenMM::Platform& platform, int deviceIndex, int precision,
+                            OpenMM::ContextImpl* owner = 0)
+        : CalcGridForceKernel(name, platform), deviceIndex(deviceIndex), precision(precision), dev(0), numParticles(0), owner(owner) {}
     ~B200CalcGridForceKernel();
     void initialize(const OpenMM::System& system, const GridForce& force);
     double execute(OpenMM::ContextImpl& context, bool includeForces, bool includeEnergy);
@@ -44,6 +47,15 @@ private:
     void release();
     void build(const GridForce& force);
     const OpenMM::System* system = 0;       // for the auto-derived inputs (NonbondedForce parameters)
+    // ---- step fusion -------------------------------------------------------------------------------------------------
+    friend struct B200StepFusion;
+    double executeFused(OpenMM::ContextImpl& context, const double* pos, double* frc, bool& done);
+    B200StepFusion* fusion = 0;
+    std::string fusionKey;                  // kernels with equal, non-empty keys can share a launch
+    int forceGroup = 0;
+    std::vector<double> scalingCopy;        // this force's scaling factors (a fused state concatenates the members')
+    std::vector<int> ligandCopy;
+    double invPowerCopy = 0.0, oobKCopy = 0.0;
     int deviceIndex, precision;
     gfb_device* dev;
     std::shared_ptr<SharedGrid> grid;
@@ -51,6 +63,7 @@ private:
     int numGroups = 0;
     std::vector<double> lastGroupEnergies;
     int numParticles;
+    OpenMM::ContextImpl* owner;             // the Context this kernel belongs to (fusion registry key), or null
     bool groupMode = false;
 };
 

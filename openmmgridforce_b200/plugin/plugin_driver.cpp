@@ -3,6 +3,7 @@
 // B200CalcGridForceKernel::execute — so that tests/test_plugin.py can compare it with the oracle from Python (there is
 // no SWIG or OpenMM in the build container; with them, python/gridforceplugin_b200.i exposes the same classes).
 // Mirrors oracle/ref_driver.cpp's call shape on purpose: same inputs, two implementations.
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -178,6 +179,23 @@ OPENMM_EXPORT int b200_plugin_execute(void* handle, const double* positions, int
         h->context->setPositions(pos);
         *energy = h->context->computeForcesAndEnergy(true, true, groups);
         if (forces) memcpy(forces, &h->context->getForces()[0], sizeof(double) * 3 * h->numParticles);
+    })
+}
+
+// `reps` back-to-back evaluations from C++, as an integrator's step loop issues them (no marshalling inside the loop):
+// seconds per call through *seconds, last energy through *energy. Used by bench.py's configs[1] figure.
+OPENMM_EXPORT int b200_plugin_time_execute(void* handle, const double* positions, int groups, int reps, double* seconds, double* energy) {
+    Handle* h = static_cast<Handle*>(handle);
+    GUARD({
+        if (!h->context) throw OpenMMException("finalize first");
+        std::vector<Vec3> pos(h->numParticles);
+        for (int i = 0; i < h->numParticles; i++) pos[i] = Vec3(positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]);
+        h->context->setPositions(pos);
+        double e = 0.0;
+        const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        for (int r = 0; r < reps; r++) e = h->context->computeForcesAndEnergy(true, true, groups);
+        *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / (reps > 0 ? reps : 1);
+        *energy = e;
     })
 }
 

@@ -327,3 +327,69 @@ def test_plugin_auto_inputs_errors():
     force.setReceptorPositions(np.zeros((0, 3)))
     with pytest.raises(RuntimeError, match="Receptor positions must be set"):
         gfp.Context(system, platform)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["mixed", "double"])
+def test_step_fusion_matches_separate_launches(precision, monkeypatch):
+    """Three GridForces of one geometry in one Context share a launch per evaluation (B200StepFusion). Every force-group
+    subset must give what the per-force golden outputs say — all three, pairs (a smaller fused launch), singles (no
+    fusion) — in any order, and updateParametersInContext must invalidate the fused state."""
+    import openmmgridforce_b200.gridforceplugin as gfp
+    c, ref = cases.load_golden("ligand_three_grids")
+    platform = gfp.Platform.getPlatformByName("B200")
+    platform.setPropertyDefaultValue("Precision", precision)
+    system, forces = _build_system(gfp, c)
+    ctx = gfp.Context(system, platform)
+    ctx.setPositions(c["pos"])
+    te, tf = (1e-6, 1e-5) if precision == "mixed" else (1e-12, 1e-12)
+    scale_f = np.abs(ref["forces"]).max()
+    for groups in (0b111, 0b011, 0b101, 0b110, 0b001, 0b100, 0b111, 0b010, 0b111):
+        st = ctx.getState(getEnergy=True, getForces=True, groups=groups)
+        sel = [g for g in range(3) if (groups >> g) & 1]
+        e_ref = sum(ref["grid_energies"][g] for g in sel)
+        f_ref = sum(ref["grid_forces"][g] for g in sel)
+        assert abs(st.getPotentialEnergy() - e_ref) <= te * max(abs(ref["grid_energies"][g]) for g in sel), bin(groups)
+        assert np.abs(st.getForces() - f_ref).max() <= tf * scale_f, bin(groups)
+    forces[1].setScalingFactors(3.0 * c["scaling"][1])
+    forces[1].updateParametersInContext(ctx)
+    st = ctx.getState(getEnergy=True, getForces=True)
+    e_ref = ref["grid_energies"][0] + 3.0 * ref["grid_energies"][1] + ref["grid_energies"][2]
+    f_ref = ref["grid_forces"][0] + 3.0 * ref["grid_forces"][1] + ref["grid_forces"][2]
+    assert abs(st.getPotentialEnergy() - e_ref) <= te * max(abs(e) for e in ref["grid_energies"]) * 3
+    assert np.abs(st.getForces() - f_ref).max() <= tf * np.abs(f_ref).max()
+    secs, e = ctx.timeEvaluations(200)
+    assert abs(e - e_ref) <= te * max(abs(x) for x in ref["grid_energies"]) * 3 and secs > 0
+    print(f"{precision}: {secs * 1e6:.1f} us per fused 3-force evaluation")
+    platform.setPropertyDefaultValue("Precision", "mixed")
+
+
+@pytest.mark.gpu
+def test_step_fusion_keeps_unlike_forces_apart():
+    """Forces on different geometries, or with particle groups, never join a fused launch; a second Context on the same
+    System has its own fusion state."""
+    import openmmgridforce_b200.gridforceplugin as gfp
+    a, ref_a = cases.load_golden("ligand_three_grids")
+    platform = gfp.Platform.getPlatformByName("B200")
+    platform.setPropertyDefaultValue("Precision", "double")
+    system, forces = _build_system(gfp, a)
+    # a fourth force on a coarser grid cut out of grid 0 (different geometry, same atoms)
+    extra = gfp.GridForce()
+    extra.addGridCounts(20, 20, 20)
+    extra.addGridSpacing(0.1, 0.1, 0.1)
+    extra.setGridOrigin(*a["origin"])
+    extra.setGridValues(a["grids"][0][::2, ::2, ::2])
+    for s in a["scaling"][0]:
+        extra.addScalingFactor(s)
+    extra.setForceGroup(3)
+    system.addForce(extra)
+    ctx1 = gfp.Context(system, platform)
+    ctx2 = gfp.Context(system, platform)
+    for ctx in (ctx1, ctx2, ctx1):
+        ctx.setPositions(a["pos"])
+        e_all = ctx.getState(getEnergy=True, getForces=True).getPotentialEnergy()
+        e_3 = ctx.getState(getEnergy=True, groups=0b0111).getPotentialEnergy()
+        e_x = ctx.getState(getEnergy=True, groups=0b1000).getPotentialEnergy()
+        assert abs(e_3 - ref_a["energy"]) <= 1e-12 * max(abs(x) for x in ref_a["grid_energies"])
+        assert abs(e_all - (e_3 + e_x)) <= 1e-12 * (abs(e_3) + abs(e_x))
+    platform.setPropertyDefaultValue("Precision", "mixed")
