@@ -233,3 +233,30 @@ def test_lines_off_switch_matches(gpu_device):
     assert np.abs(e0 - e1).max() <= 1e-9 * np.abs(e1).max()
     assert np.abs(f0 - f1).max() <= 2e-6 * np.abs(f1).max()
     _close(grids, k)
+
+
+def test_host_path_pinned_and_pageable_buffers_agree(gpu_device):
+    """gfb_kernel_execute_host: with pinned caller buffers the kernels store forces straight into them (zero-copy), with
+    pageable ones into the handle's pinned staging first; both must give bit-identical results, for odd replica counts
+    (chunk boundaries), and an ADD call must take the copy pipeline and accumulate."""
+    import torch
+    import openmmgridforce_b200 as gf
+    from openmmgridforce_b200 import workloads as W
+    w = W.c5_sharded_replicas(n_local=9001, n=64)
+    grids = [gf.Grid(gpu_device, w.counts, w.spacing, w.origin, v, gf.PRECISION_MIXED) for v in w.grids]
+    k = gf.Kernel(gpu_device, grids, w.scaling, oob_k=w.oob_k)
+    assert k.uses_lines_kernel()
+    e_page, f_page, _ = k.execute_host(w.pos)
+    pos_pin = torch.from_numpy(w.pos.copy()).pin_memory()
+    f_pin = torch.full(w.pos.shape, 7.0, dtype=torch.float64).pin_memory()
+    e_pin = torch.zeros(w.n_replicas, dtype=torch.float64).pin_memory()
+    k.execute_host(pos_pin.numpy(), forces=f_pin.numpy(), energies_out=e_pin.numpy())
+    assert np.array_equal(f_pin.numpy(), f_page), int((f_pin.numpy() != f_page).sum())
+    # a replica's atoms sit in two warps: two FP64 atomics whose order is not fixed
+    assert np.abs(e_pin.numpy() - e_page).max() <= 1e-13 * np.abs(e_page).max()
+    acc = f_page.copy()
+    k.execute_host(w.pos, forces=acc, force_mode=gf.FORCE_F64_ADD)
+    assert np.abs(acc - 2.0 * f_page).max() <= 1e-12 * np.abs(f_page).max()
+    k.close()
+    for g in grids:
+        g.close()
