@@ -197,6 +197,14 @@ GFB_API int gfb_kernel_eval_path(const gfb_kernel* k);
  * contiguous in the atom list (one atomic per run of equal slot per warp). */
 GFB_API int gfb_kernel_set_energy_slots(gfb_kernel* k, const int* slots, int n_slots);
 
+/* Device path only: with enable != 0 every gfb_kernel_execute_device launch of this state is made with programmatic
+ * stream serialization (PDL): its blocks may start, fetch positions and grid records while the tail of the PREVIOUS
+ * kernel on the same stream is still running, and wait for that kernel to complete before their first write. The
+ * caller promises that d_pos is not written by the kernel launched immediately before on that stream (true for
+ * back-to-back evaluations of resident replicas; NOT true right after an integrator kernel that moves the atoms).
+ * Default off. No reference counterpart. */
+GFB_API int gfb_kernel_set_launch_overlap(gfb_kernel* k, int enable);
+
 /* CalcGridForceKernel::execute for host-resident data (Reference-platform style), batched over replicas.
  *   pos       host [n_replicas][n_particles][3] doubles (std::vector<Vec3> layout)
  *   energies  host out [n_replicas] (sum over grids) or NULL   ([n_replicas][n_slots] with energy slots)

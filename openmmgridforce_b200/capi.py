@@ -66,6 +66,7 @@ SIGNATURES = {
     "gfb_kernel_update_parameters": (_i, [_vp, _vp, _vp]),
     "gfb_kernel_set_energy_slots": (_i, [_vp, _vp, _i]),
     "gfb_kernel_eval_path": (_i, [_vp]),
+    "gfb_kernel_set_launch_overlap": (_i, [_vp, _i]),
     "gfb_kernel_execute_host": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i]),
     "gfb_kernel_execute_device": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp]),
     "gfb_kernel_sort_atoms": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
@@ -317,6 +318,11 @@ class Kernel:
     def uses_lines_kernel(self):
         """True when launches of this state go to gf_eval_lines_kernel (see gfb_kernel_eval_path)."""
         return bool(load_library().gfb_kernel_eval_path(self._h))
+
+    def set_launch_overlap(self, enable=True):
+        """PDL for execute_device launches (see gfb_kernel_set_launch_overlap: positions must not come from the kernel
+        launched just before)."""
+        _check(load_library().gfb_kernel_set_launch_overlap(self._h, 1 if enable else 0))
 
     def update_parameters(self, scaling=None, inv_power=None):
         sc = _host_f64(scaling).reshape(self.n_grids, self.n_atoms) if scaling is not None else None

@@ -127,6 +127,7 @@ struct gfb_kernel {
     PinnedBuffer h_stage, h_energy;
     // one-ligand-per-step path (execute_host_small): host-mapped staging the kernel reads and writes over PCIe
     PinnedBuffer h_small;
+    bool launch_overlap;     // gfb_kernel_set_launch_overlap: device-path launches may overlap the previous launch's tail
     bool unique_particles;   // no particle index occurs twice: a plain store per evaluated particle is the whole force
 };
 
@@ -559,6 +560,7 @@ int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int 
     k->n_slots = 1;
     k->max_particle = n_atoms - 1;
     k->unique_particles = true;
+    k->launch_overlap = false;
     for (int g = 0; g < n_grids; g++) {
         k->grids[g] = grids[g];
         k->inv_power[g] = inv_power ? inv_power[g] : 0.0;
@@ -673,6 +675,12 @@ int gfb_kernel_set_energy_slots(gfb_kernel* k, const int* slots, int n_slots) {
     return GFB_OK;
 }
 
+int gfb_kernel_set_launch_overlap(gfb_kernel* k, int enable) {
+    if (!k) return fail(GFB_ERR_INVALID, "gfb_kernel_set_launch_overlap: NULL kernel");
+    k->launch_overlap = enable != 0;
+    return GFB_OK;
+}
+
 int gfb_kernel_update_parameters(gfb_kernel* k, const double* scaling, const double* inv_power) {
     if (!k) return fail(GFB_ERR_INVALID, "gfb_kernel_update_parameters: NULL kernel");
     CUDA_TRY(cudaSetDevice(k->dev->ordinal));
@@ -764,8 +772,18 @@ template <int NG, int FMODE, int FPATH, bool SINGLE>
 static void launch_lines4(const EvalParams& p, cudaStream_t stream) {
     constexpr int block = lines_block(NG);
     const unsigned blocks = (unsigned) ((p.total + block - 1) / block);
-    if (p.grid_energies) gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, true><<<blocks, block, 0, stream>>>(p);
-    else gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, false><<<blocks, block, 0, stream>>>(p);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(block);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = p.pdl ? 1 : 0;
+    if (p.grid_energies) cudaLaunchKernelEx(&cfg, gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, true>, p);
+    else cudaLaunchKernelEx(&cfg, gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, false>, p);
 }
 
 template <int NG, int FMODE, int FPATH>
@@ -829,13 +847,14 @@ static void launch_bspline(const EvalParams& p, int fmode, cudaStream_t stream) 
 static int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos, double* d_energies,
                         double* d_grid_energies, void* d_forces, int force_mode, long long force_stride,
                         const int* d_order, double* d_energies_clear, cudaStream_t stream, bool energy_store = false,
-                        int atom_begin = 0, int atom_count = -1) {
+                        int atom_begin = 0, int atom_count = -1, bool overlap = false) {
     // atom_begin/atom_count: evaluate only atoms [atom_begin, atom_begin + atom_count) of a state without particle
     // indirection (the host path cuts one large replica into atom ranges); d_pos/d_forces then point at the range.
     const int n_atoms = atom_count >= 0 ? atom_count : k->n_atoms;
     EvalParams p;
     memset(&p, 0, sizeof p);
     p.energy_store = energy_store ? 1 : 0;
+    p.pdl = overlap ? 1u : 0u;
     for (int g = 0; g < k->n_grids; g++) {
         fill_grid_view(k, g, p.grid[g]);
         p.grid[g].scaling += atom_begin;
@@ -972,7 +991,7 @@ int gfb_kernel_execute_device(gfb_kernel* k, int n_replicas, int n_particles, co
     CUDA_TRY(cudaSetDevice(k->dev->ordinal));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : k->dev->stream;
     return enqueue_eval(k, n_replicas, n_particles, d_pos, d_energies, d_grid_energies, d_forces, force_mode, force_stride,
-                        d_order, d_energies_clear, s);
+                        d_order, d_energies_clear, s, false, 0, -1, k->launch_overlap);
 }
 
 // Host path. The batch is cut into replica chunks so that the H2D of chunk i+1, the kernel of chunk i and

@@ -171,7 +171,10 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 10) gf_eval_lin
     const unsigned t = t0 + tid;
     const unsigned total = (unsigned) p.total;
     const bool active = t < total;
-    if (p.energies_clear && t < (unsigned) (p.n_replicas * p.n_slots)) p.energies_clear[t] = 0.0;
+    // Programmatic dependent launch (sm_90+): let the NEXT launch on this stream start its blocks as soon as all of ours
+    // have started, so that its position/record fetches overlap our tail; it blocks at griddepcontrol.wait (below, before
+    // the first global write) until this grid has completed. Both are no-ops in a launch without the PDL attribute.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // ---- who am I: replica, atom ordinal, particle -------------------------------------------------------------
     unsigned rep = 0, ia = t;
@@ -329,6 +332,10 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 10) gf_eval_lin
     // slice and leave as 48 coalesced 16-byte stores (the mirror image of the position staging) instead of 96 scalar
     // stores at stride 24 — which matters most when `forces` is host-mapped memory (PCIe write TLPs of 128 bytes
     // instead of 8): gfb_kernel_execute_host's zero-copy path.
+    // Everything above only READ inputs that no evaluation launch writes (positions, grids, scaling factors). From here on
+    // the kernel writes what the previous launch may still be writing or accumulating: wait for it to finish.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (p.energies_clear && t < (unsigned) (p.n_replicas * p.n_slots)) p.energies_clear[t] = 0.0;
     const bool stage_f = FMODE == GFB_FORCE_F64_STORE && p.forces != nullptr && plain && (t - lane) + 32u <= total &&
                          (reinterpret_cast<uintptr_t>(p.forces) & 15) == 0;   // warp-uniform
     if (stage_f) {

@@ -50,7 +50,7 @@ struct EvalParams {
     // gf_eval_lines_kernel only (gf_eval_lines.cuh)
     const void* lines;       // 2-4 grids of one geometry: one 128-byte record per cell = 4 slots of 8 packed corners
     unsigned div_magic;      // floor(2^32 / n_atoms) (saturated): t / n_atoms = umulhi(t, div_magic) or that + 1
-    unsigned pad3_;
+    unsigned pdl;            // launch with programmatic stream serialization (gfb_kernel_set_launch_overlap)
     double near_int[3];      // 1.8e-15 * cells per axis: fractions this close to 0 or 1 take the exact division
 };
 

@@ -260,3 +260,44 @@ def test_host_path_pinned_and_pageable_buffers_agree(gpu_device):
     k.close()
     for g in grids:
         g.close()
+
+
+@pytest.mark.parametrize("n_grids", [1, 3])
+def test_launch_overlap_pdl_gives_same_results(gpu_device, n_grids):
+    """gfb_kernel_set_launch_overlap: back-to-back device launches made with programmatic stream serialization (a launch's
+    blocks fetch their inputs during the previous launch's tail and wait for it before their first write) must leave
+    exactly the fixed-point forces and (to summation order) the energies that serialized launches leave — with rotating
+    energy accumulators cleared by the previous launch, forces accumulated over all launches into ONE buffer."""
+    import torch
+    import openmmgridforce_b200 as gf
+    from openmmgridforce_b200 import workloads as W
+    w = W.c5_sharded_replicas(n_local=6000, n=96)
+    grids = [gf.Grid(gpu_device, w.counts, w.spacing, w.origin, v, gf.PRECISION_MIXED) for v in w.grids[:n_grids]]
+    k = gf.Kernel(gpu_device, grids, w.scaling[:n_grids], oob_k=w.oob_k[:n_grids])
+    tdev = torch.device("cuda:0")
+    r, a = w.n_replicas, w.n_atoms
+    stride = ((r * a + 31) // 32) * 32
+    rng = np.random.default_rng(3)
+    sets = [torch.from_numpy(w.pos + rng.uniform(-0.01, 0.01, size=3)).to(tdev) for _ in range(5)]
+    stream = torch.cuda.Stream()
+    out = {}
+    for pdl in (False, True):
+        k.set_launch_overlap(pdl)
+        d_f = torch.zeros(3 * stride, dtype=torch.int64, device=tdev)
+        d_e = [torch.zeros(r, dtype=torch.float64, device=tdev) for _ in range(3)]
+        kept = []
+        with torch.cuda.stream(stream):
+            for i in range(15):
+                k.execute_device(r, a, sets[i % 5].data_ptr(), d_e[i % 3].data_ptr(), None, d_f.data_ptr(), gf.FORCE_FIXED_ADD, stride,
+                                 None, stream.cuda_stream, d_energies_clear=d_e[(i + 1) % 3].data_ptr())
+                if i >= 12:
+                    kept.append(d_e[i % 3].clone())        # stream-ordered copy of step i's energies
+        stream.synchronize()
+        out[pdl] = (d_f.cpu().numpy(), [x.cpu().numpy() for x in kept])
+    k.set_launch_overlap(False)
+    assert np.array_equal(out[False][0], out[True][0])             # integer accumulation: order-independent, exact
+    for e0, e1 in zip(out[False][1], out[True][1]):
+        assert np.abs(e0 - e1).max() <= 1e-13 * np.abs(e0).max()
+    k.close()
+    for g in grids:
+        g.close()

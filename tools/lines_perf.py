@@ -13,7 +13,7 @@ tdev = torch.device("cuda:0")
 side = torch.cuda.Stream()
 torch.cuda.set_stream(side)
 stream = side.cuda_stream
-tag = f"LINES={os.environ.get('GFB_LINES', '1')} FPATH={os.environ.get('GFB_FORCE_PATH', '0')}"
+tag = f"LINES={os.environ.get('GFB_LINES', '1')} FPATH={os.environ.get('GFB_FORCE_PATH', '0')} PDL={os.environ.get('GFB_PDL', '0')}"
 
 
 def time_kernel(k, R, P, pos_sets, fmode, iters=60):
@@ -52,6 +52,7 @@ for name in names:
         sets = [w.pos]
     grids = [gf.Grid(dev, w.counts, w.spacing, w.origin, v, gf.PRECISION_MIXED) for v in w.grids]
     k = gf.Kernel(dev, grids, w.scaling, oob_k=w.oob_k)
+    k.set_launch_overlap(os.environ.get("GFB_PDL", "0") == "1")
     pos_sets = [torch.from_numpy(np.ascontiguousarray(p)).to(tdev) for p in sets]
     for fm, fname in ((gf.FORCE_FIXED_ADD, "fixed_add"), (gf.FORCE_F64_STORE, "f64_store"), (gf.FORCE_F64_ADD, "f64_add")):
         us = time_kernel(k, w.n_replicas, w.n_atoms, pos_sets, fm)
