@@ -111,7 +111,7 @@ def pinned_array(shape, dtype=np.float64):
 # device-timed loops
 # ----------------------------------------------------------------------------------------------------------------
 def time_device_steps(torch, gf, kern, pos_sets, n_replicas, n_atoms, steps, warmup, stream, post_step=None,
-                      force_mode=None, energy_bufs_out=None):
+                      force_mode=None, energy_bufs_out=None, final_step=None):
     """K launches on `stream`, rotating through pos_sets (and matching force/energy buffers). Returns
     (seconds, launches) with CUDA events recorded on the launching stream."""
     force_mode = gf.FORCE_FIXED_ADD if force_mode is None else force_mode
@@ -158,6 +158,8 @@ def time_device_steps(torch, gf, kern, pos_sets, n_replicas, n_atoms, steps, war
         for i in range(steps):
             step(warmup + i)
         drain()                  # the last gathers are inside the timed region
+        if final_step is not None:   # the one gather of a "final" run: after the last step, before the clock stops
+            stream.wait_event(final_step(d_e3[(warmup + steps - 1) % 4]).ev)     # the clock stops after the gather
         e1.record(stream)
         stream.synchronize()
         launches = gf.launch_count() - l0
@@ -363,10 +365,11 @@ def workload_config(n_gpus):
                   "3 grids; no L2 flush between steps",
             "launch_overlap": "programmatic dependent launch: a step's blocks may fetch their (static) inputs during the "
                               "previous step's tail and wait for it before their first write (gfb_kernel_set_launch_overlap)",
-            "energy_gather": "per-replica energies of every rank gathered on every rank every step (N>1), asynchronously: the "
-                             "gather of step i overlaps the kernels of steps i+1, i+2 and is waited for (on the host) before i+3; mode in "
-                             "config.energy_gather_mode (peer-put = copy-engine puts over NVLink into symmetric memory + "
-                             "signal barrier; nccl = all_gather_into_tensor)"}
+            "energy_gather": "N>1: per-replica energies of every rank gathered on every rank; config.energy_gather_when = final "
+                             "(once, after the last step, inside the timed region: BASELINE.json north_star) or every (after "
+                             "every step, overlapping the next two steps); config.energy_gather_mode = nccl "
+                             "(all_gather_into_tensor) or peer-put (copy-engine puts over NVLink into symmetric memory + "
+                             "signal barrier)"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -377,6 +380,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip C3/C4 and the CPU baseline (N=1 only)")
+    ap.add_argument("--energy-gather", default=os.environ.get("GFB_ENERGY_GATHER_WHEN", "final"), choices=["final", "every"],
+                    help="N>1: gather per-replica energies once, after the last step (what BASELINE.json's north_star asks "
+                         "for; inside the timed region), or after every step (overlapping the next steps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -410,7 +416,8 @@ def main():
     kern = gf.Kernel(dev, grids, w.scaling, oob_k=w.oob_k)
     # back-to-back evaluations of resident poses: a launch may start while the previous one's tail is still running (PDL);
     # its inputs are not produced by that previous launch. Host-path (e2e) launches are unaffected.
-    kern.set_launch_overlap(True)
+    # (with a gather after EVERY step the overlap is switched off: the two together measured slower, 88.2 vs 84.7 us at N=2)
+    kern.set_launch_overlap(os.environ.get("GFB_BENCH_PDL", "1") != "0" and (world == 1 or args.energy_gather == "final"))
     d_pos = torch.from_numpy(w.pos).to(tdev)
 
     from openmmgridforce_b200 import sharding
@@ -448,8 +455,8 @@ def main():
         def wait(self):
             self.ev.synchronize()
 
-    def post_step(d_e):
-        if world == 1:
+    def post_step(d_e, force=False):
+        if world == 1 or (args.energy_gather == "final" and not force):
             return None
         counter[0] += 1
         b = counter[0] % 2
@@ -482,7 +489,9 @@ def main():
     sampler.start()
     energy_bufs = []
     secs, launches, bufs = time_device_steps(torch, gf, kern, [d_pos], REPLICAS_PER_GPU, N_ATOMS, args.steps, args.warmup, stream,
-                                             post_step=post_step, energy_bufs_out=energy_bufs)
+                                             post_step=post_step, energy_bufs_out=energy_bufs,
+                                             final_step=(lambda d_e: post_step(d_e, force=True))
+                                             if world > 1 and args.energy_gather == "final" else None)
     torch.cuda.synchronize()
     if world > 1:
         # outside the timed region: the last step's gathered energies must equal a plain blocking NCCL all-gather of them
@@ -530,7 +539,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": secs_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 interpolation, f64 index/energy, i64 fixed-point forces", "data": "synthetic",
-                "config": dict(workload_config(world), energy_gather_mode=gather_mode),
+                "config": dict(workload_config(world), energy_gather_mode=gather_mode,
+                               energy_gather_when=args.energy_gather if world > 1 else "none"),
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
                              "traffic": C5_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch",
                              "traffic_source": "profiles/r1b_c5_lines_warm_raw.csv: dram__bytes_read.sum 397.0 MB + "
