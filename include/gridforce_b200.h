@@ -56,9 +56,10 @@ typedef enum { GFB_PRECISION_MIXED = 0, GFB_PRECISION_DOUBLE = 1 } gfb_precision
  *   AUTO   CELLS while that copy is at most 1/16 of the GPU's memory (11 GB on B200), else ROWS.
  * The layout also fixes the INTERPOLATION METHOD (GridForce::setInterpolationMethod, openmmapi/include/GridForce.h:296):
  * the four above are trilinear (method 0, ReferenceGridForceKernels.cpp:1016-1084);
- *   BSPLINE cubic B-spline (method 1, :727-795): the index clamping of the 4x4x4 stencil is baked into a padded copy cut
- *          into tiles of 4 y-rows x 8 z-values (one 128-byte line in MIXED) advancing by 1 row / 5 values, so a stencil is
- *          4 lines read with 16 aligned 32-byte loads; 6.4x the raw grid. Never chosen by AUTO. */
+ *   BSPLINE cubic B-spline (method 1, :727-795): the index clamping of the 4x4x4 stencil is baked into a padded copy, and
+ *          for every cell and padded x-plane the 4x4 (y,z) window is stored as one contiguous 64-byte brick (128 bytes in
+ *          DOUBLE), so a stencil is 4 bricks read with 8 (16) aligned 32-byte loads of exactly its 64 values; 16x the
+ *          raw grid. Never chosen by AUTO. */
 typedef enum {
     GFB_LAYOUT_AUTO = 0, GFB_LAYOUT_CELLS = 1, GFB_LAYOUT_ROWS = 2, GFB_LAYOUT_PAIRS = 3, GFB_LAYOUT_BSPLINE = 4
 } gfb_layout;

@@ -268,10 +268,10 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
         g->row_chunks = (counts[2] - 2) / 3 + 1;
         n_units = (size_t) counts[0] * (counts[1] - 1) * g->row_chunks;
         g->bytes = n_units * 32;
-    } else {   // BSPLINE: tiles (a < nx+2, ty < ny-1, tc) of 4 rows x 8 values, one thread per tile row
-        g->row_chunks = (counts[2] - 2) / 5 + 1;
-        n_units = (size_t) (counts[0] + 2) * (counts[1] - 1) * g->row_chunks * 4;
-        g->bytes = n_units * 8 * (precision == GFB_PRECISION_MIXED ? sizeof(float) : sizeof(double));
+    } else {   // BSPLINE: bricks (a < nx+2, iy < ny-1, iz < nz-1) of 4 rows x 4 values, one thread per brick row
+        g->row_chunks = counts[2] - 1;
+        n_units = (size_t) (counts[0] + 2) * (counts[1] - 1) * (counts[2] - 1) * 4;
+        g->bytes = n_units * 4 * (precision == GFB_PRECISION_MIXED ? sizeof(float) : sizeof(double));
     }
     g->cells = nullptr;
 
@@ -297,8 +297,8 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
         } else if (layout == GFB_LAYOUT_PAIRS) {
             gf_repack_pairs_kernel<<<blocks, 256, 0, dev->stream>>>(d_vals, cf, counts[0], counts[1], counts[2], g->row_chunks);
         } else {
-            if (mixed) gf_repack_bspline_kernel<float><<<blocks, 256, 0, dev->stream>>>(d_vals, cf, counts[0], counts[1], counts[2], g->row_chunks);
-            else gf_repack_bspline_kernel<double><<<blocks, 256, 0, dev->stream>>>(d_vals, cd, counts[0], counts[1], counts[2], g->row_chunks);
+            if (mixed) gf_repack_bspline_kernel<float><<<blocks, 256, 0, dev->stream>>>(d_vals, cf, counts[0], counts[1], counts[2]);
+            else gf_repack_bspline_kernel<double><<<blocks, 256, 0, dev->stream>>>(d_vals, cd, counts[0], counts[1], counts[2]);
         }
         g_launches++;
         err = cudaGetLastError();
@@ -828,7 +828,7 @@ static bool bspline_tiles_eligible(const gfb_kernel* k, const EvalParams& p) {
     }();
     if (off || k->precision != GFB_PRECISION_MIXED || k->grids[0]->layout != GFB_LAYOUT_BSPLINE || !k->same_geom) return false;
     if (p.order != nullptr) return false;
-    return k->grids[0]->bytes / 128 < 0x7fffffffull;
+    return k->grids[0]->bytes / 64 < 0x7fffffffull;   // 32-bit brick index
 }
 
 template <int FMODE>

@@ -1,16 +1,14 @@
-// Cubic B-spline evaluation kernel for MIXED-precision grids in the BSPLINE tile layout that share one geometry
+// Cubic B-spline evaluation kernel for MIXED-precision grids in the BSPLINE brick layout that share one geometry
 // (GridForce::setInterpolationMethod(1); reference platforms/reference/src/ReferenceGridForceKernels.cpp:727-795).
 // Everything else B-spline (DOUBLE precision, grids of different geometry, an evaluation order) runs
 // gf_eval_kernel<S, BSPLINE, ...> in gf_kernels.cuh, which holds the layout's description and the reference arithmetic.
 //
-// Why a second kernel. The general kernel reads a stencil with 16 LDG.E.256 per lane and grid. An SM retires about one
-// gather LANE per clock whatever the load width, so 16 x 3 grids x 3.08 M atoms of C5's shape cost
-// 0.53 ms in the L1 pipeline alone (measured: 1.07 ms at 63 % L1 throughput, 128 registers, 24 % of warp slots).
-// Here a stencil's four 128-byte tiles are fetched as four full LINES: the eight lanes of an octet copy the eight
-// 16-byte granules of one tile with cp.async (LDGSTS.128), one warp instruction = the 4 tiles of one atom = 4 L2
-// requests instead of 16 x 32 B from one lane. The tiles land in an XOR-swizzled slice of shared memory (16 KB per warp,
-// no bank conflicts on either side); the owning lane then reads its 64+64 values with LDS.128. Per warp and grid:
-// 32 LDGSTS + 32 x 32 LDS.128 instead of 512 LDG.256-lanes.
+// Why a second kernel. The general kernel reads a stencil with 8 LDG.E.256 per lane and grid. An SM retires about one
+// gather LANE per clock whatever the load width, so the L1 pipeline bounds it. Here a stencil's four
+// 64-byte bricks are fetched cooperatively: four lanes copy the four 16-byte rows of one brick with cp.async
+// (LDGSTS.128), so ONE warp instruction brings the 8 bricks of two atoms (8 L2 requests of 64 bytes) instead of 8 x 32 B
+// from one lane. The bricks land in an XOR-swizzled slice of shared memory (8 KB per warp, no bank conflicts on either
+// side); the owning lane then reads its 64 values with 16 LDS.128. Per warp and grid: 16 LDGSTS + 16 x 32 LDS.128.
 #ifndef GF_EVAL_BSPLINE_CUH_
 #define GF_EVAL_BSPLINE_CUH_
 
@@ -18,33 +16,32 @@
 
 namespace gfb {
 
-constexpr int kBsBlock = 64;                 // 2 warps x 16 KB of tiles: 6 blocks (12 warps, 198 KB of smem) per SM
-constexpr unsigned kBsWarpBytes = 32 * 512;  // 32 atoms x 4 tiles x 128 bytes
+#ifndef GFB_BS_MINBLOCKS
+#define GFB_BS_MINBLOCKS 4
+#endif
+constexpr int kBsBlock = 128;                // 4 warps x 8 KB of bricks: 6 blocks (24 warps, 192 KB of smem) per SM
+constexpr unsigned kBsWarpBytes = 32 * 256;  // 32 atoms x 4 bricks x 64 bytes
 
 // Per-atom interpolation weights, computed once and used for every grid (all grids share the geometry).
 struct BsWeights {
-    double bx[4], by[4], wz[8];            // value path, FP64; z folded into 8 zero-padded weights (bspline_interpolate)
-    float dbx[4], dby[4], dwz[8];          // gradient path, FP32
+    double bx[4], by[4], bz[4];            // value path, FP64
+    float dbx[4], dby[4], dbz[4];          // gradient path, FP32
 };
-__device__ __forceinline__ void bspline_weights(double fx, double fy, double fz, int off, BsWeights& w) {
-    double d[4], bz[4], dbz[4];
+__device__ __forceinline__ void bspline_weights(double fx, double fy, double fz, BsWeights& w) {
+    double d[4];
     bspline_basis(fx, w.bx, d);   // :741-748
 #pragma unroll
     for (int k = 0; k < 4; k++) w.dbx[k] = (float) d[k];
     bspline_basis(fy, w.by, d);
 #pragma unroll
     for (int k = 0; k < 4; k++) w.dby[k] = (float) d[k];
-    bspline_basis(fz, bz, dbz);
+    bspline_basis(fz, w.bz, d);
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const int m = k - off;
-        w.wz[k] = m == 0 ? bz[0] : m == 1 ? bz[1] : m == 2 ? bz[2] : m == 3 ? bz[3] : 0.0;
-        w.dwz[k] = (float) (m == 0 ? dbz[0] : m == 1 ? dbz[1] : m == 2 ? dbz[2] : m == 3 ? dbz[3] : 0.0);
-    }
+    for (int k = 0; k < 4; k++) w.dbz[k] = (float) d[k];
 }
 
-// One lane's stencil out of its 512-byte smem region (4 tiles of 4 rows x 8 floats; granule c of a tile stored at
-// c ^ (lane & 7)). Value FP64 from the FP32 points, gradient FP32.
+// One lane's stencil out of its 256-byte smem region: 16 granules of 16 bytes, granule 4*i + r = row r of x-plane i,
+// stored at position (4*i + r) ^ (lane & 7). Value FP64 from the FP32 points, gradient FP32.
 __device__ __forceinline__ void bspline_from_smem(unsigned rbase, unsigned sw, const BsWeights& w, double& val, float& gx,
                                                   float& gy, float& gz) {
     val = 0.0;
@@ -55,18 +52,18 @@ __device__ __forceinline__ void bspline_from_smem(unsigned rbase, unsigned sw, c
         float pdy = 0.f, pdz = 0.f;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            float v[8];
-            lds128(rbase + 128u * i + (((2u * r) << 4) ^ sw), v);
-            lds128(rbase + 128u * i + (((2u * r + 1u) << 4) ^ sw), v + 4);
+            float v[4];
+            lds128(rbase + (((4u * i + r) << 4) ^ sw), v);
             double rz = 0.0;
-            float drz = 0.f;
+            float rzs = 0.f, drz = 0.f;
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                rz = fma(w.wz[k], (double) v[k], rz);
-                drz = fmaf(w.dwz[k], v[k], drz);
+            for (int k = 0; k < 4; k++) {
+                rz = fma(w.bz[k], (double) v[k], rz);
+                rzs = fmaf((float) w.bz[k], v[k], rzs);
+                drz = fmaf(w.dbz[k], v[k], drz);
             }
             pv = fma(w.by[r], rz, pv);
-            pdy = fmaf(w.dby[r], (float) rz, pdy);
+            pdy = fmaf(w.dby[r], rzs, pdy);
             pdz = fmaf((float) w.by[r], drz, pdz);
         }
         val = fma(w.bx[i], pv, val);
@@ -78,7 +75,7 @@ __device__ __forceinline__ void bspline_from_smem(unsigned rbase, unsigned sw, c
 
 //   FMODE  gfb_force_mode;  SINGLE  one replica and no energy slots (block-level energy reduction)
 template <int FMODE, bool SINGLE>
-__global__ void __launch_bounds__(kBsBlock, 6) gf_eval_bspline_kernel(const __grid_constant__ EvalParams p) {
+__global__ void __launch_bounds__(kBsBlock, GFB_BS_MINBLOCKS) gf_eval_bspline_kernel(const __grid_constant__ EvalParams p) {
     __shared__ __align__(128) unsigned char s_tiles[(kBsBlock / 32) * kBsWarpBytes];
 
     const unsigned tid = threadIdx.x;
@@ -118,17 +115,16 @@ __global__ void __launch_bounds__(kBsBlock, 6) gf_eval_bspline_kernel(const __gr
     const GridView& G = p.grid[0];
     const FastCell fc = classify_fast(G, p.near_int, x, y, z, active);
     const bool inside = fc.inside;
-    const int tc = fc.iz / 5, off = fc.iz - 5 * tc;
-    const unsigned tile0 = inside ? (unsigned) ((fc.ix * G.nc[1] + fc.iy) * G.row_chunks + tc) : 0xffffffffu;
-    const unsigned plane_tiles = (unsigned) (G.nc[1] * G.row_chunks);   // tiles from one x-plane to the next
+    const unsigned brick0 = inside ? (unsigned) ((fc.ix * G.nc[1] + fc.iy) * G.nc[2] + fc.iz) : 0xffffffffu;
+    const unsigned plane_bricks = (unsigned) (G.nc[1] * G.nc[2]);   // bricks from one x-plane to the next
 
     const unsigned warp_base = (unsigned) __cvta_generic_to_shared(s_tiles) + (tid >> 5) * kBsWarpBytes;
-    const unsigned gran = lane & 7u, octet = lane >> 3;
-    const unsigned rbase = warp_base + lane * 512u;
+    const unsigned sub = lane & 15u, half = lane >> 4;   // sub = 4*plane + row: which 16 bytes of an atom's 256 this lane copies
+    const unsigned rbase = warp_base + lane * 256u;
     const unsigned sw = (lane & 7u) << 4;
 
     BsWeights wts;
-    bspline_weights(fc.fx, fc.fy, fc.fz, off, wts);
+    bspline_weights(fc.fx, fc.fy, fc.fz, wts);
 
     double e_total = 0.0;
     double Fx = 0.0, Fy = 0.0, Fz = 0.0;
@@ -144,15 +140,15 @@ __global__ void __launch_bounds__(kBsBlock, 6) gf_eval_bspline_kernel(const __gr
         const GridView& Gg = p.grid[g];
         const double s = active ? Gg.scaling[ia] : 0.0;
         const bool interp = inside && s != 0.0;   // :706
-        // ---- fetch: round i brings the four tiles (x-planes) of lane i's atom, one octet per tile -----------------
-        const unsigned mytile = interp ? tile0 : 0xffffffffu;
-        const char* lane_base = static_cast<const char*>(Gg.cells) + 16u * gran + 128ull * (unsigned long long) octet * plane_tiles;
-        __syncwarp();   // the previous grid's tiles have been consumed
+        // ---- fetch: round i brings the four bricks of the atoms of lanes 2i and 2i+1, sixteen lanes per atom --------
+        const unsigned mybrick = interp ? brick0 : 0xffffffffu;
+        const char* lane_base = static_cast<const char*>(Gg.cells) + 16u * (sub & 3u) + 64ull * (unsigned long long) (sub >> 2) * plane_bricks;
+        __syncwarp();   // the previous grid's bricks have been consumed
 #pragma unroll 8
-        for (int i = 0; i < 32; i++) {
-            const unsigned tl = __shfl_sync(kFull, mytile, i);
-            if (tl != 0xffffffffu)
-                cp_async16(warp_base + (unsigned) i * 512u + octet * 128u + ((gran ^ ((unsigned) i & 7u)) << 4), lane_base + 128ull * tl);
+        for (int i = 0; i < 16; i++) {
+            const unsigned A = 2u * (unsigned) i + half;
+            const unsigned bk = __shfl_sync(kFull, mybrick, (int) A);
+            if (bk != 0xffffffffu) cp_async16(warp_base + A * 256u + ((sub ^ (A & 7u)) << 4), lane_base + 64ull * bk);
         }
         cp_async_wait_all();
         __syncwarp();

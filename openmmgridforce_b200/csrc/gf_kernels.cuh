@@ -275,14 +275,15 @@ __device__ __forceinline__ void accumulate_inside(const GridView& G, const S v[8
 // Cubic B-spline interpolation (GridForce::setInterpolationMethod(1); ReferenceGridForceKernels.cpp:727-795):
 // 4x4x4 points ix-1..ix+2 (indices clamped into the grid), separable weights bx[i]*by[j]*bz[k].
 //
-// Layout GFB_LAYOUT_BSPLINE (gf_repack_bspline_kernel): the clamping is baked into a padded copy
-// P[a][b][c] = V[clamp(a-1)][clamp(b-1)][clamp(c-1)], so the stencil of cell (ix,iy,iz) is P[ix..ix+3][iy..iy+3][iz..iz+3],
-// and the copy is cut into TILES of 4 y-rows x 8 z-values (128 bytes of floats = one L2/HBM line; 256 bytes of doubles):
-// tile (a, ty, tc) holds P[a][ty..ty+3][5tc..5tc+7]. Consecutive tiles advance by ONE row in y and by FIVE values in z,
-// so every 4x4 (y,z) window lies inside a single tile: a stencil is 4 lines (one per x-plane), read with 16 aligned
-// 32-byte loads, instead of 64 scattered 4-byte loads to 16 lines (reference CUDA kernel, gridForce.cu:103-147).
-// The per-lane z offset inside the tile (0..4) is folded into the WEIGHTS (8 weights, zero outside the window), so
-// no value has to be selected at a run-time register index. Copy size: 6.4x the raw grid.
+// Layout GFB_LAYOUT_BSPLINE (gf_repack_bspline_kernel) — the "brick" layout SURVEY.md §8f anticipates: the clamping is
+// baked into a padded copy P[a][b][c] = V[clamp(a-1)][clamp(b-1)][clamp(c-1)], so the stencil of cell (ix,iy,iz) is
+// P[ix..ix+3][iy..iy+3][iz..iz+3], and for EVERY cell (iy,iz) and every padded plane a the 4x4 (y,z) window
+// P[a][iy..iy+3][iz..iz+3] is stored as one contiguous brick of 16 values (64 bytes of floats, 128 of doubles), z
+// fastest: brick (a, iy, iz) at ((a*(ny-1) + iy)*(nz-1) + iz). A stencil is the 4 bricks a = ix..ix+3: 8 aligned
+// 32-byte loads (16 in FP64) of exactly the 64 values it needs — no unaligned windows, no zero-padded weights — instead
+// of 64 scattered 4-byte loads to 16 lines (reference CUDA kernel, gridForce.cu:103-147). Copy size: 16x the raw grid
+// (192^3: 453 MB; the first tile layout, 4 rows x 8 z-values advancing by 5, was 6.4x but moved twice the bytes and
+// spent half of its conversions and FMAs on zero weights).
 //
 // Arithmetic: S = double -> everything FP64. S = float -> gradient FP32, interpolated VALUE FP64 from the FP32-stored
 // points and FP64 weights (same reasoning as trilinear_value_f64).
@@ -300,10 +301,16 @@ __device__ __forceinline__ void bspline_basis(double t, double b[4], double d[4]
     d[3] = t2 * 0.5;
 }
 
-__device__ __forceinline__ void load_row8(const float* p, float v[8]) { load32(p, v); }
-__device__ __forceinline__ void load_row8(const double* p, double v[8]) {
+// The 16 values [row][z] of one brick.
+__device__ __forceinline__ void load_brick(const float* p, float v[16]) {
+    load32(p, v);
+    load32(p + 8, v + 8);
+}
+__device__ __forceinline__ void load_brick(const double* p, double v[16]) {
     load32(p, v);
     load32(p + 4, v + 4);
+    load32(p + 8, v + 8);
+    load32(p + 12, v + 12);
 }
 
 template <typename S>
@@ -314,27 +321,14 @@ __device__ __forceinline__ void bspline_interpolate(const GridView& G, int ix, i
     bspline_basis(fx, bx, dbx);   // :741-748
     bspline_basis(fy, by, dby);
     bspline_basis(fz, bz, dbz);
-    const int tc = iz / 5, off = iz - 5 * tc;
-    double wz[8];        // value weights over the tile's 8 z-values
-    S wzs[8], dwz[8];    // gradient path (S); wzs aliases wz when S = double
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const int m = k - off;
-        const double w = m == 0 ? bz[0] : m == 1 ? bz[1] : m == 2 ? bz[2] : m == 3 ? bz[3] : 0.0;
-        const double dw = m == 0 ? dbz[0] : m == 1 ? dbz[1] : m == 2 ? dbz[2] : m == 3 ? dbz[3] : 0.0;
-        wz[k] = w;
-        wzs[k] = (S) w;
-        dwz[k] = (S) dw;
-    }
-    const S* tile = static_cast<const S*>(G.cells) + (((size_t) ix * G.nc[1] + iy) * G.row_chunks + tc) * 32;
-    const size_t plane = (size_t) G.nc[1] * G.row_chunks * 32;    // tiles of the next x-plane
+    const S* brick = static_cast<const S*>(G.cells) + (((size_t) ix * G.nc[1] + iy) * G.nc[2] + iz) * 16;
+    const size_t plane = (size_t) G.nc[1] * G.nc[2] * 16;    // bricks of the next x-plane
     val = 0.0;
     gx = gy = gz = (S) 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        S v[4][8];
-#pragma unroll
-        for (int r = 0; r < 4; r++) load_row8(tile + i * plane + 8 * r, v[r]);   // one line (two in FP64)
+        S v[16];
+        load_brick(brick + i * plane, v);
         double pv = 0.0;          // sum over (j,k) of by*bz*V in this x-plane
         S pdy = (S) 0, pdz = (S) 0;
 #pragma unroll
@@ -342,10 +336,10 @@ __device__ __forceinline__ void bspline_interpolate(const GridView& G, int ix, i
             double rz = 0.0;
             S rzs = (S) 0, drz = (S) 0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                rz = fma(wz[k], (double) v[r][k], rz);
-                if (!F64) rzs = fma(wzs[k], v[r][k], rzs);
-                drz = fma(dwz[k], v[r][k], drz);
+            for (int k = 0; k < 4; k++) {
+                rz = fma(bz[k], (double) v[4 * r + k], rz);
+                if (!F64) rzs = fma((S) bz[k], v[4 * r + k], rzs);
+                drz = fma((S) dbz[k], v[4 * r + k], drz);
             }
             if (F64) rzs = (S) rz;
             pv = fma(by[r], rz, pv);
@@ -713,25 +707,25 @@ __global__ void __launch_bounds__(256) gf_repack_pairs_kernel(const double* __re
     }
 }
 
-// BSPLINE tiles (see bspline_interpolate): one thread per (tile, row r): 8 values
-// P[a][ty+r][5tc+k] = V[clamp(a-1)][clamp(ty+r-1)][clamp(5tc+k-1)], k = 0..7. a < nx+2, ty < ny-1, tc < row_chunks.
+// BSPLINE bricks (see bspline_interpolate): one thread per (brick, row r): the 4 values
+// P[a][iy+r][iz+k] = V[clamp(a-1)][clamp(iy+r-1)][clamp(iz+k-1)], k = 0..3. a < nx+2, iy < ny-1, iz < nz-1.
 template <typename S>
 __global__ void __launch_bounds__(256) gf_repack_bspline_kernel(const double* __restrict__ vals, S* __restrict__ out,
-                                                                int nx, int ny, int nz, int row_chunks) {
-    const size_t total = (size_t) (nx + 2) * (ny - 1) * row_chunks * 4;
+                                                                int nx, int ny, int nz) {
+    const size_t total = (size_t) (nx + 2) * (ny - 1) * (nz - 1) * 4;
     for (size_t c = (size_t) blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (size_t) gridDim.x * blockDim.x) {
         const int r = (int) (c & 3);
         size_t t = c >> 2;
-        const int tc = (int) (t % row_chunks);
-        t /= row_chunks;
-        const int ty = (int) (t % (ny - 1));
+        const int iz = (int) (t % (nz - 1));
+        t /= (nz - 1);
+        const int iy = (int) (t % (ny - 1));
         const int a = (int) (t / (ny - 1));
         const int gx = min(max(a - 1, 0), nx - 1);
-        const int gy = min(max(ty + r - 1, 0), ny - 1);
+        const int gy = min(max(iy + r - 1, 0), ny - 1);
         const double* src = vals + ((size_t) gx * ny + gy) * nz;
-        S* o = out + c * 8;
+        S* o = out + c * 4;
 #pragma unroll
-        for (int k = 0; k < 8; k++) o[k] = (S) src[min(max(5 * tc + k - 1, 0), nz - 1)];
+        for (int k = 0; k < 4; k++) o[k] = (S) src[min(max(iz + k - 1, 0), nz - 1)];
     }
 }
 

@@ -55,7 +55,7 @@ def test_bspline_golden_vectors(gpu_device, name, precision):
 @pytest.mark.parametrize("precision", [0, 1], ids=["mixed", "double"])
 def test_bspline_batched_replicas_mixed_geometries(gpu_device, oracle_built, precision):
     """64 replicas x 47 atoms x 3 B-spline grids; the oracle evaluates replica by replica, grid by grid. Odd point counts
-    exercise the z tiling (5 values per tile step) at every remainder."""
+    exercise odd and even brick counts on every axis."""
     import openmmgridforce_b200 as gf
     from openmmgridforce_b200 import workloads as W
     lig, q = W.ligand47()
@@ -115,8 +115,8 @@ def test_bspline_memory_footprint(gpu_device):
     import openmmgridforce_b200 as gf
     counts = (50, 60, 72)
     g = gf.Grid(gpu_device, counts, (0.1, 0.1, 0.1), (0, 0, 0), np.zeros(counts), 0, layout=gf.LAYOUT_BSPLINE)
-    tiles = (counts[0] + 2) * (counts[1] - 1) * ((counts[2] - 2) // 5 + 1)
-    assert g.device_bytes == tiles * 128
+    bricks = (counts[0] + 2) * (counts[1] - 1) * (counts[2] - 1)      # one 4x4 (y,z) window per padded plane and cell
+    assert g.device_bytes == bricks * 64
     g.close()
     with pytest.raises(gf.GridForceB200Error):
         gf.Kernel(gpu_device, [gf.Grid(gpu_device, counts, (0.1, 0.1, 0.1), (0, 0, 0), np.zeros(counts), 0, layout=gf.LAYOUT_BSPLINE),
