@@ -503,10 +503,13 @@ def main():
         dist.all_gather_into_tensor(check, energy_bufs[last])
         if not torch.equal(check, gathered_view(counter[0] % 2)):
             raise SystemExit(f"rank {rank}: energy gather ({gather_mode}) does not match NCCL all_gather")
+    per_rank_us = [secs / args.steps * 1e6]
     if world > 1:
         t = torch.tensor([secs], dtype=torch.float64, device=tdev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        secs_max = float(t.item())
+        all_t = torch.empty(world, dtype=torch.float64, device=tdev)
+        dist.all_gather_into_tensor(all_t, t)          # every rank's own device-timed loop: the value uses the MAX
+        per_rank_us = [float(x) / args.steps * 1e6 for x in all_t.tolist()]
+        secs_max = float(all_t.max().item())
         dist.barrier()
     else:
         secs_max = secs
@@ -557,7 +560,8 @@ def main():
                         "h2d_bytes_per_step": int(w.pos.nbytes), "d2h_bytes_per_step": int(w.pos.nbytes + 8 * REPLICAS_PER_GPU),
                         "api": "gfb_kernel_execute_host (pinned host positions in, forces + energies out; H2D by copy engine in 8 chunks, "
                                "forces stored by the kernels straight into the pinned host buffer)"},
-                "gpu_launches": int(launches), "clocks": clocks}
+                "gpu_launches": int(launches), "clocks": clocks,
+                "per_rank_us_per_step": [round(x, 2) for x in per_rank_us]}
         if world == 1 and not args.no_extras:
             line["other_workloads"] = extras
             line["cpu_baseline"] = cpu_baseline(w)
