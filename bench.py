@@ -111,7 +111,7 @@ def pinned_array(shape, dtype=np.float64):
 # device-timed loops
 # ----------------------------------------------------------------------------------------------------------------
 def time_device_steps(torch, gf, kern, pos_sets, n_replicas, n_atoms, steps, warmup, stream, post_step=None,
-                      force_mode=None, energy_bufs_out=None, final_step=None):
+                      force_mode=None, energy_bufs_out=None, final_step=None, barrier=None):
     """K launches on `stream`, rotating through pos_sets (and matching force/energy buffers). Returns
     (seconds, launches) with CUDA events recorded on the launching stream."""
     force_mode = gf.FORCE_FIXED_ADD if force_mode is None else force_mode
@@ -154,6 +154,8 @@ def time_device_steps(torch, gf, kern, pos_sets, n_replicas, n_atoms, steps, war
         if final_step is not None:   # untimed: the collective's first call sets up NCCL's connections (milliseconds)
             final_step(d_e3[(warmup - 1) % 4]).wait()
         stream.synchronize()
+        if barrier is not None:      # all ranks enter the timed region together (barrier + synchronize on both sides)
+            barrier()
         l0 = gf.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -164,6 +166,8 @@ def time_device_steps(torch, gf, kern, pos_sets, n_replicas, n_atoms, steps, war
             stream.wait_event(final_step(d_e3[(warmup + steps - 1) % 4]).ev)     # the clock stops after the gather
         e1.record(stream)
         stream.synchronize()
+        if barrier is not None:
+            barrier()
         launches = gf.launch_count() - l0
     return e0.elapsed_time(e1) * 1e-3, launches, bufs
 
@@ -494,7 +498,8 @@ def main():
     secs, launches, bufs = time_device_steps(torch, gf, kern, [d_pos], REPLICAS_PER_GPU, N_ATOMS, args.steps, args.warmup, stream,
                                              post_step=post_step, energy_bufs_out=energy_bufs,
                                              final_step=(lambda d_e: post_step(d_e, force=True))
-                                             if world > 1 and args.energy_gather == "final" else None)
+                                             if world > 1 and args.energy_gather == "final" else None,
+                                             barrier=(lambda: (dist.barrier(), torch.cuda.synchronize())) if world > 1 else None)
     torch.cuda.synchronize()
     if world > 1:
         # outside the timed region: the last step's gathered energies must equal a plain blocking NCCL all-gather of them
