@@ -150,6 +150,13 @@ class GridForce:
             raise RuntimeError("GridForce: inv_power must be non-zero when mode != NONE")
         if mode == InvPowerMode_NONE and inv_power != 0.0:
             raise RuntimeError("GridForce: inv_power must be 0 when mode == NONE")
+        if len(self._vals):      # conflicting mode changes once a grid is loaded (reference GridForce.cpp:199-211)
+            if self._inv_power_mode == InvPowerMode_STORED and mode == InvPowerMode_RUNTIME:
+                raise RuntimeError("GridForce: Cannot set RUNTIME mode on grid that already has STORED transformation. "
+                                   "This would apply transformation twice!")
+            if self._inv_power_mode == InvPowerMode_RUNTIME and mode == InvPowerMode_STORED:
+                raise RuntimeError("GridForce: Cannot set STORED mode on untransformed grid loaded with RUNTIME mode. "
+                                   "Call applyInvPowerTransformation() first.")
         self._inv_power_mode, self._inv_power = mode, float(inv_power)
 
     def getInvPower(self):

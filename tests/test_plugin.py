@@ -37,6 +37,32 @@ def test_api_validation_matches_reference_messages():
         f.setInvPowerMode(gfp.InvPowerMode_STORED, 0.0)
 
 
+def test_inv_power_mode_bookkeeping_matches_reference():
+    """Mode transitions and their exceptions (reference GridForce.cpp:190-272); none of this needs a GPU because the
+    checks come before any device work."""
+    import openmmgridforce_b200.gridforceplugin as gfp
+    f = gfp.GridForce()
+    f.addGridCounts(2, 2, 2)
+    f.addGridSpacing(0.1, 0.1, 0.1)
+    with pytest.raises(RuntimeError, match="inv_power must be 0 when mode == NONE"):
+        f.setInvPowerMode(gfp.InvPowerMode_NONE, 2.0)
+    f.setInvPowerMode(gfp.InvPowerMode_STORED, 4.0)          # no values yet: any mode may be chosen
+    f.setGridValues(np.ones(8))
+    with pytest.raises(RuntimeError, match="already has STORED transformation"):
+        f.setInvPowerMode(gfp.InvPowerMode_RUNTIME, 4.0)
+    with pytest.raises(RuntimeError, match="when mode == RUNTIME"):
+        f.applyInvPowerTransformation()                      # STORED grids are already transformed
+    g = gfp.GridForce()
+    g.setGridValues(np.ones(8))
+    g.setInvPowerMode(gfp.InvPowerMode_RUNTIME, 4.0)
+    with pytest.raises(RuntimeError, match="Call applyInvPowerTransformation"):
+        g.setInvPowerMode(gfp.InvPowerMode_STORED, 4.0)
+    h = gfp.GridForce()
+    h.setInvPowerMode(gfp.InvPowerMode_RUNTIME, 4.0)
+    with pytest.raises(RuntimeError, match="No grid values to transform"):
+        h.applyInvPowerTransformation()
+
+
 def _build_system(gfp, c, ligand_atoms=None):
     system = gfp.System()
     for _ in range(c["pos"].shape[0]):
