@@ -212,7 +212,12 @@ GFB_API int gfb_kernel_set_launch_overlap(gfb_kernel* k, int enable);
  *   grid_energies host out [n_replicas][n_grids] or NULL
  *   forces    host [n_replicas][n_particles][3]; force_mode STORE overwrites the evaluated particles'
  *             entries with the total grid force, ADD adds to what is there. NULL = energy only.
- * Synchronous: returns after the results are in the host buffers. H2D/D2H go through pinned staging. */
+ * Synchronous: returns after the results are in the host buffers. How the data moves:
+ *   - one replica of <= 4096 particles (a ligand per MD step): ONE launch on host-mapped pinned staging — positions read
+ *     and forces/energy stored over PCIe by the kernel itself, no copy-engine transfers;
+ *   - batches: positions uploaded by the copy engine in up to 8 chunks on their own stream; with STORE and no particle
+ *     indirection the kernels store the forces straight into the caller's pinned buffer (pageable buffers: into pinned
+ *     staging, then memcpy), otherwise chunked D2H copies on a third stream. */
 GFB_API int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, const double* pos,
                                     double* energies, double* grid_energies, double* forces, int force_mode);
 
