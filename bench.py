@@ -39,7 +39,7 @@ REPLICAS_PER_GPU = 65536
 N_ATOMS = 47
 N_GRIDS = 3
 GRID_N = 192
-C5_DRAM_BYTES_PER_LAUNCH = 494.7e6     # measured once per change with ncu --set full (profiles/README.md, r1b)
+C5_DRAM_BYTES_PER_LAUNCH = 495.4e6     # measured once per change with ncu --set full (profiles/README.md, r1c)
 
 
 def b_alg(n_grids, precision=0):
@@ -576,8 +576,8 @@ def main():
                                energy_gather_when=args.energy_gather if world > 1 else "none"),
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
                              "traffic": C5_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch",
-                             "traffic_source": "profiles/r1b_c5_lines_warm_raw.csv: dram__bytes_read.sum 397.0 MB + "
-                                               "dram__bytes_write.sum 97.7 MB (ncu --set full, this kernel, this workload)",
+                             "traffic_source": "profiles/r1c_c5_lines_warm_raw.csv: dram__bytes_read.sum 397.1 MB + "
+                                               "dram__bytes_write.sum 98.3 MB (ncu --set full, this kernel, this workload)",
                              "peak_source": peak_src, "kernel": "gf_eval_lines_kernel<3 grids, FIXED_ADD> (one 128-byte record per cell)",
                              "bytes_per_eval": b_alg(N_GRIDS), "evals_per_launch": evals_step_rank,
                              "launch_us": kernel_us},
