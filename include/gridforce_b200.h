@@ -57,9 +57,9 @@ typedef enum { GFB_PRECISION_MIXED = 0, GFB_PRECISION_DOUBLE = 1 } gfb_precision
  * The layout also fixes the INTERPOLATION METHOD (GridForce::setInterpolationMethod, openmmapi/include/GridForce.h:296):
  * the four above are trilinear (method 0, ReferenceGridForceKernels.cpp:1016-1084);
  *   BSPLINE cubic B-spline (method 1, :727-795): the index clamping of the 4x4x4 stencil is baked into a padded copy, and
- *          for every cell and padded x-plane the 4x4 (y,z) window is stored as one contiguous 64-byte brick (128 bytes in
- *          DOUBLE), so a stencil is 4 bricks read with 8 (16) aligned 32-byte loads of exactly its 64 values; 16x the
- *          raw grid. Never chosen by AUTO. */
+ *          for every cell and padded x-plane a the 4x4 (y,z) windows of planes a and a+1 are stored back to back as one
+ *          128-byte record (256 bytes in DOUBLE), so a stencil is 2 records = 2 full lines read with 8 (16) aligned
+ *          32-byte loads of exactly its 64 values; 32x the raw grid. Never chosen by AUTO. */
 typedef enum {
     GFB_LAYOUT_AUTO = 0, GFB_LAYOUT_CELLS = 1, GFB_LAYOUT_ROWS = 2, GFB_LAYOUT_PAIRS = 3, GFB_LAYOUT_BSPLINE = 4
 } gfb_layout;

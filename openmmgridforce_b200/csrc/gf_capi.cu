@@ -268,9 +268,9 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
         g->row_chunks = (counts[2] - 2) / 3 + 1;
         n_units = (size_t) counts[0] * (counts[1] - 1) * g->row_chunks;
         g->bytes = n_units * 32;
-    } else {   // BSPLINE: bricks (a < nx+2, iy < ny-1, iz < nz-1) of 4 rows x 4 values, one thread per brick row
+    } else {   // BSPLINE: records (a < nx+1, iy < ny-1, iz < nz-1) of 2 planes x 4 rows x 4 values, one thread per row
         g->row_chunks = counts[2] - 1;
-        n_units = (size_t) (counts[0] + 2) * (counts[1] - 1) * (counts[2] - 1) * 4;
+        n_units = (size_t) (counts[0] + 1) * (counts[1] - 1) * (counts[2] - 1) * 8;
         g->bytes = n_units * 4 * (precision == GFB_PRECISION_MIXED ? sizeof(float) : sizeof(double));
     }
     g->cells = nullptr;
@@ -828,7 +828,7 @@ static bool bspline_tiles_eligible(const gfb_kernel* k, const EvalParams& p) {
     }();
     if (off || k->precision != GFB_PRECISION_MIXED || k->grids[0]->layout != GFB_LAYOUT_BSPLINE || !k->same_geom) return false;
     if (p.order != nullptr) return false;
-    return k->grids[0]->bytes / 64 < 0x7fffffffull;   // 32-bit brick index
+    return k->grids[0]->bytes / 128 < 0x7fffffffull;   // 32-bit record index
 }
 
 template <int FMODE>

@@ -4,11 +4,11 @@
 // gf_eval_kernel<S, BSPLINE, ...> in gf_kernels.cuh, which holds the layout's description and the reference arithmetic.
 //
 // Why a second kernel. The general kernel reads a stencil with 8 LDG.E.256 per lane and grid. An SM retires about one
-// gather LANE per clock whatever the load width, so the L1 pipeline bounds it. Here a stencil's four
-// 64-byte bricks are fetched cooperatively: four lanes copy the four 16-byte rows of one brick with cp.async
-// (LDGSTS.128), so ONE warp instruction brings the 8 bricks of two atoms (8 L2 requests of 64 bytes) instead of 8 x 32 B
-// from one lane. The bricks land in an XOR-swizzled slice of shared memory (8 KB per warp, no bank conflicts on either
-// side); the owning lane then reads its 64 values with 16 LDS.128. Per warp and grid: 16 LDGSTS + 16 x 32 LDS.128.
+// gather LANE per clock whatever the load width, so the L1 pipeline bounds it. Here a stencil's two
+// 128-byte records are fetched as two full LINES: eight lanes copy the eight 16-byte rows of one record with cp.async
+// (LDGSTS.128), so ONE warp instruction brings the 4 records of two atoms (4 L2 requests of one line each) instead of
+// 8 x 32 B from one lane. The records land in an XOR-swizzled slice of shared memory (8 KB per warp, no bank conflicts on
+// either side); the owning lane then reads its 64 values with 16 LDS.128. Per warp and grid: 16 LDGSTS + 16 x 32 LDS.128.
 #ifndef GF_EVAL_BSPLINE_CUH_
 #define GF_EVAL_BSPLINE_CUH_
 
@@ -20,7 +20,7 @@ namespace gfb {
 #define GFB_BS_MINBLOCKS 4
 #endif
 constexpr int kBsBlock = 128;                // 4 warps x 8 KB of bricks: 6 blocks (24 warps, 192 KB of smem) per SM
-constexpr unsigned kBsWarpBytes = 32 * 256;  // 32 atoms x 4 bricks x 64 bytes
+constexpr unsigned kBsWarpBytes = 32 * 256;  // 32 atoms x 2 records x 128 bytes
 
 // Per-atom interpolation weights, computed once and used for every grid (all grids share the geometry).
 struct BsWeights {
@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(kBsBlock, GFB_BS_MINBLOCKS) gf_eval_bspline_ke
     const GridView& G = p.grid[0];
     const FastCell fc = classify_fast(G, p.near_int, x, y, z, active);
     const bool inside = fc.inside;
-    const unsigned brick0 = inside ? (unsigned) ((fc.ix * G.nc[1] + fc.iy) * G.nc[2] + fc.iz) : 0xffffffffu;
-    const unsigned plane_bricks = (unsigned) (G.nc[1] * G.nc[2]);   // bricks from one x-plane to the next
+    const unsigned brick0 = inside ? (unsigned) ((fc.ix * G.nc[1] + fc.iy) * G.nc[2] + fc.iz) : 0xffffffffu;   // record (ix,iy,iz)
+    const unsigned plane_recs = (unsigned) (G.nc[1] * G.nc[2]);   // records from one x-plane to the next
 
     const unsigned warp_base = (unsigned) __cvta_generic_to_shared(s_tiles) + (tid >> 5) * kBsWarpBytes;
     const unsigned sub = lane & 15u, half = lane >> 4;   // sub = 4*plane + row: which 16 bytes of an atom's 256 this lane copies
@@ -142,13 +142,14 @@ __global__ void __launch_bounds__(kBsBlock, GFB_BS_MINBLOCKS) gf_eval_bspline_ke
         const bool interp = inside && s != 0.0;   // :706
         // ---- fetch: round i brings the four bricks of the atoms of lanes 2i and 2i+1, sixteen lanes per atom --------
         const unsigned mybrick = interp ? brick0 : 0xffffffffu;
-        const char* lane_base = static_cast<const char*>(Gg.cells) + 16u * (sub & 3u) + 64ull * (unsigned long long) (sub >> 2) * plane_bricks;
+        // sub = 8*(which record: a = ix | ix+2) + 4*(which plane of it) + row: 16 bytes of a 128-byte record
+        const char* lane_base = static_cast<const char*>(Gg.cells) + 16u * (sub & 7u) + 128ull * (unsigned long long) (2u * (sub >> 3)) * plane_recs;
         __syncwarp();   // the previous grid's bricks have been consumed
 #pragma unroll 8
         for (int i = 0; i < 16; i++) {
             const unsigned A = 2u * (unsigned) i + half;
             const unsigned bk = __shfl_sync(kFull, mybrick, (int) A);
-            if (bk != 0xffffffffu) cp_async16(warp_base + A * 256u + ((sub ^ (A & 7u)) << 4), lane_base + 64ull * bk);
+            if (bk != 0xffffffffu) cp_async16(warp_base + A * 256u + ((sub ^ (A & 7u)) << 4), lane_base + 128ull * bk);
         }
         cp_async_wait_all();
         __syncwarp();

@@ -277,13 +277,14 @@ __device__ __forceinline__ void accumulate_inside(const GridView& G, const S v[8
 //
 // Layout GFB_LAYOUT_BSPLINE (gf_repack_bspline_kernel) — the "brick" layout SURVEY.md §8f anticipates: the clamping is
 // baked into a padded copy P[a][b][c] = V[clamp(a-1)][clamp(b-1)][clamp(c-1)], so the stencil of cell (ix,iy,iz) is
-// P[ix..ix+3][iy..iy+3][iz..iz+3], and for EVERY cell (iy,iz) and every padded plane a the 4x4 (y,z) window
-// P[a][iy..iy+3][iz..iz+3] is stored as one contiguous brick of 16 values (64 bytes of floats, 128 of doubles), z
-// fastest: brick (a, iy, iz) at ((a*(ny-1) + iy)*(nz-1) + iz). A stencil is the 4 bricks a = ix..ix+3: 8 aligned
-// 32-byte loads (16 in FP64) of exactly the 64 values it needs — no unaligned windows, no zero-padded weights — instead
-// of 64 scattered 4-byte loads to 16 lines (reference CUDA kernel, gridForce.cu:103-147). Copy size: 16x the raw grid
-// (192^3: 453 MB; the first tile layout, 4 rows x 8 z-values advancing by 5, was 6.4x but moved twice the bytes and
-// spent half of its conversions and FMAs on zero weights).
+// P[ix..ix+3][iy..iy+3][iz..iz+3]. For EVERY cell (iy,iz) and every padded plane a <= nx, the two 4x4 (y,z) windows
+// P[a][iy..iy+3][iz..iz+3] and P[a+1][..][..] are stored back to back as one record of 2 x 16 values (128 bytes of floats
+// = exactly one L2/HBM line, 256 bytes of doubles), z fastest: record (a, iy, iz) at ((a*(ny-1) + iy)*(nz-1) + iz).
+// A stencil is the TWO records a = ix and a = ix+2: 8 aligned 32-byte loads (16 in FP64) of exactly the 64 values it
+// needs, in two full lines — no unaligned windows, no zero-padded weights, no partly used lines — instead of 64
+// scattered 4-byte loads to 16 lines (reference CUDA kernel, gridForce.cu:103-147). Copy size: 32x the raw grid
+// (192^3: 906 MB). Earlier layouts, for the record: tiles of 4 rows x 8 z-values advancing by 5 (6.4x; twice the bytes
+// per stencil, half of the FMAs on zero weights) and single 64-byte bricks (16x; a brick still cost 89 bytes of DRAM).
 //
 // Arithmetic: S = double -> everything FP64. S = float -> gradient FP32, interpolated VALUE FP64 from the FP32-stored
 // points and FP64 weights (same reasoning as trilinear_value_f64).
@@ -321,14 +322,14 @@ __device__ __forceinline__ void bspline_interpolate(const GridView& G, int ix, i
     bspline_basis(fx, bx, dbx);   // :741-748
     bspline_basis(fy, by, dby);
     bspline_basis(fz, bz, dbz);
-    const S* brick = static_cast<const S*>(G.cells) + (((size_t) ix * G.nc[1] + iy) * G.nc[2] + iz) * 16;
-    const size_t plane = (size_t) G.nc[1] * G.nc[2] * 16;    // bricks of the next x-plane
+    const S* rec = static_cast<const S*>(G.cells) + (((size_t) ix * G.nc[1] + iy) * G.nc[2] + iz) * 32;
+    const size_t plane2 = (size_t) G.nc[1] * G.nc[2] * 64;    // records two x-planes further on
     val = 0.0;
     gx = gy = gz = (S) 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         S v[16];
-        load_brick(brick + i * plane, v);
+        load_brick(rec + (i >> 1) * plane2 + (i & 1) * 16, v);   // planes ix, ix+1 | ix+2, ix+3
         double pv = 0.0;          // sum over (j,k) of by*bz*V in this x-plane
         S pdy = (S) 0, pdz = (S) 0;
 #pragma unroll
@@ -707,20 +708,21 @@ __global__ void __launch_bounds__(256) gf_repack_pairs_kernel(const double* __re
     }
 }
 
-// BSPLINE bricks (see bspline_interpolate): one thread per (brick, row r): the 4 values
-// P[a][iy+r][iz+k] = V[clamp(a-1)][clamp(iy+r-1)][clamp(iz+k-1)], k = 0..3. a < nx+2, iy < ny-1, iz < nz-1.
+// BSPLINE records (see bspline_interpolate): one thread per (record, half h, row r): the 4 values
+// P[a+h][iy+r][iz+k] = V[clamp(a+h-1)][clamp(iy+r-1)][clamp(iz+k-1)], k = 0..3. a < nx+1, iy < ny-1, iz < nz-1.
 template <typename S>
 __global__ void __launch_bounds__(256) gf_repack_bspline_kernel(const double* __restrict__ vals, S* __restrict__ out,
                                                                 int nx, int ny, int nz) {
-    const size_t total = (size_t) (nx + 2) * (ny - 1) * (nz - 1) * 4;
+    const size_t total = (size_t) (nx + 1) * (ny - 1) * (nz - 1) * 8;
     for (size_t c = (size_t) blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (size_t) gridDim.x * blockDim.x) {
         const int r = (int) (c & 3);
-        size_t t = c >> 2;
+        const int h = (int) ((c >> 2) & 1);
+        size_t t = c >> 3;
         const int iz = (int) (t % (nz - 1));
         t /= (nz - 1);
         const int iy = (int) (t % (ny - 1));
         const int a = (int) (t / (ny - 1));
-        const int gx = min(max(a - 1, 0), nx - 1);
+        const int gx = min(max(a + h - 1, 0), nx - 1);
         const int gy = min(max(iy + r - 1, 0), ny - 1);
         const double* src = vals + ((size_t) gx * ny + gy) * nz;
         S* o = out + c * 4;

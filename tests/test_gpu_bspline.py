@@ -115,8 +115,8 @@ def test_bspline_memory_footprint(gpu_device):
     import openmmgridforce_b200 as gf
     counts = (50, 60, 72)
     g = gf.Grid(gpu_device, counts, (0.1, 0.1, 0.1), (0, 0, 0), np.zeros(counts), 0, layout=gf.LAYOUT_BSPLINE)
-    bricks = (counts[0] + 2) * (counts[1] - 1) * (counts[2] - 1)      # one 4x4 (y,z) window per padded plane and cell
-    assert g.device_bytes == bricks * 64
+    records = (counts[0] + 1) * (counts[1] - 1) * (counts[2] - 1)     # two 4x4 (y,z) windows per padded plane and cell
+    assert g.device_bytes == records * 128
     g.close()
     with pytest.raises(gf.GridForceB200Error):
         gf.Kernel(gpu_device, [gf.Grid(gpu_device, counts, (0.1, 0.1, 0.1), (0, 0, 0), np.zeros(counts), 0, layout=gf.LAYOUT_BSPLINE),
