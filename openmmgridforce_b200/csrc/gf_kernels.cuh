@@ -417,7 +417,7 @@ __device__ __forceinline__ void accumulate_restraint(const GridView& G, double x
 
 template <typename S, int LAYOUT, int NG>
 __host__ __device__ constexpr int eval_min_blocks() {
-    return LAYOUT == GFB_LAYOUT_BSPLINE ? (sizeof(S) == 4 ? 2 : 1) : ((NG == 1 && sizeof(S) == 4) ? 6 : 4);
+    return LAYOUT == GFB_LAYOUT_BSPLINE ? 2 : ((NG == 1 && sizeof(S) == 4) ? 6 : 4);
 }
 
 template <typename S, int LAYOUT, int NG, bool SAME, int FMODE, bool SINGLE>
