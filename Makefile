@@ -25,18 +25,35 @@ $(LIBDIR)/libOpenMMGridForceB200.so: $(PLUGIN_SRCS) $(PLUGIN_HDRS) $(LIBDIR)/lib
 
 lib: $(LIBDIR)/libgridforce_b200.so
 
-$(LIBDIR)/libgridforce_b200.so: $(CSRC)/gf_capi.cu $(CSRC)/gf_kernels.cuh $(CSRC)/gf_eval_lines.cuh $(CSRC)/gf_gridfile.h $(CSRC)/gf_params.h include/gridforce_b200.h
-	mkdir -p $(LIBDIR)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/gf_capi.cu
+# One object per translation unit so that `make -j` builds the kernel families in parallel (the single-file build took
+# 90 s). Every header of csrc/ is a prerequisite of every object: an edit anywhere rebuilds, a stale .so cannot happen.
+CUDA_HDRS := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/gridforce_b200.h
+OBJDIR    := build/obj
+CUDA_OBJS := $(addprefix $(OBJDIR)/, gf_capi.o gf_grids.o gf_aux.o gf_multi.o gf_launch_general_f32.o gf_launch_general_f64.o \
+               gf_launch_lines_1.o gf_launch_lines_2.o gf_launch_lines_3.o gf_launch_lines_4.o gf_launch_records_f64.o gf_launch_bspline.o)
+
+$(OBJDIR)/gf_launch_lines_%.o: $(CSRC)/gf_launch_lines.cu $(CUDA_HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -DGFB_LINES_NG=$* -c -o $@ $<
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(CUDA_HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
+
+$(LIBDIR)/libgridforce_b200.so: $(CUDA_OBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -o $@ $(CUDA_OBJS) -ldl
 
 ptxas-info:
-	$(NVCC) $(NVFLAGS) -Xptxas -v -cubin -o /tmp/gf_capi.cubin $(CSRC)/gf_capi.cu
+	$(NVCC) $(NVFLAGS) -Xptxas -v -DGFB_LINES_NG=3 -cubin -o /tmp/gf_lines3.cubin $(CSRC)/gf_launch_lines.cu
+	$(NVCC) $(NVFLAGS) -Xptxas -v -cubin -o /tmp/gf_lines_f64.cubin $(CSRC)/gf_launch_records_f64.cu
 
 oracle:
 	$(MAKE) -C oracle all
 
 clean:
 	rm -f $(LIBDIR)/*.so
+	rm -rf $(OBJDIR)
 	$(MAKE) -C oracle clean
 
 .PHONY: all lib plugin oracle clean ptxas-info

@@ -28,8 +28,11 @@ extern "C" {
 #define GFB_API
 #endif
 
-#define GFB_VERSION 100          /* 0.1.0 */
+#define GFB_VERSION 200          /* 0.2.0 */
 #define GFB_MAX_GRIDS 8          /* grids fused into one launch (a System rarely has more than ele/LJr/LJa) */
+#define GFB_MAX_PEERS 16         /* GPUs of one replica-sharded run (one NVSwitch box has 8) */
+#define GFB_COMM_ID_BYTES 128    /* ncclUniqueId */
+#define GFB_IPC_HANDLE_BYTES 64  /* cudaIpcMemHandle_t */
 
 typedef enum {
     GFB_OK = 0,
@@ -72,12 +75,21 @@ typedef enum {
  *   GFB_FORCE_FIXED_ADD : OpenMM CUDA long-force buffer: unsigned 64-bit, component-planar
  *                         [3][padded_atoms], value = (long long)(f * 2^32), atomically accumulated
  *                         (platforms/cuda/src/kernels/gridForce.cu:487-499). padded_atoms is
- *                         n_replicas*n_particles rounded up to `force_stride` given at execute. */
-typedef enum { GFB_FORCE_F64_STORE = 0, GFB_FORCE_F64_ADD = 1, GFB_FORCE_FIXED_ADD = 2 } gfb_force_mode;
+ *                         n_replicas*n_particles rounded up to `force_stride` given at execute.
+ *   GFB_FORCE_F32_STORE : float [n_replicas][n_particles][3], plain stores. MIXED precision forms the gradient in
+ *                         FP32 anyway (the FP64 modes widen it only to store it), so this halves the force bytes
+ *                         that leave the GPU — what the host path's PCIe transfer is bound by. No reference
+ *                         counterpart (the reference CUDA platform's forces are FP32-accurate fixed point).
+ * forces == NULL anywhere means energy only (CalcGridForceKernel::execute with includeForces == false,
+ * GridForceBatch::evaluate): the record kernels then skip the gradient arithmetic and the force read-modify-write. */
+typedef enum { GFB_FORCE_F64_STORE = 0, GFB_FORCE_F64_ADD = 1, GFB_FORCE_FIXED_ADD = 2, GFB_FORCE_F32_STORE = 3 } gfb_force_mode;
 
 typedef struct gfb_device gfb_device;   /* one GPU: ordinal, default stream, staging buffers */
 typedef struct gfb_grid gfb_grid;       /* one grid, repacked cell-major and resident in HBM */
 typedef struct gfb_kernel gfb_kernel;   /* state of a CalcGridForceKernel after initialize() */
+typedef struct gfb_graph gfb_graph;     /* a captured sequence of launches (CUDA graph) */
+typedef struct gfb_comm gfb_comm;       /* this process's end of a replica-sharded multi-GPU run (one rank = one GPU) */
+typedef struct gfb_multi gfb_multi;     /* a replica-sharded multi-GPU run driven by ONE process */
 
 typedef struct {
     char name[128];
@@ -185,9 +197,10 @@ GFB_API int gfb_kernel_destroy(gfb_kernel* k);
  * factors [n_grids][n_atoms] and inv_power [n_grids] (NULL = keep). */
 GFB_API int gfb_kernel_update_parameters(gfb_kernel* k, const double* scaling, const double* inv_power);
 
-/* Which evaluation kernel a launch of this state (without an evaluation order) uses: 1 = gf_eval_lines_kernel (MIXED,
- * packed cells, one geometry, 1-4 grids, no inv-power: the 2-4 grid case reads one 128-byte record per atom), 0 = the
- * general gf_eval_kernel. Introspection for tests and bench.py; no reference counterpart. */
+/* Which evaluation kernel a launch of this state uses: 1 = gf_eval_lines_kernel (MIXED, packed cells, one geometry,
+ * 1-4 grids, no inv-power: the 2-4 grid case reads one 128-byte record per atom), 2 = gf_eval_lines_f64_kernel (DOUBLE,
+ * same conditions, 2-4 grids, one 256-byte record per atom), 3 = gf_eval_bspline_kernel (MIXED B-spline records),
+ * 0 = the general gf_eval_kernel. Introspection for tests and bench.py; no reference counterpart. */
 GFB_API int gfb_kernel_eval_path(const gfb_kernel* k);
 
 /* Particle groups (GridForce::addParticleGroup / getParticleGroupEnergies, openmmapi/include/GridForce.h:433-508;
@@ -219,7 +232,20 @@ GFB_API int gfb_kernel_set_launch_overlap(gfb_kernel* k, int enable);
  *     indirection the kernels store the forces straight into the caller's pinned buffer (pageable buffers: into pinned
  *     staging, then memcpy), otherwise chunked D2H copies on a third stream. */
 GFB_API int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, const double* pos,
-                                    double* energies, double* grid_energies, double* forces, int force_mode);
+                                    double* energies, double* grid_energies, void* forces, int force_mode);
+
+/* Page-locks a caller-owned host buffer (cudaHostRegister, portable + mapped) so that gfb_kernel_execute_host DMAs
+ * from/into it directly instead of staging through its own pinned buffer — what GridForceBatch does with the caller's
+ * position/force arrays. Registering twice is not an error. No reference counterpart. */
+GFB_API int gfb_host_register(void* ptr, size_t bytes);
+GFB_API int gfb_host_unregister(void* ptr);
+
+/* Per-atom energies (GridForce::getParticleAtomEnergies, openmmapi/include/GridForce.h:508; reference CUDA platform:
+ * atomEnergyBuffer, platforms/cuda/src/kernels/gridForce.cu:502-504). After request(enable != 0) every
+ * gfb_kernel_execute_host call also keeps each evaluated atom's energy (summed over the kernel's grids) on the device;
+ * get() copies the last call's [n_replicas][n_atoms] values (atom-list order) to the host. */
+GFB_API int gfb_kernel_request_atom_energies(gfb_kernel* k, int enable);
+GFB_API int gfb_kernel_get_atom_energies(gfb_kernel* k, double* out, size_t n);
 
 /* CalcGridForceKernel::execute for device-resident data (CUDA-platform style): enqueues ONE kernel on
  * `stream` (a cudaStream_t; NULL = the device's own stream) and returns without synchronising.
@@ -236,9 +262,10 @@ GFB_API int gfb_kernel_execute_device(gfb_kernel* k, int n_replicas, int n_parti
                                       int force_mode, long long force_stride, const int* d_order,
                                       double* d_energies_clear, void* stream);
 
-/* Morton order of the atoms by the grid cell they sit in (grid 0), so neighbouring lanes read neighbouring
- * sectors. Positions move less than a cell per MD step, so the order is reused for many steps.
- * d_order: device out [n_replicas*n_atoms]. Stream-ordered. */
+/* Order of the atoms by the brick of grid cells they sit in (grid 0; bricks of 4^3 cells numbered along a Morton
+ * curve), so neighbouring lanes read neighbouring lines. Positions move less than a cell per MD step, so the order is
+ * reused for many steps. Own counting sort (histogram, scan, scatter): three small kernels, no library.
+ * d_order: device out [n_replicas*n_atoms], a permutation of the flattened [replica][atom] list. Stream-ordered. */
 GFB_API int gfb_kernel_sort_atoms(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos,
                                   int* d_order, void* stream);
 
@@ -261,12 +288,89 @@ GFB_API int gfb_forces_fixed_to_f64(gfb_device* dev, const void* d_fixed, long l
 GFB_API int gfb_peer_put(gfb_device* dev, const void* d_src, void* const* peer_dst, int n_peers, size_t dst_offset,
                          size_t bytes, int first_peer, void* stream);
 
+/* ---- CUDA graphs ------------------------------------------------------------------------------------------------
+ * Launch-bound loops (a few-microsecond evaluation per step: one ligand, or one rank's shard of a strong-scaled batch)
+ * are captured once and replayed: begin() puts `stream` into capture mode, every gfb_kernel_execute_device /
+ * gfb_comm_* call made on that stream until end() is recorded instead of run (programmatic-dependent-launch edges
+ * included), and launch() replays the whole sequence with one driver call. No reference counterpart. */
+GFB_API int gfb_graph_begin(gfb_device* dev, void* stream);
+GFB_API int gfb_graph_end(gfb_device* dev, void* stream, gfb_graph** out);
+GFB_API int gfb_graph_launch(gfb_graph* g, void* stream);
+GFB_API int gfb_graph_destroy(gfb_graph* g);
+
+/* ---- Replica-sharded multi-GPU runs (replaces the sequential replica loop of the reference's
+ * example/sampler.py:130-164) -----------------------------------------------------------------------------------------
+ * Replicas are independent, so GPU g of N evaluates replicas [g*R/N, (g+1)*R/N) against its own copy of the grids and
+ * nothing is exchanged on the force path. The one collective is the gather of per-replica energies. Two deployments:
+ *
+ * (a) one process per GPU (torchrun/mpirun as the launcher): gfb_comm. Rank 0 calls gfb_comm_unique_id and hands the
+ *     128 bytes to every rank by whatever the launcher offers; every rank calls gfb_comm_create (ncclCommInitRank).
+ *     NCCL is loaded with dlopen("libnccl.so.2") at that moment; the library itself does not link it.
+ *       gfb_comm_all_gather        ncclAllGather of `count` doubles per rank on `stream`.
+ *       fused gather               gfb_comm_gather_alloc allocates this rank's gathered array ([2][count_total] doubles,
+ *                                  double-buffered) + arrival flags and returns its cudaIpc handle; the launcher
+ *                                  all-gathers the handles; gfb_comm_gather_attach maps every peer's array.
+ *                                  gfb_kernel_execute_device_gather is then an evaluation launch whose LAST block
+ *                                  copies the launch's energies into every rank's gathered array at `gather_offset`
+ *                                  (plain stores over NVLink/NVSwitch peer mappings) and raises its arrival flag on
+ *                                  every rank: compute and collective in one kernel, no NCCL launch, no extra kernel on
+ *                                  the producing side. gfb_comm_gather_wait enqueues a one-warp kernel that waits for
+ *                                  all ranks' flags of the most recent gather and returns the array. Rule: every
+ *                                  gather launch is followed by a gather_wait on the same stream before the next one.
+ * (b) one process for all GPUs: gfb_multi (ncclCommInitAll, peer access enabled between the devices, one host thread
+ *     per device on the host path). This is what GridForceBatch(devices) uses.
+ */
+GFB_API int gfb_comm_unique_id(unsigned char id[GFB_COMM_ID_BYTES]);
+GFB_API int gfb_comm_create(gfb_device* dev, int world_size, int rank, const unsigned char id[GFB_COMM_ID_BYTES], gfb_comm** out);
+GFB_API int gfb_comm_destroy(gfb_comm* c);
+GFB_API int gfb_comm_all_gather(gfb_comm* c, const double* d_send, double* d_recv, size_t count, void* stream);
+GFB_API int gfb_comm_gather_alloc(gfb_comm* c, size_t count_total, unsigned char handle_out[GFB_IPC_HANDLE_BYTES]);
+GFB_API int gfb_comm_gather_attach(gfb_comm* c, const unsigned char* handles /* [world_size][GFB_IPC_HANDLE_BYTES], rank order */);
+/* As gfb_kernel_execute_device (no per-grid energies, no evaluation order) + the fused gather of d_energies
+ * (n_replicas * n_slots doubles) into every rank's gathered array at element gather_offset. */
+GFB_API int gfb_kernel_execute_device_gather(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos,
+                                             double* d_energies, void* d_forces, int force_mode, long long force_stride,
+                                             double* d_energies_clear, gfb_comm* c, size_t gather_offset, void* stream);
+/* Waits (on `stream`, device side) until every rank's slice of the most recent gather has arrived; *d_gathered is then
+ * this rank's complete [count_total] array. A peer that does not arrive within ~20 s raises a flag that
+ * gfb_comm_gather_status reports after the stream has been synchronised (the wait kernel never spins forever). */
+GFB_API int gfb_comm_gather_wait(gfb_comm* c, void* stream, const double** d_gathered);
+GFB_API int gfb_comm_gather_status(gfb_comm* c);   /* GFB_OK, or GFB_ERR_CUDA after a timed-out wait */
+
+/* One process, n_devices GPUs. add_grid uploads and repacks the grid on every device; build creates one evaluation
+ * state per device (arguments as gfb_kernel_create, identity particles).
+ *   gfb_multi_execute_host   pos host [n_replicas][n_atoms][3] -> energies host [n_replicas], forces host (layout of
+ *                            force_mode, STORE modes; NULL = energy only). Replicas are block-partitioned over the
+ *                            devices; one host thread per device drives that device's gfb_kernel_execute_host on its
+ *                            slice of the caller's arrays, so the per-replica energies land where they belong with no
+ *                            device-side collective at all.
+ *   gfb_multi_upload         block-partitions and uploads positions once (device-resident shards; forces are kept in
+ *                            OpenMM's fixed-point buffer per device).
+ *   gfb_multi_step           one evaluation of every shard (one launch per device); gather: 0 none, 1 ncclAllGather of
+ *                            the energies on every device, 2 fused in-kernel gather over peer memory.
+ *   gfb_multi_download       energies [n_replicas] as gathered on device `from_device` (after a gathering step; any
+ *                            device holds all of them) and, when forces != NULL, the shards' forces as double [R][A][3]. */
+GFB_API int gfb_multi_create(int n_devices, const int* ordinals, gfb_multi** out);
+GFB_API int gfb_multi_destroy(gfb_multi* m);
+GFB_API int gfb_multi_num_devices(const gfb_multi* m);
+GFB_API int gfb_multi_add_grid(gfb_multi* m, const int counts[3], const double spacing[3], const double origin[3],
+                               const double* vals, size_t n_vals, int precision, int layout);
+GFB_API int gfb_multi_build(gfb_multi* m, int n_atoms, const double* scaling, const double* inv_power, const double* oob_k);
+GFB_API int gfb_multi_execute_host(gfb_multi* m, int n_replicas, const double* pos, double* energies, void* forces, int force_mode);
+GFB_API int gfb_multi_upload(gfb_multi* m, int n_replicas, const double* pos);
+GFB_API int gfb_multi_step(gfb_multi* m, int gather);
+GFB_API int gfb_multi_download(gfb_multi* m, int from_device, double* energies, double* forces);
+
 /* Number of kernels this library has launched on any device since load (bench.py's gpu_launches). */
 GFB_API unsigned long long gfb_launch_count(void);
 
 /* Microbenchmark used for the roofline denominator: random 32-byte-sector gather over `bytes` of device
  * memory (n_loads loads per launch, `reps` launches, CUDA-event timed). Returns GB/s through *gbs. */
 GFB_API int gfb_bench_sector_gather(gfb_device* dev, size_t bytes, long long n_loads, int reps, double* gbs);
+/* Pinned-host <-> device copy bandwidth of this process on this GPU's link: gbs[0] H2D alone, gbs[1] D2H alone, gbs[2]
+ * both directions at once (sum). bench.py prints it beside the end-to-end figure (every rank measures at the same time,
+ * so it is the share of the host's PCIe/memory path each GPU gets). */
+GFB_API int gfb_bench_host_copy(gfb_device* dev, size_t bytes, int reps, double gbs[3]);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,12 @@ from .capi import (  # noqa: F401
     FORCE_F64_STORE,
     FORCE_F64_ADD,
     FORCE_FIXED_ADD,
+    FORCE_F32_STORE,
+    Graph,
+    Comm,
+    Multi,
+    host_register,
+    host_unregister,
     PRECISION_MIXED,
     PRECISION_DOUBLE,
     MAX_GRIDS,
@@ -29,4 +35,4 @@ from .capi import (  # noqa: F401
     write_grid_file,
 )
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

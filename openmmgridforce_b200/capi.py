@@ -14,6 +14,9 @@ PRECISION_DOUBLE = 1
 FORCE_F64_STORE = 0
 FORCE_F64_ADD = 1
 FORCE_FIXED_ADD = 2
+FORCE_F32_STORE = 3
+COMM_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 LAYOUT_AUTO, LAYOUT_CELLS, LAYOUT_ROWS, LAYOUT_PAIRS, LAYOUT_BSPLINE = 0, 1, 2, 3, 4
 LAYOUT_NAMES = {0: "auto", 1: "cells", 2: "rows", 3: "pairs", 4: "bspline"}
 MAX_GRIDS = 8
@@ -75,6 +78,33 @@ SIGNATURES = {
     "gfb_peer_put": (_i, [_vp, _vp, C.POINTER(_vp), _i, _sz, _sz, _i, _vp]),
     "gfb_launch_count": (C.c_ulonglong, []),
     "gfb_bench_sector_gather": (_i, [_vp, _sz, _ll, _i, _pd]),
+    "gfb_bench_host_copy": (_i, [_vp, _sz, _i, _pd]),
+    "gfb_host_register": (_i, [_vp, _sz]),
+    "gfb_host_unregister": (_i, [_vp]),
+    "gfb_kernel_request_atom_energies": (_i, [_vp, _i]),
+    "gfb_kernel_get_atom_energies": (_i, [_vp, _vp, _sz]),
+    "gfb_graph_begin": (_i, [_vp, _vp]),
+    "gfb_graph_end": (_i, [_vp, _vp, C.POINTER(_vp)]),
+    "gfb_graph_launch": (_i, [_vp, _vp]),
+    "gfb_graph_destroy": (_i, [_vp]),
+    "gfb_comm_unique_id": (_i, [_vp]),
+    "gfb_comm_create": (_i, [_vp, _i, _i, _vp, C.POINTER(_vp)]),
+    "gfb_comm_destroy": (_i, [_vp]),
+    "gfb_comm_all_gather": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "gfb_comm_gather_alloc": (_i, [_vp, _sz, _vp]),
+    "gfb_comm_gather_attach": (_i, [_vp, _vp]),
+    "gfb_kernel_execute_device_gather": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _ll, _vp, _vp, _sz, _vp]),
+    "gfb_comm_gather_wait": (_i, [_vp, _vp, C.POINTER(_vp)]),
+    "gfb_comm_gather_status": (_i, [_vp]),
+    "gfb_multi_create": (_i, [_i, _pi, C.POINTER(_vp)]),
+    "gfb_multi_destroy": (_i, [_vp]),
+    "gfb_multi_num_devices": (_i, [_vp]),
+    "gfb_multi_add_grid": (_i, [_vp, _pi, _pd, _pd, _vp, _sz, _i, _i]),
+    "gfb_multi_build": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "gfb_multi_execute_host": (_i, [_vp, _i, _vp, _vp, _vp, _i]),
+    "gfb_multi_upload": (_i, [_vp, _i, _vp]),
+    "gfb_multi_step": (_i, [_vp, _i]),
+    "gfb_multi_download": (_i, [_vp, _i, _vp, _vp]),
 }
 
 
@@ -181,6 +211,12 @@ class Device:
         out = C.c_double(0.0)
         _check(load_library().gfb_bench_sector_gather(self._h, nbytes, n_loads, reps, C.byref(out)))
         return out.value
+
+    def bench_host_copy(self, nbytes=64 << 20, reps=5):
+        """Pinned-host <-> device copy bandwidth on this GPU's link: (h2d, d2h, both directions together) in GB/s."""
+        out = (C.c_double * 3)()
+        _check(load_library().gfb_bench_host_copy(self._h, nbytes, reps, out))
+        return tuple(out)
 
     def inv_power_transform(self, values, inv_power, device_ptr=None, n=None):
         """GridForce::applyInvPowerTransformation on the GPU: G -> sign(G)|G|^(1/inv_power). Host array in -> new host
@@ -331,7 +367,8 @@ class Kernel:
 
     def execute_host(self, pos, forces=None, force_mode=FORCE_F64_STORE, want_forces=True, want_grid_energies=False,
                      energies_out=None):
-        """pos: [R, P, 3] (or [P, 3]) float64. Returns (energies[R], forces[R,P,3] or None, grid_energies or None)."""
+        """pos: [R, P, 3] (or [P, 3]) float64. Returns (energies[R], forces[R,P,3] or None, grid_energies or None).
+        force_mode FORCE_F32_STORE returns/needs float32 forces; want_forces=False is an energy-only evaluation."""
         pos = np.asarray(pos)
         if pos.dtype != np.float64 or not pos.flags.c_contiguous:
             pos = _host_f64(pos)
@@ -341,10 +378,30 @@ class Kernel:
         ne = r * self.n_slots
         en = energies_out if energies_out is not None else np.empty(ne, dtype=np.float64)
         ge = np.empty((ne, self.n_grids), dtype=np.float64) if want_grid_energies else None
+        fdtype = np.float32 if force_mode == FORCE_F32_STORE else np.float64
         if forces is None and want_forces:
-            forces = np.zeros((r, p, 3), dtype=np.float64)
+            forces = np.zeros((r, p, 3), dtype=fdtype)
+        if forces is not None and (forces.dtype != fdtype or not forces.flags.c_contiguous):
+            raise GridForceB200Error(f"forces must be a C-contiguous {np.dtype(fdtype).name} array for force_mode {force_mode}")
         _check(load_library().gfb_kernel_execute_host(self._h, r, p, _ptr(pos), _ptr(en), _ptr(ge), _ptr(forces), force_mode))
         return en, forces, ge
+
+    def request_atom_energies(self, enable=True):
+        """GridForce::getParticleAtomEnergies: keep each evaluated atom's energy of the following execute_host calls."""
+        _check(load_library().gfb_kernel_request_atom_energies(self._h, 1 if enable else 0))
+
+    def atom_energies(self, n_replicas):
+        """[R, A] per-atom energies (summed over the kernel's grids) of the last execute_host call."""
+        out = np.empty((n_replicas, self.n_atoms), dtype=np.float64)
+        _check(load_library().gfb_kernel_get_atom_energies(self._h, _ptr(out), out.size))
+        return out
+
+    def execute_device_gather(self, comm, gather_offset, n_replicas, n_particles, d_pos, d_energies, d_forces=None,
+                              force_mode=FORCE_FIXED_ADD, force_stride=0, stream=0, d_energies_clear=None):
+        """execute_device whose last block also stores the energies into every rank's gathered array (fused gather)."""
+        _check(load_library().gfb_kernel_execute_device_gather(self._h, n_replicas, n_particles, _ptr(d_pos), _ptr(d_energies),
+                                                               _ptr(d_forces), force_mode, force_stride, _ptr(d_energies_clear),
+                                                               comm._h, gather_offset, _ptr(stream or None)))
 
     def execute_device(self, n_replicas, n_particles, d_pos, d_energies=None, d_grid_energies=None, d_forces=None,
                        force_mode=FORCE_FIXED_ADD, force_stride=0, d_order=None, stream=0, d_energies_clear=None):
@@ -369,4 +426,145 @@ class Kernel:
     def close(self):
         if self._h:
             load_library().gfb_kernel_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def host_register(array):
+    """Page-locks a numpy array's memory (gfb_host_register) so that execute_host DMAs from/into it directly."""
+    _check(load_library().gfb_host_register(_ptr(array), array.nbytes))
+
+
+def host_unregister(array):
+    _check(load_library().gfb_host_unregister(_ptr(array)))
+
+
+class Graph:
+    """gfb_graph: launches captured on a stream between Graph.begin() and Graph.end(), replayed with launch()."""
+
+    def __init__(self, device, handle):
+        self.device, self._h = device, handle
+
+    @staticmethod
+    def begin(device, stream=0):
+        _check(load_library().gfb_graph_begin(device._h, _ptr(stream or None)))
+
+    @classmethod
+    def end(cls, device, stream=0):
+        h = C.c_void_p()
+        _check(load_library().gfb_graph_end(device._h, _ptr(stream or None), C.byref(h)))
+        return cls(device, h)
+
+    def launch(self, stream=0):
+        _check(load_library().gfb_graph_launch(self._h, _ptr(stream or None)))
+
+    def close(self):
+        if self._h:
+            load_library().gfb_graph_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class Comm:
+    """gfb_comm: this process's end of a replica-sharded run with one process per GPU. `unique_id` comes from
+    Comm.unique_id() on rank 0 and reaches the other ranks through the launcher; None = no NCCL communicator."""
+
+    def __init__(self, device, world_size, rank, unique_id=None):
+        self.device, self.world_size, self.rank = device, world_size, rank
+        self._h = C.c_void_p()
+        uid = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(bytes(unique_id)) if unique_id is not None else None
+        _check(load_library().gfb_comm_create(device._h, world_size, rank, uid, C.byref(self._h)))
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * COMM_ID_BYTES)()
+        _check(load_library().gfb_comm_unique_id(buf))
+        return bytes(buf)
+
+    def all_gather(self, d_send, d_recv, count, stream=0):
+        _check(load_library().gfb_comm_all_gather(self._h, _ptr(d_send), _ptr(d_recv), count, _ptr(stream or None)))
+
+    def gather_alloc(self, count_total):
+        """Allocates this rank's gathered array; returns the 64-byte IPC handle the other ranks attach with."""
+        buf = (C.c_ubyte * IPC_HANDLE_BYTES)()
+        _check(load_library().gfb_comm_gather_alloc(self._h, count_total, buf))
+        return bytes(buf)
+
+    def gather_attach(self, handles):
+        """handles: every rank's gather_alloc() result, in rank order."""
+        blob = b"".join(bytes(h) for h in handles)
+        if len(blob) != self.world_size * IPC_HANDLE_BYTES:
+            raise GridForceB200Error("gather_attach needs one 64-byte handle per rank")
+        _check(load_library().gfb_comm_gather_attach(self._h, (C.c_ubyte * len(blob)).from_buffer_copy(blob)))
+
+    def gather_wait(self, stream=0):
+        """Enqueues the wait for the most recent fused gather; returns the device address of the gathered array."""
+        out = C.c_void_p()
+        _check(load_library().gfb_comm_gather_wait(self._h, _ptr(stream or None), C.byref(out)))
+        return out.value
+
+    def gather_status(self):
+        _check(load_library().gfb_comm_gather_status(self._h))
+
+    def close(self):
+        if self._h:
+            load_library().gfb_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class Multi:
+    """gfb_multi: a replica-sharded run over several GPUs driven by this one process."""
+
+    def __init__(self, ordinals):
+        ords = (C.c_int * len(ordinals))(*[int(o) for o in ordinals])
+        self._h = C.c_void_p()
+        _check(load_library().gfb_multi_create(len(ordinals), ords, C.byref(self._h)))
+        self.n_devices = len(ordinals)
+        self.n_atoms = 0
+        self.n_replicas = 0
+
+    def add_grid(self, counts, spacing, origin, values, precision=PRECISION_MIXED, layout=LAYOUT_AUTO):
+        v = _host_f64(values).ravel()
+        rc = load_library().gfb_multi_add_grid(self._h, (C.c_int * 3)(*[int(c) for c in counts]), (C.c_double * 3)(*spacing),
+                                               (C.c_double * 3)(*origin), _ptr(v), v.size, precision, layout)
+        if rc < 0:
+            _check(rc)
+        return rc
+
+    def build(self, scaling, inv_power=None, oob_k=None):
+        sc = _host_f64(scaling)
+        if sc.ndim == 1:
+            sc = sc.reshape(1, -1)
+        g = sc.shape[0]
+        ok = _host_f64(oob_k if oob_k is not None else [10000.0] * g).ravel()
+        ip = _host_f64(inv_power).ravel() if inv_power is not None else None
+        _check(load_library().gfb_multi_build(self._h, sc.shape[1], _ptr(sc), _ptr(ip), _ptr(ok)))
+        self.n_atoms = sc.shape[1]
+
+    def execute_host(self, pos, want_forces=True, force_mode=FORCE_F64_STORE, forces=None, energies_out=None):
+        pos = _host_f64(pos)
+        r = pos.shape[0]
+        en = energies_out if energies_out is not None else np.empty(r, dtype=np.float64)
+        fdtype = np.float32 if force_mode == FORCE_F32_STORE else np.float64
+        if forces is None and want_forces:
+            forces = np.zeros(pos.shape, dtype=fdtype)
+        _check(load_library().gfb_multi_execute_host(self._h, r, _ptr(pos), _ptr(en), _ptr(forces), force_mode))
+        return en, forces
+
+    def upload(self, pos):
+        pos = _host_f64(pos)
+        _check(load_library().gfb_multi_upload(self._h, pos.shape[0], _ptr(pos)))
+        self.n_replicas = pos.shape[0]
+
+    def step(self, gather=0):
+        """gather: 0 none, 1 ncclAllGather, 2 fused in-kernel gather over peer memory."""
+        _check(load_library().gfb_multi_step(self._h, gather))
+
+    def download(self, from_device=0, want_forces=True):
+        en = np.empty(self.n_replicas, dtype=np.float64)
+        f = np.empty((self.n_replicas, self.n_atoms, 3), dtype=np.float64) if want_forces else None
+        _check(load_library().gfb_multi_download(self._h, from_device, _ptr(en), _ptr(f)))
+        return en, f
+
+    def close(self):
+        if self._h:
+            load_library().gfb_multi_destroy(self._h)
             self._h = C.c_void_p()

@@ -73,8 +73,8 @@ __device__ __forceinline__ void bspline_from_smem(unsigned rbase, unsigned sw, c
     }
 }
 
-//   FMODE  gfb_force_mode;  SINGLE  one replica and no energy slots (block-level energy reduction)
-template <int FMODE, bool SINGLE>
+//   SINGLE  one replica and no energy slots (block-level energy reduction); the force mode is p.force_mode (launch-uniform)
+template <bool SINGLE>
 __global__ void __launch_bounds__(kBsBlock, GFB_BS_MINBLOCKS) gf_eval_bspline_kernel(const __grid_constant__ EvalParams p) {
     __shared__ __align__(128) unsigned char s_tiles[(kBsBlock / 32) * kBsWarpBytes];
 
@@ -191,17 +191,25 @@ __global__ void __launch_bounds__(kBsBlock, GFB_BS_MINBLOCKS) gf_eval_bspline_ke
         }
     }
 
+    if (p.atom_energies && active) p.atom_energies[t] = e_total;   // uniform branch
+
     // ---- forces --------------------------------------------------------------------------------------------------------
     if (active && p.forces) {
-        if (FMODE == GFB_FORCE_FIXED_ADD) {   // OpenMM's 2^32 fixed point, gridForce.cu:487-499
+        const int fmode = p.force_mode;   // launch-uniform
+        if (fmode == GFB_FORCE_FIXED_ADD) {   // OpenMM's 2^32 fixed point, gridForce.cu:487-499
             unsigned long long* f = static_cast<unsigned long long*>(p.forces);
             const double scale = 4294967296.0;
             red_add_u64(f + gidx, (unsigned long long) (long long) (Fx * scale));
             red_add_u64(f + p.force_stride + gidx, (unsigned long long) (long long) (Fy * scale));
             red_add_u64(f + 2 * p.force_stride + gidx, (unsigned long long) (long long) (Fz * scale));
+        } else if (fmode == GFB_FORCE_F32_STORE) {
+            float* f = static_cast<float*>(p.forces) + 3 * (size_t) gidx;
+            f[0] = (float) Fx;
+            f[1] = (float) Fy;
+            f[2] = (float) Fz;
         } else {
             double* f = static_cast<double*>(p.forces) + 3 * (size_t) gidx;
-            if (FMODE == GFB_FORCE_F64_STORE) {
+            if (fmode == GFB_FORCE_F64_STORE) {
                 f[0] = Fx;
                 f[1] = Fy;
                 f[2] = Fz;

@@ -33,7 +33,7 @@ struct ExactCell {
     int ix, iy, iz;
     double fx, fy, fz;
 };
-__device__ __noinline__ ExactCell exact_cell(const GridView& G, double px, double py, double pz) {
+static __device__ __noinline__ ExactCell exact_cell(const GridView& G, double px, double py, double pz) {
     ExactCell c;
     const double qx = px / G.spacing[0], qy = py / G.spacing[1], qz = pz / G.spacing[2];
     c.ix = min(__double2int_rz(qx), G.nc[0] - 1);
@@ -86,25 +86,6 @@ __device__ __forceinline__ FastCell classify_fast(const GridView& G, const doubl
     return c;
 }
 
-// Classification only, through classify_fast (parity tests of the lines kernel's index math).
-__global__ void __launch_bounds__(256) gf_classify_lines_kernel(const __grid_constant__ ClassifyParams p) {
-    const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= p.total) return;
-    const int rep = (int) (t / p.n_atoms);
-    const int ia = (int) (t - (long long) rep * p.n_atoms);
-    const int particle = p.particles ? p.particles[ia] : ia;
-    const double* pp = p.pos + 3 * ((long long) rep * p.n_particles + particle);
-    const FastCell c = classify_fast(p.grid, p.near_int, pp[0], pp[1], pp[2], true);
-    const double s = p.grid.scaling[ia];
-    gfb_class out;
-    out.inside = c.inside ? 1 : 0;
-    const bool interp = c.inside && s != 0.0;
-    out.cell[0] = interp ? c.ix : -1;
-    out.cell[1] = interp ? c.iy : -1;
-    out.cell[2] = interp ? c.iz : -1;
-    p.out[t] = out;
-}
-
 // Restraint of an atom outside the (shared) grid box for all NG GridForces (:1093-1117): every force adds its own
 // harmonic wall with its own constant. Rare; out of line.
 template <int NG>
@@ -113,7 +94,7 @@ struct RestraintAll {
     float fx, fy, fz;
 };
 template <int NG>
-__device__ __noinline__ RestraintAll<NG> restraint_all(const EvalParams& p, double x, double y, double z) {
+static __device__ __noinline__ RestraintAll<NG> restraint_all(const EvalParams& p, double x, double y, double z) {
     RestraintAll<NG> r;
     double fx = 0.0, fy = 0.0, fz = 0.0;
 #pragma unroll
@@ -136,6 +117,49 @@ __device__ __forceinline__ void lds128(unsigned addr, float* v) {
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 constexpr int kForceRed = 0, kForcePrefetch = 1;
+// Internal force mode of an energy-only launch (forces == NULL; GridForceBatch::evaluate, includeForces = false): no
+// gradient arithmetic, no force read-modify-write.
+constexpr int kForceNone = 4;
+
+// ---- fused energy gather (EvalParams::gather) ------------------------------------------------------------------------
+// Called by every thread of every block at the very end of an evaluation kernel. The block that takes the last ticket
+// knows that all other blocks' energy atomics have been performed (each block fences before its ticket), copies the
+// launch's energies into every peer's gathered array over NVLink (plain 8/16-byte stores to peer-mapped memory, local
+// memory for itself), fences at system scope and publishes gather_seq in its flag slot on every peer. The consumer is
+// gf_gather_wait_kernel (gf_multi.cu). No NCCL launch, no extra kernel on the producing side.
+template <int BLOCK>
+__device__ __forceinline__ void gather_tail(const EvalParams& p) {
+    __shared__ unsigned s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&p.gather->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    GatherTable* const gt = p.gather;
+    const int n = p.n_replicas * p.n_slots;
+    const long long base = (long long) p.gather_parity * gt->count_total + p.gather_offset;
+    const int np = gt->n_peers;
+    const bool vec = ((base | (long long) n) & 1) == 0 && (reinterpret_cast<uintptr_t>(p.energies) & 15) == 0;
+    for (int r = 0; r < np; r++) {
+        const int peer = (gt->my_rank + 1 + r) % np;   // staggered: ranks do not all start on the same peer
+        double* dst = gt->peer_data[peer] + base;
+        if (vec) {
+            const double2* src2 = reinterpret_cast<const double2*>(p.energies);
+            double2* dst2 = reinterpret_cast<double2*>(dst);
+            for (int i = threadIdx.x; i < n / 2; i += BLOCK) dst2[i] = __ldcg(src2 + i);
+        } else {
+            for (int i = threadIdx.x; i < n; i += BLOCK) dst[i] = __ldcg(p.energies + i);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int) threadIdx.x < np) {
+        unsigned long long* flag = gt->peer_flags[threadIdx.x] + p.gather_parity * kMaxPeers + gt->my_rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(p.gather_seq) : "memory");
+    }
+    if (threadIdx.x == 0) gt->ticket = 0;
+}
 
 // Threads per block: no block barrier is used, so the block is only the scheduling granule. 128 threads keep the tail
 // of a launch short (C4 is 1.02 waves of 256-thread blocks); one grid + one replica keeps 256 because it ends in one
@@ -150,7 +174,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 
 //   NG     grids evaluated per atom, 1..4 (1: the grid's own packed cells; 2..4: 128-byte records of 4 slots)
-//   FMODE  gfb_force_mode
+//   FMODE  gfb_force_mode, or kForceNone (energy only)
 //   FPATH  kForceRed | kForcePrefetch (ADD modes only)
 //   SINGLE one replica and no energy slots: block-level energy reduction, one atomic per block
 //   GE     per-grid energies wanted (p.grid_energies): a template flag so that the per-grid terms cost no registers
@@ -177,17 +201,19 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 10) gf_eval_lin
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // ---- who am I: replica, atom ordinal, particle -------------------------------------------------------------
-    unsigned rep = 0, ia = t;
-    if (!SINGLE) {   // t / n_atoms by the host's magic multiplier floor(2^32 / n_atoms): estimate is q or q-1
-        rep = __umulhi(t, p.div_magic);
-        ia = t - rep * (unsigned) p.n_atoms;
+    // Evaluation order (gfb_kernel_sort_atoms): thread t evaluates atom order[t] of the flattened [replica][atom] list.
+    const unsigned a = (p.order != nullptr && active) ? (unsigned) p.order[t] : t;
+    unsigned rep = 0, ia = a;
+    if (!SINGLE) {   // a / n_atoms by the host's magic multiplier floor(2^32 / n_atoms): estimate is q or q-1
+        rep = __umulhi(a, p.div_magic);
+        ia = a - rep * (unsigned) p.n_atoms;
         if (ia >= (unsigned) p.n_atoms) {
             ia -= (unsigned) p.n_atoms;
             rep++;
         }
     }
     if (!active) ia = 0;
-    const bool plain = p.particles == nullptr && p.n_particles == p.n_atoms;   // uniform
+    const bool plain = p.particles == nullptr && p.n_particles == p.n_atoms && p.order == nullptr;   // uniform
     unsigned gidx = t;                                                         // particle slot in pos / forces
     if (!plain) gidx = rep * (unsigned) p.n_particles + (p.particles ? (unsigned) p.particles[ia] : ia);
     int key = -1;
@@ -198,7 +224,7 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 10) gf_eval_lin
 
     unsigned long long* const ffix = static_cast<unsigned long long*>(p.forces);
     double* const fdbl = static_cast<double*>(p.forces);
-    if (p.forces && FMODE != GFB_FORCE_F64_STORE && FPATH == kForcePrefetch) {
+    if (p.forces && (FMODE == GFB_FORCE_F64_ADD || FMODE == GFB_FORCE_FIXED_ADD) && FPATH == kForcePrefetch) {
         if (FMODE == GFB_FORCE_FIXED_ADD) {
             if (active && (lane & 15u) == 0) {   // 16 lanes x 8 bytes = one line per plane
                 prefetch_l2(ffix + gidx);
@@ -266,12 +292,14 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 10) gf_eval_lin
         for (int g = 0; g < (GE ? NG : 1); g++) e_g[g] = 0.0;
     }
     auto one_grid = [&](int g, const float* v, double s) {
-        float val, dx, dy, dz;
-        trilinear<float>(v, fx, fy, fz, val, dx, dy, dz);
-        const float sf = (float) s;
-        sx = fmaf(sf, dx, sx);
-        sy = fmaf(sf, dy, sy);
-        sz = fmaf(sf, dz, sz);
+        if (FMODE != kForceNone) {
+            float val, dx, dy, dz;
+            trilinear<float>(v, fx, fy, fz, val, dx, dy, dz);
+            const float sf = (float) s;
+            sx = fmaf(sf, dx, sx);
+            sy = fmaf(sf, dy, sy);
+            sz = fmaf(sf, dz, sz);
+        }
         const double e = s * trilinear_value_f64(v, dfx, dfy, dfz);   // :1061
         e_total += e;
         if (GE) e_g[GE ? g : 0] = e;
@@ -328,29 +356,42 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 10) gf_eval_lin
     }
 
     // ---- forces --------------------------------------------------------------------------------------------------------
-    // F64_STORE without indirection: a full warp's 32 forces are 768 contiguous bytes. They go through the warp's smem
-    // slice and leave as 48 coalesced 16-byte stores (the mirror image of the position staging) instead of 96 scalar
-    // stores at stride 24 — which matters most when `forces` is host-mapped memory (PCIe write TLPs of 128 bytes
-    // instead of 8): gfb_kernel_execute_host's zero-copy path.
+    // STORE modes without indirection: a full warp's 32 forces are 768 (F64) or 384 (F32) contiguous bytes. They go
+    // through the warp's smem slice and leave as coalesced 16-byte stores (the mirror image of the position staging)
+    // instead of 96 scalar stores at stride 24/12 — which matters most when `forces` is host-mapped memory (PCIe write
+    // TLPs of 128 bytes instead of 8): gfb_kernel_execute_host's zero-copy path.
     // Everything above only READ inputs that no evaluation launch writes (positions, grids, scaling factors). From here on
     // the kernel writes what the previous launch may still be writing or accumulating: wait for it to finish.
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (p.energies_clear && t < (unsigned) (p.n_replicas * p.n_slots)) p.energies_clear[t] = 0.0;
-    const bool stage_f = FMODE == GFB_FORCE_F64_STORE && p.forces != nullptr && plain && (t - lane) + 32u <= total &&
+    if (p.atom_energies && active) p.atom_energies[a] = e_total;   // uniform branch
+    constexpr bool kStore = FMODE == GFB_FORCE_F64_STORE || FMODE == GFB_FORCE_F32_STORE;
+    const bool stage_f = kStore && p.forces != nullptr && plain && (t - lane) + 32u <= total &&
                          (reinterpret_cast<uintptr_t>(p.forces) & 15) == 0;   // warp-uniform
-    if (stage_f) {
-        double* const s_f = reinterpret_cast<double*>(s_pos2 + (tid >> 5) * kWarpSlice16);
+    if (kStore && stage_f) {
         __syncwarp();   // every lane has consumed its record from this slice
-        s_f[3 * lane] = (double) Fx;
-        s_f[3 * lane + 1] = (double) Fy;
-        s_f[3 * lane + 2] = (double) Fz;
-        __syncwarp();
-        const double2* const s_f2 = reinterpret_cast<const double2*>(s_f);
-        double2* const dst = reinterpret_cast<double2*>(static_cast<double*>(p.forces) + 3 * (size_t) (t - lane));
-        dst[lane] = s_f2[lane];
-        if (lane < 16) dst[32 + lane] = s_f2[32 + lane];
+        if (FMODE == GFB_FORCE_F64_STORE) {
+            double* const s_f = reinterpret_cast<double*>(s_pos2 + (tid >> 5) * kWarpSlice16);
+            s_f[3 * lane] = (double) Fx;
+            s_f[3 * lane + 1] = (double) Fy;
+            s_f[3 * lane + 2] = (double) Fz;
+            __syncwarp();
+            const double2* const s_f2 = reinterpret_cast<const double2*>(s_f);
+            double2* const dst = reinterpret_cast<double2*>(static_cast<double*>(p.forces) + 3 * (size_t) (t - lane));
+            dst[lane] = s_f2[lane];
+            if (lane < 16) dst[32 + lane] = s_f2[32 + lane];
+        } else {   // F32: 384 bytes = 24 x 16
+            float* const s_f = reinterpret_cast<float*>(s_pos2 + (tid >> 5) * kWarpSlice16);
+            s_f[3 * lane] = Fx;
+            s_f[3 * lane + 1] = Fy;
+            s_f[3 * lane + 2] = Fz;
+            __syncwarp();
+            const float4* const s_f4 = reinterpret_cast<const float4*>(s_f);
+            float4* const dst = reinterpret_cast<float4*>(static_cast<float*>(p.forces) + 3 * (size_t) (t - lane));
+            if (lane < 24) dst[lane] = s_f4[lane];
+        }
     }
-    if (active && p.forces) {
+    if (FMODE != kForceNone && active && p.forces) {
         if (FMODE == GFB_FORCE_FIXED_ADD) {   // OpenMM's 2^32 fixed point, gridForce.cu:487-499
             const unsigned long long ax = (unsigned long long) __float2ll_rz(Fx * 4294967296.f);
             const unsigned long long ay = (unsigned long long) __float2ll_rz(Fy * 4294967296.f);
@@ -358,6 +399,13 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 10) gf_eval_lin
             red_add_u64(ffix + gidx, ax);
             red_add_u64(ffix + p.force_stride + gidx, ay);
             red_add_u64(ffix + 2 * p.force_stride + gidx, az);
+        } else if (FMODE == GFB_FORCE_F32_STORE) {
+            if (!stage_f) {
+                float* f = static_cast<float*>(p.forces) + 3 * (size_t) gidx;
+                f[0] = Fx;
+                f[1] = Fy;
+                f[2] = Fz;
+            }
         } else {
             double* f = fdbl + 3 * (size_t) gidx;
             if (FMODE == GFB_FORCE_F64_STORE) {
@@ -427,6 +475,7 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 10) gf_eval_lin
             if (head) red_add_f64(p.energies + key, e_total);
         }
     }
+    if (p.gather) gather_tail<kBlock>(p);   // uniform branch: fused energy gather of a replica-sharded run
 }
 
 }  // namespace gfb

@@ -1,11 +1,11 @@
 // V3 "OMGRID" binary grid files — the reference's on-disk format (openmmapi/src/GridForce.cpp:495-692 load,
 // :694-799 save; openmmapi/src/GridData.cpp:181-267 save with trailer). Host-side, header-only.
 //
-//   0   char[8]  "OMGRID\0\0"          40  f64 dx,dy,dz          96  f64 inv_power
-//   8   u32 version = 3                64  u64 data_offset=128   104 u32 inv_power_mode (0 NONE,1 RUNTIME,2 STORED)
-//   12  u32 header_size = 128          72  f64 origin[3]         108 20 zero bytes
-//   16  i32 nx,ny,nz                   96-8: u32 grid_type (0 none,1 charge,2 ljr,3 lja), u32 flags
-//   28  u32 deriv_count (0 | 27)
+//   0   char[8]  "OMGRID\0\0"          32  f64 dx,dy,dz          88  u32 grid_type (0 none,1 charge,2 ljr,3 lja)
+//   8   u32 version = 3                56  u64 data_offset=128   92  u32 flags
+//   12  u32 header_size = 128          64  f64 origin[3]         96  f64 inv_power
+//   16  i32 nx,ny,nz                                             104 u32 inv_power_mode (0 NONE,1 RUNTIME,2 STORED)
+//   28  u32 deriv_count (0 | 27)                                 108 20 zero bytes
 // then nx*ny*nz f64 (x-major, z fastest) — or deriv_count*N f64, derivative-major, function values first.
 // GridData::saveToFile appends a trailer: i32 nScaling(=0), f64 origin[3] (and optionally "DERIVS" + data).
 #ifndef GF_GRIDFILE_H_

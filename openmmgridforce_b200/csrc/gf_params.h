@@ -28,6 +28,19 @@ struct GridView {
     double oob_k;
 };
 
+// Peer tables of the fused energy gather, in DEVICE memory of each rank (built once by gfb_comm_gather_attach /
+// gfb_multi_create). peer_data[r] / peer_flags[r] are addresses valid on THIS device that point into rank r's memory
+// (cudaIpcOpenMemHandle mappings, or plain peer pointers inside one process; r == my_rank: local memory).
+constexpr int kMaxPeers = 16;
+struct GatherTable {
+    double* peer_data[kMaxPeers];                // rank r's gathered array: [2][count_total] doubles
+    unsigned long long* peer_flags[kMaxPeers];   // rank r's flags: [2][kMaxPeers]; entry [parity][s] = last seq published by rank s
+    long long count_total;
+    int n_peers, my_rank;
+    unsigned int ticket;                         // blocks of the current launch that have finished (reset by the last one)
+    unsigned int timed_out;                      // set by gf_gather_wait_kernel when a peer's flag did not arrive in time
+};
+
 struct EvalParams {
     GridView grid[GFB_MAX_GRIDS];
     int n_grids;
@@ -48,10 +61,21 @@ struct EvalParams {
     void* forces;            // layout per force mode, or null
     long long force_stride;  // FIXED_ADD plane stride
     // gf_eval_lines_kernel only (gf_eval_lines.cuh)
-    const void* lines;       // 2-4 grids of one geometry: one 128-byte record per cell = 4 slots of 8 packed corners
+    const void* lines;       // 2-4 grids of one geometry: one record per cell = 4 slots of 8 packed corners (128 B MIXED,
+                             // 256 B DOUBLE)
     unsigned div_magic;      // floor(2^32 / n_atoms) (saturated): t / n_atoms = umulhi(t, div_magic) or that + 1
     unsigned pdl;            // launch with programmatic stream serialization (gfb_kernel_set_launch_overlap)
     double near_int[3];      // 1.8e-15 * cells per axis: fractions this close to 0 or 1 take the exact division
+    double* atom_energies;   // [n_replicas][n_atoms] or null: each evaluated atom's energy, summed over the grids, stored
+                             // (GridForce::getParticleAtomEnergies)
+    // Fused energy gather (replica-sharded multi-GPU runs, gf_eval_lines_kernel only): the LAST block of the launch to
+    // finish copies this launch's n_replicas*n_slots energies into every peer's gathered array at gather_offset and
+    // then publishes gather_seq in its slot of every peer's flag array. nullptr = off.
+    GatherTable* gather;
+    unsigned long long gather_seq;
+    long long gather_offset; // first element of this rank's slice in the gathered array
+    int gather_parity;       // which half of the double-buffered gathered array / flag array
+    int force_mode;          // gfb_force_mode for the kernels that switch on it at run time (general, B-spline)
 };
 
 struct ClassifyParams {

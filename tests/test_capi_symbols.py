@@ -35,7 +35,7 @@ def test_binding_covers_header():
 def test_version_and_no_silent_fallback():
     import openmmgridforce_b200 as gf
     lib = gf.load_library()
-    assert lib.gfb_version() == 100
+    assert lib.gfb_version() == 200
     try:
         n = gf.Device.count()
     except gf.GridForceB200Error:
