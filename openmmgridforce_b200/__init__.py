@@ -18,6 +18,7 @@ from .capi import (  # noqa: F401
     Comm,
     Multi,
     host_register,
+    DeviceArrayView,
     host_unregister,
     PRECISION_MIXED,
     PRECISION_DOUBLE,

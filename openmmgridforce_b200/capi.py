@@ -429,6 +429,15 @@ class Kernel:
             self._h = C.c_void_p()
 
 
+class DeviceArrayView:
+    """Zero-copy description of device memory owned by the library (e.g. the gathered energies of Comm.gather_wait) in
+    the CUDA array interface, so that torch.as_tensor(view, device=...) / cupy.asarray(view) can read it in place."""
+
+    def __init__(self, ptr, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
 def host_register(array):
     """Page-locks a numpy array's memory (gfb_host_register) so that execute_host DMAs from/into it directly."""
     _check(load_library().gfb_host_register(_ptr(array), array.nbytes))

@@ -208,8 +208,9 @@ def test_lines_kernel_adversarial_quotients_three_grids(gpu_device, oracle_built
     _close(g3, k)
 
 
-def test_lines_off_switch_matches(gpu_device):
-    """The general kernel (reached with an evaluation order) and the lines kernel agree on the same state."""
+def test_identity_order_matches_no_order(gpu_device):
+    """The lines kernel with an (identity) evaluation order — gathered positions, scattered force stores — and without
+    one (warp-staged positions and stores) agree on the same state."""
     import torch
     import openmmgridforce_b200 as gf
     r, a = 64, 47
