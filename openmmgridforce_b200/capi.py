@@ -353,7 +353,11 @@ class Kernel:
 
     def uses_lines_kernel(self):
         """True when launches of this state go to gf_eval_lines_kernel (see gfb_kernel_eval_path)."""
-        return bool(load_library().gfb_kernel_eval_path(self._h))
+        return self.eval_path() == 1
+
+    def eval_path(self):
+        """gfb_kernel_eval_path: 1 gf_eval_lines_kernel, 2 gf_eval_lines_f64_kernel, 3 gf_eval_bspline_kernel, 0 general."""
+        return int(load_library().gfb_kernel_eval_path(self._h))
 
     def set_launch_overlap(self, enable=True):
         """PDL for execute_device launches (see gfb_kernel_set_launch_overlap: positions must not come from the kernel

@@ -420,6 +420,12 @@ int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d
         launch_bspline(p, stream);
     } else if (lines) {
         p.lines = k->d_interleaved;
+        static const bool ahead_off = env_off("GFB_POS_PREFETCH");   // A/B measurements
+        if (!ahead_off) {
+            const int block = lines_block_threads(k->n_grids);
+            const int per_sm = k->n_grids == 1 ? 6 : 1280 / block;
+            p.ahead_blocks = (unsigned) (k->dev->prop.multiProcessorCount * per_sm);
+        }
         launch_lines(p, force_mode, force_path_default(k->n_grids), stream);
     } else if (lines64) {
         p.lines = k->d_interleaved;

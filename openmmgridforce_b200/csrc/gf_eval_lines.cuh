@@ -164,7 +164,12 @@ __device__ __forceinline__ void gather_tail(const EvalParams& p) {
 // Threads per block: no block barrier is used, so the block is only the scheduling granule. 128 threads keep the tail
 // of a launch short (C4 is 1.02 waves of 256-thread blocks); one grid + one replica keeps 256 because it ends in one
 // atomic per block on a single address.
-__host__ __device__ constexpr int lines_block(int ng) { return ng == 1 ? 256 : 128; }
+#ifndef GFB_LINES_BLOCK_MULTI
+#define GFB_LINES_BLOCK_MULTI 64    // threads per block of the 2-4 grid kernels: 20 blocks per SM. Measured against 128
+                                    // (A/B builds, -DGFB_LINES_BLOCK_MULTI=128): C5 83.7 -> 81.8 us, a 1/8 shard of it
+                                    // 13.5 -> 13.3 us, C4 unchanged
+#endif
+__host__ __device__ constexpr int lines_block(int ng) { return ng == 1 ? 256 : GFB_LINES_BLOCK_MULTI; }
 
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
@@ -182,7 +187,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // Occupancy: 40 registers x 6 blocks of 256 (one grid), 48 registers x 10 blocks of 128 with 16 KB of smem each (2-4 grids;
 // 12 blocks / 40 registers measured no faster on C5 and slower on C4).
 template <int NG, int FMODE, int FPATH, bool SINGLE, bool GE>
-__global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 10) gf_eval_lines_kernel(const __grid_constant__ EvalParams p) {
+__global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 1280 / lines_block(NG)) gf_eval_lines_kernel(const __grid_constant__ EvalParams p) {
     constexpr int kBlock = lines_block(NG);
     // One slice per warp: first the warp's 32 positions (768 bytes), then (NG > 1) its 32 records of 128 bytes.
     constexpr unsigned kWarpSlice16 = NG == 1 ? 48 : 256;                // slice size in 16-byte units
@@ -233,6 +238,16 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 10) gf_eval_lin
             }
         } else if (active && (lane & 3u) == 0) {   // 4 lanes x 24 bytes < one line
             prefetch_l2(fdbl + 3 * (size_t) gidx);
+        }
+    }
+
+    // Positions of the block that will run in this block's SM slot NEXT (p.ahead_blocks = resident blocks of the launch)
+    // are pulled into L2 now: when that block starts, its first dependent load is an L2 hit instead of a DRAM round trip.
+    if (p.ahead_blocks && plain) {
+        const unsigned long long first = ((unsigned long long) blockIdx.x + p.ahead_blocks) * kBlock;   // its first atom
+        if (first < total && tid < (kBlock * 24u + 127u) / 128u) {
+            const char* line = reinterpret_cast<const char*>(p.pos + 3 * first) + 128u * tid;
+            if (line < reinterpret_cast<const char*>(p.pos + 3 * (size_t) total)) prefetch_l2(line);
         }
     }
 
@@ -362,6 +377,28 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 10) gf_eval_lin
     // TLPs of 128 bytes instead of 8): gfb_kernel_execute_host's zero-copy path.
     // Everything above only READ inputs that no evaluation launch writes (positions, grids, scaling factors). From here on
     // the kernel writes what the previous launch may still be writing or accumulating: wait for it to finish.
+    // Exception: the ADD modes under programmatic dependent launch. Their force updates are commutative atomics, so they
+    // may interleave with the previous evaluation launch's (the caller's promise for launch overlap covers d_forces: the
+    // kernel launched just before only ACCUMULATES into it); issuing them before the wait leaves a block parked at the
+    // wait with nothing but its energy atomics to do, which shortens the bubble between two small launches.
+    constexpr bool kAdd = FMODE == GFB_FORCE_F64_ADD || FMODE == GFB_FORCE_FIXED_ADD;
+    const bool early_forces = kAdd && p.pdl != 0u;   // uniform
+    auto add_forces = [&]() {
+        if (FMODE == GFB_FORCE_FIXED_ADD) {   // OpenMM's 2^32 fixed point, gridForce.cu:487-499
+            const unsigned long long ax = (unsigned long long) __float2ll_rz(Fx * 4294967296.f);
+            const unsigned long long ay = (unsigned long long) __float2ll_rz(Fy * 4294967296.f);
+            const unsigned long long az = (unsigned long long) __float2ll_rz(Fz * 4294967296.f);
+            red_add_u64(ffix + gidx, ax);
+            red_add_u64(ffix + p.force_stride + gidx, ay);
+            red_add_u64(ffix + 2 * p.force_stride + gidx, az);
+        } else {
+            double* f = fdbl + 3 * (size_t) gidx;
+            red_add_f64(f, (double) Fx);
+            red_add_f64(f + 1, (double) Fy);
+            red_add_f64(f + 2, (double) Fz);
+        }
+    };
+    if (kAdd && early_forces && active && p.forces) add_forces();
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (p.energies_clear && t < (unsigned) (p.n_replicas * p.n_slots)) p.energies_clear[t] = 0.0;
     if (p.atom_energies && active) p.atom_energies[a] = e_total;   // uniform branch
@@ -391,34 +428,18 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 10) gf_eval_lin
             if (lane < 24) dst[lane] = s_f4[lane];
         }
     }
-    if (FMODE != kForceNone && active && p.forces) {
-        if (FMODE == GFB_FORCE_FIXED_ADD) {   // OpenMM's 2^32 fixed point, gridForce.cu:487-499
-            const unsigned long long ax = (unsigned long long) __float2ll_rz(Fx * 4294967296.f);
-            const unsigned long long ay = (unsigned long long) __float2ll_rz(Fy * 4294967296.f);
-            const unsigned long long az = (unsigned long long) __float2ll_rz(Fz * 4294967296.f);
-            red_add_u64(ffix + gidx, ax);
-            red_add_u64(ffix + p.force_stride + gidx, ay);
-            red_add_u64(ffix + 2 * p.force_stride + gidx, az);
-        } else if (FMODE == GFB_FORCE_F32_STORE) {
-            if (!stage_f) {
-                float* f = static_cast<float*>(p.forces) + 3 * (size_t) gidx;
-                f[0] = Fx;
-                f[1] = Fy;
-                f[2] = Fz;
-            }
+    if (kAdd && !early_forces && active && p.forces) add_forces();
+    if (kStore && active && p.forces && !stage_f) {
+        if (FMODE == GFB_FORCE_F32_STORE) {
+            float* f = static_cast<float*>(p.forces) + 3 * (size_t) gidx;
+            f[0] = Fx;
+            f[1] = Fy;
+            f[2] = Fz;
         } else {
             double* f = fdbl + 3 * (size_t) gidx;
-            if (FMODE == GFB_FORCE_F64_STORE) {
-                if (!stage_f) {
-                    f[0] = (double) Fx;
-                    f[1] = (double) Fy;
-                    f[2] = (double) Fz;
-                }
-            } else {
-                red_add_f64(f, (double) Fx);
-                red_add_f64(f + 1, (double) Fy);
-                red_add_f64(f + 2, (double) Fz);
-            }
+            f[0] = (double) Fx;
+            f[1] = (double) Fy;
+            f[2] = (double) Fz;
         }
     }
 

@@ -89,8 +89,25 @@ __device__ __forceinline__ AtomCell classify(const GridView& g, double x, double
 // .nc: the grid is read-only for the life of the kernel. L2::evict_last: the grid is the only data
 // with reuse across atoms/steps; positions and forces stream through.
 // ------------------------------------------------------------------------------------------------
+// The stencil load carries the L2 prefetch-size hint .L2::64B (SASS LDG.E.ELL2.LTC64B.256): measured on C3 (one random
+// 32-byte stencil per atom out of 530 MB of packed cells) against no hint / .L2::128B in A/B builds
+// (-DGFB_STENCIL_LD_VARIANT=0/2/3): FIXED_ADD 31.8 -> 29.8 us, F32 stores 25.4 -> 24.2 us.
+#ifndef GFB_STENCIL_LD_VARIANT
+#define GFB_STENCIL_LD_VARIANT 1
+#endif
+#if GFB_STENCIL_LD_VARIANT == 0
+#define GFB_STENCIL_LD "ld.global.nc.L2::evict_last.v8.f32"
+#elif GFB_STENCIL_LD_VARIANT == 1
+#define GFB_STENCIL_LD "ld.global.nc.L2::evict_last.L2::64B.v8.f32"
+#elif GFB_STENCIL_LD_VARIANT == 2
+#define GFB_STENCIL_LD "ld.global.nc.L2::evict_last.L2::128B.v8.f32"
+#elif GFB_STENCIL_LD_VARIANT == 3
+#define GFB_STENCIL_LD "ld.global.nc.v8.f32"
+#else
+#define GFB_STENCIL_LD "ld.global.nc.L2::64B.v8.f32"
+#endif
 __device__ __forceinline__ void load32(const float* p, float v[8]) {
-    asm volatile("ld.global.nc.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile(GFB_STENCIL_LD " {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                  : "l"(p));
 }

@@ -28,7 +28,10 @@ inline void launch_lines(const EvalParams& p, int fmode, int fpath, cudaStream_t
         default: launch_lines_ng<4>(p, fmode, fpath, stream); break;
     }
 }
-constexpr int lines_block_threads(int n_grids) { return n_grids == 1 ? 256 : 128; }
+#ifndef GFB_LINES_BLOCK_MULTI
+#define GFB_LINES_BLOCK_MULTI 64
+#endif
+constexpr int lines_block_threads(int n_grids) { return n_grids == 1 ? 256 : GFB_LINES_BLOCK_MULTI; }
 
 // gf_eval_lines_f64_kernel (gf_eval_lines_f64.cuh): DOUBLE 256-byte records, 2-4 grids of one geometry, no inv-power.
 void launch_lines_f64(const EvalParams& p, int fmode, cudaStream_t stream);

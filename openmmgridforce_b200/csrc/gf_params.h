@@ -65,6 +65,7 @@ struct EvalParams {
                              // 256 B DOUBLE)
     unsigned div_magic;      // floor(2^32 / n_atoms) (saturated): t / n_atoms = umulhi(t, div_magic) or that + 1
     unsigned pdl;            // launch with programmatic stream serialization (gfb_kernel_set_launch_overlap)
+    unsigned ahead_blocks;   // gf_eval_lines_kernel: blocks resident at once (SMs x blocks per SM); 0 = no position prefetch
     double near_int[3];      // 1.8e-15 * cells per axis: fractions this close to 0 or 1 take the exact division
     double* atom_energies;   // [n_replicas][n_atoms] or null: each evaluated atom's energy, summed over the grids, stored
                              // (GridForce::getParticleAtomEnergies)

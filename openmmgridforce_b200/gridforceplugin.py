@@ -50,7 +50,14 @@ def _lib():
                                              C.c_void_p, C.c_int]
         lib.b200_plugin_get_force_data.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]
         lib.b200_plugin_add_particle_group.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]
-        lib.b200_plugin_finalize.argtypes = [C.c_void_p, C.c_char_p]
+        lib.b200_plugin_finalize.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int]
+        lib.b200_plugin_get_property.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
+        lib.b200_plugin_get_default_property.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        lib.b200_plugin_set_particles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        lib.b200_plugin_atom_energies.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        lib.b200_plugin_batch_evaluate_buffers.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                                           C.c_void_p, C.c_int]
+        lib.b200_plugin_pin_buffer.argtypes = [C.c_void_p, C.c_longlong, C.c_int]
         lib.b200_plugin_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.b200_plugin_time_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.b200_plugin_update_scaling.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
@@ -86,7 +93,19 @@ class Platform:
         return self._name
 
     def setPropertyDefaultValue(self, prop, value):
+        """Platform::setPropertyDefaultValue (base-class method): "DeviceIndex", "Precision"; unknown names raise."""
         _check(_lib().b200_plugin_set_property(prop.encode(), str(value).encode()))
+
+    def getPropertyDefaultValue(self, prop):
+        buf = C.create_string_buffer(256)
+        _check(_lib().b200_plugin_get_default_property(prop.encode(), buf, 256))
+        return buf.value.decode()
+
+    def getPropertyValue(self, context, prop):
+        """Platform::getPropertyValue(context, name): the value this Context uses (its own property, else the default)."""
+        buf = C.create_string_buffer(256)
+        _check(_lib().b200_plugin_get_property(context._h, prop.encode(), buf, 256))
+        return buf.value.decode()
 
 
 class GridForce:
@@ -97,7 +116,7 @@ class GridForce:
         self._origin = (0.0, 0.0, 0.0)
         self._inv_power, self._inv_power_mode = 0.0, InvPowerMode_NONE
         self._oob_k, self._interp, self._group = 10000.0, 0, 0
-        self._ligand_atoms, self._groups = [], []
+        self._ligand_atoms, self._groups, self._particles = [], [], []
         self._context, self._index = None, None
         self._auto_scaling, self._scaling_property = False, ""
         self._auto_generate, self._grid_type, self._grid_cap = False, "", 41840.0
@@ -231,6 +250,13 @@ class GridForce:
     def setLigandAtoms(self, atoms):
         self._ligand_atoms = [int(a) for a in atoms]
 
+    def setParticles(self, particles):
+        """Only these particles feel the grid (GridForce.h:433-440); empty = all."""
+        self._particles = [int(p) for p in particles]
+
+    def getParticles(self):
+        return list(self._particles)
+
     def setForceGroup(self, group):
         self._group = int(group)
 
@@ -249,6 +275,14 @@ class GridForce:
         n = C.c_int(0)
         _check(_lib().b200_plugin_group_energies(context._h, self._index, _p(out), out.size, C.byref(n)))
         return list(out[:n.value])
+
+    def getParticleAtomEnergies(self, context):
+        """Per-atom energies of the last evaluation, in the order particles were added to the groups (empty without groups)."""
+        cap = max(1, sum(len(g[1]) for g in self._groups))
+        out = np.zeros(cap)
+        n = C.c_int(0)
+        _check(_lib().b200_plugin_atom_energies(context._h, self._index, _p(out), out.size, C.byref(n)))
+        return out[:n.value].copy()
 
     def updateParametersInContext(self, context):
         sc = np.ascontiguousarray(self._scaling, dtype=np.float64)
@@ -300,9 +334,11 @@ class State:
 
 
 class Context:
-    """Context(system, platform): creating it runs GridForceImpl::initialize -> kernel initialize() for every GridForce."""
+    """Context(system, platform[, properties]): creating it runs GridForceImpl::initialize -> kernel initialize() for every
+    GridForce. `properties` are the platform-specific properties of OpenMM's Context constructor ({"Precision": "double"});
+    they apply to this Context only and win over the platform defaults."""
 
-    def __init__(self, system, platform):
+    def __init__(self, system, platform, properties=None):
         lib = _lib()
         self._n = system.getNumParticles()
         self._h = C.c_void_p(lib.b200_plugin_create(self._n))
@@ -333,8 +369,14 @@ class Context:
                 ia = np.ascontiguousarray(idx, dtype=np.int32)
                 sa = np.ascontiguousarray(scl, dtype=np.float64) if scl else None
                 _check(lib.b200_plugin_add_particle_group(self._h, index, name.encode(), _p(ia), _p(sa), ia.size))
+            if f._particles:
+                pa = np.ascontiguousarray(f._particles, dtype=np.int32)
+                _check(lib.b200_plugin_set_particles(self._h, index, _p(pa), pa.size))
             f._context, f._index = self, index
-        _check(lib.b200_plugin_finalize(self._h, platform.getName().encode()))
+        props = dict(properties or {})
+        names = (C.c_char_p * max(1, len(props)))(*[k.encode() for k in props])
+        values = (C.c_char_p * max(1, len(props)))(*[str(v).encode() for v in props.values()])
+        _check(lib.b200_plugin_finalize(self._h, platform.getName().encode(), names, values, len(props)))
 
     def setPositions(self, positions):
         pos = np.ascontiguousarray(positions, dtype=np.float64)
@@ -368,6 +410,15 @@ class Context:
         _check(_lib().b200_plugin_batch_evaluate(self._h, precision.encode(), _p(pos), r, _p(en), _p(f)))
         return en, f
 
+    def evaluateBatchBuffers(self, positions, energies, forces=None, precision="mixed", devices=None):
+        """GridForceBatch's pointer overloads on caller-owned numpy buffers (no copies): positions [R, A, 3] float64,
+        energies [R] float64, forces [R, A, 3] float64 or float32 (None = energy only); devices: GPU ordinals."""
+        r = positions.shape[0]
+        dv = np.ascontiguousarray(devices, dtype=np.int32) if devices is not None else None
+        f32 = forces is not None and forces.dtype == np.float32
+        _check(_lib().b200_plugin_batch_evaluate_buffers(self._h, precision.encode(), _p(dv), 0 if dv is None else dv.size, _p(positions),
+                                                         r, _p(energies), _p(forces), 1 if f32 else 0))
+
     def __del__(self):
         try:
             if self._h:
@@ -375,3 +426,8 @@ class Context:
                 self._h = None
         except Exception:
             pass
+
+
+def pin_buffer(array, pin=True):
+    """GridForceBatch::pinBuffer / unpinBuffer on a numpy array: page-lock it once so that batched calls DMA directly."""
+    _check(_lib().b200_plugin_pin_buffer(_p(array), array.nbytes, 1 if pin else 0))

@@ -4,6 +4,7 @@
 
 #include "B200GridForceKernels.h"
 #include "B200Platform.h"
+#include "openmm/Context.h"
 #include "openmm/OpenMMException.h"
 #include "openmm/internal/windowsExport.h"
 
@@ -11,25 +12,49 @@ using namespace OpenMM;
 
 namespace GridForcePlugin {
 
-B200Platform::B200Platform() : ReferencePlatform("B200") {
-    defaults[DeviceIndex()] = "0";
-    defaults[Precision()] = "mixed";
+B200Platform::B200Platform() {
+    platformProperties.push_back(DeviceIndex());
+    platformProperties.push_back(Precision());
+    setPropertyDefaultValue(DeviceIndex(), "0");
+    setPropertyDefaultValue(Precision(), "mixed");
 }
 
-const std::string& B200Platform::getPropertyDefaultValue(const std::string& property) const {
-    std::map<std::string, std::string>::const_iterator it = defaults.find(property);
-    if (it == defaults.end()) throw OpenMMException("B200 platform: unknown property '" + property + "'");
-    return it->second;
+void B200Platform::contextCreated(ContextImpl& context, const std::map<std::string, std::string>& properties) const {
+    ReferencePlatform::contextCreated(context, properties);      // the host arrays every Reference kernel works on
+    std::lock_guard<std::mutex> g(lock);
+    contextProperties[&context] = properties;
+}
+
+void B200Platform::contextDestroyed(ContextImpl& context) const {
+    {
+        std::lock_guard<std::mutex> g(lock);
+        contextProperties.erase(&context);
+    }
+    ReferencePlatform::contextDestroyed(context);
+}
+
+const std::string& B200Platform::propertyFor(const ContextImpl& context, const std::string& property) const {
+    std::lock_guard<std::mutex> g(lock);
+    std::map<const ContextImpl*, std::map<std::string, std::string> >::const_iterator c = contextProperties.find(&context);
+    if (c != contextProperties.end()) {
+        std::map<std::string, std::string>::const_iterator it = c->second.find(property);
+        if (it != c->second.end()) return it->second;
+    }
+    return getPropertyDefaultValue(property);       // throws "Illegal property name" for an unknown one
+}
+
+const std::string& B200Platform::getPropertyValue(const Context& context, const std::string& property) const {
+    return propertyFor(getContextImpl(context), property);
 }
 
 KernelImpl* B200GridForceKernelFactory::createKernelImpl(std::string name, const Platform& platform, ContextImpl& context) const {
     if (name != CalcGridForceKernel::Name())
         throw OpenMMException("Tried to create kernel with illegal kernel name '" + name + "'");
     const B200Platform& b200 = dynamic_cast<const B200Platform&>(platform);
-    const std::string& prec = b200.getPropertyDefaultValue(B200Platform::Precision());
+    const std::string& prec = b200.propertyFor(context, B200Platform::Precision());
     if (prec != "mixed" && prec != "double")
         throw OpenMMException("B200 platform: Precision must be 'mixed' or 'double', got '" + prec + "'");
-    const int device = atoi(b200.getPropertyDefaultValue(B200Platform::DeviceIndex()).c_str());
+    const int device = atoi(b200.propertyFor(context, B200Platform::DeviceIndex()).c_str());
     return new B200CalcGridForceKernel(name, platform, device, prec == "double" ? GFB_PRECISION_DOUBLE : GFB_PRECISION_MIXED, &context);
 }
 

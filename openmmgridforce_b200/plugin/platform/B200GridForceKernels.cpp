@@ -63,13 +63,24 @@ std::shared_ptr<SharedGrid> b200AcquireGrid(gfb_device* dev, int ordinal, int pr
                                             const std::vector<double>& spacing, const double origin[3],
                                             const std::vector<double>& vals) {
     static std::map<std::string, std::weak_ptr<SharedGrid> > cache;
-    unsigned long long h = hashWords(vals.data(), vals.size() * sizeof(double));
-    h = hashWords(counts.data(), 3 * sizeof(int), h);
-    h = hashWords(spacing.data(), 3 * sizeof(double), h);
-    h = hashWords(origin, 3 * sizeof(double), h);
+    // Two independent 64-bit hashes of the values (different seeds and a different word order for the second) plus the
+    // geometry: a hit needs all 128 bits and the size to agree, so one unlucky collision cannot hand a force another
+    // force's grid.
+    unsigned long long h1 = hashWords(vals.data(), vals.size() * sizeof(double));
+    unsigned long long h2 = hashWords(vals.data(), vals.size() * sizeof(double), 0xD6E8FEB86659FD93ull);
+    h1 = hashWords(counts.data(), 3 * sizeof(int), h1);
+    h1 = hashWords(spacing.data(), 3 * sizeof(double), h1);
+    h1 = hashWords(origin, 3 * sizeof(double), h1);
+    h2 = hashWords(origin, 3 * sizeof(double), h2);
+    h2 = hashWords(spacing.data(), 3 * sizeof(double), h2);
+    h2 = hashWords(counts.data(), 3 * sizeof(int), h2);
     std::ostringstream key;
-    key << ordinal << ':' << precision << ':' << layout << ':' << vals.size() << ':' << h;
+    key << ordinal << ':' << precision << ':' << layout << ':' << vals.size() << ':' << h1 << ':' << h2;
     std::lock_guard<std::mutex> lock(registryMutex);
+    for (std::map<std::string, std::weak_ptr<SharedGrid> >::iterator it = cache.begin(); it != cache.end();) {
+        if (it->second.expired()) cache.erase(it++);      // grids whose last Context is gone
+        else ++it;
+    }
     std::shared_ptr<SharedGrid> hit = cache[key.str()].lock();
     if (hit) return hit;
     gfb_grid* g = 0;
@@ -93,9 +104,20 @@ struct B200StepFusion {
     std::mutex lock;
     std::vector<B200CalcGridForceKernel*> members;
     std::map<unsigned, gfb_kernel*> fused;     // by member mask
+    // Per member: the energy a fused launch of ANOTHER member computed for it, valid only for the evaluation that
+    // produced it — same force-group flags and same positions (stamp = hash of a sample of the position array).
+    // A member consumes its own entry when OpenMM calls it; nobody else's entries are touched by that.
     std::vector<double> cachedEnergy;
+    std::vector<int> pendingGroups;
+    std::vector<unsigned long long> pendingStamp;
     unsigned pendingMask = 0;
-    int pendingGroups = 0;
+    void resize(size_t n) {
+        if (cachedEnergy.size() == n) return;
+        cachedEnergy.assign(n, 0.0);
+        pendingGroups.assign(n, 0);
+        pendingStamp.assign(n, 0);
+        pendingMask = 0;
+    }
     void dropFused() {
         for (std::map<unsigned, gfb_kernel*>::iterator it = fused.begin(); it != fused.end(); ++it) gfb_kernel_destroy(it->second);
         fused.clear();
@@ -242,24 +264,51 @@ void B200CalcGridForceKernel::build(const GridForce& force) {
                                 &oobK, &k), "kernel setup");
         kernels.push_back(k);
         check(gfb_kernel_set_energy_slots(k, slots.data(), numGroups), "particle group slots");
+        check(gfb_kernel_request_atom_energies(k, 1), "per-atom energies");   // getParticleAtomEnergies (GridForce.h:508)
+        numGroupAtoms = particlesFlat.size();
         fusionKey.clear();
         return;
     }
     numGroups = 0;
     // Single mode: scaling factor ia belongs to particle ligandAtoms[ia] (identity when no ligand atoms are set).
     // The loop bound is the number of scaling factors, not the particle count (reference quirk Q6).
-    const std::vector<int>& ligand = force.getLigandAtoms();
-    const int* particles = 0;
+    std::vector<int> ligand = force.getLigandAtoms();
     if (!ligand.empty()) {
         if (ligand.size() != scaling.size())
             throw OpenMMException("GridForce[B200]: number of ligand atoms differs from the number of scaling factors");
         for (size_t i = 0; i < ligand.size(); i++)
             if (ligand[i] < 0 || ligand[i] >= numParticles)
                 throw OpenMMException("GridForce[B200]: ligand atom index outside the System");
-        particles = ligand.data();
     } else if ((int) scaling.size() > numParticles) {
         throw OpenMMException("GridForce[B200]: more scaling factors than particles in the System");
     }
+    // Particle filter (GridForce::setParticles, openmmapi/include/GridForce.h:433-440), honoured the way the reference
+    // CUDA platform does (CudaGridForceKernels.cpp:122-127, 512-515; gridForce.cu:45-49): only the listed particles are
+    // evaluated, each with the scaling factor that belongs to ITS particle index (zero when the force has none for it,
+    // the CUDA platform's zero padding, :398-424). With ligand atoms set, the filter keeps the ligand atoms it lists.
+    const std::vector<int>& filter = force.getParticles();
+    if (!filter.empty()) {
+        std::vector<double> byParticle(numParticles, 0.0);
+        std::vector<char> has(numParticles, 0);
+        for (size_t ia = 0; ia < scaling.size(); ia++) {
+            const int particle = ligand.empty() ? (int) ia : ligand[ia];
+            byParticle[particle] = scaling[ia];
+            has[particle] = 1;
+        }
+        std::vector<int> keptParticles;
+        std::vector<double> keptScaling;
+        for (size_t i = 0; i < filter.size(); i++) {
+            if (filter[i] < 0 || filter[i] >= numParticles)
+                throw OpenMMException("GridForce[B200]: setParticles() index outside the System");
+            if (!ligand.empty() && !has[filter[i]]) continue;
+            keptParticles.push_back(filter[i]);
+            keptScaling.push_back(byParticle[filter[i]]);
+        }
+        ligand = keptParticles;
+        scaling = keptScaling;
+        // (a filter that keeps nothing leaves an empty atom list: the force then evaluates nothing)
+    }
+    const int* particles = ligand.empty() ? 0 : ligand.data();
     gfb_kernel* k = 0;
     check(gfb_kernel_create(dev, 1, &handle, (int) scaling.size(), scaling.data(), particles, &invPower, &oobK, &k), "kernel setup");
     kernels.push_back(k);
@@ -318,6 +367,7 @@ double B200CalcGridForceKernel::execute(ContextImpl& context, bool includeForces
     double total = 0.0;
     lastGroupEnergies.assign(groupMode ? numGroups : 1, 0.0);      // one energy per group slot (or the single total)
     check(gfb_kernel_execute_host(kernels[0], 1, numParticles, p, lastGroupEnergies.data(), 0, f, GFB_FORCE_F64_ADD), "execute");
+    evaluatedOnce = true;
     for (size_t i = 0; i < lastGroupEnergies.size(); i++) total += lastGroupEnergies[i];
     (void) includeEnergy;
     return total;
@@ -333,19 +383,23 @@ double B200CalcGridForceKernel::executeFused(ContextImpl& context, const double*
         if (fu.members[i] == this) me = i;
     if (me == n || n < 2) return 0.0;
     const int groups = context.getLastForceGroups();
-    if (fu.cachedEnergy.size() != n) {
-        fu.cachedEnergy.assign(n, 0.0);
-        fu.pendingMask = 0;
+    fu.resize(n);
+    // Which evaluation is this? OpenMM calls every ForceImpl once per evaluation, in System order, with the same
+    // force-group flags and the same positions: flags + a hash over a sample of the positions identify it.
+    const size_t nd = (size_t) numParticles * 3;
+    unsigned long long stamp = hashWords(pos, std::min<size_t>(nd, 96) * sizeof(double), (unsigned long long) nd);
+    if (nd > 96) {
+        stamp = hashWords(pos + nd - 96, 96 * sizeof(double), stamp);
+        const size_t stride = std::max<size_t>(1, nd / 64);
+        for (size_t i = 0; i < nd; i += stride) stamp = hashWords(pos + i, sizeof(double), stamp);
     }
     if ((fu.pendingMask >> me) & 1u) {
-        if (fu.pendingGroups == groups) {   // evaluated moments ago by the member OpenMM called first
-            fu.pendingMask &= ~(1u << me);
+        fu.pendingMask &= ~(1u << me);      // consumed, or stale: either way this member's entry is gone
+        if (fu.pendingGroups[me] == groups && fu.pendingStamp[me] == stamp) {   // evaluated moments ago by the member called first
             done = true;
             return fu.cachedEnergy[me];
         }
-        fu.pendingMask = 0;                 // left over from an evaluation that did not finish
     }
-    fu.pendingMask = 0;
     // members that OpenMM will call in this evaluation and that can share a launch with this one
     unsigned mask = 0;
     int count = 0;
@@ -381,14 +435,15 @@ double B200CalcGridForceKernel::executeFused(ContextImpl& context, const double*
     for (size_t i = 0; i < n; i++) {
         if (!((mask >> i) & 1u)) continue;
         if (i == me) mine = perGrid[slot];
-        else {
+        else {                              // only the bits of THIS launch's members change
             fu.cachedEnergy[i] = perGrid[slot];
+            fu.pendingGroups[i] = groups;
+            fu.pendingStamp[i] = stamp;
             fu.pendingMask |= 1u << i;
         }
         fu.members[i]->lastGroupEnergies.assign(1, perGrid[slot]);
         slot++;
     }
-    fu.pendingGroups = groups;
     done = true;
     return mine;
 }
@@ -402,8 +457,16 @@ std::vector<double> B200CalcGridForceKernel::getParticleGroupEnergies() {
     return groupMode ? lastGroupEnergies : std::vector<double>();
 }
 
-// Per-atom energies are a diagnostic of the reference's CUDA platform only (the Reference platform returns an empty
-// vector, ReferenceGridForceKernels.cpp:1134-1137); not produced here.
-std::vector<double> B200CalcGridForceKernel::getParticleAtomEnergies() { return std::vector<double>(); }
+// Per-atom energies of the most recent evaluation, in the order the particles were added to the groups; empty without
+// particle groups (openmmapi/include/GridForce.h:500-508; reference CUDA platform CudaGridForceKernels.cpp:1057-1069 —
+// its Reference platform returns an empty vector, ReferenceGridForceKernels.cpp:1134-1137). The kernel keeps them on
+// the device; they are copied out only when asked for.
+std::vector<double> B200CalcGridForceKernel::getParticleAtomEnergies() {
+    std::vector<double> out;
+    if (!groupMode || kernels.empty() || !evaluatedOnce) return out;
+    out.resize(numGroupAtoms);
+    check(gfb_kernel_get_atom_energies(kernels[0], out.data(), out.size()), "per-atom energies");
+    return out;
+}
 
 }  // namespace GridForcePlugin

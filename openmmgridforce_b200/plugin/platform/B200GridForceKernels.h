@@ -61,6 +61,8 @@ private:
     std::shared_ptr<SharedGrid> grid;
     std::vector<gfb_kernel*> kernels;       // the one evaluation state of this force
     int numGroups = 0;
+    size_t numGroupAtoms = 0;               // atoms over all particle groups (length of getParticleAtomEnergies())
+    bool evaluatedOnce = false;
     std::vector<double> lastGroupEnergies;
     int numParticles;
     OpenMM::ContextImpl* owner;             // the Context this kernel belongs to (fusion registry key), or null

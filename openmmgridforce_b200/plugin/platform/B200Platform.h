@@ -2,11 +2,19 @@
 // ReferencePlatform::PlatformData — what OpenMM hands a Reference kernel, ReferenceGridForceKernels.cpp:134-142), so every
 // stock kernel of ReferencePlatform (integrators, bonded forces) keeps working, while "CalcGridForce" is served by
 // the sm_100a kernels behind libgridforce_b200.so. Scripts select it by name: Platform.getPlatformByName("B200").
-// Platform properties: "DeviceIndex" (default "0"), "Precision" ("mixed" default, or "double").
+//
+// Properties, registered the OpenMM way (names pushed into Platform::platformProperties, defaults through the
+// base class's non-virtual setPropertyDefaultValue — the reference CUDA platform's pattern, and what
+// platforms/reference/src/ReferenceGridForceKernelFactory.cpp:44-72 relies on for the Reference platform):
+//   "DeviceIndex"  GPU ordinal, default "0"
+//   "Precision"    "mixed" (default) or "double"
+// Per-Context values given to the Context constructor arrive in contextCreated() and win over the defaults;
+// getPropertyValue(context, name) reports what a Context uses.
 #ifndef B200_PLATFORM_H_
 #define B200_PLATFORM_H_
 
 #include <map>
+#include <mutex>
 #include <string>
 
 #include "openmm/reference/ReferencePlatform.h"
@@ -21,8 +29,12 @@ public:
         return name;
     }
     double getSpeed() const { return 200.0; }
-    void setPropertyDefaultValue(const std::string& property, const std::string& value) { defaults[property] = value; }
-    const std::string& getPropertyDefaultValue(const std::string& property) const;
+    bool supportsDoublePrecision() const { return true; }
+    const std::string& getPropertyValue(const OpenMM::Context& context, const std::string& property) const;
+    void contextCreated(OpenMM::ContextImpl& context, const std::map<std::string, std::string>& properties) const;
+    void contextDestroyed(OpenMM::ContextImpl& context) const;
+    // The value a kernel of `context` uses: the Context's own property if it gave one, else the platform default.
+    const std::string& propertyFor(const OpenMM::ContextImpl& context, const std::string& property) const;
     static const std::string& DeviceIndex() {
         static const std::string key = "DeviceIndex";
         return key;
@@ -33,7 +45,8 @@ public:
     }
 
 private:
-    std::map<std::string, std::string> defaults;
+    mutable std::mutex lock;
+    mutable std::map<const OpenMM::ContextImpl*, std::map<std::string, std::string> > contextProperties;
 };
 
 }  // namespace GridForcePlugin

@@ -7,38 +7,61 @@ using OpenMM::OpenMMException;
 
 namespace GridForcePlugin {
 
-GridForceBatch::GridForceBatch(int deviceIndex, const std::string& precisionName)
-    : deviceIndex(deviceIndex), precision(GFB_PRECISION_MIXED), dev(0), kernel(0) {
-    if (precisionName == "double") precision = GFB_PRECISION_DOUBLE;
-    else if (precisionName != "mixed") throw OpenMMException("GridForceBatch: precision must be 'mixed' or 'double'");
+void GridForceBatch::setPrecision(const std::string& name) {
+    precision = GFB_PRECISION_MIXED;
+    if (name == "double") precision = GFB_PRECISION_DOUBLE;
+    else if (name != "mixed") throw OpenMMException("GridForceBatch: precision must be 'mixed' or 'double'");
 }
 
-GridForceBatch::~GridForceBatch() {
+GridForceBatch::GridForceBatch(int deviceIndex, const std::string& precisionName)
+    : devices(1, deviceIndex), dev(0), kernel(0), multi(0), numAtoms(0), built(false) {
+    setPrecision(precisionName);
+}
+
+GridForceBatch::GridForceBatch(const std::vector<int>& deviceIndices, const std::string& precisionName)
+    : devices(deviceIndices), dev(0), kernel(0), multi(0), numAtoms(0), built(false) {
+    setPrecision(precisionName);
+    if (devices.empty()) throw OpenMMException("GridForceBatch: the device list is empty");
+    if ((int) devices.size() > GFB_MAX_PEERS) throw OpenMMException("GridForceBatch: too many devices");
+}
+
+GridForceBatch::~GridForceBatch() { release(); }
+
+void GridForceBatch::release() {
     if (kernel) gfb_kernel_destroy(kernel);
+    if (multi) gfb_multi_destroy(multi);
+    kernel = 0;
+    multi = 0;
+    grids.clear();
+    built = false;
 }
 
 int GridForceBatch::addForce(const GridForce& force) {
     if ((int) forces.size() >= GFB_MAX_GRIDS) throw OpenMMException("GridForceBatch: too many forces in one batch");
     forces.push_back(&force);
-    if (kernel) {
-        gfb_kernel_destroy(kernel);
-        kernel = 0;
-    }
+    release();
     return (int) forces.size() - 1;
 }
 
 int GridForceBatch::getNumAtoms() const {
+    if (built) return numAtoms;
     if (forces.empty()) return 0;
     std::vector<int> c;
     std::vector<double> s, v, sc;
-    forces[0]->getGridParameters(c, s, v, sc);
+    forces[0]->getGridParameters(c, s, v, sc);      // before the first evaluation only: copies the grid to read one size
     return (int) sc.size();
 }
 
 void GridForceBatch::build() {
     if (forces.empty()) throw OpenMMException("GridForceBatch: add at least one GridForce before evaluating");
-    dev = b200Device(deviceIndex);
-    grids.clear();
+    release();
+    const bool several = devices.size() > 1;
+    if (several) {
+        if (gfb_multi_create((int) devices.size(), devices.data(), &multi) != GFB_OK)
+            throw OpenMMException(std::string("GridForceBatch: ") + gfb_last_error());
+    } else {
+        dev = b200Device(devices[0]);
+    }
     std::vector<gfb_grid*> handles;
     std::vector<double> scalingAll, invPower, oobK;
     size_t nAtoms = 0;
@@ -57,40 +80,82 @@ void GridForceBatch::build() {
             throw OpenMMException("GridForceBatch: all forces must have the same number of scaling factors");
         double origin[3];
         f.getGridOrigin(origin[0], origin[1], origin[2]);
-        grids.push_back(b200AcquireGrid(dev, deviceIndex, precision, layout, counts, spacing, origin, vals));
-        handles.push_back(grids.back()->handle);
+        if (several) {
+            if (gfb_multi_add_grid(multi, counts.data(), spacing.data(), origin, vals.data(), vals.size(), precision, layout) < 0)
+                throw OpenMMException(std::string("GridForceBatch: ") + gfb_last_error());
+        } else {
+            grids.push_back(b200AcquireGrid(dev, devices[0], precision, layout, counts, spacing, origin, vals));
+            handles.push_back(grids.back()->handle);
+        }
         scalingAll.insert(scalingAll.end(), scaling.begin(), scaling.end());
         invPower.push_back(f.getInvPower());
         oobK.push_back(f.getOutOfBoundsRestraint());
     }
-    if (gfb_kernel_create(dev, (int) handles.size(), handles.data(), (int) nAtoms, scalingAll.data(), 0, invPower.data(),
-                          oobK.data(), &kernel) != GFB_OK)
-        throw OpenMMException(std::string("GridForceBatch: ") + gfb_last_error());
+    const int rc = several ? gfb_multi_build(multi, (int) nAtoms, scalingAll.data(), invPower.data(), oobK.data())
+                           : gfb_kernel_create(dev, (int) handles.size(), handles.data(), (int) nAtoms, scalingAll.data(), 0,
+                                               invPower.data(), oobK.data(), &kernel);
+    if (rc != GFB_OK) throw OpenMMException(std::string("GridForceBatch: ") + gfb_last_error());
+    numAtoms = (int) nAtoms;
+    built = true;
 }
 
-void GridForceBatch::run(const std::vector<double>& positions, int numReplicas, std::vector<double>& energies, double* forcesOut) {
-    if (!kernel) build();
-    const int nAtoms = getNumAtoms();
-    if (numReplicas < 0 || positions.size() != (size_t) numReplicas * nAtoms * 3)
+void GridForceBatch::run(const double* positions, size_t nPositions, int numReplicas, double* energies, void* forcesOut,
+                         int forceMode, bool wantGridEnergies) {
+    if (!built) build();
+    if (numReplicas < 0 || nPositions != (size_t) numReplicas * numAtoms * 3)
         throw OpenMMException("GridForceBatch: positions must hold numReplicas * numAtoms * 3 values");
-    energies.assign(numReplicas, 0.0);
-    lastGridEnergies.assign((size_t) numReplicas * forces.size(), 0.0);
     if (numReplicas == 0) return;
-    if (gfb_kernel_execute_host(kernel, numReplicas, nAtoms, positions.data(), energies.data(), lastGridEnergies.data(), forcesOut,
-                                GFB_FORCE_F64_STORE) != GFB_OK)
-        throw OpenMMException(std::string("GridForceBatch: ") + gfb_last_error());
+    if (!positions || !energies) throw OpenMMException("GridForceBatch: NULL positions or energies buffer");
+    int rc;
+    if (multi) {
+        lastGridEnergies.clear();
+        rc = gfb_multi_execute_host(multi, numReplicas, positions, energies, forcesOut, forceMode);
+    } else {
+        double* ge = 0;
+        if (wantGridEnergies) {
+            lastGridEnergies.resize((size_t) numReplicas * forces.size());
+            ge = lastGridEnergies.data();
+        }
+        rc = gfb_kernel_execute_host(kernel, numReplicas, numAtoms, positions, energies, ge, forcesOut, forceMode);
+    }
+    if (rc != GFB_OK) throw OpenMMException(std::string("GridForceBatch: ") + gfb_last_error());
 }
 
 std::vector<double> GridForceBatch::evaluate(const std::vector<double>& positions, int numReplicas) {
-    std::vector<double> energies;
-    run(positions, numReplicas, energies, 0);
+    std::vector<double> energies(numReplicas > 0 ? numReplicas : 0);
+    run(positions.data(), positions.size(), numReplicas, energies.data(), 0, GFB_FORCE_F64_STORE, true);
     return energies;
 }
 
 void GridForceBatch::evaluateWithForces(const std::vector<double>& positions, int numReplicas, std::vector<double>& energies,
                                         std::vector<double>& forcesOut) {
-    forcesOut.assign(positions.size(), 0.0);
-    run(positions, numReplicas, energies, forcesOut.empty() ? 0 : forcesOut.data());
+    energies.resize(numReplicas > 0 ? numReplicas : 0);     // resize, not assign: every entry is overwritten by the kernels
+    forcesOut.resize(positions.size());
+    run(positions.data(), positions.size(), numReplicas, energies.data(), forcesOut.empty() ? 0 : forcesOut.data(),
+        GFB_FORCE_F64_STORE, true);
+}
+
+void GridForceBatch::evaluate(const double* positions, int numReplicas, double* energies) {
+    if (!built) build();
+    run(positions, (size_t) (numReplicas > 0 ? numReplicas : 0) * numAtoms * 3, numReplicas, energies, 0, GFB_FORCE_F64_STORE, false);
+}
+
+void GridForceBatch::evaluateWithForces(const double* positions, int numReplicas, double* energies, double* forcesOut) {
+    if (!built) build();
+    run(positions, (size_t) (numReplicas > 0 ? numReplicas : 0) * numAtoms * 3, numReplicas, energies, forcesOut, GFB_FORCE_F64_STORE, false);
+}
+
+void GridForceBatch::evaluateWithForcesF32(const double* positions, int numReplicas, double* energies, float* forcesOut) {
+    if (!built) build();
+    run(positions, (size_t) (numReplicas > 0 ? numReplicas : 0) * numAtoms * 3, numReplicas, energies, forcesOut, GFB_FORCE_F32_STORE, false);
+}
+
+void GridForceBatch::pinBuffer(void* ptr, size_t bytes) {
+    if (gfb_host_register(ptr, bytes) != GFB_OK) throw OpenMMException(std::string("GridForceBatch: ") + gfb_last_error());
+}
+
+void GridForceBatch::unpinBuffer(void* ptr) {
+    if (gfb_host_unregister(ptr) != GFB_OK) throw OpenMMException(std::string("GridForceBatch: ") + gfb_last_error());
 }
 
 }  // namespace GridForcePlugin

@@ -4,7 +4,9 @@
 // no SWIG or OpenMM in the build container; with them, python/gridforceplugin_b200.i exposes the same classes).
 // Mirrors oracle/ref_driver.cpp's call shape on purpose: same inputs, two implementations.
 #include <chrono>
+#include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -26,12 +28,16 @@ struct Handle {
     System system;
     std::vector<GridForce*> forces;   // owned by system
     Context* context;
-    GridForceBatch* batch;
+    GridForceBatch* batch;          // std::vector entry points
+    GridForceBatch* batchBuffers;   // caller-buffer entry points (possibly several devices)
+    std::vector<int> batchDevices;
+    std::string batchPrecision;
     int numParticles;
-    Handle() : context(0), batch(0), numParticles(0) {}
+    Handle() : context(0), batch(0), batchBuffers(0), numParticles(0) {}
     ~Handle() {
         delete context;
         delete batch;
+        delete batchBuffers;
     }
 };
 thread_local std::string lastError;
@@ -63,7 +69,18 @@ OPENMM_EXPORT int b200_plugin_register() {
 OPENMM_EXPORT int b200_plugin_set_property(const char* name, const char* value) {
     GUARD({
         registerB200GridForceKernelFactories();
-        dynamic_cast<B200Platform&>(Platform::getPlatformByName("B200")).setPropertyDefaultValue(name, value);
+        // through the BASE class, as a script's platform.setPropertyDefaultValue(...) does (the method is not virtual in
+        // OpenMM): works because the B200 platform registers its property names, throws for an unknown name
+        Platform& base = Platform::getPlatformByName("B200");
+        base.setPropertyDefaultValue(name, value);
+    })
+}
+
+OPENMM_EXPORT int b200_plugin_get_default_property(const char* name, char* out, int capacity) {
+    GUARD({
+        registerB200GridForceKernelFactories();
+        const std::string& v = Platform::getPlatformByName("B200").getPropertyDefaultValue(name);
+        snprintf(out, capacity, "%s", v.c_str());
     })
 }
 
@@ -162,11 +179,39 @@ OPENMM_EXPORT int b200_plugin_add_particle_group(void* handle, int force, const 
 }
 
 // Context creation on the platform named `platform` ("B200"): GridForceImpl::initialize -> kernel initialize().
-OPENMM_EXPORT int b200_plugin_finalize(void* handle, const char* platform) {
+// properties: n (name, value) pairs, the Context constructor's platform-specific properties (OpenMM: Context(system,
+// integrator, platform, properties)); they win over the platform's defaults for this Context only.
+OPENMM_EXPORT int b200_plugin_finalize(void* handle, const char* platform, const char* const* names, const char* const* values, int n) {
     Handle* h = static_cast<Handle*>(handle);
     GUARD({
         registerB200GridForceKernelFactories();
-        h->context = new Context(h->system, Platform::getPlatformByName(platform));
+        std::map<std::string, std::string> props;
+        for (int i = 0; i < n; i++) props[names[i]] = values[i];
+        h->context = new Context(h->system, Platform::getPlatformByName(platform), props);
+    })
+}
+
+// Platform::getPropertyValue(context, name): what this Context actually uses.
+OPENMM_EXPORT int b200_plugin_get_property(void* handle, const char* name, char* out, int capacity) {
+    Handle* h = static_cast<Handle*>(handle);
+    GUARD({
+        if (!h->context) throw OpenMMException("finalize first");
+        const std::string& v = h->context->getPlatform().getPropertyValue(*h->context, name);
+        snprintf(out, capacity, "%s", v.c_str());
+    })
+}
+
+OPENMM_EXPORT int b200_plugin_set_particles(void* handle, int force, const int* particles, int n) {
+    Handle* h = static_cast<Handle*>(handle);
+    GUARD({ h->forces.at(force)->setParticles(std::vector<int>(particles, particles + n)); })
+}
+
+OPENMM_EXPORT int b200_plugin_atom_energies(void* handle, int force, double* out, int capacity, int* count) {
+    Handle* h = static_cast<Handle*>(handle);
+    GUARD({
+        std::vector<double> e = h->forces.at(force)->getParticleAtomEnergies(*h->context);
+        *count = (int) e.size();
+        for (int i = 0; i < (int) e.size() && i < capacity; i++) out[i] = e[i];
     })
 }
 
@@ -217,6 +262,7 @@ OPENMM_EXPORT int b200_plugin_group_energies(void* handle, int force, double* ou
 }
 
 // Batched entry point over the forces added so far (GridForceBatch): positions [R][A][3] -> energies [R], forces.
+// The std::vector overloads (what SWIG's vectord typemaps call).
 OPENMM_EXPORT int b200_plugin_batch_evaluate(void* handle, const char* precision, const double* positions, int numReplicas,
                                              double* energies, double* forces) {
     Handle* h = static_cast<Handle*>(handle);
@@ -234,6 +280,37 @@ OPENMM_EXPORT int b200_plugin_batch_evaluate(void* handle, const char* precision
             e = h->batch->evaluate(pos, numReplicas);
         }
         memcpy(energies, e.data(), sizeof(double) * numReplicas);
+    })
+}
+
+// The pointer overloads on caller-owned buffers (numpy arrays through the SWIG buffer typemaps), optionally over several
+// devices: no copy, no vector. forcesF32 != 0: `forces` is float [R][A][3]. devices == NULL: device 0.
+OPENMM_EXPORT int b200_plugin_batch_evaluate_buffers(void* handle, const char* precision, const int* devices, int nDevices,
+                                                     const double* positions, int numReplicas, double* energies, void* forces,
+                                                     int forcesF32) {
+    Handle* h = static_cast<Handle*>(handle);
+    GUARD({
+        const std::vector<int> devs = devices && nDevices > 0 ? std::vector<int>(devices, devices + nDevices) : std::vector<int>(1, 0);
+        if (h->batchBuffers && (h->batchDevices != devs || h->batchPrecision != precision)) {
+            delete h->batchBuffers;
+            h->batchBuffers = 0;
+        }
+        if (!h->batchBuffers) {
+            h->batchBuffers = devs.size() > 1 ? new GridForceBatch(devs, precision) : new GridForceBatch(devs[0], precision);
+            h->batchDevices = devs;
+            h->batchPrecision = precision;
+            for (size_t i = 0; i < h->forces.size(); i++) h->batchBuffers->addForce(*h->forces[i]);
+        }
+        if (!forces) h->batchBuffers->evaluate(positions, numReplicas, energies);
+        else if (forcesF32) h->batchBuffers->evaluateWithForcesF32(positions, numReplicas, energies, static_cast<float*>(forces));
+        else h->batchBuffers->evaluateWithForces(positions, numReplicas, energies, static_cast<double*>(forces));
+    })
+}
+
+OPENMM_EXPORT int b200_plugin_pin_buffer(void* ptr, long long bytes, int pin) {
+    GUARD({
+        if (pin) GridForceBatch::pinBuffer(ptr, (size_t) bytes);
+        else GridForceBatch::unpinBuffer(ptr);
     })
 }
 

@@ -56,7 +56,7 @@ struct CoutSilencer {
 Platform& referencePlatform() {
     static ReferencePlatform* platform = 0;
     if (!platform) {
-        platform = new ReferencePlatform("Reference");
+        platform = new ReferencePlatform();
         Platform::registerPlatform(platform);
         registerKernelFactories();
     }

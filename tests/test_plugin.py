@@ -419,3 +419,198 @@ def test_step_fusion_keeps_unlike_forces_apart():
         assert abs(e_3 - ref_a["energy"]) <= 1e-12 * max(abs(x) for x in ref_a["grid_energies"])
         assert abs(e_all - (e_3 + e_x)) <= 1e-12 * (abs(e_3) + abs(e_x))
     platform.setPropertyDefaultValue("Precision", "mixed")
+
+
+def _extra_force(gfp, a, group, counts=(20, 20, 20), spacing=0.1, stride=2):
+    """A force on a coarser grid cut out of grid 0 (different geometry, same atoms): never fusable with the others."""
+    extra = gfp.GridForce()
+    extra.addGridCounts(*counts)
+    extra.addGridSpacing(spacing, spacing, spacing)
+    extra.setGridOrigin(*a["origin"])
+    extra.setGridValues(a["grids"][0][::stride, ::stride, ::stride])
+    for s in a["scaling"][0]:
+        extra.addScalingFactor(s)
+    extra.setForceGroup(group)
+    return extra
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", ["unlike_between", "two_interleaved_sets"])
+def test_step_fusion_with_other_forces_between_members(order):
+    """System order [A, X, B, C] with X unfusable, and two interleaved fusable sets [A1, A2, B1, B2]: a member that does
+    not belong to a fused launch must not disturb the others' pending results — forces must come out ONCE (a second
+    fused launch would add them twice) and a second evaluation must not return the first one's energies."""
+    import openmmgridforce_b200.gridforceplugin as gfp
+    a, ref = cases.load_golden("ligand_three_grids")
+    platform = gfp.Platform.getPlatformByName("B200")
+    system = gfp.System()
+    for _ in range(a["pos"].shape[0]):
+        system.addParticle(1.0)
+    _, members = _build_system(gfp, a)                  # three fusable forces (groups 0, 1, 2)
+    if order == "unlike_between":
+        seq = [members[0], _extra_force(gfp, a, 3), members[1], members[2]]
+        fused_groups = [(0b0111, [0, 1, 2])]
+    else:
+        twin = [_extra_force(gfp, a, 3), _extra_force(gfp, a, 4)]       # a second fusable set (same coarse geometry)
+        seq = [members[0], twin[0], members[1], twin[1], members[2]]
+        fused_groups = [(0b00111, [0, 1, 2])]
+    for f in seq:
+        system.addForce(f)
+    ctx = gfp.Context(system, platform, {"Precision": "double"})
+    all_groups = (1 << 5) - 1
+    for shift in (0.0, 0.013):                          # second pass: moved atoms, nothing cached may survive
+        pos = a["pos"] + shift
+        ctx.setPositions(pos)
+        singles = {}
+        for g in range(5):
+            st = ctx.getState(getEnergy=True, getForces=True, groups=1 << g)
+            singles[g] = (st.getPotentialEnergy(), st.getForces().copy())
+        st = ctx.getState(getEnergy=True, getForces=True, groups=all_groups)
+        e_sum = sum(v[0] for v in singles.values())
+        f_sum = sum(v[1] for v in singles.values())
+        assert abs(st.getPotentialEnergy() - e_sum) <= 1e-11 * sum(abs(v[0]) for v in singles.values())
+        assert np.abs(st.getForces() - f_sum).max() <= 1e-11 * np.abs(f_sum).max()
+        if shift == 0.0:
+            for mask, sel in fused_groups:
+                s2 = ctx.getState(getEnergy=True, getForces=True, groups=mask)
+                assert abs(s2.getPotentialEnergy() - ref["energy"]) <= 1e-12 * max(abs(x) for x in ref["grid_energies"])
+                assert np.abs(s2.getForces() - ref["forces"]).max() <= 1e-12 * np.abs(ref["forces"]).max()
+
+
+@pytest.mark.gpu
+def test_platform_properties_the_openmm_way():
+    """Property names are registered with the platform: the BASE class's setPropertyDefaultValue accepts them and rejects
+    others; per-Context properties win over the defaults and are reported by getPropertyValue."""
+    import openmmgridforce_b200.gridforceplugin as gfp
+    c, ref = cases.load_golden("ligand_three_grids")
+    platform = gfp.Platform.getPlatformByName("B200")
+    assert platform.getPropertyDefaultValue("Precision") == "mixed" and platform.getPropertyDefaultValue("DeviceIndex") == "0"
+    with pytest.raises(RuntimeError, match="Illegal property name"):
+        platform.setPropertyDefaultValue("NoSuchProperty", "1")
+    system, _ = _build_system(gfp, c)
+    with pytest.raises(RuntimeError, match="Illegal property name"):
+        gfp.Context(system, platform, {"Presicion": "double"})
+    system, _ = _build_system(gfp, c)
+    with pytest.raises(RuntimeError, match="Precision must be"):
+        gfp.Context(system, platform, {"Precision": "single"})
+    system, _ = _build_system(gfp, c)
+    ctx_d = gfp.Context(system, platform, {"Precision": "double"})
+    system2, _ = _build_system(gfp, c)
+    ctx_m = gfp.Context(system2, platform)
+    assert platform.getPropertyValue(ctx_d, "Precision") == "double" and platform.getPropertyValue(ctx_m, "Precision") == "mixed"
+    assert platform.getPropertyDefaultValue("Precision") == "mixed"          # the default did not move
+    ctx_d.setPositions(c["pos"])
+    ctx_m.setPositions(c["pos"])
+    e_d = ctx_d.getState(getEnergy=True).getPotentialEnergy()
+    e_m = ctx_m.getState(getEnergy=True).getPotentialEnergy()
+    assert abs(e_d - ref["energy"]) <= 1e-12 * abs(ref["energy"])
+    assert abs(e_m - ref["energy"]) <= 1e-6 * abs(ref["energy"]) and e_m != e_d
+
+
+@pytest.mark.gpu
+def test_set_particles_filter_and_atom_energies(oracle_built):
+    """GridForce::setParticles (only the listed particles feel the grid, each with the scaling factor of ITS particle
+    index — the reference CUDA platform's semantics, CudaGridForceKernels.cpp:122-127) and getParticleAtomEnergies."""
+    import openmmgridforce_b200.gridforceplugin as gfp
+    c, ref = cases.load_golden("ligand_three_grids")
+    platform = gfp.Platform.getPlatformByName("B200")
+    keep = [1, 4, 5, 9, 20, 33, 46]
+    system = gfp.System()
+    for _ in range(47):
+        system.addParticle(1.0)
+    force = gfp.GridForce()
+    force.addGridCounts(*c["counts"])
+    force.addGridSpacing(*c["spacing"])
+    force.setGridOrigin(*c["origin"])
+    force.setGridValues(c["grids"][0])
+    force.setScalingFactors(c["scaling"][0])
+    force.setParticles(keep)
+    system.addForce(force)
+    ctx = gfp.Context(system, platform, {"Precision": "double"})
+    ctx.setPositions(c["pos"])
+    st = ctx.getState(getEnergy=True, getForces=True)
+    port = oracle_built.PortOracle(c["counts"], c["spacing"], c["origin"], c["grids"][:1], c["scaling"][:1, keep], oob_k=c["oob_k"][:1])
+    ge, f = port.execute_batched(np.ascontiguousarray(c["pos"][keep])[None])
+    assert abs(st.getPotentialEnergy() - ge[0, 0]) <= 1e-12 * abs(ge[0, 0])
+    got = st.getForces()
+    assert np.abs(got[keep] - f[0]).max() <= 1e-12 * np.abs(f[0]).max()
+    others = np.setdiff1d(np.arange(47), keep)
+    assert not got[others].any()
+    assert len(force.getParticleAtomEnergies(ctx)) == 0          # no particle groups: empty, as the reference
+    # particle groups: per-atom energies in group order, summing to the group energies
+    system2 = gfp.System()
+    for _ in range(47):
+        system2.addParticle(1.0)
+    f2 = gfp.GridForce()
+    f2.addGridCounts(*c["counts"])
+    f2.addGridSpacing(*c["spacing"])
+    f2.setGridOrigin(*c["origin"])
+    f2.setGridValues(c["grids"][0])
+    ga, gb = list(range(30, 47)), list(range(0, 12))
+    f2.addParticleGroup("a", ga, list(c["scaling"][0][ga]))
+    f2.addParticleGroup("b", gb, list(c["scaling"][0][gb]))
+    system2.addForce(f2)
+    ctx2 = gfp.Context(system2, platform, {"Precision": "double"})
+    ctx2.setPositions(c["pos"])
+    ctx2.getState(getEnergy=True, getForces=True)
+    eg = f2.getParticleGroupEnergies(ctx2)
+    ae = f2.getParticleAtomEnergies(ctx2)
+    assert len(ae) == len(ga) + len(gb)
+    assert abs(ae[:len(ga)].sum() - eg[0]) <= 1e-12 * np.abs(ae).sum() and abs(ae[len(ga):].sum() - eg[1]) <= 1e-12 * np.abs(ae).sum()
+    order = ga + gb
+    for j in (0, 5, len(ga), len(order) - 1):                    # spot-check single atoms against the oracle
+        ia = order[j]
+        p1 = oracle_built.PortOracle(c["counts"], c["spacing"], c["origin"], c["grids"][:1], c["scaling"][:1, ia:ia + 1], oob_k=c["oob_k"][:1])
+        ge1, _ = p1.execute_batched(c["pos"][ia:ia + 1][None])
+        assert abs(ae[j] - ge1[0, 0]) <= 1e-12 * max(abs(ge1[0, 0]), 1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["mixed", "double"])
+def test_batch_buffer_overloads(oracle_built, precision):
+    """GridForceBatch's pointer overloads on caller-owned numpy buffers: E+F in float64 and float32, energy only, with
+    pageable and page-locked (pinBuffer) arrays; all against the oracle and against the std::vector overloads."""
+    import openmmgridforce_b200.gridforceplugin as gfp
+    c, ref = cases.load_golden("ligand_three_grids")
+    platform = gfp.Platform.getPlatformByName("B200")
+    system, forces = _build_system(gfp, c)
+    ctx = gfp.Context(system, platform, {"Precision": precision})
+    rng = np.random.default_rng(4)
+    r = 301
+    pos = np.stack([c["pos"] + rng.uniform(-0.05, 0.05, size=3) for _ in range(r)])
+    port = oracle_built.PortOracle(c["counts"], c["spacing"], c["origin"], c["grids"], c["scaling"], oob_k=c["oob_k"])
+    ge_ref, f_ref = port.execute_batched(pos, n_threads=4)
+    e_ref = ge_ref.sum(axis=1)
+    te, tf = (1e-6, 1e-5) if precision == "mixed" else (1e-12, 1e-12)
+    e_vec, f_vec = ctx.evaluateBatch(pos, precision=precision)
+    en = np.full(r, np.nan)
+    f64 = np.full(pos.shape, np.nan)
+    ctx.evaluateBatchBuffers(pos, en, f64, precision=precision)
+    assert np.abs(en - e_ref).max() <= te * max(np.abs(e_ref).max(), np.abs(ge_ref).max())
+    assert np.abs(f64 - f_ref).max() <= tf * np.abs(f_ref).max()
+    assert np.array_equal(f64, f_vec) and np.abs(en - e_vec).max() <= 1e-13 * np.abs(e_vec).max()
+    f32 = np.full(pos.shape, np.nan, dtype=np.float32)
+    gfp.pin_buffer(pos)
+    gfp.pin_buffer(f32)
+    try:
+        en32 = np.zeros(r)
+        ctx.evaluateBatchBuffers(pos, en32, f32, precision=precision)
+    finally:
+        gfp.pin_buffer(f32, False)
+        gfp.pin_buffer(pos, False)
+    assert np.abs(f32 - f_ref).max() <= max(tf, 1.2e-7) * np.abs(f_ref).max()
+    assert np.abs(en32 - en).max() <= 1e-13 * np.abs(en).max()
+    e_only = np.zeros(r)
+    ctx.evaluateBatchBuffers(pos, e_only, None, precision=precision)
+    assert np.abs(e_only - en).max() <= 1e-13 * np.abs(en).max()
+
+
+def test_plugin_sources_compile_against_the_reference_headers():
+    """`make plugin-check-reference`: the three platform sources compiled with the REFERENCE's openmmapi/include in place
+    of the in-repo stand-ins (only where the reference tree exists: the build container)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir("/root/reference/openmmapi/include"):
+        pytest.skip("no reference tree here")
+    out = subprocess.run(["make", "-C", root, "plugin-check-reference"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]

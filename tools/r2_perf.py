@@ -78,7 +78,7 @@ def report(tag, evals, t):
     print(f"{tag:58s} {med:8.2f} us (min {lo:7.2f} max {hi:7.2f})  {evals / med / 1e3:8.2f} G evals/s", flush=True)
 
 
-names = sys.argv[1:] or ["modes", "strong", "double", "e2e", "c3"]
+names = sys.argv[1:] or ["modes", "strong", "double", "e2e", "c4", "c3", "c3sort"]
 MODES = ((gf.FORCE_FIXED_ADD, "fixed_add"), (gf.FORCE_F64_STORE, "f64_store"), (gf.FORCE_F32_STORE, "f32_store"), (NONE, "energy_only"))
 
 if any(n in names for n in ("modes", "strong", "double", "e2e")):
@@ -129,7 +129,23 @@ if any(n in names for n in ("modes", "strong", "double", "e2e")):
             g.close()
         del full
 
-if "c3" in names:
+if "c4" in names:
+    w = W.c4_batched_replicas()
+    sets = [w.pos] + [W.ligand_replicas(w.n_replicas, W.ligand47()[0].mean(axis=0), seed=W.SEED + 10 + i,
+                                        escape_shift=(1.0, 0.0, 0.0)) for i in range(15)]
+    grids = [gf.Grid(dev, w.counts, w.spacing, w.origin, v, gf.PRECISION_MIXED) for v in w.grids]
+    k = gf.Kernel(dev, grids, w.scaling, oob_k=w.oob_k)
+    pos_sets = [torch.from_numpy(np.ascontiguousarray(p)).to(tdev) for p in sets]
+    for pdl, graph in ((False, False), (True, False), (True, True)):
+        k.set_launch_overlap(pdl)
+        for fm, fname in MODES:
+            report(f"C4 pdl={int(pdl)} graph={int(graph)} {fname}", w.evals, time_steps(k, w.n_replicas, w.n_atoms, pos_sets, fm, iters=64, graph=graph))
+    k.close()
+    for g in grids:
+        g.close()
+    del pos_sets
+
+if "c3" in names or "c3sort" in names:
     w = W.c3_million_atoms()
     rng = np.random.default_rng(99)
     length = w.spacing[0] * (w.counts[0] - 1)
@@ -141,6 +157,11 @@ if "c3" in names:
         k.set_launch_overlap(pdl)
         for fm, fname in MODES:
             report(f"C3 pdl={int(pdl)} {fname}", w.evals, time_steps(k, 1, w.n_atoms, pos_sets, fm, iters=40))
+    if "c3sort" not in names:
+        k.close()
+        for g in grids:
+            g.close()
+        sys.exit(0) if "c4" not in names else None
     # sorted evaluation order (indirection) and physically sorted positions (what a platform that owns the atom order does)
     k.set_launch_overlap(False)
     d_order = torch.empty(w.n_atoms, dtype=torch.int32, device=tdev)
