@@ -5,21 +5,30 @@
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...                          # the reference's own CPU kernel, all host cores
 
-Workload (config.workload): BASELINE.json configs[4] — ligand replicas x 47 atoms x 3 grids of 192^3 — with 65,536
-replicas PER GPU (weak scaling: rank g evaluates its own 65,536-replica batch; grids replicated; no collective on the
-force path; one NCCL all-gather of per-replica energies per step). At N=1 that is configs[4] itself on one GPU. The
-single-GPU configs C3 (1M atoms x 256^3) and C4 (4096 replicas x 3 grids) are timed in the same run and reported
-under "other_workloads" (N=1 only).
+Workload (config.workload): BASELINE.json configs[4] — 65,536 ligand replicas x 47 atoms x 3 grids of 192^3.
+  N = 1   the whole batch on one GPU.
+  N > 1   STRONG scaling (default, what configs[4] names): the 65,536 replicas are block-partitioned over the N ranks
+          (shard_bounds), grids replicated, no collective on the force path, and ONE gather of the per-replica energies
+          after the last step, inside the timed region. --scaling weak gives every rank 65,536 replicas instead.
+A "step" = one evaluation of the whole batch: positions -> per-replica energies + forces for every atom on every grid,
+one kernel launch per GPU. Successive steps evaluate DIFFERENT pose sets (2N sets of the shard size rotate), so that the
+bytes touched between two uses of the same data are the same at every N and exceed L2.
 
-A "step" = one evaluation of the whole batch: positions -> per-replica energies + forces for every atom on every grid.
-  value      device-resident inputs, CUDA-event time on the launching stream, max over ranks
-  e2e        the same through gfb_kernel_execute_host with pinned HOST buffers (H2D of positions and D2H of forces and
-             energies inside the timed region)
+  value      device-resident inputs; K steps per window, W_n windows, CUDA events on the launching stream around each
+             window, max over ranks per window, median over windows. The K-step loop (+ the final gather) is a CUDA graph
+             whose launches carry programmatic-dependent-launch edges; the same loop with direct launches and without
+             launch overlap is timed in the same run and reported under "variants".
+  e2e        the same through the plugin's batched entry point GridForceBatch (pinned HOST positions in, energies + FP32
+             forces out; H2D/D2H inside the timed region); FP64 forces, energy-only and the bare C ABI beside it.
   roofline   algorithmic bytes per evaluation (36 + 52/G bytes, G grids per atom) x evaluations per launch /
              average launch duration, against the measured HBM copy bandwidth in MEASURED_PEAKS.json
-Only the cpu_baseline leg and --impl reference load anything from oracle/ (the test-only CPU oracle).
+The data path of an N > 1 run is the C ABI only (gfb_comm_*: fused in-kernel gather over peer memory, or ncclAllGather);
+torch.distributed is the launcher's bootstrap channel (NCCL id, IPC handles), the barrier and the max over ranks.
+Only the cpu_baseline leg and --impl reference load anything from oracle/ (the test-only CPU oracle); the cpu_baseline
+leg also uses it to CHECK a sample of the timed kernel's output — a mismatch refuses the JSON line.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -35,16 +44,19 @@ sys.path.insert(0, ROOT)
 
 METRIC = "atom-grid evals/s (E+F)"
 UNIT = "evals/s"
-REPLICAS_PER_GPU = 65536
+REPLICAS_TOTAL = 65536
+REPLICAS_PER_GPU = REPLICAS_TOTAL          # weak scaling, and N = 1
 N_ATOMS = 47
 N_GRIDS = 3
 GRID_N = 192
-C5_DRAM_BYTES_PER_LAUNCH = 495.4e6     # measured once per change with ncu --set full (profiles/README.md, r1c)
+KERNEL_SOURCES = ("gf_eval_lines.cuh", "gf_kernels.cuh", "gf_params.h", "gf_launch_lines.cu")
 
 
-def b_alg(n_grids, precision=0):
-    """Algorithmic bytes per atom-grid evaluation (SURVEY.md §8d / DESIGN.md §4)."""
-    return (36.0 + 52.0 / n_grids) if precision == 0 else (72.0 + 52.0 / n_grids)
+def b_alg(n_grids, precision=0, forces=True):
+    """Algorithmic bytes per atom-grid evaluation (SURVEY.md §8d / DESIGN.md §4): stencil + scaling factor + (position +
+    force accumulate + order) / G. Energy-only evaluations do not touch the 24 force bytes."""
+    per_atom = 52.0 if forces else 28.0
+    return (36.0 + per_atom / n_grids) if precision == 0 else (72.0 + per_atom / n_grids)
 
 
 def measured_peaks():
@@ -53,6 +65,28 @@ def measured_peaks():
         d = json.load(open(path))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def kernel_source_hash():
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        h.update(open(os.path.join(ROOT, "openmmgridforce_b200", "csrc", name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(workload_key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/r2_traffic.json,
+    written by tools/ncu_traffic.py) — reported only while the kernel sources still hash to what was profiled."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(path):
+        return None, "no ncu capture committed for this round"
+    doc = json.load(open(path))
+    entry = doc.get(workload_key)
+    if not entry:
+        return None, f"profiles/r2_traffic.json has no entry for {workload_key}"
+    if entry.get("source_sha256_16") != kernel_source_hash():
+        return None, "kernel sources changed since the ncu capture in profiles/r2_traffic.json"
+    return float(entry["dram_bytes_per_launch"]), entry.get("source", "profiles/r2_traffic.json")
 
 
 class ClockSampler:
@@ -102,8 +136,7 @@ class ClockSampler:
 
 def bind_to_gpu_cpus(gpu_index):
     """Restrict this process to the CPU cores NVML reports as local to the GPU (what `nvidia-smi topo -m` prints), so that
-    its pinned buffers are allocated on that NUMA node: with 8 ranks streaming 2 x 74 MB per step each, host memory on the
-    wrong socket halves the PCIe rate. Returns a short description for the JSON line; never fatal."""
+    its pinned buffers are allocated on that NUMA node. Returns a short description for the JSON line; never fatal."""
     if os.environ.get("GFB_BIND_CPUS", "1") == "0":
         return "off"
     try:
@@ -124,83 +157,254 @@ def bind_to_gpu_cpus(gpu_index):
 def pinned_array(shape, dtype=np.float64):
     """numpy view over page-locked host memory (torch is the allocator; no torch type crosses the C ABI)."""
     import torch
-    t = torch.empty(tuple(shape), dtype={np.float64: torch.float64, np.int64: torch.int64}[dtype], pin_memory=True)
+    t = torch.empty(tuple(shape), dtype={np.float64: torch.float64, np.float32: torch.float32, np.int64: torch.int64}[dtype],
+                    pin_memory=True)
     return t.numpy(), t
+
+
+def workload_config(n_gpus, scaling="strong"):
+    """The workload both arms (this repo's and --impl reference) run. Nothing arm-specific in here."""
+    strong = scaling == "strong" or n_gpus == 1
+    total = REPLICAS_TOTAL if strong else REPLICAS_PER_GPU * n_gpus
+    return {"workload": f"configs[4]: {total} ligand replicas x {N_ATOMS} atoms x {N_GRIDS} grids of {GRID_N}^3"
+                        + (f", sharded over {n_gpus} GPUs" if n_gpus > 1 else " on one GPU"),
+            "replicas_total": total, "replicas_per_gpu": total // n_gpus, "atoms_per_replica": N_ATOMS,
+            "grids": N_GRIDS, "grid_points": [GRID_N] * 3, "precision": "mixed", "scaling": "strong" if strong else "weak",
+            "parallelism": f"replica-sharded x{n_gpus}",
+            "evals_per_step": total * N_ATOMS * N_GRIDS}
+
+
+def pose_sets(W, rank, world, strong, n_sets):
+    """This rank's pose sets. Set 0 is its block of the canonical batch (replicas [lo, hi) of the 65,536 generated from
+    SEED, or — weak scaling — a 65,536-replica batch of its own); the other sets are the same number of replicas drawn
+    with other seeds. Returns (workload of set 0, [pos arrays], (lo, hi))."""
+    from openmmgridforce_b200.sharding import shard_bounds
+    if strong:
+        lo, hi = shard_bounds(REPLICAS_TOTAL, world, rank)
+        w = W.c5_sharded_replicas(n_replicas=REPLICAS_TOTAL, n=GRID_N, replica_offset=lo, n_local=hi - lo)
+    else:
+        lo, hi = rank * REPLICAS_PER_GPU, (rank + 1) * REPLICAS_PER_GPU
+        w = W.c5_sharded_replicas(n_replicas=REPLICAS_PER_GPU, n=GRID_N, pose_seed=W.SEED + rank)
+    half = 0.5 * w.spacing[0] * (GRID_N - 1)
+    sets = [w.pos]
+    for j in range(1, n_sets):
+        sets.append(W.ligand_replicas(hi - lo, (half, half, half), seed=W.SEED + 7919 * j + rank, escape_shift=(0.9, 0.0, 0.0)))
+    return w, sets, (lo, hi)
 
 
 # ----------------------------------------------------------------------------------------------------------------
 # device-timed loops
 # ----------------------------------------------------------------------------------------------------------------
-def time_device_steps(torch, gf, kern, pos_sets, n_replicas, n_atoms, steps, warmup, stream, post_step=None,
-                      force_mode=None, energy_bufs_out=None, final_step=None, barrier=None):
-    """K launches on `stream`, rotating through pos_sets (and matching force/energy buffers). Returns
-    (seconds, launches) with CUDA events recorded on the launching stream."""
-    force_mode = gf.FORCE_FIXED_ADD if force_mode is None else force_mode
-    dev = pos_sets[0].device
-    n = n_replicas * n_atoms
-    stride = ((n + 31) // 32) * 32
-    bufs = []
-    for _ in pos_sets:
-        d_f = torch.zeros(3 * stride, dtype=torch.int64, device=dev)
-        bufs.append(d_f)
-    # four per-replica energy accumulators: step i adds into e[i % 4] and zero-fills e[(i + 1) % 4] in the same launch;
-    # the energy gather of step i (N > 1) reads e[i % 4] on its own stream while steps i+1, i+2 run, and is waited for
-    # (on the host: it finished long before) ahead of step i+3, whose launch clears e[i % 4] again.
-    d_e3 = [torch.zeros(n_replicas, dtype=torch.float64, device=dev) for _ in range(4)]
-    if energy_bufs_out is not None:
-        energy_bufs_out.extend(d_e3)
-    pending = {}
-    torch.cuda.synchronize()
+class DeviceLoop:
+    """Device-resident pose sets + per-set fixed-point force buffers + rotating energy accumulators, and the K-step window
+    that is timed: K evaluation launches on `stream`, the last of which carries (or is followed by) the energy gather."""
 
-    def step(i):
-        s = i % len(pos_sets)
-        d_f, d_e, d_next = bufs[s], d_e3[i % 4], d_e3[(i + 1) % 4]
-        if i - 3 in pending:
-            pending.pop(i - 3).wait()
-        kern.execute_device(n_replicas, n_atoms, pos_sets[s].data_ptr(), d_e.data_ptr(), None, d_f.data_ptr(), force_mode,
-                            stride, None, stream.cuda_stream, d_energies_clear=d_next.data_ptr())
-        if post_step is not None:
-            work = post_step(d_e)
-            if work is not None:
-                pending[i] = work
+    def __init__(self, torch, gf, dev, kern, sets, n_atoms, stream, comm=None, gather_mode="none", lo=0, total=0,
+                 force_mode=None):
+        self.torch, self.gf, self.dev, self.kern, self.stream, self.comm = torch, gf, dev, kern, stream, comm
+        self.gather_mode = gather_mode
+        tdev = torch.device("cuda", dev.ordinal)
+        self.r, self.a = sets[0].shape[0], n_atoms
+        n = self.r * self.a
+        self.stride = ((n + 31) // 32) * 32
+        self.force_mode = gf.FORCE_FIXED_ADD if force_mode is None else force_mode
+        self.d_pos = [torch.from_numpy(np.ascontiguousarray(p)).to(tdev) for p in sets]
+        if self.force_mode == gf.FORCE_FIXED_ADD:
+            self.d_f = [torch.zeros(3 * self.stride, dtype=torch.int64, device=tdev) for _ in sets]
+        elif self.force_mode == gf.FORCE_F32_STORE:
+            self.d_f = [torch.zeros(3 * n, dtype=torch.float32, device=tdev) for _ in sets]
+        elif self.force_mode < 0:
+            self.d_f = [None for _ in sets]
+        else:
+            self.d_f = [torch.zeros(3 * n, dtype=torch.float64, device=tdev) for _ in sets]
+        self.d_e = [torch.zeros(self.r, dtype=torch.float64, device=tdev) for _ in range(3)]
+        self.lo, self.total = lo, total
+        self.d_gathered = torch.zeros(max(total, 1), dtype=torch.float64, device=tdev)
+        self.set_evals = [0] * len(sets)      # evaluations accumulated into each set's force buffer
+        self.last = None                      # (set index, accumulator index) of the most recent step
+        torch.cuda.synchronize()
 
-    def drain():
-        for key in sorted(pending):
-            pending.pop(key).wait()
+    @staticmethod
+    def accumulators(steps):
+        """Which of the three accumulators step j adds into: consecutive steps differ, and the last differs from the
+        first (whose buffer it clears for the next window). Step j's launch clears a[j + 1] (a[steps] = a[0])."""
+        a = [j % 3 for j in range(steps)]
+        if steps > 1 and a[-1] == a[0]:
+            a[-1] = next(x for x in (1, 2) if x != a[-2])
+        return a
 
-    with torch.cuda.stream(stream):
-        for i in range(warmup):
-            step(i)
-        drain()
-        if final_step is not None:   # untimed: the collective's first call sets up NCCL's connections (milliseconds)
-            final_step(d_e3[(warmup - 1) % 4]).wait()
-        stream.synchronize()
-        if barrier is not None:      # all ranks enter the timed region together (barrier + synchronize on both sides)
-            barrier()
-        l0 = gf.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for i in range(steps):
-            step(warmup + i)
-        drain()                  # the last gathers are inside the timed region
-        if final_step is not None:   # the one gather of a "final" run: after the last step, before the clock stops
-            stream.wait_event(final_step(d_e3[(warmup + steps - 1) % 4]).ev)     # the clock stops after the gather
-        e1.record(stream)
-        stream.synchronize()
-        if barrier is not None:
-            barrier()
-        launches = gf.launch_count() - l0
-    return e0.elapsed_time(e1) * 1e-3, launches, bufs
+    def window(self, first, steps, count=True):
+        gf, kern, s = self.gf, self.kern, self.stream.cuda_stream
+        acc = self.accumulators(steps)
+        for j in range(steps):
+            si = (first + j) % len(self.d_pos)
+            e = self.d_e[acc[j]]
+            nxt = self.d_e[acc[(j + 1) % steps]] if steps > 1 else None
+            f = self.d_f[si].data_ptr() if self.d_f[si] is not None else None
+            last = j == steps - 1
+            if steps == 1:
+                e.zero_()
+            if last and self.gather_mode == "fused":
+                kern.execute_device_gather(self.comm, self.lo, self.r, self.a, self.d_pos[si].data_ptr(), e.data_ptr(), f,
+                                           max(self.force_mode, 0), self.stride, s, d_energies_clear=nxt.data_ptr() if nxt is not None else None)
+                self.comm.gather_wait(self.d_gathered.data_ptr(), s)
+            else:
+                kern.execute_device(self.r, self.a, self.d_pos[si].data_ptr(), e.data_ptr(), None, f, max(self.force_mode, 0),
+                                    self.stride, None, s, d_energies_clear=nxt.data_ptr() if nxt is not None else None)
+                if last and self.gather_mode == "nccl":
+                    self.comm.all_gather(e.data_ptr(), self.d_gathered.data_ptr(), self.r, s)
+            if count:
+                self.set_evals[si] += 1
+            self.last = (si, acc[j])
+
+    def time_windows(self, steps, warmup, windows, pdl, graph, barrier=None, reduce_max=None):
+        """Returns per-window milliseconds (max over ranks when reduce_max is given) and the launches per window."""
+        torch, gf = self.torch, self.gf
+        self.kern.set_launch_overlap(pdl)
+        n_sets = len(self.d_pos)
+        with torch.cuda.stream(self.stream):
+            done = 0
+            while done < warmup:                      # untimed warm-up steps, in windows of at most K
+                k = min(steps, warmup - done)
+                self.window(done, k)
+                done += k
+            self.stream.synchronize()
+            g = None
+            if graph and steps > 1:
+                gf.Graph.begin(self.dev, self.stream.cuda_stream)
+                self.window(0, steps, count=False)
+                g = gf.Graph.end(self.dev, self.stream.cuda_stream)
+                g.launch(self.stream.cuda_stream)             # untimed first replay (graph upload)
+                self._count_replay(0, steps)
+                self.stream.synchronize()
+            out = []
+            for w in range(windows):
+                first = (w * steps) % n_sets if g is None else 0
+                if barrier is not None:
+                    barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(self.stream)
+                if g is not None:
+                    g.launch(self.stream.cuda_stream)
+                    self._count_replay(0, steps)
+                else:
+                    self.window(first, steps)
+                e1.record(self.stream)
+                self.stream.synchronize()
+                if barrier is not None:
+                    barrier()
+                out.append(e0.elapsed_time(e1))
+            if g is not None:
+                g.close()
+        self.kern.set_launch_overlap(False)
+        if reduce_max is not None:
+            out = reduce_max(out)
+        launches = steps + (1 if self.gather_mode == "fused" else 0)
+        return out, launches
+
+    def _count_replay(self, first, steps):
+        acc = self.accumulators(steps)
+        for j in range(steps):
+            self.set_evals[(first + j) % len(self.d_pos)] += 1
+        self.last = ((first + steps - 1) % len(self.d_pos), acc[-1])
+
+    def last_step_results(self, n_sample):
+        """(positions, energies, forces per evaluation) of the first n_sample replicas of the set the most recent step
+        evaluated — what the timed kernel left in its buffers."""
+        torch, gf = self.torch, self.gf
+        si, ai = self.last
+        n = min(n_sample, self.r)
+        en = self.d_e[ai][:n].cpu().numpy()
+        pos = self.d_pos[si][:n].cpu().numpy()
+        tdev = self.d_pos[si].device
+        na = self.r * self.a
+        if self.force_mode == gf.FORCE_FIXED_ADD:
+            d_out = torch.empty(na, 3, dtype=torch.float64, device=tdev)
+            self.dev.fixed_to_f64(self.d_f[si].data_ptr(), self.stride, na, d_out.data_ptr(), self.stream.cuda_stream)
+            self.stream.synchronize()
+            f = d_out.view(self.r, self.a, 3)[:n].cpu().numpy() / float(self.set_evals[si])
+        else:
+            f = None
+        return pos, en, f
 
 
-def time_e2e_steps(gf, kern, pos_host, forces_host, energies_host, steps, warmup):
-    """Public host API, pinned host buffers, wall clock around synchronous calls (each returns with results on the host)."""
+def summarize(ms_windows, steps):
+    s = sorted(ms_windows)
+    med = s[len(s) // 2]
+    return {"ms_per_step": med / steps, "min_ms_per_step": s[0] / steps, "max_ms_per_step": s[-1] / steps, "windows": len(s)}
+
+
+VARIANTS = (("pdl+graph", True, True), ("pdl", True, False), ("graph", False, True), ("plain", False, False))
+
+
+def run_variants(loop, steps, warmup, windows, barrier=None, reduce_max=None, which=VARIANTS):
+    out = {}
+    launches = 0
+    for name, pdl, graph in which:
+        ms, launches = loop.time_windows(steps, warmup, windows, pdl, graph, barrier, reduce_max)
+        out[name] = summarize(ms, steps)
+    return out, launches
+
+
+def time_e2e(fn, steps, warmup):
     for _ in range(warmup):
-        kern.execute_host(pos_host, forces=forces_host, energies_out=energies_host)
+        fn()
     t0 = time.perf_counter()
     for _ in range(steps):
-        kern.execute_host(pos_host, forces=forces_host, energies_out=energies_host)
+        fn()
     return time.perf_counter() - t0
+
+
+def grid_forces_for(gfp, w):
+    """The workload as a script would hand it to the plugin: one GridForce per grid (bulk setters)."""
+    forces = []
+    for g in range(w.n_grids):
+        f = gfp.GridForce()
+        f.addGridCounts(*w.counts)
+        f.addGridSpacing(*w.spacing)
+        f.setGridOrigin(*w.origin)
+        f.setGridValues(w.grids[g])
+        f.setScalingFactors(w.scaling[g])
+        f.setOutOfBoundsRestraint(w.oob_k[g])
+        f.setForceGroup(g)
+        forces.append(f)
+    return forces
+
+
+def run_e2e(gf, kern, w, local_rank, steps, reduce_max_scalar=None, barrier=None):
+    """End to end through the plugin's batched entry point (GridForceBatch, pointer overloads on pinned caller buffers)
+    and, for comparison, through the bare C ABI. Every call returns with the results in host memory."""
+    import openmmgridforce_b200.gridforceplugin as gfp
+    r = w.n_replicas
+    pos_h, _k1 = pinned_array(w.pos.shape)
+    pos_h[...] = w.pos
+    f64_h, _k2 = pinned_array(w.pos.shape)
+    f32_h, _k3 = pinned_array(w.pos.shape, np.float32)
+    e_h, _k4 = pinned_array((r,))
+    batch = gfp.GridForceBatch(local_rank, "mixed")
+    for f in grid_forces_for(gfp, w):
+        batch.addForce(f)
+    calls = {
+        "GridForceBatch::evaluateWithForcesF32": lambda: batch.evaluateWithForcesF32(pos_h, r, e_h, f32_h),
+        "GridForceBatch::evaluateWithForces": lambda: batch.evaluateWithForces(pos_h, r, e_h, f64_h),
+        "GridForceBatch::evaluate (energy only)": lambda: batch.evaluate(pos_h, r, e_h),
+        "gfb_kernel_execute_host (C ABI, FP64 forces)": lambda: kern.execute_host(pos_h, forces=f64_h, energies_out=e_h),
+    }
+    d2h = {"GridForceBatch::evaluateWithForcesF32": w.pos.nbytes // 2 + 8 * r, "GridForceBatch::evaluateWithForces": w.pos.nbytes + 8 * r,
+           "GridForceBatch::evaluate (energy only)": 8 * r, "gfb_kernel_execute_host (C ABI, FP64 forces)": w.pos.nbytes + 8 * r}
+    out = {}
+    for name, fn in calls.items():
+        if barrier is not None:
+            barrier()
+        secs = time_e2e(fn, steps, 3)
+        if reduce_max_scalar is not None:
+            secs = reduce_max_scalar(secs)
+        out[name] = {"ms_per_step": secs / steps * 1e3, "h2d_bytes_per_step": int(w.pos.nbytes), "d2h_bytes_per_step": int(d2h[name])}
+    # the energies the batched entry point returned last (energy-only call ran third, C ABI last): keep them for the check
+    batch.evaluateWithForcesF32(pos_h, r, e_h, f32_h)
+    result = (e_h.copy(), f32_h.copy())
+    batch.close()
+    return out, result
 
 
 def run_single_ligand(gf, dev, steps=2000):
@@ -215,7 +419,7 @@ def run_single_ligand(gf, dev, steps=2000):
     pos_h[...] = w.pos
     f_h, _t2 = pinned_array(w.pos.shape)
     e_h, _t3 = pinned_array((1,))
-    secs = time_e2e_steps(gf, kern, pos_h, f_h, e_h, steps, 50)
+    secs = time_e2e(lambda: kern.execute_host(pos_h, forces=f_h, energies_out=e_h), steps, 50)
     kern.close()
     for g in grids:
         g.close()
@@ -229,15 +433,7 @@ def run_single_ligand(gf, dev, steps=2000):
         system = gfp.System()
         for _ in range(w.n_atoms):
             system.addParticle(1.0)
-        for g in range(w.n_grids):
-            f = gfp.GridForce()
-            f.addGridCounts(*w.counts)
-            f.addGridSpacing(*w.spacing)
-            f.setGridOrigin(*w.origin)
-            f.setGridValues(w.grids[g])
-            f.setScalingFactors(w.scaling[g])
-            f.setOutOfBoundsRestraint(w.oob_k[g])
-            f.setForceGroup(g)
+        for f in grid_forces_for(gfp, w):
             system.addForce(f)
         ctx = gfp.Context(system, gfp.Platform.getPlatformByName("B200"))
         ctx.setPositions(w.pos.reshape(-1, 3))
@@ -250,43 +446,56 @@ def run_single_ligand(gf, dev, steps=2000):
         plugin = {"error": repr(exc)}
     return {"workload": w.name, "us_per_step": secs / steps * 1e6, "steps_per_s": sps, "openmm_plugin_path": plugin,
             "grid_force_limited_ns_per_day": sps * 4e-6 * 86400.0, "value": w.evals * sps, "unit": UNIT,
-            "note": "latency-bound: one launch per step on host-mapped memory (15.6 us per call from C++, the rest is ctypes); "
-                    "upper bound on MD ns/day at 4 fs"}
+            "note": "latency-bound: one launch per step on host-mapped memory + one synchronize; upper bound on MD ns/day at 4 fs"}
 
 
-def run_other_workload(torch, gf, dev, tdev, stream, name, steps, warmup, peak_gbs, l2_gbs):
+def run_other_workload(torch, gf, dev, stream, name, steps, warmup, windows, peak_gbs, l2_gbs):
+    """C3 / C4 (and C5 in DOUBLE precision / energy only) device-resident on one GPU, rotating sets, the same window
+    machinery; FIXED_ADD unless the name says otherwise."""
     from openmmgridforce_b200 import workloads as W
+    precision, force_mode, forces = gf.PRECISION_MIXED, gf.FORCE_FIXED_ADD, True
     if name == "C3":
         w = W.c3_million_atoms()
-        n_sets = 8          # 8 x (24 MB positions + 24 MB forces + touched grid lines) >> 126 MB L2
         rng = np.random.default_rng(99)
         length = w.spacing[0] * (w.counts[0] - 1)
-        sets = [w.pos] + [rng.uniform(0.0, 0.999 * length, size=w.pos.shape) for _ in range(n_sets - 1)]
-    else:
+        sets = [w.pos] + [rng.uniform(0.0, 0.999 * length, size=w.pos.shape) for _ in range(7)]
+    elif name == "C4":
         w = W.c4_batched_replicas()
         sets = [w.pos] + [W.ligand_replicas(w.n_replicas, W.ligand47()[0].mean(axis=0), seed=W.SEED + 10 + i,
                                             escape_shift=(1.0, 0.0, 0.0)) for i in range(15)]
-    grids = [gf.Grid(dev, w.counts, w.spacing, w.origin, v, gf.PRECISION_MIXED) for v in w.grids]
+    else:      # C5 variants on the resident grids' workload
+        w, sets, _ = pose_sets(W, 0, 1, True, 2)
+        if name == "C5_double":
+            precision = gf.PRECISION_DOUBLE
+        elif name == "C5_energy_only":
+            force_mode, forces = -1, False
+    grids = [gf.Grid(dev, w.counts, w.spacing, w.origin, v, precision) for v in w.grids]
     kern = gf.Kernel(dev, grids, w.scaling, oob_k=w.oob_k)
-    kern.set_launch_overlap(True)
-    pos_sets = [torch.from_numpy(np.ascontiguousarray(p)).to(tdev) for p in sets]
-    secs, launches, _ = time_device_steps(torch, gf, kern, pos_sets, w.n_replicas, w.n_atoms, steps, warmup, stream)
-    # e2e on the first set
-    pos_h, _t1 = pinned_array(w.pos.shape)
-    pos_h[...] = w.pos
-    f_h, _t2 = pinned_array(w.pos.shape)
-    e_h, _t3 = pinned_array((w.n_replicas,))
-    e2e_steps = max(3, min(steps, 20))
-    e2e_secs = time_e2e_steps(gf, kern, pos_h, f_h, e_h, e2e_steps, 5)
-    rate = w.evals * steps / secs
-    ach = rate * b_alg(w.n_grids) / 1e9
-    out = {"workload": w.name, "value": rate, "unit": UNIT, "us_per_step": secs / steps * 1e6,
-           "l2": f"rotating {len(pos_sets)} position/force sets (aggregate footprint > L2)",
+    loop = DeviceLoop(torch, gf, dev, kern, sets, w.n_atoms, stream, force_mode=force_mode)
+    variants, _ = run_variants(loop, steps, warmup, windows, which=(VARIANTS[0], VARIANTS[3]))
+    best = variants["pdl+graph"]
+    rate = w.evals / (best["ms_per_step"] * 1e-3)
+    bpe = b_alg(w.n_grids, 1 if precision == gf.PRECISION_DOUBLE else 0, forces)
+    ach = rate * bpe / 1e9
+    traffic, traffic_src = measured_traffic(name)
+    out = {"workload": w.name + (" (DOUBLE precision)" if name == "C5_double" else " (energy only)" if name == "C5_energy_only" else ""),
+           "value": rate, "unit": UNIT, "us_per_step": best["ms_per_step"] * 1e3,
+           "us_per_step_no_overlap_direct_launches": variants["plain"]["ms_per_step"] * 1e3,
+           "eval_path": kern.eval_path(),
+           "l2": f"rotating {len(sets)} position/force sets (aggregate footprint > L2)",
            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
-                        "traffic": None, "bytes_per_eval": b_alg(w.n_grids)},
-           "roofline_l2_gather": {"achieved": ach, "peak": l2_gbs, "unit": "GB/s", "frac": ach / l2_gbs},
-           "e2e": {"value": w.evals * e2e_steps / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": int(w.pos.nbytes),
-                   "d2h_bytes_per_step": int(w.pos.nbytes + 8 * w.n_replicas)}}
+                        "traffic": traffic, "traffic_source": traffic_src, "bytes_per_eval": bpe},
+           "roofline_l2_gather": {"achieved": ach, "peak": l2_gbs, "unit": "GB/s", "frac": ach / l2_gbs if l2_gbs else None}}
+    if name in ("C3", "C4"):
+        pos_h, _t1 = pinned_array(w.pos.shape)
+        pos_h[...] = w.pos
+        f_h, _t2 = pinned_array(w.pos.shape, np.float32)
+        e_h, _t3 = pinned_array((w.n_replicas,))
+        e2e_steps = 10
+        secs = time_e2e(lambda: kern.execute_host(pos_h, forces=f_h, force_mode=gf.FORCE_F32_STORE, energies_out=e_h), e2e_steps, 3)
+        out["e2e"] = {"value": w.evals * e2e_steps / secs, "unit": UNIT, "h2d_bytes_per_step": int(w.pos.nbytes),
+                      "d2h_bytes_per_step": int(w.pos.nbytes // 2 + 8 * w.n_replicas), "api": "gfb_kernel_execute_host, FP32 forces"}
+    del loop
     kern.close()
     for g in grids:
         g.close()
@@ -296,30 +505,53 @@ def run_other_workload(torch, gf, dev, tdev, stream, name, steps, warmup, peak_g
 # ----------------------------------------------------------------------------------------------------------------
 # CPU legs (the only users of oracle/)
 # ----------------------------------------------------------------------------------------------------------------
-def _cpu_oracle_for_sample(bindings, w, n_sample):
+def _cpu_oracle_for_sample(bindings, w, pos):
     """One Context holding the sample's atoms (replicas flattened), G GridForces — evaluated by the reference's own
     kernel when oracle/_ref is present, else by the C restatement."""
+    n_sample = pos.shape[0]
     n = n_sample * w.n_atoms
-    pos = np.ascontiguousarray(w.pos[:n_sample].reshape(n, 3))
+    flat = np.ascontiguousarray(pos.reshape(n, 3))
     scaling = np.tile(w.scaling, (1, n_sample))
     if bindings.ref_available():
         ref = bindings.RefOracle(n, w.counts, w.spacing, w.origin, w.grids, scaling, oob_k=w.oob_k)
-        return "reference", (lambda reps: ref.execute_repeat(pos, reps)), n * w.n_grids
+        return "reference", (lambda reps: ref.execute_repeat(flat, reps)), n * w.n_grids
     port = bindings.PortOracle(w.counts, w.spacing, w.origin, w.grids, scaling, oob_k=w.oob_k)
 
     def run(reps):
         for _ in range(reps):
             for g in range(w.n_grids):
-                port.execute(pos, g)
+                port.execute(flat, g)
     return "port", run, n * w.n_grids
 
 
-def cpu_baseline(w, target_seconds=12.0, n_sample=2048):
-    """Single-threaded (the reference is single-threaded as written) on a bounded sample of the same workload."""
+def cpu_baseline(w, target_seconds=12.0, n_sample=2048, check=None):
+    """Single-threaded (the reference is single-threaded as written) on a bounded sample of the same workload. With
+    `check` = [(label, positions, energies, forces or None), ...] the oracle also CHECKS what the timed GPU paths
+    produced: per replica |E - E_ref| <= max(1e-6 |E_ref|, 6e-8 sum|s v|), forces 1e-5 relative (max-norm)."""
     from oracle import bindings
+    from openmmgridforce_b200 import workloads as W
     bindings.build()
+    checked = []
+    for label, pos, en, f in (check or []):
+        port = bindings.PortOracle(w.counts, w.spacing, w.origin, w.grids, w.scaling, oob_k=w.oob_k)
+        ge_ref, f_ref = port.execute_batched(np.ascontiguousarray(pos), n_threads=os.cpu_count() or 1)
+        e_ref = ge_ref.sum(axis=1)
+        bound = np.maximum(1e-6 * np.abs(e_ref), 6e-8 * W.mixed_energy_bound(w, pos))
+        bad_e = np.abs(en - e_ref) > bound
+        msg = None
+        if bad_e.any():
+            i = int(np.argmax(np.abs(en - e_ref) / np.maximum(bound, 1e-300)))
+            msg = f"{label}: energy of replica {i} is {en[i]!r}, the oracle says {e_ref[i]!r} (bound {bound[i]:.3e})"
+        if msg is None and f is not None:
+            err = np.abs(f - f_ref).max() / np.abs(f_ref).max()
+            if not err <= 1e-5:
+                msg = f"{label}: forces differ from the oracle by {err:.3e} relative (max-norm)"
+        if msg:
+            raise SystemExit("bench.py: the timed path's output failed the oracle check — " + msg)
+        checked.append({"what": label, "replicas": int(pos.shape[0]), "max_energy_err_over_bound": float((np.abs(en - e_ref) / np.maximum(bound, 1e-300)).max()),
+                        "force_rel_err": float(np.abs(f - f_ref).max() / np.abs(f_ref).max()) if f is not None else None})
     n_sample = min(n_sample, w.n_replicas)
-    kind, run, evals = _cpu_oracle_for_sample(bindings, w, n_sample)
+    kind, run, evals = _cpu_oracle_for_sample(bindings, w, w.pos[:n_sample])
     run(3)                                      # warm-up (also gets the reference's debug prints out of the way)
     t0 = time.perf_counter()
     run(2)
@@ -329,74 +561,60 @@ def cpu_baseline(w, target_seconds=12.0, n_sample=2048):
     run(reps)
     secs = time.perf_counter() - t0
     return {"value": evals * reps / secs, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": f"first {n_sample} replicas ({n_sample * w.n_atoms} atoms x {w.n_grids} grids), {reps} passes, {secs:.1f} s"}
+            "sample": f"first {n_sample} replicas ({n_sample * w.n_atoms} atoms x {w.n_grids} grids), {reps} passes, {secs:.1f} s",
+            "output_check": checked}
 
 
 def reference_arm(args):
-    """The reference's own CPU implementation on all host threads: one Context per thread over disjoint replica shards."""
+    """The reference's own CPU implementation on all host threads, on the SAME workload as the repo arm: the 65,536
+    replicas are cut into one contiguous block per host thread (one reference Context per thread, as example/sampler.py
+    keeps one per replica), and a step is ONE pass of every thread over its block = the whole batch once."""
     from oracle import bindings
     from openmmgridforce_b200 import workloads as W
+    from openmmgridforce_b200.sharding import shard_bounds
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     bindings.build()
     threads = os.cpu_count() or 1
-    per_thread = 256
-    w = W.c5_sharded_replicas(n_replicas=REPLICAS_PER_GPU, n=GRID_N, n_local=threads * per_thread)
-    runs = []
-    kind = "port"
+    cfg = workload_config(args.gpus, args.scaling)
+    passes = max(1, cfg["replicas_total"] // REPLICAS_TOTAL)      # weak scaling at N > 1: the 65,536 poses N times per step
+    total = REPLICAS_TOTAL
+    if os.environ.get("GFB_REF_REPLICAS"):            # bounded sample for slow hosts; the JSON line then says so
+        total = min(total, int(os.environ["GFB_REF_REPLICAS"]))
+    w = W.c5_sharded_replicas(n_replicas=REPLICAS_TOTAL, n=GRID_N, n_local=total)
+    runs, kind = [], "port"
     for t in range(threads):
-        sub = W.Workload(w.name, w.counts, w.spacing, w.origin, w.grids, w.scaling,
-                         w.pos[t * per_thread:(t + 1) * per_thread], w.oob_k, w.inv_power)
-        kind, run, evals = _cpu_oracle_for_sample(bindings, sub, per_thread)
+        lo, hi = shard_bounds(total, threads, t)
+        if hi == lo:
+            continue
+        kind, run, _ = _cpu_oracle_for_sample(bindings, w, w.pos[lo:hi])
         runs.append(run)
-    evals_per_pass = threads * per_thread * w.n_atoms * w.n_grids
+    evals_per_step = total * passes * w.n_atoms * w.n_grids
     runs[0](3)                                  # serial warm-up: the reference's static debug counters are not thread-safe
 
-    def one_step(reps):
-        th = [threading.Thread(target=r, args=(reps,)) for r in runs]
+    def one_step():
+        th = [threading.Thread(target=r, args=(passes,)) for r in runs]
         for t in th:
             t.start()
         for t in th:
             t.join()
 
-    one_step(1)
-    t0 = time.perf_counter()
-    one_step(2)
-    per = (time.perf_counter() - t0) / 2
-    reps = max(1, int(2.0 / max(per, 1e-6)))    # ~2 s of wall clock per step
     for _ in range(args.warmup):
-        one_step(reps)
+        one_step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        one_step(reps)
+        one_step()
     secs = time.perf_counter() - t0
-    value = evals_per_pass * reps * args.steps / secs
-    sample = (f"{threads} threads x {per_thread} replicas x {w.n_atoms} atoms x {w.n_grids} grids, {reps} passes per step "
-              f"(ctypes releases the GIL; one reference Context per thread)")
+    value = evals_per_step * args.steps / secs
+    sample = (f"{len(runs)} host threads x {total // max(len(runs), 1)} replicas x {w.n_atoms} atoms x {w.n_grids} grids = "
+              f"{total} replicas, {passes} pass(es) per step (ctypes releases the GIL; one reference Context per thread)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+            "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": cfg["scaling"],
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": len(runs), "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
-
-
-def workload_config(n_gpus):
-    return {"workload": f"configs[4]: ligand replicas x {N_ATOMS} atoms x {N_GRIDS} grids of {GRID_N}^3, "
-                        f"{REPLICAS_PER_GPU} replicas per GPU (N=1 is configs[4] on one GPU)",
-            "replicas_per_gpu": REPLICAS_PER_GPU, "replicas_total": REPLICAS_PER_GPU * n_gpus, "atoms_per_replica": N_ATOMS,
-            "grids": N_GRIDS, "grid_points": [GRID_N] * 3, "precision": "mixed", "parallelism": f"replica-sharded x{n_gpus}",
-            "l2": "inputs larger than L2: each step streams 74 MB of positions + 74 MB of forces per GPU and gathers from "
-                  "3 grids; no L2 flush between steps",
-            "launch_overlap": "programmatic dependent launch: a step's blocks may fetch their (static) inputs during the "
-                              "previous step's tail and wait for it before their first write (gfb_kernel_set_launch_overlap)",
-            "energy_gather": "N>1: per-replica energies of every rank gathered on every rank; config.energy_gather_when = final "
-                             "(once, after the last step, inside the timed region: BASELINE.json north_star) or every (after "
-                             "every step, overlapping the next two steps); config.energy_gather_mode = nccl "
-                             "(all_gather_into_tensor) or peer-put (copy-engine puts over NVLink into symmetric memory + "
-                             "signal barrier)"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -406,12 +624,16 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-extras", action="store_true", help="skip C3/C4 and the CPU baseline (N=1 only)")
-    ap.add_argument("--energy-gather", default=os.environ.get("GFB_ENERGY_GATHER_WHEN", "final"), choices=["final", "every"],
-                    help="N>1: gather per-replica energies once, after the last step (what BASELINE.json's north_star asks "
-                         "for; inside the timed region), or after every step (overlapping the next steps)")
+    ap.add_argument("--scaling", default=os.environ.get("GFB_BENCH_SCALING", "strong"), choices=["strong", "weak"],
+                    help="N>1: strong = the named config (65,536 replicas in total, sharded); weak = 65,536 per GPU")
+    ap.add_argument("--energy-gather", default=os.environ.get("GFB_ENERGY_GATHER", "fused"), choices=["fused", "nccl"],
+                    help="N>1: the one gather of per-replica energies after the last step — fused into the last launch "
+                         "(peer stores over NVLink + flags) or ncclAllGather; the other one is checked against it")
+    ap.add_argument("--windows", type=int, default=5, help="timed K-step windows (median reported)")
+    ap.add_argument("--no-extras", action="store_true", help="skip C2/C3/C4/C5 variants and the CPU baseline (N=1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.windows = max(args.windows, 1)
 
     if args.impl == "reference":
         reference_arm(args)
@@ -426,175 +648,165 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    strong = args.scaling == "strong" or world == 1
     torch.cuda.set_device(local_rank)
     tdev = torch.device("cuda", local_rank)
     numa = bind_to_gpu_cpus(local_rank)     # pinned host buffers are then first-touched on the GPU's own NUMA node
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=tdev)
-
-    dev = gf.Device(local_rank)         # raises if the CUDA library or an sm_100 GPU is missing: no fallback
+    dev = gf.Device(local_rank)             # raises if the CUDA library or an sm_100 GPU is missing: no fallback
     stream = torch.cuda.Stream(device=tdev)
     peak_gbs, peak_src = measured_peaks()
 
-    # this rank's batch: its own 65,536 replica poses (same grids and scaling factors on every rank)
-    w = W.c5_sharded_replicas(n_replicas=REPLICAS_PER_GPU, n=GRID_N, pose_seed=W.SEED + rank)
+    # ---- launcher-side plumbing (N > 1): torch.distributed carries the NCCL id and the IPC handles, the barrier and
+    #      the max over ranks; the energy gather itself is gfb_comm_* ----------------------------------------------------
+    dist, comm = None, None
+    barrier = reduce_max = reduce_max_scalar = None
+    n_sets = 2 * world if strong else 2
+    w, sets, (lo, hi) = pose_sets(W, rank, world, strong, n_sets)
+    total = REPLICAS_TOTAL if strong else REPLICAS_PER_GPU * world
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=tdev)
+        uid = [gf.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = gf.Comm(dev, world, rank, uid[0])
+        handles = [None] * world
+        dist.all_gather_object(handles, comm.gather_alloc(total))
+        comm.gather_attach(handles)
+
+        def barrier():
+            dist.barrier()
+            torch.cuda.synchronize()
+
+        def reduce_max(ms_list):
+            t = torch.tensor(ms_list, dtype=torch.float64, device=tdev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.tolist()
+
+        def reduce_max_scalar(x):
+            return reduce_max([x])[0]
+
     grids = [gf.Grid(dev, w.counts, w.spacing, w.origin, v, gf.PRECISION_MIXED) for v in w.grids]
     kern = gf.Kernel(dev, grids, w.scaling, oob_k=w.oob_k)
-    # back-to-back evaluations of resident poses: a launch may start while the previous one's tail is still running (PDL);
-    # its inputs are not produced by that previous launch. Host-path (e2e) launches are unaffected.
-    # (with a gather after EVERY step the overlap is switched off: the two together measured slower, 88.2 vs 84.7 us at N=2)
-    kern.set_launch_overlap(os.environ.get("GFB_BENCH_PDL", "1") != "0" and (world == 1 or args.energy_gather == "final"))
-    d_pos = torch.from_numpy(w.pos).to(tdev)
-
-    from openmmgridforce_b200 import sharding
-
-    # The one collective (N > 1): per-replica energies of every rank, every step, overlapping the next step's kernel.
-    #   "nccl"      torch.distributed all_gather_into_tensor, asynchronous (default: what the north star names);
-    #   "peer-put"  GFB_ENERGY_GATHER=peer-put: each rank copies its 512 KB into its slot of every peer's buffer with the
-    #               copy engines over NVLink (gfb_peer_put on torch symmetric-memory buffers) and then passes a signal-pad
-    #               barrier, so no SM is taken from the evaluation kernel running alongside. Measured on the same boxes:
-    #               N=8 807 vs 791 G evals/s, N=2 209 vs 213 — within box-to-box noise, so NCCL stays the default.
-    gather_mode = "none"
-    counter = [0]
-    if world > 1:
-        gather_mode = os.environ.get("GFB_ENERGY_GATHER", "nccl")
-        if gather_mode == "peer-put":
-            try:
-                import torch.distributed._symmetric_memory as symm
-                sym_buf = symm.empty(2 * world * REPLICAS_PER_GPU, dtype=torch.float64, device=tdev)
-                sym_hdl = symm.rendezvous(sym_buf, dist.group.WORLD)
-                peer_ptrs = [int(p) for p in sym_hdl.buffer_ptrs]
-            except Exception as exc:      # no symmetric memory on this box/build: use NCCL, and say so
-                print(f"[bench] symmetric memory unavailable ({exc!r}); energy gather falls back to NCCL", file=sys.stderr)
-                gather_mode = "nccl"
-        if gather_mode == "nccl":
-            gathered2 = [torch.empty(world * REPLICAS_PER_GPU, dtype=torch.float64, device=tdev) for _ in range(2)]
-        gather_stream = torch.cuda.Stream(device=tdev)
-
-    class _GatherDone:
-        """Completion of a gather issued on gather_stream: .wait() makes the launching stream wait for it (what an NCCL
-        Work's wait() does); .ev is the CUDA event."""
-        def __init__(self, ev):
-            self.ev = ev
-
-        def wait(self):
-            torch.cuda.current_stream().wait_event(self.ev)
-
-    def post_step(d_e, force=False):
-        if world == 1 or (args.energy_gather == "final" and not force):
-            return None
-        counter[0] += 1
-        b = counter[0] % 2
-        if gather_mode == "nccl" and not force:
-            return dist.all_gather_into_tensor(gathered2[b], d_e, async_op=True)     # NCCL's own stream; Work.wait()
-        ready = torch.cuda.Event()
-        ready.record(stream)                       # the step's kernel has produced d_e
-        gather_stream.wait_event(ready)
-        if gather_mode == "nccl":
-            with torch.cuda.stream(gather_stream):
-                dist.all_gather_into_tensor(gathered2[b], d_e)      # enqueued behind gather_stream; returns at once
-        else:
-            dev.peer_put(d_e.data_ptr(), peer_ptrs, (b * world + rank) * REPLICAS_PER_GPU * 8, REPLICAS_PER_GPU * 8,
-                         first_peer=rank + 1, stream=gather_stream.cuda_stream)
-            with torch.cuda.stream(gather_stream):
-                sym_hdl.barrier(channel=b)         # every rank's puts of this step have landed everywhere
-        done = torch.cuda.Event()
-        done.record(gather_stream)
-        return _GatherDone(done)
-
-    def gathered_view(b):
-        if gather_mode == "nccl":
-            return gathered2[b]
-        return sym_buf.view(2, world * REPLICAS_PER_GPU)[b]
+    gather_mode = args.energy_gather if world > 1 else "none"
+    loop = DeviceLoop(torch, gf, dev, kern, sets, N_ATOMS, stream, comm=comm, gather_mode=gather_mode, lo=lo, total=total)
 
     l2_gbs = dev.bench_sector_gather(32 << 20, 1 << 24, 10) if rank == 0 else 0.0
-
+    if barrier is not None:
+        barrier()
+    host_copy = dev.bench_host_copy(64 << 20, 5)        # every rank at the same time: the share each GPU gets
     sampler = ClockSampler(local_rank)
-    if world > 1:
-        dist.barrier()
+    if barrier is not None:
+        barrier()
     torch.cuda.synchronize()
     sampler.start()
-    energy_bufs = []
-    secs, launches, bufs = time_device_steps(torch, gf, kern, [d_pos], REPLICAS_PER_GPU, N_ATOMS, args.steps, args.warmup, stream,
-                                             post_step=post_step, energy_bufs_out=energy_bufs,
-                                             final_step=(lambda d_e: post_step(d_e, force=True))
-                                             if world > 1 and args.energy_gather == "final" else None,
-                                             barrier=(lambda: (dist.barrier(), torch.cuda.synchronize())) if world > 1 else None)
-    torch.cuda.synchronize()
-    if world > 1:
-        # outside the timed region: the last step's gathered energies must equal a plain blocking NCCL all-gather of them
-        last = (args.warmup + args.steps - 1) % 4
-        check = torch.empty(world * REPLICAS_PER_GPU, dtype=torch.float64, device=tdev)
-        dist.all_gather_into_tensor(check, energy_bufs[last])
-        if not torch.equal(check, gathered_view(counter[0] % 2)):
-            raise SystemExit(f"rank {rank}: energy gather ({gather_mode}) does not match NCCL all_gather")
-    per_rank_us = [secs / args.steps * 1e6]
-    if world > 1:
-        t = torch.tensor([secs], dtype=torch.float64, device=tdev)
-        all_t = torch.empty(world, dtype=torch.float64, device=tdev)
-        dist.all_gather_into_tensor(all_t, t)          # every rank's own device-timed loop: the value uses the MAX
-        per_rank_us = [float(x) / args.steps * 1e6 for x in all_t.tolist()]
-        secs_max = float(all_t.max().item())
-        dist.barrier()
-    else:
-        secs_max = secs
 
-    # e2e: public host API with pinned buffers, every rank on its own batch
-    pos_h, _k1 = pinned_array(w.pos.shape)
-    pos_h[...] = w.pos
-    f_h, _k2 = pinned_array(w.pos.shape)
-    e_h, _k3 = pinned_array((REPLICAS_PER_GPU,))
+    variants, launches = run_variants(loop, args.steps, args.warmup, args.windows, barrier, reduce_max)
+    headline = variants["pdl+graph"] if args.steps > 1 else variants["pdl"]
+    gather_check = None
+    if world > 1:
+        comm.gather_status()
+        # the gathered energies of the last window must equal the OTHER gather method's result on the same accumulators
+        si, ai = loop.last
+        other = torch.zeros(total, dtype=torch.float64, device=tdev)
+        if gather_mode == "fused":
+            comm.all_gather(loop.d_e[ai].data_ptr(), other.data_ptr(), loop.r, stream.cuda_stream)
+        else:
+            dist.all_gather_into_tensor(other, loop.d_e[ai])
+        torch.cuda.synchronize()
+        if not torch.equal(other, loop.d_gathered):
+            raise SystemExit(f"rank {rank}: energy gather ({gather_mode}) does not match the reference all-gather")
+        gather_check = f"{gather_mode} gather == " + ("ncclAllGather via gfb_comm_all_gather" if gather_mode == "fused" else "torch all_gather_into_tensor") + " (bit-identical, outside the timed region)"
+    dev_sample = loop.last_step_results(1024)
+    # this rank's own per-step time (not the max over ranks, no gather) for the roofline of ITS kernel
+    saved_mode, loop.gather_mode = loop.gather_mode, "none"
+    own_ms, _ = loop.time_windows(args.steps, 0, 3, True, args.steps > 1)
+    loop.gather_mode = saved_mode
+    kernel_us = sorted(own_ms)[1] / args.steps * 1e3
+
+    weak = None
+    if world > 1 and strong and os.environ.get("GFB_BENCH_WEAK", "1") != "0":
+        # the weak-scaling curve as a second figure: every rank evaluates 65,536 replicas of its own (no gather change)
+        w_weak, sets_weak, _ = pose_sets(W, rank, world, False, 2)
+        comm_w_total = REPLICAS_PER_GPU * world
+        loop_w = DeviceLoop(torch, gf, dev, kern, sets_weak, N_ATOMS, stream, comm=None, gather_mode="none", lo=0, total=0)
+        steps_w = max(4, min(args.steps, 40))
+        vw, _ = run_variants(loop_w, steps_w, 4, 3, barrier, reduce_max, which=(VARIANTS[0],))
+        weak = {"scaling": "weak", "replicas_total": comm_w_total, "ms_per_step": vw["pdl+graph"]["ms_per_step"],
+                "value": comm_w_total * N_ATOMS * N_GRIDS / (vw["pdl+graph"]["ms_per_step"] * 1e-3), "unit": UNIT,
+                "note": "65,536 replicas per GPU, no energy gather in this window"}
+        del loop_w
+
+    # ---- end to end --------------------------------------------------------------------------------------------------
     e2e_steps = max(3, min(args.steps, 20))
-    if world > 1:
-        dist.barrier()
-    e2e_secs = time_e2e_steps(gf, kern, pos_h, f_h, e_h, e2e_steps, 5)
-    if world > 1:
-        t = torch.tensor([e2e_secs], dtype=torch.float64, device=tdev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_secs = float(t.item())
+    e2e, e2e_result = run_e2e(gf, kern, w, local_rank, e2e_steps, reduce_max_scalar, barrier)
+    if barrier is not None:
+        barrier()
+    host_copy_after = dev.bench_host_copy(64 << 20, 5)
 
     extras = {}
     if rank == 0 and world == 1 and not args.no_extras:
-        for name in ("C3", "C4"):
-            extras[name] = run_other_workload(torch, gf, dev, tdev, stream, name, max(20, min(args.steps, 200)), args.warmup,
-                                              peak_gbs, l2_gbs)
+        x_steps = max(20, min(args.steps, 200))
+        for name in ("C3", "C4", "C5_double", "C5_energy_only"):
+            extras[name] = run_other_workload(torch, gf, dev, stream, name, x_steps, args.warmup, 3, peak_gbs, l2_gbs)
         extras["C2"] = run_single_ligand(gf, dev)
     clocks = sampler.stop()
 
-    evals_step_rank = REPLICAS_PER_GPU * N_ATOMS * N_GRIDS
-    value = evals_step_rank * world * args.steps / secs_max
-    kernel_us = secs / args.steps * 1e6        # this rank's average step (N=1: exactly the kernel's launch-to-launch time)
+    evals_step_rank = w.n_replicas * N_ATOMS * N_GRIDS
+    evals_step = total * N_ATOMS * N_GRIDS
+    value = evals_step / (headline["ms_per_step"] * 1e-3)
     ach = evals_step_rank * b_alg(N_GRIDS) / (kernel_us * 1e-6) / 1e9
+    host_copy_all = [list(host_copy)]
+    if world > 1:
+        t = torch.tensor(list(host_copy) + list(host_copy_after), dtype=torch.float64, device=tdev)
+        allt = torch.empty(world * 6, dtype=torch.float64, device=tdev)
+        dist.all_gather_into_tensor(allt, t)
+        host_copy_all = allt.view(world, 6).tolist()
 
     if rank == 0:
+        cfg = workload_config(world, args.scaling)
+        head_api = "GridForceBatch::evaluateWithForcesF32"
+        traffic, traffic_src = measured_traffic("C5" if world == 1 else f"C5_shard_{world}")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": secs_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 interpolation, f64 index/energy, i64 fixed-point forces", "data": "synthetic",
-                "config": dict(workload_config(world), energy_gather_mode=gather_mode,
-                               energy_gather_when=args.energy_gather if world > 1 else "none"),
+                "ms_per_step": headline["ms_per_step"], "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
+                "dtype": "f32 interpolation, f64 index/energy, i64 fixed-point forces", "data": "synthetic", "config": cfg,
+                "run": {"windows": headline["windows"], "min_ms_per_step": headline["min_ms_per_step"],
+                        "max_ms_per_step": headline["max_ms_per_step"],
+                        "launch": "CUDA graph of the K-step loop; launches carry programmatic-dependent-launch edges (a step's "
+                                  "blocks fetch positions/records and issue their force atomics during the previous step's "
+                                  "tail, and wait for it before their energy writes)" if args.steps > 1 else "direct launches, PDL",
+                        "pose_sets": f"{n_sets} sets of {w.n_replicas} replicas rotate (inputs larger than L2 between re-uses; no L2 flush)",
+                        "energy_gather": gather_mode if world > 1 else "none (one GPU)",
+                        "energy_gather_when": "once per window, after the last step, inside the timed region" if world > 1 else "n/a",
+                        "gather_check": gather_check,
+                        "data_path": "C ABI only (gfb_kernel_execute_device[_gather], gfb_comm_*, gfb_graph_*); torch.distributed = bootstrap, barrier, max over ranks"},
+                "variants": {k: {"ms_per_step": v["ms_per_step"], "value": evals_step / (v["ms_per_step"] * 1e-3)} for k, v in variants.items()},
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
-                             "traffic": C5_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch",
-                             "traffic_source": "profiles/r1c_c5_lines_warm_raw.csv: dram__bytes_read.sum 397.1 MB + "
-                                               "dram__bytes_write.sum 98.3 MB (ncu --set full, this kernel, this workload)",
+                             "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
                              "peak_source": peak_src, "kernel": "gf_eval_lines_kernel<3 grids, FIXED_ADD> (one 128-byte record per cell)",
-                             "bytes_per_eval": b_alg(N_GRIDS), "evals_per_launch": evals_step_rank,
-                             "launch_us": kernel_us},
+                             "bytes_per_eval": b_alg(N_GRIDS), "evals_per_launch": evals_step_rank, "launch_us": kernel_us},
                 "roofline_l2_gather": {"achieved": ach, "peak": l2_gbs, "unit": "GB/s", "frac": ach / l2_gbs if l2_gbs else None,
                                        "peak_source": "gfb_bench_sector_gather: random 32-byte sectors over 32 MB, this run"},
-                "e2e": {"value": evals_step_rank * world * e2e_steps / e2e_secs, "unit": UNIT,
-                        "h2d_bytes_per_step": int(w.pos.nbytes), "d2h_bytes_per_step": int(w.pos.nbytes + 8 * REPLICAS_PER_GPU),
-                        "api": "gfb_kernel_execute_host (pinned host positions in, forces + energies out; H2D by copy engine in 8 chunks, "
-                               "forces stored by the kernels straight into the pinned host buffer)"},
-                "gpu_launches": int(launches), "clocks": clocks,
-                "per_rank_us_per_step": [round(x, 2) for x in per_rank_us], "cpu_binding": numa}
+                "e2e": {"value": evals_step / (e2e[head_api]["ms_per_step"] * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": e2e[head_api]["h2d_bytes_per_step"], "d2h_bytes_per_step": e2e[head_api]["d2h_bytes_per_step"],
+                        "ms_per_step": e2e[head_api]["ms_per_step"],
+                        "api": head_api + " (plugin batched entry point, pointer overloads on pinned caller buffers: positions uploaded by the "
+                               "copy engine in 8 chunks, FP32 forces stored by the kernels straight into the caller's buffer); per rank on its shard, max over ranks",
+                        "variants": {k: dict(v, value=evals_step / (v["ms_per_step"] * 1e-3)) for k, v in e2e.items()},
+                        "host_copy_gbs": {"per_rank_h2d_d2h_both_before_and_after": host_copy_all,
+                                          "note": "gfb_bench_host_copy, 64 MB pinned, every rank at the same time: the PCIe/host-memory share each GPU gets",
+                                          "h2d_floor_ms_per_step": w.pos.nbytes / (min(r[0] for r in host_copy_all) * 1e9) * 1e3}},
+                "gpu_launches": int(launches * args.windows), "clocks": clocks, "cpu_binding": numa}
+        if weak is not None:
+            line["weak_scaling"] = weak
         if world == 1 and not args.no_extras:
             line["other_workloads"] = extras
-            line["cpu_baseline"] = cpu_baseline(w)
+            checks = [("device loop, last timed step (FIXED_ADD, PDL + graph)",) + dev_sample,
+                      ("GridForceBatch::evaluateWithForcesF32", w.pos[:1024], e2e_result[0][:1024], e2e_result[1][:1024].astype(np.float64))]
+            line["cpu_baseline"] = cpu_baseline(w, check=checks)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        comm.close()
         dist.destroy_process_group()
 
 

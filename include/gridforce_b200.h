@@ -314,9 +314,9 @@ GFB_API int gfb_graph_destroy(gfb_graph* g);
  *                                  copies the launch's energies into every rank's gathered array at `gather_offset`
  *                                  (plain stores over NVLink/NVSwitch peer mappings) and raises its arrival flag on
  *                                  every rank: compute and collective in one kernel, no NCCL launch, no extra kernel on
- *                                  the producing side. gfb_comm_gather_wait enqueues a one-warp kernel that waits for
- *                                  all ranks' flags of the most recent gather and returns the array. Rule: every
- *                                  gather launch is followed by a gather_wait on the same stream before the next one.
+ *                                  the producing side. gfb_comm_gather_wait enqueues a small kernel that waits for
+ *                                  all ranks' flags of that gather and copies the array out. Rule: every gather
+ *                                  launch is followed by a gather_wait on the same stream before the next one.
  * (b) one process for all GPUs: gfb_multi (ncclCommInitAll, peer access enabled between the devices, one host thread
  *     per device on the host path). This is what GridForceBatch(devices) uses.
  */
@@ -331,10 +331,12 @@ GFB_API int gfb_comm_gather_attach(gfb_comm* c, const unsigned char* handles /* 
 GFB_API int gfb_kernel_execute_device_gather(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos,
                                              double* d_energies, void* d_forces, int force_mode, long long force_stride,
                                              double* d_energies_clear, gfb_comm* c, size_t gather_offset, void* stream);
-/* Waits (on `stream`, device side) until every rank's slice of the most recent gather has arrived; *d_gathered is then
- * this rank's complete [count_total] array. A peer that does not arrive within ~20 s raises a flag that
- * gfb_comm_gather_status reports after the stream has been synchronised (the wait kernel never spins forever). */
-GFB_API int gfb_comm_gather_wait(gfb_comm* c, void* stream, const double** d_gathered);
+/* Waits (on `stream`, device side) until every rank's slice of the oldest gather not yet consumed has arrived, then
+ * copies the complete [count_total] array into d_out (device memory of the caller). Gather sequence numbers live on the
+ * device, so a launch/wait sequence captured with gfb_graph_* can be replayed. A peer that does not arrive within ~20 s
+ * raises a flag that gfb_comm_gather_status reports after the stream has been synchronised (the wait kernel never
+ * spins forever). */
+GFB_API int gfb_comm_gather_wait(gfb_comm* c, double* d_out, void* stream);
 GFB_API int gfb_comm_gather_status(gfb_comm* c);   /* GFB_OK, or GFB_ERR_CUDA after a timed-out wait */
 
 /* One process, n_devices GPUs. add_grid uploads and repacks the grid on every device; build creates one evaluation

@@ -94,7 +94,7 @@ SIGNATURES = {
     "gfb_comm_gather_alloc": (_i, [_vp, _sz, _vp]),
     "gfb_comm_gather_attach": (_i, [_vp, _vp]),
     "gfb_kernel_execute_device_gather": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _ll, _vp, _vp, _sz, _vp]),
-    "gfb_comm_gather_wait": (_i, [_vp, _vp, C.POINTER(_vp)]),
+    "gfb_comm_gather_wait": (_i, [_vp, _vp, _vp]),
     "gfb_comm_gather_status": (_i, [_vp]),
     "gfb_multi_create": (_i, [_i, _pi, C.POINTER(_vp)]),
     "gfb_multi_destroy": (_i, [_vp]),
@@ -508,11 +508,9 @@ class Comm:
             raise GridForceB200Error("gather_attach needs one 64-byte handle per rank")
         _check(load_library().gfb_comm_gather_attach(self._h, (C.c_ubyte * len(blob)).from_buffer_copy(blob)))
 
-    def gather_wait(self, stream=0):
-        """Enqueues the wait for the most recent fused gather; returns the device address of the gathered array."""
-        out = C.c_void_p()
-        _check(load_library().gfb_comm_gather_wait(self._h, _ptr(stream or None), C.byref(out)))
-        return out.value
+    def gather_wait(self, d_out, stream=0):
+        """Enqueues the wait for the oldest unconsumed fused gather; the complete array is copied to device address d_out."""
+        _check(load_library().gfb_comm_gather_wait(self._h, _ptr(d_out), _ptr(stream or None)))
 
     def gather_status(self):
         _check(load_library().gfb_comm_gather_status(self._h))

@@ -403,9 +403,7 @@ int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d
     p.force_mode = force_mode;
     p.force_stride = force_stride;
     p.gather = x.gather;
-    p.gather_seq = x.gather_seq;
     p.gather_offset = x.gather_offset;
-    p.gather_parity = x.gather_parity;
     if (p.total == 0 && !x.gather) return GFB_OK;
     p.div_magic = (unsigned) std::min<unsigned long long>(0x100000000ull / (unsigned long long) std::max(n_atoms, 1), 0xffffffffull);
     for (int a = 0; a < 3; a++) p.near_int[a] = 1.8e-15 * (double) std::max(1, p.grid[0].nc[a]);

@@ -137,8 +137,10 @@ __device__ __forceinline__ void gather_tail(const EvalParams& p) {
     if (!s_last) return;
     __threadfence();
     GatherTable* const gt = p.gather;
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&gt->issued) + 1ull;   // this gather's number
+    const int parity = (int) (seq & 1ull);
     const int n = p.n_replicas * p.n_slots;
-    const long long base = (long long) p.gather_parity * gt->count_total + p.gather_offset;
+    const long long base = (long long) parity * gt->count_total + p.gather_offset;
     const int np = gt->n_peers;
     const bool vec = ((base | (long long) n) & 1) == 0 && (reinterpret_cast<uintptr_t>(p.energies) & 15) == 0;
     for (int r = 0; r < np; r++) {
@@ -155,10 +157,13 @@ __device__ __forceinline__ void gather_tail(const EvalParams& p) {
     __threadfence_system();
     __syncthreads();
     if ((int) threadIdx.x < np) {
-        unsigned long long* flag = gt->peer_flags[threadIdx.x] + p.gather_parity * kMaxPeers + gt->my_rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(p.gather_seq) : "memory");
+        unsigned long long* flag = gt->peer_flags[threadIdx.x] + parity * kMaxPeers + gt->my_rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
     }
-    if (threadIdx.x == 0) gt->ticket = 0;
+    if (threadIdx.x == 0) {
+        gt->issued = seq;
+        gt->ticket = 0;
+    }
 }
 
 // Threads per block: no block barrier is used, so the block is only the scheduling granule. 128 threads keep the tail

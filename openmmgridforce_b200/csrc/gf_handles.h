@@ -126,9 +126,7 @@ struct EvalExtra {
     bool overlap = false;              // programmatic dependent launch
     double* atom_energies = nullptr;   // [n_replicas][n_atoms] per-atom energies, stored
     GatherTable* gather = nullptr;     // fused energy gather (gf_multi.cu)
-    unsigned long long gather_seq = 0;
     long long gather_offset = 0;
-    int gather_parity = 0;
 };
 // Enqueues ONE evaluation kernel on `stream` (gf_capi.cu); no synchronisation.
 int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos, double* d_energies,

@@ -78,28 +78,54 @@ NcclApi* nccl_api() {
     } while (0)
 
 // ---- consumer side of the fused gather ------------------------------------------------------------------------------
-// One warp: lane r waits until rank r has published `seq` in this rank's flag array (written by the last block of rank
-// r's evaluation launch with st.release.sys after its data stores and a system-scope fence). Bounded: after ~20 s it
-// raises *timed_out instead of spinning forever (a rank that died must not hang the GPU).
-__global__ void __launch_bounds__(32) gf_gather_wait_kernel(const unsigned long long* flags, int n_peers, unsigned long long seq,
-                                                            unsigned int* timed_out) {
-    if ((int) threadIdx.x >= n_peers) return;
-    const unsigned long long* f = flags + threadIdx.x;
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (unsigned spin = 0;; spin++) {
-        unsigned long long v;
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-        if (v >= seq) break;
-        if ((spin & 1023u) == 1023u) {
-            unsigned long long t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 20000000000ull) {
-                *timed_out = 1u;
-                break;
+// kWaitBlocks blocks of 256 threads. In every block, lane r of warp 0 waits until rank r has published this gather's
+// sequence number in this rank's flag array (written by the last block of rank r's evaluation launch with
+// st.release.sys after its data stores and a system-scope fence); then the block copies its share of the gathered array
+// into `out`, the caller's stable result buffer (the gathered array itself is double-buffered and will be overwritten
+// two gathers later). The sequence number is read from the device-resident table, so a captured graph replays
+// correctly; the last block to finish advances it. Bounded: after ~20 s a block raises *timed_out instead of spinning
+// forever (a rank that died must not hang the GPU).
+constexpr int kWaitBlocks = 8;
+__global__ void __launch_bounds__(256) gf_gather_wait_kernel(GatherTable* gt, const unsigned long long* flags_base,
+                                                             const double* data_base, double* out) {
+    __shared__ int s_ok;
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&gt->waited) + 1ull;
+    const int parity = (int) (seq & 1ull);
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if ((int) threadIdx.x < gt->n_peers) {
+        const unsigned long long* f = flags_base + (size_t) parity * kMaxPeers + threadIdx.x;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (unsigned spin = 0;; spin++) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= seq) break;
+            if ((spin & 1023u) == 1023u) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 20000000000ull) {
+                    gt->timed_out = 1u;
+                    s_ok = 0;
+                    break;
+                }
             }
+            if (spin > 64) __nanosleep(100);
         }
-        if (spin > 64) __nanosleep(100);
+    }
+    __syncthreads();
+    if (s_ok && out) {
+        const double* src = data_base + (size_t) parity * gt->count_total;
+        const long long n = gt->count_total;
+        for (long long i = (long long) blockIdx.x * 256 + threadIdx.x; i < n; i += (long long) gridDim.x * 256) out[i] = __ldcg(src + i);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&gt->wait_ticket, 1u) == gridDim.x - 1) {   // every block has read `waited` by now
+            gt->waited = seq;
+            gt->wait_ticket = 0;
+        }
     }
 }
 
@@ -157,7 +183,6 @@ struct gfb_comm {
     GatherTable* d_table;
     void* peer_base[kMaxPeers];   // cudaIpcOpenMemHandle mappings (self: mem.base)
     bool attached;
-    unsigned long long seq;       // gathers issued so far; the next one publishes seq + 1 into parity (seq + 1) & 1
 };
 
 struct MultiShard {
@@ -167,6 +192,7 @@ struct MultiShard {
     long long stride = 0;
     double* d_e[2] = {nullptr, nullptr};  // alternating accumulators: a launch adds into one and clears the other
     double* d_padded = nullptr;           // ncclAllGather result, [n][width]
+    double* d_gathered = nullptr;         // fused gather result, [n_replicas]
     GatherMem mem;
     GatherTable* d_table = nullptr;
 };
@@ -179,7 +205,7 @@ struct gfb_multi {
     std::vector<ncclComm_t> nccl;                  // created at the first gather == 1 step
     std::vector<MultiShard> shards;
     int n_atoms, n_replicas, width;                // width = largest shard
-    unsigned long long steps, seq;
+    unsigned long long steps;
     int last_gather;
 };
 
@@ -267,7 +293,6 @@ int gfb_comm_create(gfb_device* dev, int world_size, int rank, const unsigned ch
     c->nccl = nullptr;
     c->d_table = nullptr;
     c->attached = false;
-    c->seq = 0;
     memset(c->peer_base, 0, sizeof c->peer_base);
     if (id) {   // id == NULL: no NCCL communicator (fused gather only)
         NcclApi* api = nccl_api();
@@ -359,25 +384,19 @@ int gfb_kernel_execute_device_gather(gfb_kernel* k, int n_replicas, int n_partic
     EvalExtra x;
     x.overlap = k->launch_overlap;
     x.gather = c->d_table;
-    x.gather_seq = c->seq + 1;
-    x.gather_parity = (int) ((c->seq + 1) & 1);
     x.gather_offset = (long long) gather_offset;
-    rc = enqueue_eval(k, n_replicas, n_particles, d_pos, d_energies, nullptr, d_forces, force_mode, force_stride, nullptr,
-                      d_energies_clear, stream ? static_cast<cudaStream_t>(stream) : k->dev->stream, x);
-    if (rc == GFB_OK) c->seq++;
-    return rc;
+    return enqueue_eval(k, n_replicas, n_particles, d_pos, d_energies, nullptr, d_forces, force_mode, force_stride, nullptr,
+                        d_energies_clear, stream ? static_cast<cudaStream_t>(stream) : k->dev->stream, x);
 }
 
-int gfb_comm_gather_wait(gfb_comm* c, void* stream, const double** d_gathered) {
+int gfb_comm_gather_wait(gfb_comm* c, double* d_out, void* stream) {
     if (!c || !c->attached) return fail(GFB_ERR_INVALID, "gfb_comm_gather_wait: communicator without attached gather memory");
-    if (c->seq == 0) return fail(GFB_ERR_INVALID, "gfb_comm_gather_wait: no gather has been launched");
+    if (!d_out) return fail(GFB_ERR_INVALID, "gfb_comm_gather_wait: d_out is NULL");
     CUDA_TRY(cudaSetDevice(c->dev->ordinal));
-    const int parity = (int) (c->seq & 1);
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->dev->stream;
-    gf_gather_wait_kernel<<<1, 32, 0, s>>>(c->mem.flags(parity), c->world, c->seq, &c->d_table->timed_out);
+    gf_gather_wait_kernel<<<kWaitBlocks, 256, 0, s>>>(c->d_table, c->mem.flags(0), c->mem.data(0), d_out);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
-    if (d_gathered) *d_gathered = c->mem.data(parity);
     return GFB_OK;
 }
 
@@ -403,6 +422,7 @@ static void multi_free_shards(gfb_multi* m) {
         if (s.d_e[0]) cudaFree(s.d_e[0]);
         if (s.d_e[1]) cudaFree(s.d_e[1]);
         if (s.d_padded) cudaFree(s.d_padded);
+        if (s.d_gathered) cudaFree(s.d_gathered);
         if (s.mem.base) cudaFree(s.mem.base);
         if (s.d_table) cudaFree(s.d_table);
     }
@@ -417,7 +437,7 @@ int gfb_multi_create(int n_devices, const int* ordinals, gfb_multi** out) {
     if (!m) return fail(GFB_ERR_NOMEM, "gfb_multi_create: out of host memory");
     m->n = n_devices;
     m->n_atoms = m->n_replicas = m->width = 0;
-    m->steps = m->seq = 0;
+    m->steps = 0;
     m->last_gather = 0;
     for (int d = 0; d < n_devices; d++) {
         const int ord = ordinals ? ordinals[d] : d;
@@ -538,7 +558,7 @@ int gfb_multi_upload(gfb_multi* m, int n_replicas, const double* pos) {
     m->shards.resize(m->n);
     m->n_replicas = n_replicas;
     m->width = 0;
-    m->steps = m->seq = 0;
+    m->steps = 0;
     m->last_gather = 0;
     const size_t per_rep = (size_t) m->n_atoms * 3;
     for (int d = 0; d < m->n; d++) {
@@ -559,6 +579,7 @@ int gfb_multi_upload(gfb_multi* m, int n_replicas, const double* pos) {
             CUDA_TRY(cudaMemset(s.d_e[b], 0, (size_t) m->width * sizeof(double)));
         }
         CUDA_TRY(cudaMalloc((void**) &s.d_padded, (size_t) m->n * m->width * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void**) &s.d_gathered, (size_t) n_replicas * sizeof(double)));
         CUDA_TRY(cudaMemcpy(s.d_pos, pos + (size_t) s.lo * per_rep, reps * per_rep * sizeof(double), cudaMemcpyHostToDevice));
         int rc = s.mem.alloc((size_t) n_replicas);
         if (rc != GFB_OK) return rc;
@@ -589,15 +610,12 @@ int gfb_multi_step(gfb_multi* m, int gather) {
         }
     }
     const int cur = (int) (m->steps & 1);
-    const unsigned long long seq = m->seq + 1;
     for (int d = 0; d < m->n; d++) {
         MultiShard& s = m->shards[d];
         CUDA_TRY(cudaSetDevice(m->devs[d]->ordinal));
         EvalExtra x;
         if (gather == 2) {
             x.gather = s.d_table;
-            x.gather_seq = seq;
-            x.gather_parity = (int) (seq & 1);
             x.gather_offset = s.lo;
         }
         int rc = enqueue_eval(m->kernels[d], s.hi - s.lo, m->n_atoms, s.d_pos, s.d_e[cur], nullptr, s.d_forces, GFB_FORCE_FIXED_ADD,
@@ -619,11 +637,10 @@ int gfb_multi_step(gfb_multi* m, int gather) {
         for (int d = 0; d < m->n; d++) {
             MultiShard& s = m->shards[d];
             CUDA_TRY(cudaSetDevice(m->devs[d]->ordinal));
-            gf_gather_wait_kernel<<<1, 32, 0, m->devs[d]->stream>>>(s.mem.flags((int) (seq & 1)), m->n, seq, &s.d_table->timed_out);
+            gf_gather_wait_kernel<<<kWaitBlocks, 256, 0, m->devs[d]->stream>>>(s.d_table, s.mem.flags(0), s.mem.data(0), s.d_gathered);
             g_launches++;
             CUDA_TRY(cudaGetLastError());
         }
-        m->seq = seq;
     }
     m->steps++;
     m->last_gather = gather;
@@ -646,7 +663,7 @@ int gfb_multi_download(gfb_multi* m, int from_device, double* energies, double* 
             unsigned int flag = 0;
             CUDA_TRY(cudaMemcpy(&flag, &s.d_table->timed_out, sizeof flag, cudaMemcpyDeviceToHost));
             if (flag) return fail(GFB_ERR_CUDA, "gfb_multi_download: the fused gather timed out on device %d", m->devs[from_device]->ordinal);
-            CUDA_TRY(cudaMemcpy(energies, s.mem.data((int) (m->seq & 1)), (size_t) m->n_replicas * sizeof(double), cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(energies, s.d_gathered, (size_t) m->n_replicas * sizeof(double), cudaMemcpyDeviceToHost));
         } else if (m->last_gather == 1) {
             std::vector<double> padded((size_t) m->n * m->width);
             CUDA_TRY(cudaMemcpy(padded.data(), s.d_padded, padded.size() * sizeof(double), cudaMemcpyDeviceToHost));

@@ -39,6 +39,12 @@ struct GatherTable {
     int n_peers, my_rank;
     unsigned int ticket;                         // blocks of the current launch that have finished (reset by the last one)
     unsigned int timed_out;                      // set by gf_gather_wait_kernel when a peer's flag did not arrive in time
+    // Sequence numbers live on the DEVICE so that a captured graph can be replayed: nothing about "which gather is this"
+    // is baked into a launch's arguments. Every rank issues and waits for gathers in the same order.
+    unsigned long long issued;                   // gathers this rank has published (gather_tail)
+    unsigned long long waited;                   // gathers this rank has consumed (gf_gather_wait_kernel)
+    unsigned int wait_ticket;                    // blocks of the current wait kernel that have finished
+    unsigned int pad_;
 };
 
 struct EvalParams {
@@ -71,11 +77,9 @@ struct EvalParams {
                              // (GridForce::getParticleAtomEnergies)
     // Fused energy gather (replica-sharded multi-GPU runs, gf_eval_lines_kernel only): the LAST block of the launch to
     // finish copies this launch's n_replicas*n_slots energies into every peer's gathered array at gather_offset and
-    // then publishes gather_seq in its slot of every peer's flag array. nullptr = off.
+    // then publishes its gather sequence number in its slot of every peer's flag array. nullptr = off.
     GatherTable* gather;
-    unsigned long long gather_seq;
     long long gather_offset; // first element of this rank's slice in the gathered array
-    int gather_parity;       // which half of the double-buffered gathered array / flag array
     int force_mode;          // gfb_force_mode for the kernels that switch on it at run time (general, B-spline)
 };
 

@@ -428,6 +428,97 @@ class Context:
             pass
 
 
+class GridForceBatch:
+    """Python face of GridForcePlugin::GridForceBatch (plugin/platform/GridForceBatch.h; SWIG: python/gridforceplugin_b200.i):
+    R replicas x A atoms x G GridForces per call, one launch per GPU.
+
+        batch = GridForceBatch()                      # device 0, mixed precision; GridForceBatch([0, 1, 2, 3]) shards replicas
+        for f in (ele, ljr, lja): batch.addForce(f)
+        energies = batch.evaluate(pos, R)                            # energy-only evaluation
+        batch.evaluateWithForces(pos, R, energies, forces)           # caller-owned numpy buffers, no copies
+        batch.evaluateWithForcesF32(pos, R, energies, forces_f32)
+    """
+
+    def __init__(self, devices=0, precision="mixed"):
+        self._devices = [int(devices)] if np.isscalar(devices) else [int(d) for d in devices]
+        self._precision = precision
+        self._h = None
+        self._forces = []
+
+    def addForce(self, force):
+        if self._h is not None:
+            raise RuntimeError("GridForceBatch: add every force before the first evaluation")
+        self._forces.append(force)
+        return len(self._forces) - 1
+
+    def getNumForces(self):
+        return len(self._forces)
+
+    def getNumAtoms(self):
+        return len(self._forces[0]._scaling) if self._forces else 0
+
+    def getNumDevices(self):
+        return len(self._devices)
+
+    def _handle(self):
+        if self._h is None:
+            lib = _lib()
+            _check(lib.b200_plugin_register())
+            self._h = C.c_void_p(lib.b200_plugin_create(self.getNumAtoms()))
+            for f in self._forces:
+                counts = np.asarray(f._counts, dtype=np.int32)
+                spacing = np.asarray(f._spacing, dtype=np.float64)
+                vals = np.ascontiguousarray(f._vals, dtype=np.float64)
+                sc = np.ascontiguousarray(f._scaling, dtype=np.float64)
+                og = np.asarray(f._origin, dtype=np.float64)
+                _check(lib.b200_plugin_add_grid(self._h, _p(counts), _p(spacing), _p(og), _p(vals), vals.size, _p(sc), sc.size, None, 0,
+                                                f._inv_power, f._oob_k, f._interp, f._group))
+        return self._h
+
+    def _run(self, positions, n_replicas, energies, forces):
+        pos = np.asarray(positions)
+        if pos.dtype != np.float64 or not pos.flags.c_contiguous or pos.size != n_replicas * self.getNumAtoms() * 3:
+            raise RuntimeError("GridForceBatch: positions must hold numReplicas * numAtoms * 3 C-contiguous float64 values")
+        dv = np.ascontiguousarray(self._devices, dtype=np.int32)
+        f32 = forces is not None and forces.dtype == np.float32
+        _check(_lib().b200_plugin_batch_evaluate_buffers(self._handle(), self._precision.encode(), _p(dv), dv.size, _p(pos), n_replicas,
+                                                         _p(energies), _p(forces), 1 if f32 else 0))
+
+    def evaluate(self, positions, n_replicas, energies=None):
+        en = energies if energies is not None else np.empty(n_replicas)
+        self._run(positions, n_replicas, en, None)
+        return en
+
+    def evaluateWithForces(self, positions, n_replicas, energies, forces):
+        if forces.dtype != np.float64:
+            raise RuntimeError("GridForceBatch.evaluateWithForces: forces must be float64 (evaluateWithForcesF32 takes float32)")
+        self._run(positions, n_replicas, energies, forces)
+
+    def evaluateWithForcesF32(self, positions, n_replicas, energies, forces):
+        if forces.dtype != np.float32:
+            raise RuntimeError("GridForceBatch.evaluateWithForcesF32: forces must be float32")
+        self._run(positions, n_replicas, energies, forces)
+
+    @staticmethod
+    def pinBuffer(array):
+        pin_buffer(array, True)
+
+    @staticmethod
+    def unpinBuffer(array):
+        pin_buffer(array, False)
+
+    def close(self):
+        if self._h is not None:
+            _lib().b200_plugin_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def pin_buffer(array, pin=True):
     """GridForceBatch::pinBuffer / unpinBuffer on a numpy array: page-lock it once so that batched calls DMA directly."""
     _check(_lib().b200_plugin_pin_buffer(_p(array), array.nbytes, 1 if pin else 0))

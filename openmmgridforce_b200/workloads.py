@@ -150,3 +150,30 @@ def c5_sharded_replicas(n_replicas=65536, n=192, replica_offset=0, n_local=None,
         pos = np.ascontiguousarray(pos[replica_offset:replica_offset + n_local])
     return Workload(f"C5 {n_replicas} replicas x 47 atoms x 3 grids of {n}^3", counts, sp, (0.0, 0.0, 0.0), grids,
                     _ligand_scaling(3), pos, [10000.0] * 3, [0.0] * 3)
+
+
+def mixed_energy_bound(w, pos):
+    """Per-replica sum over atoms and grids of |s| * trilinear(|V|): the scale of the irreducible MIXED-precision energy
+    error. Grid values are stored in FP32 (relative rounding 2^-24 = 6e-8 per corner) and the trilinear weights are
+    non-negative and sum to one, so however exact the arithmetic, a replica's energy can differ from the FP64 reference by
+    up to 6e-8 times this bound — which is why a replica whose terms cancel (|E| much smaller than the sum of |terms|)
+    cannot meet 1e-6 of |E| and the parity tests assert  |E - E_ref| <= max(1e-6 |E_ref|, 6e-8 * bound).
+    Input-side helper (numpy only, no evaluation path involved). pos: [R, A, 3]; atoms outside the grid contribute 0."""
+    pos = np.asarray(pos, dtype=np.float64)
+    sp, og = np.asarray(w.spacing), np.asarray(w.origin)
+    counts = np.asarray(w.counts)
+    rel = (pos - og) / sp
+    inside = ((pos - og >= 0) & (pos - og <= sp * (counts - 1))).all(axis=-1)
+    idx = np.clip(np.floor(rel).astype(np.int64), 0, counts - 2)
+    f = np.clip(rel - idx, 0.0, 1.0)
+    out = np.zeros(pos.shape[0])
+    for g in range(w.n_grids):
+        v = np.abs(np.asarray(w.grids[g]))
+        acc = np.zeros(pos.shape[:2])
+        for dx in (0, 1):
+            for dy in (0, 1):
+                for dz in (0, 1):
+                    wgt = (f[..., 0] if dx else 1 - f[..., 0]) * (f[..., 1] if dy else 1 - f[..., 1]) * (f[..., 2] if dz else 1 - f[..., 2])
+                    acc += wgt * v[idx[..., 0] + dx, idx[..., 1] + dy, idx[..., 2] + dz]
+        out += (np.abs(w.scaling[g])[None, :] * acc * inside).sum(axis=1)
+    return out

@@ -63,8 +63,9 @@ def main():
             cur, nxt = d_e[step % 2], d_e[(step + 1) % 2]
             k.execute_device_gather(comm, lo, r, a, d_pos.data_ptr(), cur.data_ptr(), d_f.data_ptr(), gf.FORCE_FIXED_ADD, stride,
                                     stream.cuda_stream, d_energies_clear=nxt.data_ptr())
-            ptr = comm.gather_wait(stream.cuda_stream)
-            fused.append(torch.as_tensor(gf.DeviceArrayView(ptr, (n_total,)), device=tdev).clone())   # stream-ordered copy
+            got = torch.full((n_total,), float("nan"), dtype=torch.float64, device=tdev)
+            comm.gather_wait(got.data_ptr(), stream.cuda_stream)
+            fused.append(got)
             padded = torch.empty(world * width, dtype=torch.float64, device=tdev)
             comm.all_gather(cur.data_ptr(), padded.data_ptr(), width, stream.cuda_stream)
             nccl.append(padded)

@@ -20,15 +20,38 @@ def test_algorithmic_bytes_per_evaluation():
     assert b.b_alg(1) == 88.0                      # 32 + 4 + 52/G
     assert abs(b.b_alg(3) - 53.333333333333336) < 1e-12
     assert b.b_alg(1, precision=1) == 124.0        # double mode: 72 + 52/G
-    evals = b.REPLICAS_PER_GPU * b.N_ATOMS * b.N_GRIDS
+    evals = b.REPLICAS_TOTAL * b.N_ATOMS * b.N_GRIDS
     assert evals == 9240576 and abs(evals * b.b_alg(3) - 492.8e6) < 0.1e6
+    assert abs(b.b_alg(3, forces=False) - (36.0 + 28.0 / 3)) < 1e-12      # energy only: no force bytes
 
 
 def test_workload_config_names_the_baseline_config():
+    """configs[4] as BASELINE.json names it: 65,536 replicas IN TOTAL, sharded over the GPUs (strong scaling) by default;
+    the same dictionary for both arms (nothing arm-specific in it)."""
     b = _bench()
     cfg = b.workload_config(8)
-    assert "configs[4]" in cfg["workload"] and cfg["replicas_total"] == 8 * 65536 and cfg["grid_points"] == [192, 192, 192]
+    assert "configs[4]" in cfg["workload"] and cfg["replicas_total"] == 65536 and cfg["replicas_per_gpu"] == 8192
+    assert cfg["scaling"] == "strong" and cfg["grid_points"] == [192, 192, 192] and cfg["evals_per_step"] == 9240576
     assert "model" not in cfg
+    weak = b.workload_config(8, "weak")
+    assert weak["scaling"] == "weak" and weak["replicas_total"] == 8 * 65536
+    assert b.workload_config(1, "weak") == b.workload_config(1, "strong")      # one GPU: the same run
+
+
+def test_window_accumulator_rotation():
+    """The K-step window's energy accumulators: consecutive steps never share one, and the last step's differs from the
+    first's (whose buffer the last launch clears for the next window / graph replay)."""
+    b = _bench()
+    for steps in range(2, 40):
+        a = b.DeviceLoop.accumulators(steps)
+        assert len(a) == steps and all(0 <= x < 3 for x in a)
+        assert all(a[j] != a[j + 1] for j in range(steps - 1)) and a[-1] != a[0]
+
+
+def test_traffic_is_only_reported_for_the_profiled_sources(tmp_path, monkeypatch):
+    b = _bench()
+    val, why = b.measured_traffic("no_such_workload")
+    assert val is None and why
 
 
 def test_oracle_is_only_reached_from_the_cpu_legs():
@@ -52,6 +75,6 @@ def test_reference_arm_other_ranks_exit_quietly(monkeypatch, capsys):
     monkeypatch.setenv("RANK", "3")
 
     class Args:
-        gpus, steps, warmup = 4, 1, 3
+        gpus, steps, warmup, scaling = 4, 1, 3, "strong"
     b.reference_arm(Args())
     assert capsys.readouterr().out == ""
