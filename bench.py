@@ -700,8 +700,10 @@ def main():
     torch.cuda.synchronize()
     sampler.start()
 
-    variants, launches = run_variants(loop, args.steps, args.warmup, args.windows, barrier, reduce_max)
-    headline = variants["pdl+graph"] if args.steps > 1 else variants["pdl"]
+    head_name = "pdl+graph" if args.steps > 1 else "pdl"
+    variants, launches = run_variants(loop, args.steps, args.warmup, args.windows, barrier, reduce_max,
+                                      which=[v for v in VARIANTS if v[0] == head_name])
+    headline = variants[head_name]
     gather_check = None
     if world > 1:
         comm.gather_status()
@@ -720,8 +722,12 @@ def main():
     # this rank's own per-step time (not the max over ranks, no gather) for the roofline of ITS kernel
     saved_mode, loop.gather_mode = loop.gather_mode, "none"
     own_ms, _ = loop.time_windows(args.steps, 0, 3, True, args.steps > 1)
-    loop.gather_mode = saved_mode
     kernel_us = sorted(own_ms)[1] / args.steps * 1e3
+    # the same loop launched the other ways (direct launches, no launch overlap): reported, not the headline
+    loop.gather_mode = saved_mode
+    others, _ = run_variants(loop, args.steps, 0, max(3, args.windows // 2), barrier, reduce_max,
+                             which=[v for v in VARIANTS if v[0] != head_name])
+    variants.update(others)
 
     weak = None
     if world > 1 and strong and os.environ.get("GFB_BENCH_WEAK", "1") != "0":

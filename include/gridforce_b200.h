@@ -174,6 +174,13 @@ GFB_API int gfb_grid_generate(gfb_device* dev, const int counts[3], const double
 GFB_API int gfb_inv_power_transform(gfb_device* dev, double* vals, size_t n_vals, double inv_power, int vals_on_device);
 
 GFB_API int gfb_grid_destroy(gfb_grid* grid);
+/* Frees the grid's own packed-cell copy and keeps the handle (geometry) alive. For a grid that is read ONLY through the
+ * interleaved records of kernel states already created from it (2-4 grids of one geometry, no inv-power: the record
+ * kernels never touch the per-grid arrays), this returns 8x the raw grid per grid (3 x 192^3: 638 MB of 1.5 GB).
+ * Afterwards the grid cannot be used to create further kernel states, and a state that needs the per-grid arrays
+ * (one grid, inv-power > 0, more than 4 grids) fails with GFB_ERR_INVALID instead of evaluating. gfb_multi_build does
+ * this for the grids it owns. No reference counterpart. */
+GFB_API int gfb_grid_release_cells(gfb_grid* grid);
 GFB_API size_t gfb_grid_device_bytes(const gfb_grid* grid);
 GFB_API int gfb_grid_layout(const gfb_grid* grid);   /* the layout actually chosen (resolves AUTO) */
 

@@ -63,6 +63,7 @@ SIGNATURES = {
     "gfb_grid_create_from_file": (_i, [_vp, C.c_char_p, _i, _i, C.POINTER(_vp), C.POINTER(GridFileHeader)]),
     "gfb_inv_power_transform": (_i, [_vp, _vp, _sz, C.c_double, _i]),
     "gfb_grid_destroy": (_i, [_vp]),
+    "gfb_grid_release_cells": (_i, [_vp]),
     "gfb_grid_device_bytes": (_sz, [_vp]),
     "gfb_kernel_create": (_i, [_vp, _i, C.POINTER(_vp), _i, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "gfb_kernel_destroy": (_i, [_vp]),
@@ -308,6 +309,10 @@ class Grid:
     @property
     def device_bytes(self):
         return int(load_library().gfb_grid_device_bytes(self._h))
+
+    def release_cells(self):
+        """gfb_grid_release_cells: free the per-grid packed cells once only record kernels read this grid."""
+        _check(load_library().gfb_grid_release_cells(self._h))
 
     def close(self):
         if self._h:

@@ -143,6 +143,7 @@ int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int 
     for (int g = 0; g < n_grids; g++) {
         if (!grids[g]) return fail(GFB_ERR_INVALID, "gfb_kernel_create: grids[%d] is NULL", g);
         if (grids[g]->dev != dev) return fail(GFB_ERR_INVALID, "gfb_kernel_create: grids[%d] lives on another device", g);
+        if (!grids[g]->cells) return fail(GFB_ERR_INVALID, "gfb_kernel_create: grids[%d] has released its packed cells (gfb_grid_release_cells)", g);
         if (grids[g]->precision != grids[0]->precision)
             return fail(GFB_ERR_INVALID, "gfb_kernel_create: grids[%d] precision differs from grids[0]", g);
         if (grids[g]->layout != grids[0]->layout)
@@ -216,6 +217,7 @@ int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int 
     const bool want_lines = !(il && il[0] == '0');
     const size_t slot_bytes = k->precision == GFB_PRECISION_MIXED ? 32 : 64;
     const size_t n_cells0 = grids[0]->bytes / slot_bytes;
+    k->n_cells = grids[0]->layout == GFB_LAYOUT_CELLS ? n_cells0 : 0;
     if (want_lines && k->same_geom && n_grids >= 2 && n_grids <= 4 && grids[0]->layout == GFB_LAYOUT_CELLS &&
         n_cells0 < 0xffffffffull && n_cells0 * 4 * slot_bytes <= dev->prop.totalGlobalMem / 8) {
         const int slots = 4;
@@ -346,7 +348,7 @@ bool lines_eligible(const gfb_kernel* k, const EvalParams&) {
     if (off || k->precision != GFB_PRECISION_MIXED || k->grids[0]->layout != GFB_LAYOUT_CELLS || !k->same_geom) return false;
     if (k->n_grids > 4) return false;
     if (k->n_grids > 1 && !k->il_slots) return false;
-    if (k->grids[0]->bytes / 32 >= 0xffffffffull) return false;
+    if (k->n_cells >= 0xffffffffull) return false;
     for (int g = 0; g < k->n_grids; g++)
         if (k->inv_power[g] > 0.0) return false;
     return true;
@@ -357,7 +359,7 @@ bool lines_f64_eligible(const gfb_kernel* k) {
     static const bool off = env_off("GFB_LINES") || env_off("GFB_LINES_F64");
     if (off || k->precision != GFB_PRECISION_DOUBLE || k->grids[0]->layout != GFB_LAYOUT_CELLS || !k->same_geom) return false;
     if (k->n_grids < 2 || k->n_grids > 4 || !k->il_slots) return false;
-    if (k->grids[0]->bytes / 64 >= 0xffffffffull) return false;
+    if (k->n_cells >= 0xffffffffull) return false;
     for (int g = 0; g < k->n_grids; g++)
         if (k->inv_power[g] > 0.0) return false;
     return true;
@@ -408,6 +410,11 @@ int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d
     p.div_magic = (unsigned) std::min<unsigned long long>(0x100000000ull / (unsigned long long) std::max(n_atoms, 1), 0xffffffffull);
     for (int a = 0; a < 3; a++) p.near_int[a] = 1.8e-15 * (double) std::max(1, p.grid[0].nc[a]);
     const bool lines = lines_eligible(k, p), lines64 = !lines && lines_f64_eligible(k);
+    if (!((lines && k->n_grids > 1) || lines64))
+        for (int g = 0; g < k->n_grids; g++)
+            if (!k->grids[g]->cells)
+                return fail(GFB_ERR_INVALID, "grid %d released its packed cells (gfb_grid_release_cells) but this evaluation needs them "
+                                             "(one grid, inv-power, more than 4 grids or GFB_LINES=0)", g);
     if (x.gather) {
         if (!lines && !lines64)
             return fail(GFB_ERR_UNSUPPORTED, "fused energy gather needs the record kernels (packed cells, one geometry, no inv-power)");

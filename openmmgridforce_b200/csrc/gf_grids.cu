@@ -71,6 +71,7 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
         g->bytes = n_units * 4 * (precision == GFB_PRECISION_MIXED ? sizeof(float) : sizeof(double));
     }
     g->cells = nullptr;
+    g->released_bytes = 0;
 
     // Say what does not fit before cudaMalloc says "out of memory": the B-spline record layout is 32x the raw grid
     // (512^3: 17 GB MIXED, 34 GB DOUBLE), packed cells 8x.
@@ -325,6 +326,18 @@ int gfb_grid_destroy(gfb_grid* grid) {
     cudaSetDevice(grid->dev->ordinal);
     cudaFree(grid->cells);
     delete grid;
+    return GFB_OK;
+}
+
+int gfb_grid_release_cells(gfb_grid* grid) {
+    if (!grid) return fail(GFB_ERR_INVALID, "gfb_grid_release_cells: NULL grid");
+    if (!grid->cells) return GFB_OK;
+    CUDA_TRY(cudaSetDevice(grid->dev->ordinal));
+    CUDA_TRY(cudaStreamSynchronize(grid->dev->stream));
+    CUDA_TRY(cudaFree(grid->cells));
+    grid->cells = nullptr;
+    grid->released_bytes = grid->bytes;
+    grid->bytes = 0;
     return GFB_OK;
 }
 

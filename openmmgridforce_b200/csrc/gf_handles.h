@@ -84,8 +84,9 @@ struct gfb_grid {
     int precision;
     int layout;        // resolved gfb_layout (never AUTO)
     int row_chunks;    // ROWS / PAIRS: 32-byte units per row
-    void* cells;
+    void* cells;       // nullptr after gfb_grid_release_cells
     size_t bytes;
+    size_t released_bytes;   // size of the copy gfb_grid_release_cells freed (the geometry-derived cell count stays valid)
 };
 
 struct gfb_kernel {
@@ -102,6 +103,7 @@ struct gfb_kernel {
     void* d_interleaved;  // CELLS + shared geometry + 2..4 grids: one record per cell holding every grid's corners
                           // (MIXED: 4 slots x 32 B = 128 B; DOUBLE: 4 slots x 64 B = 256 B)
     int il_slots;         // grids per record incl. padding (4); 0 = not interleaved
+    size_t n_cells;       // cells per grid (CELLS layout), fixed at creation
     // host-path scratch
     gfb::DeviceBuffer d_pos, d_forces, d_energy, d_cls, d_sort, d_atom_e;
     gfb::PinnedBuffer h_stage, h_energy;

@@ -513,6 +513,8 @@ int gfb_multi_add_grid(gfb_multi* m, const int counts[3], const double spacing[3
 int gfb_multi_build(gfb_multi* m, int n_atoms, const double* scaling, const double* inv_power, const double* oob_k) {
     if (!m) return fail(GFB_ERR_INVALID, "gfb_multi_build: NULL handle");
     if (m->grids[0].empty()) return fail(GFB_ERR_INVALID, "gfb_multi_build: add at least one grid first");
+    if (m->kernels[0] && !m->grids[0][0]->cells)
+        return fail(GFB_ERR_INVALID, "gfb_multi_build: the grids' packed cells were released by the first build; create a new handle to rebuild");
     for (int d = 0; d < m->n; d++) {
         if (m->kernels[d]) gfb_kernel_destroy(m->kernels[d]);
         m->kernels[d] = nullptr;
@@ -521,6 +523,15 @@ int gfb_multi_build(gfb_multi* m, int n_atoms, const double* scaling, const doub
         if (rc != GFB_OK) return rc;
     }
     m->n_atoms = n_atoms;
+    // The grids belong to this handle alone: once every state reads them through its interleaved records, the per-grid
+    // packed cells are dead weight (3 x 192^3: 638 MB per device).
+    for (int d = 0; d < m->n; d++) {
+        EvalParams probe;
+        memset(&probe, 0, sizeof probe);
+        const gfb_kernel* k = m->kernels[d];
+        if (k->n_grids > 1 && (lines_eligible(k, probe) || lines_f64_eligible(k)))
+            for (size_t g = 0; g < m->grids[d].size(); g++) gfb_grid_release_cells(m->grids[d][g]);
+    }
     return GFB_OK;
 }
 

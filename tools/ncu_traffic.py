@@ -1,0 +1,35 @@
+"""DRAM bytes per launch of the profiled kernel out of `ncu --page raw --csv` files -> profiles/r2_traffic.json, keyed by
+the bench.py workload name and stamped with the hash of the kernel sources (bench.py reports `roofline.traffic` only while
+the sources still hash to what was profiled).
+usage: python tools/ncu_traffic.py KEY=raw.csv [KEY=raw.csv ...]     e.g. C5=profiles/r2_c5full_raw.csv"""
+import csv
+import importlib.util
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+bench = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(bench)
+
+out_path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+doc = json.load(open(out_path)) if os.path.exists(out_path) else {}
+for arg in sys.argv[1:]:
+    key, path = arg.split("=", 1)
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    r = rows[2]
+
+    def val(name):
+        i = hdr.index(name)
+        v = float(r[i].replace(",", ""))
+        u = units[i].lower()
+        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+    rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+    doc[key] = {"kernel": r[hdr.index("Kernel Name")], "dram_bytes_read": rd, "dram_bytes_write": wr,
+                "dram_bytes_per_launch": rd + wr, "duration_us_under_ncu": val("gpu__time_duration.sum") / 1e3,
+                "source": os.path.relpath(path, ROOT) + " (ncu --set full --clock-control none --cache-control none, one warm launch)",
+                "source_sha256_16": bench.kernel_source_hash()}
+    print(key, doc[key]["kernel"][:60], f"{(rd + wr) / 1e6:.1f} MB")
+json.dump(doc, open(out_path, "w"), indent=1, sort_keys=True)
