@@ -338,6 +338,10 @@ GFB_API int gfb_comm_gather_attach(gfb_comm* c, const unsigned char* handles /* 
 GFB_API int gfb_kernel_execute_device_gather(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos,
                                              double* d_energies, void* d_forces, int force_mode, long long force_stride,
                                              double* d_energies_clear, gfb_comm* c, size_t gather_offset, void* stream);
+/* The producer side as a kernel of its own: copies `count` doubles from d_energies into every rank's gathered array at
+ * gather_offset and raises the arrival flags, stream-ordered after whatever produced d_energies. Same protocol as the
+ * fused tail (one more small launch, nothing added to the evaluation kernel); pair it with gfb_comm_gather_wait. */
+GFB_API int gfb_comm_gather_push(gfb_comm* c, const double* d_energies, size_t count, size_t gather_offset, void* stream);
 /* Waits (on `stream`, device side) until every rank's slice of the oldest gather not yet consumed has arrived, then
  * copies the complete [count_total] array into d_out (device memory of the caller). Gather sequence numbers live on the
  * device, so a launch/wait sequence captured with gfb_graph_* can be replayed. A peer that does not arrive within ~20 s
@@ -356,7 +360,8 @@ GFB_API int gfb_comm_gather_status(gfb_comm* c);   /* GFB_OK, or GFB_ERR_CUDA af
  *   gfb_multi_upload         block-partitions and uploads positions once (device-resident shards; forces are kept in
  *                            OpenMM's fixed-point buffer per device).
  *   gfb_multi_step           one evaluation of every shard (one launch per device); gather: 0 none, 1 ncclAllGather of
- *                            the energies on every device, 2 fused in-kernel gather over peer memory.
+ *                            the energies on every device, 2 gather over peer memory fused into the evaluation kernel,
+ *                            3 the same peer stores as a small kernel behind it (gfb_comm_gather_push's; the fastest).
  *   gfb_multi_download       energies [n_replicas] as gathered on device `from_device` (after a gathering step; any
  *                            device holds all of them) and, when forces != NULL, the shards' forces as double [R][A][3]. */
 GFB_API int gfb_multi_create(int n_devices, const int* ordinals, gfb_multi** out);

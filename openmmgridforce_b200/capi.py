@@ -96,6 +96,7 @@ SIGNATURES = {
     "gfb_comm_gather_attach": (_i, [_vp, _vp]),
     "gfb_kernel_execute_device_gather": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _ll, _vp, _vp, _sz, _vp]),
     "gfb_comm_gather_wait": (_i, [_vp, _vp, _vp]),
+    "gfb_comm_gather_push": (_i, [_vp, _vp, _sz, _sz, _vp]),
     "gfb_comm_gather_status": (_i, [_vp]),
     "gfb_multi_create": (_i, [_i, _pi, C.POINTER(_vp)]),
     "gfb_multi_destroy": (_i, [_vp]),
@@ -513,6 +514,10 @@ class Comm:
             raise GridForceB200Error("gather_attach needs one 64-byte handle per rank")
         _check(load_library().gfb_comm_gather_attach(self._h, (C.c_ubyte * len(blob)).from_buffer_copy(blob)))
 
+    def gather_push(self, d_energies, count, gather_offset, stream=0):
+        """Stand-alone producer of the peer-store gather (same protocol as the fused tail, as its own small kernel)."""
+        _check(load_library().gfb_comm_gather_push(self._h, _ptr(d_energies), count, gather_offset, _ptr(stream or None)))
+
     def gather_wait(self, d_out, stream=0):
         """Enqueues the wait for the oldest unconsumed fused gather; the complete array is copied to device address d_out."""
         _check(load_library().gfb_comm_gather_wait(self._h, _ptr(d_out), _ptr(stream or None)))
@@ -571,7 +576,7 @@ class Multi:
         self.n_replicas = pos.shape[0]
 
     def step(self, gather=0):
-        """gather: 0 none, 1 ncclAllGather, 2 fused in-kernel gather over peer memory."""
+        """gather: 0 none, 1 ncclAllGather, 2 peer-store gather fused into the evaluation kernel, 3 peer-store push kernel."""
         _check(load_library().gfb_multi_step(self._h, gather))
 
     def download(self, from_device=0, want_forces=True):

@@ -23,6 +23,7 @@
 #define GF_EVAL_LINES_CUH_
 
 #include "gf_kernels.cuh"
+#include "gf_gather.cuh"
 
 namespace gfb {
 
@@ -120,51 +121,6 @@ constexpr int kForceRed = 0, kForcePrefetch = 1;
 // Internal force mode of an energy-only launch (forces == NULL; GridForceBatch::evaluate, includeForces = false): no
 // gradient arithmetic, no force read-modify-write.
 constexpr int kForceNone = 4;
-
-// ---- fused energy gather (EvalParams::gather) ------------------------------------------------------------------------
-// Called by every thread of every block at the very end of an evaluation kernel. The block that takes the last ticket
-// knows that all other blocks' energy atomics have been performed (each block fences before its ticket), copies the
-// launch's energies into every peer's gathered array over NVLink (plain 8/16-byte stores to peer-mapped memory, local
-// memory for itself), fences at system scope and publishes gather_seq in its flag slot on every peer. The consumer is
-// gf_gather_wait_kernel (gf_multi.cu). No NCCL launch, no extra kernel on the producing side.
-template <int BLOCK>
-__device__ __forceinline__ void gather_tail(const EvalParams& p) {
-    __shared__ unsigned s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(&p.gather->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    GatherTable* const gt = p.gather;
-    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&gt->issued) + 1ull;   // this gather's number
-    const int parity = (int) (seq & 1ull);
-    const int n = p.n_replicas * p.n_slots;
-    const long long base = (long long) parity * gt->count_total + p.gather_offset;
-    const int np = gt->n_peers;
-    const bool vec = ((base | (long long) n) & 1) == 0 && (reinterpret_cast<uintptr_t>(p.energies) & 15) == 0;
-    for (int r = 0; r < np; r++) {
-        const int peer = (gt->my_rank + 1 + r) % np;   // staggered: ranks do not all start on the same peer
-        double* dst = gt->peer_data[peer] + base;
-        if (vec) {
-            const double2* src2 = reinterpret_cast<const double2*>(p.energies);
-            double2* dst2 = reinterpret_cast<double2*>(dst);
-            for (int i = threadIdx.x; i < n / 2; i += BLOCK) dst2[i] = __ldcg(src2 + i);
-        } else {
-            for (int i = threadIdx.x; i < n; i += BLOCK) dst[i] = __ldcg(p.energies + i);
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int) threadIdx.x < np) {
-        unsigned long long* flag = gt->peer_flags[threadIdx.x] + parity * kMaxPeers + gt->my_rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
-    }
-    if (threadIdx.x == 0) {
-        gt->issued = seq;
-        gt->ticket = 0;
-    }
-}
 
 // Threads per block: no block barrier is used, so the block is only the scheduling granule. 128 threads keep the tail
 // of a launch short (C4 is 1.02 waves of 256-thread blocks); one grid + one replica keeps 256 because it ends in one
@@ -387,7 +343,7 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 1280 / lines_bl
     // kernel launched just before only ACCUMULATES into it); issuing them before the wait leaves a block parked at the
     // wait with nothing but its energy atomics to do, which shortens the bubble between two small launches.
     constexpr bool kAdd = FMODE == GFB_FORCE_F64_ADD || FMODE == GFB_FORCE_FIXED_ADD;
-    const bool early_forces = kAdd && p.pdl != 0u;   // uniform
+    const bool early_forces = kAdd && p.pdl != 0u && p.gather == nullptr;   // uniform
     auto add_forces = [&]() {
         if (FMODE == GFB_FORCE_FIXED_ADD) {   // OpenMM's 2^32 fixed point, gridForce.cu:487-499
             const unsigned long long ax = (unsigned long long) __float2ll_rz(Fx * 4294967296.f);
@@ -407,46 +363,51 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 1280 / lines_bl
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (p.energies_clear && t < (unsigned) (p.n_replicas * p.n_slots)) p.energies_clear[t] = 0.0;
     if (p.atom_energies && active) p.atom_energies[a] = e_total;   // uniform branch
-    constexpr bool kStore = FMODE == GFB_FORCE_F64_STORE || FMODE == GFB_FORCE_F32_STORE;
-    const bool stage_f = kStore && p.forces != nullptr && plain && (t - lane) + 32u <= total &&
-                         (reinterpret_cast<uintptr_t>(p.forces) & 15) == 0;   // warp-uniform
-    if (kStore && stage_f) {
-        __syncwarp();   // every lane has consumed its record from this slice
-        if (FMODE == GFB_FORCE_F64_STORE) {
-            double* const s_f = reinterpret_cast<double*>(s_pos2 + (tid >> 5) * kWarpSlice16);
-            s_f[3 * lane] = (double) Fx;
-            s_f[3 * lane + 1] = (double) Fy;
-            s_f[3 * lane + 2] = (double) Fz;
-            __syncwarp();
-            const double2* const s_f2 = reinterpret_cast<const double2*>(s_f);
-            double2* const dst = reinterpret_cast<double2*>(static_cast<double*>(p.forces) + 3 * (size_t) (t - lane));
-            dst[lane] = s_f2[lane];
-            if (lane < 16) dst[32 + lane] = s_f2[32 + lane];
-        } else {   // F32: 384 bytes = 24 x 16
-            float* const s_f = reinterpret_cast<float*>(s_pos2 + (tid >> 5) * kWarpSlice16);
-            s_f[3 * lane] = Fx;
-            s_f[3 * lane + 1] = Fy;
-            s_f[3 * lane + 2] = Fz;
-            __syncwarp();
-            const float4* const s_f4 = reinterpret_cast<const float4*>(s_f);
-            float4* const dst = reinterpret_cast<float4*>(static_cast<float*>(p.forces) + 3 * (size_t) (t - lane));
-            if (lane < 24) dst[lane] = s_f4[lane];
+    // Force writes. In a launch that carries the fused energy gather they come AFTER the energies and the block's gather
+    // ticket (the ticket's fence then waits for the energy atomics only); otherwise right here.
+    auto write_forces = [&]() {
+        constexpr bool kStore = FMODE == GFB_FORCE_F64_STORE || FMODE == GFB_FORCE_F32_STORE;
+        const bool stage_f = kStore && p.forces != nullptr && plain && (t - lane) + 32u <= total &&
+                             (reinterpret_cast<uintptr_t>(p.forces) & 15) == 0;   // warp-uniform
+        if (kStore && stage_f) {
+            __syncwarp();   // every lane has consumed its record from this slice
+            if (FMODE == GFB_FORCE_F64_STORE) {
+                double* const s_f = reinterpret_cast<double*>(s_pos2 + (tid >> 5) * kWarpSlice16);
+                s_f[3 * lane] = (double) Fx;
+                s_f[3 * lane + 1] = (double) Fy;
+                s_f[3 * lane + 2] = (double) Fz;
+                __syncwarp();
+                const double2* const s_f2 = reinterpret_cast<const double2*>(s_f);
+                double2* const dst = reinterpret_cast<double2*>(static_cast<double*>(p.forces) + 3 * (size_t) (t - lane));
+                dst[lane] = s_f2[lane];
+                if (lane < 16) dst[32 + lane] = s_f2[32 + lane];
+            } else {   // F32: 384 bytes = 24 x 16
+                float* const s_f = reinterpret_cast<float*>(s_pos2 + (tid >> 5) * kWarpSlice16);
+                s_f[3 * lane] = Fx;
+                s_f[3 * lane + 1] = Fy;
+                s_f[3 * lane + 2] = Fz;
+                __syncwarp();
+                const float4* const s_f4 = reinterpret_cast<const float4*>(s_f);
+                float4* const dst = reinterpret_cast<float4*>(static_cast<float*>(p.forces) + 3 * (size_t) (t - lane));
+                if (lane < 24) dst[lane] = s_f4[lane];
+            }
         }
-    }
-    if (kAdd && !early_forces && active && p.forces) add_forces();
-    if (kStore && active && p.forces && !stage_f) {
-        if (FMODE == GFB_FORCE_F32_STORE) {
-            float* f = static_cast<float*>(p.forces) + 3 * (size_t) gidx;
-            f[0] = Fx;
-            f[1] = Fy;
-            f[2] = Fz;
-        } else {
-            double* f = fdbl + 3 * (size_t) gidx;
-            f[0] = (double) Fx;
-            f[1] = (double) Fy;
-            f[2] = (double) Fz;
+        if (kAdd && !early_forces && active && p.forces) add_forces();
+        if (kStore && active && p.forces && !stage_f) {
+            if (FMODE == GFB_FORCE_F32_STORE) {
+                float* f = static_cast<float*>(p.forces) + 3 * (size_t) gidx;
+                f[0] = Fx;
+                f[1] = Fy;
+                f[2] = Fz;
+            } else {
+                double* f = fdbl + 3 * (size_t) gidx;
+                f[0] = (double) Fx;
+                f[1] = (double) Fy;
+                f[2] = (double) Fz;
+            }
         }
-    }
+    };
+    if (p.gather == nullptr) write_forces();
 
     // ---- energies ------------------------------------------------------------------------------------------------------
     if (SINGLE) {
@@ -501,7 +462,11 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 1280 / lines_bl
             if (head) red_add_f64(p.energies + key, e_total);
         }
     }
-    if (p.gather) gather_tail<kBlock>(p);   // uniform branch: fused energy gather of a replica-sharded run
+    if (p.gather) {   // uniform branch: fused energy gather of a replica-sharded run
+        const int copier = gather_ticket<kBlock>(p);
+        write_forces();
+        if (copier >= 0) gather_copy<kBlock>(p, (unsigned) copier);
+    }
 }
 
 }  // namespace gfb

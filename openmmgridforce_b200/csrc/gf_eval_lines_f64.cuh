@@ -148,46 +148,49 @@ __global__ void __launch_bounds__(kLinesF64Block, 6) gf_eval_lines_f64_kernel(co
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (p.energies_clear && t < (unsigned) (p.n_replicas * p.n_slots)) p.energies_clear[t] = 0.0;
     if (p.atom_energies && active) p.atom_energies[a] = e_total;
-    const bool stage_f = FMODE == GFB_FORCE_F64_STORE && p.forces != nullptr && plain && (t - lane) + 32u <= total &&
-                         (reinterpret_cast<uintptr_t>(p.forces) & 15) == 0;   // warp-uniform
-    if (FMODE == GFB_FORCE_F64_STORE && stage_f) {
-        __syncwarp();   // every lane has consumed its record from this slice
-        double* const s_f = reinterpret_cast<double*>(s_warp);
-        s_f[3 * lane] = Fx;
-        s_f[3 * lane + 1] = Fy;
-        s_f[3 * lane + 2] = Fz;
-        __syncwarp();
-        double2* const dst = reinterpret_cast<double2*>(static_cast<double*>(p.forces) + 3 * (size_t) (t - lane));
-        dst[lane] = s_warp[lane];
-        if (lane < 16) dst[32 + lane] = s_warp[32 + lane];
-    }
-    if (FMODE != kForceNone && active && p.forces) {
-        if (FMODE == GFB_FORCE_FIXED_ADD) {   // OpenMM's 2^32 fixed point, gridForce.cu:487-499
-            unsigned long long* f = static_cast<unsigned long long*>(p.forces);
-            const double scale = 4294967296.0;
-            red_add_u64(f + gidx, (unsigned long long) (long long) (Fx * scale));
-            red_add_u64(f + p.force_stride + gidx, (unsigned long long) (long long) (Fy * scale));
-            red_add_u64(f + 2 * p.force_stride + gidx, (unsigned long long) (long long) (Fz * scale));
-        } else if (FMODE == GFB_FORCE_F32_STORE) {
-            float* f = static_cast<float*>(p.forces) + 3 * (size_t) gidx;
-            f[0] = (float) Fx;
-            f[1] = (float) Fy;
-            f[2] = (float) Fz;
-        } else {
-            double* f = static_cast<double*>(p.forces) + 3 * (size_t) gidx;
-            if (FMODE == GFB_FORCE_F64_STORE) {
-                if (!stage_f) {
-                    f[0] = Fx;
-                    f[1] = Fy;
-                    f[2] = Fz;
-                }
+    auto write_forces = [&]() {   // deferred behind the gather ticket in a gather launch (see gf_eval_lines_kernel)
+        const bool stage_f = FMODE == GFB_FORCE_F64_STORE && p.forces != nullptr && plain && (t - lane) + 32u <= total &&
+                             (reinterpret_cast<uintptr_t>(p.forces) & 15) == 0;   // warp-uniform
+        if (FMODE == GFB_FORCE_F64_STORE && stage_f) {
+            __syncwarp();   // every lane has consumed its record from this slice
+            double* const s_f = reinterpret_cast<double*>(s_warp);
+            s_f[3 * lane] = Fx;
+            s_f[3 * lane + 1] = Fy;
+            s_f[3 * lane + 2] = Fz;
+            __syncwarp();
+            double2* const dst = reinterpret_cast<double2*>(static_cast<double*>(p.forces) + 3 * (size_t) (t - lane));
+            dst[lane] = s_warp[lane];
+            if (lane < 16) dst[32 + lane] = s_warp[32 + lane];
+        }
+        if (FMODE != kForceNone && active && p.forces) {
+            if (FMODE == GFB_FORCE_FIXED_ADD) {   // OpenMM's 2^32 fixed point, gridForce.cu:487-499
+                unsigned long long* f = static_cast<unsigned long long*>(p.forces);
+                const double scale = 4294967296.0;
+                red_add_u64(f + gidx, (unsigned long long) (long long) (Fx * scale));
+                red_add_u64(f + p.force_stride + gidx, (unsigned long long) (long long) (Fy * scale));
+                red_add_u64(f + 2 * p.force_stride + gidx, (unsigned long long) (long long) (Fz * scale));
+            } else if (FMODE == GFB_FORCE_F32_STORE) {
+                float* f = static_cast<float*>(p.forces) + 3 * (size_t) gidx;
+                f[0] = (float) Fx;
+                f[1] = (float) Fy;
+                f[2] = (float) Fz;
             } else {
-                red_add_f64(f, Fx);
-                red_add_f64(f + 1, Fy);
-                red_add_f64(f + 2, Fz);
+                double* f = static_cast<double*>(p.forces) + 3 * (size_t) gidx;
+                if (FMODE == GFB_FORCE_F64_STORE) {
+                    if (!stage_f) {
+                        f[0] = Fx;
+                        f[1] = Fy;
+                        f[2] = Fz;
+                    }
+                } else {
+                    red_add_f64(f, Fx);
+                    red_add_f64(f + 1, Fy);
+                    red_add_f64(f + 2, Fz);
+                }
             }
         }
-    }
+    };
+    if (p.gather == nullptr) write_forces();
 
     // ---- energies (as gf_eval_lines_kernel) ------------------------------------------------------------------------------
     if (SINGLE) {
@@ -240,7 +243,11 @@ __global__ void __launch_bounds__(kLinesF64Block, 6) gf_eval_lines_f64_kernel(co
             if (head) red_add_f64(p.energies + key, e_total);
         }
     }
-    if (p.gather) gather_tail<kBlock>(p);
+    if (p.gather) {
+        const int copier = gather_ticket<kBlock>(p);
+        write_forces();
+        if (copier >= 0) gather_copy<kBlock>(p, (unsigned) copier);
+    }
 }
 
 }  // namespace gfb

@@ -19,6 +19,7 @@
 #include <thread>
 #include <vector>
 
+#include "gf_gather.cuh"
 #include "gf_handles.h"
 
 using namespace gfb;
@@ -78,17 +79,18 @@ NcclApi* nccl_api() {
     } while (0)
 
 // ---- consumer side of the fused gather ------------------------------------------------------------------------------
-// kWaitBlocks blocks of 256 threads. In every block, lane r of warp 0 waits until rank r has published this gather's
+// kWaitBlocks blocks of 256 threads (enough that a 65,536-entry array is one 16-byte copy per thread). In every block, lane r of warp 0 waits until rank r has published this gather's
 // sequence number in this rank's flag array (written by the last block of rank r's evaluation launch with
 // st.release.sys after its data stores and a system-scope fence); then the block copies its share of the gathered array
 // into `out`, the caller's stable result buffer (the gathered array itself is double-buffered and will be overwritten
 // two gathers later). The sequence number is read from the device-resident table, so a captured graph replays
 // correctly; the last block to finish advances it. Bounded: after ~20 s a block raises *timed_out instead of spinning
 // forever (a rank that died must not hang the GPU).
-constexpr int kWaitBlocks = 8;
+constexpr int kWaitBlocks = 64;
 __global__ void __launch_bounds__(256) gf_gather_wait_kernel(GatherTable* gt, const unsigned long long* flags_base,
                                                              const double* data_base, double* out) {
     __shared__ int s_ok;
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // see launch_overlapped
     const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&gt->waited) + 1ull;
     const int parity = (int) (seq & 1ull);
     if (threadIdx.x == 0) s_ok = 1;
@@ -117,7 +119,13 @@ __global__ void __launch_bounds__(256) gf_gather_wait_kernel(GatherTable* gt, co
     if (s_ok && out) {
         const double* src = data_base + (size_t) parity * gt->count_total;
         const long long n = gt->count_total;
-        for (long long i = (long long) blockIdx.x * 256 + threadIdx.x; i < n; i += (long long) gridDim.x * 256) out[i] = __ldcg(src + i);
+        if (((n | (long long) parity * n) & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+            const double2* src2 = reinterpret_cast<const double2*>(src);
+            double2* out2 = reinterpret_cast<double2*>(out);
+            for (long long i = (long long) blockIdx.x * 256 + threadIdx.x; i < n / 2; i += (long long) gridDim.x * 256) out2[i] = __ldcg(src2 + i);
+        } else {
+            for (long long i = (long long) blockIdx.x * 256 + threadIdx.x; i < n; i += (long long) gridDim.x * 256) out[i] = __ldcg(src + i);
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -127,6 +135,36 @@ __global__ void __launch_bounds__(256) gf_gather_wait_kernel(GatherTable* gt, co
             gt->wait_ticket = 0;
         }
     }
+}
+
+// ---- stand-alone producer: the same peer stores + flags as the fused tail, as a kernel of its own -----------------------
+// (kPushBlocks x 256 threads, enqueued right after the evaluation launch: it costs one more small launch but nothing
+// inside the evaluation kernel)
+constexpr int kPushBlocks = 32;
+__global__ void __launch_bounds__(256) gf_gather_push_kernel(GatherTable* gt, const double* src, int n, long long offset) {
+    // launched with programmatic stream serialization: the blocks are resident before the evaluation kernel ends and go
+    // the moment it has completed and flushed (no launch latency on the critical path); the wait kernel behind may do
+    // the same
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    gather_publish<256>(gt, src, n, offset, blockIdx.x, gridDim.x);
+}
+
+// Launch with the programmatic-stream-serialization attribute (both gather kernels start with griddepcontrol.wait, so
+// the attribute only moves their block scheduling ahead of the previous kernel's end; the ordering is unchanged).
+template <typename... Args>
+cudaError_t launch_overlapped(void (*kernel)(Args...), int blocks, int threads, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(threads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -389,14 +427,26 @@ int gfb_kernel_execute_device_gather(gfb_kernel* k, int n_replicas, int n_partic
                         d_energies_clear, stream ? static_cast<cudaStream_t>(stream) : k->dev->stream, x);
 }
 
+int gfb_comm_gather_push(gfb_comm* c, const double* d_energies, size_t count, size_t gather_offset, void* stream) {
+    if (!c || !c->attached) return fail(GFB_ERR_INVALID, "gfb_comm_gather_push: communicator without attached gather memory");
+    if (!d_energies || count == 0) return fail(GFB_ERR_INVALID, "gfb_comm_gather_push: nothing to push");
+    if (gather_offset + count > c->mem.count_total || count > 0x7fffffffull)
+        return fail(GFB_ERR_INVALID, "gfb_comm_gather_push: slice [%zu, +%zu) exceeds the gathered array (%zu)", gather_offset, count, c->mem.count_total);
+    CUDA_TRY(cudaSetDevice(c->dev->ordinal));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->dev->stream;
+    CUDA_TRY(launch_overlapped(gf_gather_push_kernel, kPushBlocks, 256, s, c->d_table, d_energies, (int) count, (long long) gather_offset));
+    g_launches++;
+    return GFB_OK;
+}
+
 int gfb_comm_gather_wait(gfb_comm* c, double* d_out, void* stream) {
     if (!c || !c->attached) return fail(GFB_ERR_INVALID, "gfb_comm_gather_wait: communicator without attached gather memory");
     if (!d_out) return fail(GFB_ERR_INVALID, "gfb_comm_gather_wait: d_out is NULL");
     CUDA_TRY(cudaSetDevice(c->dev->ordinal));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->dev->stream;
-    gf_gather_wait_kernel<<<kWaitBlocks, 256, 0, s>>>(c->d_table, c->mem.flags(0), c->mem.data(0), d_out);
+    CUDA_TRY(launch_overlapped(gf_gather_wait_kernel, kWaitBlocks, 256, s, c->d_table, (const unsigned long long*) c->mem.flags(0),
+                               (const double*) c->mem.data(0), d_out));
     g_launches++;
-    CUDA_TRY(cudaGetLastError());
     return GFB_OK;
 }
 
@@ -608,7 +658,7 @@ int gfb_multi_upload(gfb_multi* m, int n_replicas, const double* pos) {
 
 int gfb_multi_step(gfb_multi* m, int gather) {
     if (!m || m->shards.empty()) return fail(GFB_ERR_INVALID, "gfb_multi_step: call gfb_multi_upload first");
-    if (gather < 0 || gather > 2) return fail(GFB_ERR_INVALID, "gfb_multi_step: gather must be 0, 1 or 2");
+    if (gather < 0 || gather > 3) return fail(GFB_ERR_INVALID, "gfb_multi_step: gather must be 0, 1, 2 or 3");
     NcclApi* api = nullptr;
     if (gather == 1) {
         api = nccl_api();
@@ -644,13 +694,18 @@ int gfb_multi_step(gfb_multi* m, int gather) {
             }
         }
         NCCL_TRY(api, api->GroupEnd());
-    } else if (gather == 2) {
+    } else if (gather >= 2) {
         for (int d = 0; d < m->n; d++) {
             MultiShard& s = m->shards[d];
             CUDA_TRY(cudaSetDevice(m->devs[d]->ordinal));
-            gf_gather_wait_kernel<<<kWaitBlocks, 256, 0, m->devs[d]->stream>>>(s.d_table, s.mem.flags(0), s.mem.data(0), s.d_gathered);
+            if (gather == 3) {
+                CUDA_TRY(launch_overlapped(gf_gather_push_kernel, kPushBlocks, 256, m->devs[d]->stream, s.d_table, (const double*) s.d_e[cur],
+                                           s.hi - s.lo, (long long) s.lo));
+                g_launches++;
+            }
+            CUDA_TRY(launch_overlapped(gf_gather_wait_kernel, kWaitBlocks, 256, m->devs[d]->stream, s.d_table,
+                                       (const unsigned long long*) s.mem.flags(0), (const double*) s.mem.data(0), s.d_gathered));
             g_launches++;
-            CUDA_TRY(cudaGetLastError());
         }
     }
     m->steps++;
@@ -670,7 +725,7 @@ int gfb_multi_download(gfb_multi* m, int from_device, double* energies, double* 
     if (energies) {
         MultiShard& s = m->shards[from_device];
         CUDA_TRY(cudaSetDevice(m->devs[from_device]->ordinal));
-        if (m->last_gather == 2) {
+        if (m->last_gather >= 2) {
             unsigned int flag = 0;
             CUDA_TRY(cudaMemcpy(&flag, &s.d_table->timed_out, sizeof flag, cudaMemcpyDeviceToHost));
             if (flag) return fail(GFB_ERR_CUDA, "gfb_multi_download: the fused gather timed out on device %d", m->devs[from_device]->ordinal);

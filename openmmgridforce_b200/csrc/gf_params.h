@@ -44,7 +44,7 @@ struct GatherTable {
     unsigned long long issued;                   // gathers this rank has published (gather_tail)
     unsigned long long waited;                   // gathers this rank has consumed (gf_gather_wait_kernel)
     unsigned int wait_ticket;                    // blocks of the current wait kernel that have finished
-    unsigned int pad_;
+    unsigned int copy_ticket;                    // copier blocks of the current gather that have finished their slice
 };
 
 struct EvalParams {

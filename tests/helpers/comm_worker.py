@@ -61,8 +61,13 @@ def main():
         for step in range(3):           # three gathers: both parities, and reuse of a parity
             d_pos = torch.from_numpy(np.ascontiguousarray(w.pos[lo:hi] + shifts[step])).to(tdev)
             cur, nxt = d_e[step % 2], d_e[(step + 1) % 2]
-            k.execute_device_gather(comm, lo, r, a, d_pos.data_ptr(), cur.data_ptr(), d_f.data_ptr(), gf.FORCE_FIXED_ADD, stride,
-                                    stream.cuda_stream, d_energies_clear=nxt.data_ptr())
+            if step == 1:               # the stand-alone producer (same protocol) for one of the three gathers
+                k.execute_device(r, a, d_pos.data_ptr(), cur.data_ptr(), None, d_f.data_ptr(), gf.FORCE_FIXED_ADD, stride, None,
+                                 stream.cuda_stream, d_energies_clear=nxt.data_ptr())
+                comm.gather_push(cur.data_ptr(), r, lo, stream.cuda_stream)
+            else:
+                k.execute_device_gather(comm, lo, r, a, d_pos.data_ptr(), cur.data_ptr(), d_f.data_ptr(), gf.FORCE_FIXED_ADD, stride,
+                                        stream.cuda_stream, d_energies_clear=nxt.data_ptr())
             got = torch.full((n_total,), float("nan"), dtype=torch.float64, device=tdev)
             comm.gather_wait(got.data_ptr(), stream.cuda_stream)
             fused.append(got)
