@@ -49,7 +49,7 @@ REPLICAS_PER_GPU = REPLICAS_TOTAL          # weak scaling, and N = 1
 N_ATOMS = 47
 N_GRIDS = 3
 GRID_N = 192
-KERNEL_SOURCES = ("gf_eval_lines.cuh", "gf_kernels.cuh", "gf_params.h", "gf_launch_lines.cu")
+KERNEL_SOURCES = ("gf_eval_lines.cuh", "gf_eval_lines_f64.cuh", "gf_gather.cuh", "gf_kernels.cuh", "gf_params.h", "gf_launch_lines.cu")
 
 
 def b_alg(n_grids, precision=0, forces=True):

@@ -54,10 +54,12 @@ def _close(grids, k):
 
 
 def _check(en, ge, forces, ge_ref, f_ref):
-    scale_e = np.abs(ge_ref).max()
-    assert np.abs(ge - ge_ref).max() <= TOL_E * scale_e
+    """Per replica: |E - E_ref| <= 1e-6 * max(|E_ref|, largest per-grid term of that replica). The grids of these cases are
+    FP32-representable, so no storage-rounding floor is involved (tests/test_gpu_fullsize.py measures that one)."""
+    term = np.abs(ge_ref).max(axis=1)
+    assert (np.abs(ge - ge_ref) <= TOL_E * np.maximum(np.abs(ge_ref), term[:, None])).all()
     e_ref = ge_ref.sum(axis=1)
-    assert np.abs(en - e_ref).max() <= TOL_E * max(np.abs(e_ref).max(), scale_e)
+    assert (np.abs(en - e_ref) <= TOL_E * np.maximum(np.abs(e_ref), term)).all()
     assert np.abs(forces - f_ref).max() <= TOL_F * np.abs(f_ref).max()
 
 

@@ -25,10 +25,11 @@ for arg in sys.argv[1:]:
         i = hdr.index(name)
         v = float(r[i].replace(",", ""))
         u = units[i].lower()
-        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0,
+                    "ms": 1e3, "msecond": 1e3}.get(u, 1)
     rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
     doc[key] = {"kernel": r[hdr.index("Kernel Name")], "dram_bytes_read": rd, "dram_bytes_write": wr,
-                "dram_bytes_per_launch": rd + wr, "duration_us_under_ncu": val("gpu__time_duration.sum") / 1e3,
+                "dram_bytes_per_launch": rd + wr, "duration_us_under_ncu": val("gpu__time_duration.sum"),
                 "source": os.path.relpath(path, ROOT) + " (ncu --set full --clock-control none --cache-control none, one warm launch)",
                 "source_sha256_16": bench.kernel_source_hash()}
     print(key, doc[key]["kernel"][:60], f"{(rd + wr) / 1e6:.1f} MB")
