@@ -49,6 +49,7 @@ REPLICAS_PER_GPU = REPLICAS_TOTAL          # weak scaling, and N = 1
 N_ATOMS = 47
 N_GRIDS = 3
 GRID_N = 192
+RENDEZVOUS = os.environ.get("GFB_BENCH_RENDEZVOUS", "1") != "0"     # device-side start rendezvous of the timed windows (N > 1)
 KERNEL_SOURCES = ("gf_eval_lines.cuh", "gf_eval_lines_f64.cuh", "gf_gather.cuh", "gf_kernels.cuh", "gf_params.h", "gf_launch_lines.cu")
 
 
@@ -285,6 +286,12 @@ class DeviceLoop:
                 first = (w * steps) % n_sets if g is None else 0
                 if barrier is not None:
                     barrier()
+                # N > 1: the host barrier lets the ranks go tens of microseconds apart, and the window's one collective
+                # (the energy gather) would be charged that skew. A device-side rendezvous in front of the first event
+                # starts all ranks within an NVLink round trip; it is held until this rank's window has been enqueued.
+                rendezvous = self.comm is not None and barrier is not None and self.gather_mode != "none" and RENDEZVOUS
+                if rendezvous:
+                    self.comm.rendezvous(self.stream.cuda_stream, hold=True)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(self.stream)
                 if g is not None:
@@ -293,6 +300,8 @@ class DeviceLoop:
                 else:
                     self.window(first, steps)
                 e1.record(self.stream)
+                if rendezvous:
+                    self.comm.rendezvous_release()
                 self.stream.synchronize()
                 if barrier is not None:
                     barrier()

@@ -348,7 +348,16 @@ GFB_API int gfb_comm_gather_push(gfb_comm* c, const double* d_energies, size_t c
  * raises a flag that gfb_comm_gather_status reports after the stream has been synchronised (the wait kernel never
  * spins forever). */
 GFB_API int gfb_comm_gather_wait(gfb_comm* c, double* d_out, void* stream);
-GFB_API int gfb_comm_gather_status(gfb_comm* c);   /* GFB_OK, or GFB_ERR_CUDA after a timed-out wait */
+GFB_API int gfb_comm_gather_status(gfb_comm* c);   /* GFB_OK, or GFB_ERR_CUDA after a timed-out wait or rendezvous */
+/* Device-side rendezvous of all ranks (needs gfb_comm_gather_attach): enqueues a one-block kernel on `stream` that
+ * publishes this rank's arrival to every peer over the peer mappings and waits for every peer's; work enqueued behind it
+ * starts within an NVLink round trip on all ranks — much tighter than a host barrier, whose ranks leave tens of
+ * microseconds apart (that skew is otherwise charged to the first collective that follows, i.e. to the energy gather of
+ * a few-hundred-microsecond window). hold != 0: the kernel first waits for gfb_comm_rendezvous_release(), which the host
+ * calls after it has enqueued the work that follows, so no rank leaves the rendezvous with an empty stream.
+ * Not capturable into a graph when held. No reference counterpart (MPI_Barrier of a host-driven multi-rank run). */
+GFB_API int gfb_comm_rendezvous(gfb_comm* c, int hold, void* stream);
+GFB_API int gfb_comm_rendezvous_release(gfb_comm* c);
 
 /* One process, n_devices GPUs. add_grid uploads and repacks the grid on every device; build creates one evaluation
  * state per device (arguments as gfb_kernel_create, identity particles).

@@ -98,6 +98,8 @@ SIGNATURES = {
     "gfb_comm_gather_wait": (_i, [_vp, _vp, _vp]),
     "gfb_comm_gather_push": (_i, [_vp, _vp, _sz, _sz, _vp]),
     "gfb_comm_gather_status": (_i, [_vp]),
+    "gfb_comm_rendezvous": (_i, [_vp, _i, _vp]),
+    "gfb_comm_rendezvous_release": (_i, [_vp]),
     "gfb_multi_create": (_i, [_i, _pi, C.POINTER(_vp)]),
     "gfb_multi_destroy": (_i, [_vp]),
     "gfb_multi_num_devices": (_i, [_vp]),
@@ -524,6 +526,13 @@ class Comm:
 
     def gather_status(self):
         _check(load_library().gfb_comm_gather_status(self._h))
+
+    def rendezvous(self, stream=0, hold=False):
+        """Device-side rendezvous of all ranks on `stream`; hold=True keeps the kernel waiting until rendezvous_release()."""
+        _check(load_library().gfb_comm_rendezvous(self._h, 1 if hold else 0, _ptr(stream or None)))
+
+    def rendezvous_release(self):
+        _check(load_library().gfb_comm_rendezvous_release(self._h))
 
     def close(self):
         if self._h:

@@ -131,6 +131,14 @@ constexpr int kForceNone = 4;
                                     // 13.5 -> 13.3 us, C4 unchanged
 #endif
 __host__ __device__ constexpr int lines_block(int ng) { return ng == 1 ? 256 : GFB_LINES_BLOCK_MULTI; }
+#ifndef GFB_PERSIST_THREADS_PER_SM
+#define GFB_PERSIST_THREADS_PER_SM 1024   // resident threads per SM of the tile-striding variant: 64 registers. At 1280 (48
+                                          // registers) the loop-carried state spills and a 1/8 shard of C5 takes 14.05 us
+                                          // instead of 11.60 (13.43 with one block per tile)
+#endif
+__host__ __device__ constexpr int lines_blocks_per_sm(int ng, bool persist) {
+    return ng == 1 ? 6 : (persist ? GFB_PERSIST_THREADS_PER_SM : 1280) / lines_block(ng);
+}
 
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
@@ -147,8 +155,10 @@ __device__ __forceinline__ void cp_async_wait_all() {
 //          in the common case
 // Occupancy: 40 registers x 6 blocks of 256 (one grid), 48 registers x 10 blocks of 128 with 16 KB of smem each (2-4 grids;
 // 12 blocks / 40 registers measured no faster on C5 and slower on C4).
-template <int NG, int FMODE, int FPATH, bool SINGLE, bool GE>
-__global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 1280 / lines_block(NG)) gf_eval_lines_kernel(const __grid_constant__ EvalParams p) {
+//   PERSIST the launch's blocks stride over the tiles and park their energy sums (small launches under launch overlap,
+//          see the tile loop below); false = one tile per block, code as if the loop were not there
+template <int NG, int FMODE, int FPATH, bool SINGLE, bool GE, bool PERSIST = false>
+__global__ void __launch_bounds__(lines_block(NG), lines_blocks_per_sm(NG, PERSIST)) gf_eval_lines_kernel(const __grid_constant__ EvalParams p) {
     constexpr int kBlock = lines_block(NG);
     // One slice per warp: first the warp's 32 positions (768 bytes), then (NG > 1) its 32 records of 128 bytes.
     constexpr unsigned kWarpSlice16 = NG == 1 ? 48 : 256;                // slice size in 16-byte units
@@ -157,14 +167,48 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 1280 / lines_bl
 
     const unsigned tid = threadIdx.x;
     const unsigned lane = tid & 31u;
-    const unsigned t0 = blockIdx.x * kBlock;
-    const unsigned t = t0 + tid;
     const unsigned total = (unsigned) p.total;
-    const bool active = t < total;
     // Programmatic dependent launch (sm_90+): let the NEXT launch on this stream start its blocks as soon as all of ours
     // have started, so that its position/record fetches overlap our tail; it blocks at griddepcontrol.wait (below, before
     // the first global write) until this grid has completed. Both are no-ops in a launch without the PDL attribute.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    // Tiles of kBlock atoms, block b takes tiles b, b + gridDim.x, ... The host launches one block per tile, except for
+    // SMALL launches under launch overlap (p.defer, a few waves of blocks: a 1/8 shard of C5 is two): those get a grid
+    // that is resident all at once. Every block then starts — and fires launch_dependents — right away, so the next
+    // launch is already pending when our blocks begin to exit and takes their SM slots one by one; with one block per
+    // tile the last blocks of a launch start (and release the next launch) only a block lifetime before its end, and the
+    // slots freed meanwhile sit empty for the launch latency (measured ~3 us per launch whatever its size).
+    // In that mode nothing the kernel writes needs the previous launch before the very end: forces are commutative
+    // atomics (or absent), and the per-replica energy sums of up to kDefer tiles are parked in shared memory; the block
+    // waits for the previous grid once, after its last tile, and only then issues its energy atomics and its share of
+    // the accumulator clear.
+    constexpr bool kAddMode = FMODE == GFB_FORCE_F64_ADD || FMODE == GFB_FORCE_FIXED_ADD;
+    constexpr bool kCanDefer = PERSIST && !SINGLE && !GE && (kAddMode || FMODE == kForceNone);
+    static_assert(!PERSIST || kCanDefer, "the tile-striding variant exists for the deferred-energy modes only");
+#ifndef GFB_PERSIST_DEFER
+#define GFB_PERSIST_DEFER 2
+#endif
+    constexpr int kDefer = GFB_PERSIST_DEFER;
+    __shared__ double s_def_e[kCanDefer ? kDefer * kBlock : 1];
+    __shared__ int s_def_k[kCanDefer ? kDefer * kBlock : 1];
+    const bool defer = kCanDefer && p.defer != 0u;   // uniform
+    bool waited = false;
+    auto flush_parked = [&](unsigned n) {
+        if (kCanDefer && p.energies) {
+            for (unsigned j = 0; j < n; j++) {
+                const int k = s_def_k[j * kBlock + tid];
+                if (k >= 0) red_add_f64(p.energies + k, s_def_e[j * kBlock + tid]);
+            }
+        }
+    };
+    const unsigned n_tiles = (total + (unsigned) kBlock - 1u) / (unsigned) kBlock;
+    unsigned it = 0;
+    unsigned tile = blockIdx.x;
+    do {
+    const unsigned t0 = tile * kBlock;
+    const unsigned t = t0 + tid;
+    const bool active = t < total;
 
     // ---- who am I: replica, atom ordinal, particle -------------------------------------------------------------
     // Evaluation order (gfb_kernel_sort_atoms): thread t evaluates atom order[t] of the flattened [replica][atom] list.
@@ -205,7 +249,7 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 1280 / lines_bl
     // Positions of the block that will run in this block's SM slot NEXT (p.ahead_blocks = resident blocks of the launch)
     // are pulled into L2 now: when that block starts, its first dependent load is an L2 hit instead of a DRAM round trip.
     if (p.ahead_blocks && plain) {
-        const unsigned long long first = ((unsigned long long) blockIdx.x + p.ahead_blocks) * kBlock;   // its first atom
+        const unsigned long long first = ((unsigned long long) tile + p.ahead_blocks) * kBlock;   // its first atom
         if (first < total && tid < (kBlock * 24u + 127u) / 128u) {
             const char* line = reinterpret_cast<const char*>(p.pos + 3 * first) + 128u * tid;
             if (line < reinterpret_cast<const char*>(p.pos + 3 * (size_t) total)) prefetch_l2(line);
@@ -342,7 +386,7 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 1280 / lines_bl
     // may interleave with the previous evaluation launch's (the caller's promise for launch overlap covers d_forces: the
     // kernel launched just before only ACCUMULATES into it); issuing them before the wait leaves a block parked at the
     // wait with nothing but its energy atomics to do, which shortens the bubble between two small launches.
-    constexpr bool kAdd = FMODE == GFB_FORCE_F64_ADD || FMODE == GFB_FORCE_FIXED_ADD;
+    constexpr bool kAdd = kAddMode;
     const bool early_forces = kAdd && p.pdl != 0u && p.gather == nullptr;   // uniform
     auto add_forces = [&]() {
         if (FMODE == GFB_FORCE_FIXED_ADD) {   // OpenMM's 2^32 fixed point, gridForce.cu:487-499
@@ -360,9 +404,14 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 1280 / lines_bl
         }
     };
     if (kAdd && early_forces && active && p.forces) add_forces();
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (p.energies_clear && t < (unsigned) (p.n_replicas * p.n_slots)) p.energies_clear[t] = 0.0;
-    if (p.atom_energies && active) p.atom_energies[a] = e_total;   // uniform branch
+    const bool park = defer && !waited && it < (unsigned) kDefer;   // uniform: this tile's energies are parked
+    if (!park && !waited) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        waited = true;
+        if (defer) flush_parked(it < (unsigned) kDefer ? it : (unsigned) kDefer);
+    }
+    if (!defer && p.energies_clear && t < (unsigned) (p.n_replicas * p.n_slots)) p.energies_clear[t] = 0.0;
+    if (p.atom_energies && active) p.atom_energies[a] = e_total;   // uniform branch (never with p.defer)
     // Force writes. In a launch that carries the fused energy gather they come AFTER the energies and the block's gather
     // ticket (the ticket's fence then waits for the energy atomics only); otherwise right here.
     auto write_forces = [&]() {
@@ -407,7 +456,7 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 1280 / lines_bl
             }
         }
     };
-    if (p.gather == nullptr) write_forces();
+    if (p.gather == nullptr && !park) write_forces();   // parked tiles: forces went out early (ADD) or are not wanted
 
     // ---- energies ------------------------------------------------------------------------------------------------------
     if (SINGLE) {
@@ -459,13 +508,32 @@ __global__ void __launch_bounds__(lines_block(NG), NG == 1 ? 6 : 1280 / lines_bl
         }
         if (p.energies) {
             run_sum(e_total, span);
-            if (head) red_add_f64(p.energies + key, e_total);
+            if (kCanDefer && park) {
+                s_def_e[(kCanDefer ? it : 0u) * kBlock + tid] = e_total;
+                s_def_k[(kCanDefer ? it : 0u) * kBlock + tid] = head ? key : -1;
+            } else if (head) {
+                red_add_f64(p.energies + key, e_total);
+            }
         }
     }
-    if (p.gather) {   // uniform branch: fused energy gather of a replica-sharded run
+    if (p.gather) {   // uniform branch: fused energy gather of a replica-sharded run (one tile per block)
         const int copier = gather_ticket<kBlock>(p);
         write_forces();
         if (copier >= 0) gather_copy<kBlock>(p, (unsigned) copier);
+    }
+    if (PERSIST) __syncwarp();   // the warp's smem slice is rewritten by the next tile's positions
+    tile += gridDim.x;
+    it++;
+    } while (PERSIST && tile < n_tiles);
+    if (defer) {
+        if (!waited) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            flush_parked(it < (unsigned) kDefer ? it : (unsigned) kDefer);
+        }
+        if (p.energies_clear) {
+            const unsigned n_clear = (unsigned) (p.n_replicas * p.n_slots);
+            for (unsigned c = blockIdx.x * kBlock + tid; c < n_clear; c += gridDim.x * kBlock) p.energies_clear[c] = 0.0;
+        }
     }
 }
 

@@ -11,7 +11,8 @@ namespace gfb {
 template <int NG, int FMODE, int FPATH, bool SINGLE>
 static void launch_lines4(const EvalParams& p, cudaStream_t stream) {
     constexpr int block = lines_block(NG);
-    const unsigned blocks = (unsigned) ((p.total + block - 1) / block);
+    unsigned blocks = (unsigned) ((p.total + block - 1) / block);
+    if (!SINGLE && p.defer && p.persist_blocks && p.persist_blocks < blocks) blocks = p.persist_blocks;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(blocks);
@@ -22,8 +23,14 @@ static void launch_lines4(const EvalParams& p, cudaStream_t stream) {
     attr.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = p.pdl ? 1 : 0;
-    if (p.grid_energies) cudaLaunchKernelEx(&cfg, gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, true>, p);
-    else cudaLaunchKernelEx(&cfg, gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, false>, p);
+    constexpr bool kPersistable = !SINGLE && (FMODE == GFB_FORCE_F64_ADD || FMODE == GFB_FORCE_FIXED_ADD || FMODE == kForceNone);
+    if (p.grid_energies) {
+        cudaLaunchKernelEx(&cfg, gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, true>, p);
+    } else if (kPersistable && p.defer) {
+        cudaLaunchKernelEx(&cfg, gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, false, kPersistable>, p);
+    } else {
+        cudaLaunchKernelEx(&cfg, gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, false>, p);
+    }
 }
 
 template <int NG, int FMODE, int FPATH>

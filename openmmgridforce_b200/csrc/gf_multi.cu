@@ -150,6 +150,59 @@ __global__ void __launch_bounds__(256) gf_gather_push_kernel(GatherTable* gt, co
     gather_publish<256>(gt, src, n, offset, blockIdx.x, gridDim.x);
 }
 
+// Device-side rendezvous of all ranks on their streams: every rank publishes its arrival number in its slot of every
+// peer's rendezvous row (third row of the flag array) and waits until all peers' numbers have reached its own row. With
+// `go` != nullptr the rank first waits until its own HOST has raised *go to go_value (host-mapped pinned word,
+// gfb_comm_rendezvous_release): the host enqueues the work that follows the rendezvous first and releases then, so that
+// when the ranks leave the rendezvous — within one NVLink round trip of each other — none of them has to wait for its
+// host to submit. One block; bounded like the gather wait (~20 s, then timed_out).
+__global__ void __launch_bounds__(32) gf_rendezvous_kernel(GatherTable* gt, const volatile unsigned int* go, unsigned int go_value) {
+    __shared__ int s_ok;
+    const unsigned lane = threadIdx.x;
+    if (lane == 0) s_ok = 1;
+    __syncwarp();
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    if (go != nullptr && lane == 0) {
+        for (unsigned spin = 0; *go < go_value; spin++) {
+            if ((spin & 255u) == 255u) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 20000000000ull) {
+                    s_ok = 0;
+                    break;
+                }
+            }
+            __nanosleep(200);
+        }
+    }
+    __syncwarp();
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&gt->rendezvous) + 1ull;
+    if (s_ok && (int) lane < gt->n_peers) {
+        unsigned long long* theirs = gt->peer_flags[lane] + 2 * kMaxPeers + gt->my_rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(seq) : "memory");
+        const unsigned long long* mine = gt->peer_flags[gt->my_rank] + 2 * kMaxPeers + lane;
+        for (unsigned spin = 0;; spin++) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+            if (v >= seq) break;
+            if ((spin & 1023u) == 1023u) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 20000000000ull) {
+                    s_ok = 0;
+                    break;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        if (!s_ok) gt->timed_out = 1u;
+        gt->rendezvous = seq;
+    }
+}
+
 // Launch with the programmatic-stream-serialization attribute (both gather kernels start with griddepcontrol.wait, so
 // the attribute only moves their block scheduling ahead of the previous kernel's end; the ordering is unchanged).
 template <typename... Args>
@@ -176,7 +229,7 @@ struct GatherMem {
     int alloc(size_t count) {
         count_total = count;
         flags_offset = round_up(2 * count * sizeof(double), 256);
-        bytes = flags_offset + 2 * kMaxPeers * sizeof(unsigned long long);
+        bytes = flags_offset + 3 * kMaxPeers * sizeof(unsigned long long);   // rows 0/1: gather parities, row 2: rendezvous
         CUDA_TRY(cudaMalloc(&base, bytes));
         CUDA_TRY(cudaMemset(base, 0, bytes));
         return GFB_OK;
@@ -221,6 +274,9 @@ struct gfb_comm {
     GatherTable* d_table;
     void* peer_base[kMaxPeers];   // cudaIpcOpenMemHandle mappings (self: mem.base)
     bool attached;
+    unsigned int* h_go;           // host-mapped pinned word the held rendezvous kernel polls (gfb_comm_rendezvous hold = 1)
+    unsigned int* d_go;           // its device address
+    unsigned int go_armed;        // value the most recent held rendezvous waits for
 };
 
 struct MultiShard {
@@ -331,6 +387,8 @@ int gfb_comm_create(gfb_device* dev, int world_size, int rank, const unsigned ch
     c->nccl = nullptr;
     c->d_table = nullptr;
     c->attached = false;
+    c->h_go = c->d_go = nullptr;
+    c->go_armed = 0;
     memset(c->peer_base, 0, sizeof c->peer_base);
     if (id) {   // id == NULL: no NCCL communicator (fused gather only)
         NcclApi* api = nccl_api();
@@ -359,6 +417,7 @@ int gfb_comm_destroy(gfb_comm* c) {
         if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
     if (c->mem.base) cudaFree(c->mem.base);
     if (c->d_table) cudaFree(c->d_table);
+    if (c->h_go) cudaFreeHost(c->h_go);
     delete c;
     return GFB_OK;
 }
@@ -447,6 +506,32 @@ int gfb_comm_gather_wait(gfb_comm* c, double* d_out, void* stream) {
     CUDA_TRY(launch_overlapped(gf_gather_wait_kernel, kWaitBlocks, 256, s, c->d_table, (const unsigned long long*) c->mem.flags(0),
                                (const double*) c->mem.data(0), d_out));
     g_launches++;
+    return GFB_OK;
+}
+
+int gfb_comm_rendezvous(gfb_comm* c, int hold, void* stream) {
+    if (!c || !c->attached) return fail(GFB_ERR_INVALID, "gfb_comm_rendezvous: communicator without attached gather memory");
+    CUDA_TRY(cudaSetDevice(c->dev->ordinal));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->dev->stream;
+    const unsigned int* go = nullptr;
+    if (hold) {
+        if (!c->h_go) {
+            CUDA_TRY(cudaHostAlloc((void**) &c->h_go, sizeof(unsigned int), cudaHostAllocMapped));
+            *c->h_go = 0u;
+            CUDA_TRY(cudaHostGetDevicePointer((void**) &c->d_go, c->h_go, 0));
+        }
+        c->go_armed++;
+        go = c->d_go;
+    }
+    gf_rendezvous_kernel<<<1, 32, 0, s>>>(c->d_table, go, c->go_armed);
+    CUDA_TRY(cudaGetLastError());
+    g_launches++;
+    return GFB_OK;
+}
+
+int gfb_comm_rendezvous_release(gfb_comm* c) {
+    if (!c || !c->h_go) return fail(GFB_ERR_INVALID, "gfb_comm_rendezvous_release: no held rendezvous was enqueued");
+    __atomic_store_n(c->h_go, c->go_armed, __ATOMIC_RELEASE);
     return GFB_OK;
 }
 

@@ -45,6 +45,8 @@ struct GatherTable {
     unsigned long long waited;                   // gathers this rank has consumed (gf_gather_wait_kernel)
     unsigned int wait_ticket;                    // blocks of the current wait kernel that have finished
     unsigned int copy_ticket;                    // copier blocks of the current gather that have finished their slice
+    unsigned long long rendezvous;               // device-side rendezvous of all ranks completed so far (gf_rendezvous_kernel);
+                                                 // its arrival flags are a third row of every rank's flag array
 };
 
 struct EvalParams {
@@ -72,6 +74,10 @@ struct EvalParams {
     unsigned div_magic;      // floor(2^32 / n_atoms) (saturated): t / n_atoms = umulhi(t, div_magic) or that + 1
     unsigned pdl;            // launch with programmatic stream serialization (gfb_kernel_set_launch_overlap)
     unsigned ahead_blocks;   // gf_eval_lines_kernel: blocks resident at once (SMs x blocks per SM); 0 = no position prefetch
+    unsigned defer;          // gf_eval_lines_kernel under launch overlap: park the energy sums of a block's first tiles and wait
+                             // for the previous grid once, at the block's end (ADD / no forces, no per-atom or per-grid energies)
+    unsigned persist_blocks; // gf_eval_lines_kernel: launch this many blocks (all resident) striding over the tiles; 0 = one
+                             // block per tile
     double near_int[3];      // 1.8e-15 * cells per axis: fractions this close to 0 or 1 take the exact division
     double* atom_energies;   // [n_replicas][n_atoms] or null: each evaluated atom's energy, summed over the grids, stored
                              // (GridForce::getParticleAtomEnergies)

@@ -57,10 +57,13 @@ def main():
     d_e = [torch.zeros(width, dtype=torch.float64, device=tdev) for _ in range(2)]
     stream = torch.cuda.Stream(device=tdev)
     fused, nccl = [], []
+    torch.cuda.synchronize()
     with torch.cuda.stream(stream):
         for step in range(3):           # three gathers: both parities, and reuse of a parity
             d_pos = torch.from_numpy(np.ascontiguousarray(w.pos[lo:hi] + shifts[step])).to(tdev)
             cur, nxt = d_e[step % 2], d_e[(step + 1) % 2]
+            # device-side rendezvous of all ranks before the step: plain, then held until the step has been enqueued
+            comm.rendezvous(stream.cuda_stream, hold=(step == 2))
             if step == 1:               # the stand-alone producer (same protocol) for one of the three gathers
                 k.execute_device(r, a, d_pos.data_ptr(), cur.data_ptr(), None, d_f.data_ptr(), gf.FORCE_FIXED_ADD, stride, None,
                                  stream.cuda_stream, d_energies_clear=nxt.data_ptr())
@@ -74,6 +77,8 @@ def main():
             padded = torch.empty(world * width, dtype=torch.float64, device=tdev)
             comm.all_gather(cur.data_ptr(), padded.data_ptr(), width, stream.cuda_stream)
             nccl.append(padded)
+            if step == 2:
+                comm.rendezvous_release()
     stream.synchronize()
     comm.gather_status()
     np.savez(os.path.join(xdir, f"out{rank}.npz"), fused=torch.stack(fused).cpu().numpy(), nccl=torch.stack(nccl).cpu().numpy(),

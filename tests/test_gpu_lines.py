@@ -289,6 +289,7 @@ def test_launch_overlap_pdl_gives_same_results(gpu_device, n_grids):
         d_f = torch.zeros(3 * stride, dtype=torch.int64, device=tdev)
         d_e = [torch.zeros(r, dtype=torch.float64, device=tdev) for _ in range(3)]
         kept = []
+        torch.cuda.synchronize()      # the zero fills ran on torch's default stream; `stream` does not order after it
         with torch.cuda.stream(stream):
             for i in range(15):
                 k.execute_device(r, a, sets[i % 5].data_ptr(), d_e[i % 3].data_ptr(), None, d_f.data_ptr(), gf.FORCE_FIXED_ADD, stride,
