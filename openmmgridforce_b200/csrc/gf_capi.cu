@@ -430,23 +430,15 @@ int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d
         const int per_sm = k->n_grids == 1 ? 6 : 1280 / block;
         const unsigned resident = (unsigned) (k->dev->prop.multiProcessorCount * per_sm);
         if (!ahead_off) p.ahead_blocks = resident;
-        // Launch overlap, small launches: a resident grid striding over the tiles with the energy atomics parked until
-        // the block's end (gf_eval_lines.cuh). Needs commutative (ADD) or no force writes and nothing else stored.
+        // Launch overlap, small launches: the launcher may pick the tile-striding variant (a resident grid, energy atomics
+        // parked until the block's end; gf_eval_lines.cuh / gf_launch_lines.cu). Needs commutative (ADD) or no force
+        // writes and nothing else stored.
         static const bool defer_off = env_off("GFB_DEFER");
-        static const double persist_max_waves = [] {
-            const char* e = getenv("GFB_PERSIST_MAX_WAVES");
-            return e ? atof(e) : 3.0;   // measured: 2.5 tiles per block 13.4 -> 11.6 us, 5 tiles 23.0 -> 24.3 us
-        }();
         const bool single = n_replicas == 1 && k->d_slots == nullptr;
         const bool add_or_none = d_forces == nullptr || force_mode == GFB_FORCE_FIXED_ADD || force_mode == GFB_FORCE_F64_ADD;
         if (x.overlap && !defer_off && !single && add_or_none && !x.gather && !x.atom_energies && !d_grid_energies) {
-            const unsigned long long tiles = (unsigned long long) ((p.total + block - 1) / block);
-            const unsigned grid = (unsigned) (k->dev->prop.multiProcessorCount * lines_persist_blocks_per_sm(k->n_grids));
-            if (tiles > grid && (double) tiles <= persist_max_waves * (double) grid) {
-                p.persist_blocks = grid;
-                p.defer = 1u;
-                if (!ahead_off) p.ahead_blocks = grid;
-            }
+            p.defer = 1u;
+            p.persist_blocks = (unsigned) k->dev->prop.multiProcessorCount;
         }
         launch_lines(p, force_mode, force_path_default(k->n_grids), stream);
     } else if (lines64) {

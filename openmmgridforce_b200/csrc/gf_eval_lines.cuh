@@ -136,8 +136,14 @@ __host__ __device__ constexpr int lines_block(int ng) { return ng == 1 ? 256 : G
                                           // registers) the loop-carried state spills and a 1/8 shard of C5 takes 14.05 us
                                           // instead of 11.60 (13.43 with one block per tile)
 #endif
+#ifndef GFB_PERSIST_DEFER
+#define GFB_PERSIST_DEFER 3               // tiles whose energy sums a block of the tile-striding variant can park (12 bytes per thread each)
+#endif
+#ifndef GFB_PERSIST_BLOCKS_NG1
+#define GFB_PERSIST_BLOCKS_NG1 6
+#endif
 __host__ __device__ constexpr int lines_blocks_per_sm(int ng, bool persist) {
-    return ng == 1 ? 6 : (persist ? GFB_PERSIST_THREADS_PER_SM : 1280) / lines_block(ng);
+    return ng == 1 ? (persist ? GFB_PERSIST_BLOCKS_NG1 : 6) : (persist ? GFB_PERSIST_THREADS_PER_SM : 1280) / lines_block(ng);
 }
 
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr) {
@@ -165,8 +171,6 @@ __global__ void __launch_bounds__(lines_block(NG), lines_blocks_per_sm(NG, PERSI
     __shared__ __align__(128) double2 s_pos2[(kBlock / 32) * kWarpSlice16];
     float4* const s_rec = reinterpret_cast<float4*>(s_pos2);
 
-    const unsigned tid = threadIdx.x;
-    const unsigned lane = tid & 31u;
     const unsigned total = (unsigned) p.total;
     // Programmatic dependent launch (sm_90+): let the NEXT launch on this stream start its blocks as soon as all of ours
     // have started, so that its position/record fetches overlap our tail; it blocks at griddepcontrol.wait (below, before
@@ -186,26 +190,30 @@ __global__ void __launch_bounds__(lines_block(NG), lines_blocks_per_sm(NG, PERSI
     constexpr bool kAddMode = FMODE == GFB_FORCE_F64_ADD || FMODE == GFB_FORCE_FIXED_ADD;
     constexpr bool kCanDefer = PERSIST && !SINGLE && !GE && (kAddMode || FMODE == kForceNone);
     static_assert(!PERSIST || kCanDefer, "the tile-striding variant exists for the deferred-energy modes only");
-#ifndef GFB_PERSIST_DEFER
-#define GFB_PERSIST_DEFER 2
-#endif
     constexpr int kDefer = GFB_PERSIST_DEFER;
     __shared__ double s_def_e[kCanDefer ? kDefer * kBlock : 1];
     __shared__ int s_def_k[kCanDefer ? kDefer * kBlock : 1];
-    const bool defer = kCanDefer && p.defer != 0u;   // uniform
-    bool waited = false;
+    constexpr bool defer = kCanDefer;   // the host launches the PERSIST instantiations for deferred launches only (p.defer)
     auto flush_parked = [&](unsigned n) {
         if (kCanDefer && p.energies) {
             for (unsigned j = 0; j < n; j++) {
-                const int k = s_def_k[j * kBlock + tid];
-                if (k >= 0) red_add_f64(p.energies + k, s_def_e[j * kBlock + tid]);
+                const int k = s_def_k[j * kBlock + threadIdx.x];
+                if (k >= 0) red_add_f64(p.energies + k, s_def_e[j * kBlock + threadIdx.x]);
             }
         }
     };
     const unsigned n_tiles = (total + (unsigned) kBlock - 1u) / (unsigned) kBlock;
+    // Loop state is ONE register (it): the tile follows from it, and "has this block waited for the previous grid" is
+    // it > kDefer. tid is laundered through an empty asm every iteration so that the lane-derived addresses below are
+    // recomputed (a few integer instructions) instead of being hoisted out of the loop and kept alive across it — hoisted,
+    // they cost 48 bytes of spills at 48 registers.
     unsigned it = 0;
-    unsigned tile = blockIdx.x;
     do {
+    unsigned tid = threadIdx.x;
+    if (PERSIST) asm volatile("" : "+r"(tid));
+    const unsigned lane = tid & 31u;
+    const unsigned tile = blockIdx.x + it * gridDim.x;
+    const bool waited = PERSIST ? it > (unsigned) kDefer : false;   // uniform
     const unsigned t0 = tile * kBlock;
     const unsigned t = t0 + tid;
     const bool active = t < total;
@@ -248,8 +256,8 @@ __global__ void __launch_bounds__(lines_block(NG), lines_blocks_per_sm(NG, PERSI
 
     // Positions of the block that will run in this block's SM slot NEXT (p.ahead_blocks = resident blocks of the launch)
     // are pulled into L2 now: when that block starts, its first dependent load is an L2 hit instead of a DRAM round trip.
-    if (p.ahead_blocks && plain) {
-        const unsigned long long first = ((unsigned long long) tile + p.ahead_blocks) * kBlock;   // its first atom
+    if (p.ahead_blocks && plain) {   // PERSIST: that block is this one, at its next tile
+        const unsigned long long first = ((unsigned long long) tile + (PERSIST ? gridDim.x : p.ahead_blocks)) * kBlock;   // its first atom
         if (first < total && tid < (kBlock * 24u + 127u) / 128u) {
             const char* line = reinterpret_cast<const char*>(p.pos + 3 * first) + 128u * tid;
             if (line < reinterpret_cast<const char*>(p.pos + 3 * (size_t) total)) prefetch_l2(line);
@@ -405,10 +413,9 @@ __global__ void __launch_bounds__(lines_block(NG), lines_blocks_per_sm(NG, PERSI
     };
     if (kAdd && early_forces && active && p.forces) add_forces();
     const bool park = defer && !waited && it < (unsigned) kDefer;   // uniform: this tile's energies are parked
-    if (!park && !waited) {
+    if (!park && !waited) {   // PERSIST: exactly the tile it == kDefer
         asm volatile("griddepcontrol.wait;" ::: "memory");
-        waited = true;
-        if (defer) flush_parked(it < (unsigned) kDefer ? it : (unsigned) kDefer);
+        if (defer) flush_parked((unsigned) kDefer);
     }
     if (!defer && p.energies_clear && t < (unsigned) (p.n_replicas * p.n_slots)) p.energies_clear[t] = 0.0;
     if (p.atom_energies && active) p.atom_energies[a] = e_total;   // uniform branch (never with p.defer)
@@ -522,17 +529,16 @@ __global__ void __launch_bounds__(lines_block(NG), lines_blocks_per_sm(NG, PERSI
         if (copier >= 0) gather_copy<kBlock>(p, (unsigned) copier);
     }
     if (PERSIST) __syncwarp();   // the warp's smem slice is rewritten by the next tile's positions
-    tile += gridDim.x;
     it++;
-    } while (PERSIST && tile < n_tiles);
+    } while (PERSIST && blockIdx.x + it * gridDim.x < n_tiles);
     if (defer) {
-        if (!waited) {
+        if (it <= (unsigned) kDefer) {   // every tile of this block was parked: the one wait comes here
             asm volatile("griddepcontrol.wait;" ::: "memory");
-            flush_parked(it < (unsigned) kDefer ? it : (unsigned) kDefer);
+            flush_parked(it);
         }
         if (p.energies_clear) {
             const unsigned n_clear = (unsigned) (p.n_replicas * p.n_slots);
-            for (unsigned c = blockIdx.x * kBlock + tid; c < n_clear; c += gridDim.x * kBlock) p.energies_clear[c] = 0.0;
+            for (unsigned c = blockIdx.x * kBlock + threadIdx.x; c < n_clear; c += gridDim.x * kBlock) p.energies_clear[c] = 0.0;
         }
     }
 }

@@ -32,12 +32,6 @@ inline void launch_lines(const EvalParams& p, int fmode, int fpath, cudaStream_t
 #define GFB_LINES_BLOCK_MULTI 64
 #endif
 constexpr int lines_block_threads(int n_grids) { return n_grids == 1 ? 256 : GFB_LINES_BLOCK_MULTI; }
-#ifndef GFB_PERSIST_THREADS_PER_SM
-#define GFB_PERSIST_THREADS_PER_SM 1024
-#endif
-// Blocks per SM the tile-striding variant is compiled for (its __launch_bounds__): the grid of a small launch under
-// launch overlap is SMs x this.
-constexpr int lines_persist_blocks_per_sm(int n_grids) { return n_grids == 1 ? 6 : GFB_PERSIST_THREADS_PER_SM / lines_block_threads(n_grids); }
 
 // gf_eval_lines_f64_kernel (gf_eval_lines_f64.cuh): DOUBLE 256-byte records, 2-4 grids of one geometry, no inv-power.
 void launch_lines_f64(const EvalParams& p, int fmode, cudaStream_t stream);

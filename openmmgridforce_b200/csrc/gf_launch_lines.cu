@@ -1,6 +1,8 @@
 // gf_eval_lines_kernel launcher (MIXED packed cells / 128-byte records). See gf_launch.h.
 // GFB_LINES_NG selects which grid counts this translation unit instantiates (the Makefile builds one object per count so
 // that they compile in parallel); undefined = all four.
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "gf_eval_lines.cuh"
@@ -8,11 +10,48 @@
 
 namespace gfb {
 
+// Tunables of the tile-striding launch (A/B measurements; defaults measured on B200).
+static double env_double(const char* name, double dflt) {
+    const char* e = getenv(name);
+    return e ? atof(e) : dflt;
+}
+
 template <int NG, int FMODE, int FPATH, bool SINGLE>
-static void launch_lines4(const EvalParams& p, cudaStream_t stream) {
+static void launch_lines4(const EvalParams& p_in, cudaStream_t stream) {
     constexpr int block = lines_block(NG);
+    EvalParams p = p_in;
     unsigned blocks = (unsigned) ((p.total + block - 1) / block);
-    if (!SINGLE && p.defer && p.persist_blocks && p.persist_blocks < blocks) blocks = p.persist_blocks;
+    constexpr bool kPersistable = !SINGLE && (FMODE == GFB_FORCE_F64_ADD || FMODE == GFB_FORCE_FIXED_ADD || FMODE == kForceNone);
+    bool persist = false;
+    if (kPersistable && p.defer && !p.grid_energies) {
+        // Small launch under launch overlap: a grid that is resident all at once strides over the tiles (gf_eval_lines.cuh).
+        // resident = SMs x blocks of THIS instantiation per SM (asked from the runtime: registers, parked-energy smem).
+        // Depth D: the grid is resident / D blocks, so that D consecutive launches share the SMs and every block still
+        // runs >= min_tiles tiles — a launch whose blocks live for one or two tiles is over before the launch behind it
+        // has been scheduled, and the freed slots sit empty for that latency.
+        static const int per_sm = [] {
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, false, kPersistable>, block, 0) != cudaSuccess || n < 1)
+                n = 1;
+            return n;
+        }();
+        // A block must be able to park ALL its tiles (GFB_PERSIST_DEFER): one that reaches its wait before the end stalls
+        // there until the launch in front — which started at almost the same time — is over (measured: 11.1 -> 18.1 us).
+        static const double max_waves = env_double("GFB_PERSIST_MAX_WAVES", 3.0);   // 2.5 tiles per block 13.4 -> 10.9 us, 5 tiles 23.0 -> 24.3 us
+        static const int max_depth = (int) env_double("GFB_PERSIST_MAX_DEPTH", 2.0);
+        const double resident = (double) p.persist_blocks * per_sm;   // p.persist_blocks carries the SM count
+        const double tiles = (double) blocks;
+        if (tiles > resident / max_depth && tiles <= max_waves * resident) {
+            int depth = (int) floor((double) GFB_PERSIST_DEFER * resident / tiles);
+            depth = depth < 1 ? 1 : (depth > max_depth ? max_depth : depth);
+            const unsigned grid = (unsigned) ceil(resident / depth);
+            if (grid < blocks) {
+                blocks = grid;
+                persist = true;
+            }
+        }
+    }
+    p.defer = persist ? 1u : 0u;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(blocks);
@@ -23,10 +62,9 @@ static void launch_lines4(const EvalParams& p, cudaStream_t stream) {
     attr.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = p.pdl ? 1 : 0;
-    constexpr bool kPersistable = !SINGLE && (FMODE == GFB_FORCE_F64_ADD || FMODE == GFB_FORCE_FIXED_ADD || FMODE == kForceNone);
     if (p.grid_energies) {
         cudaLaunchKernelEx(&cfg, gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, true>, p);
-    } else if (kPersistable && p.defer) {
+    } else if (kPersistable && persist) {
         cudaLaunchKernelEx(&cfg, gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, false, kPersistable>, p);
     } else {
         cudaLaunchKernelEx(&cfg, gf_eval_lines_kernel<NG, FMODE, FPATH, SINGLE, false>, p);

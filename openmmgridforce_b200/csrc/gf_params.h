@@ -74,10 +74,9 @@ struct EvalParams {
     unsigned div_magic;      // floor(2^32 / n_atoms) (saturated): t / n_atoms = umulhi(t, div_magic) or that + 1
     unsigned pdl;            // launch with programmatic stream serialization (gfb_kernel_set_launch_overlap)
     unsigned ahead_blocks;   // gf_eval_lines_kernel: blocks resident at once (SMs x blocks per SM); 0 = no position prefetch
-    unsigned defer;          // gf_eval_lines_kernel under launch overlap: park the energy sums of a block's first tiles and wait
-                             // for the previous grid once, at the block's end (ADD / no forces, no per-atom or per-grid energies)
-    unsigned persist_blocks; // gf_eval_lines_kernel: launch this many blocks (all resident) striding over the tiles; 0 = one
-                             // block per tile
+    unsigned defer;          // host -> launcher: this launch MAY run the tile-striding variant of gf_eval_lines_kernel (launch
+                             // overlap, ADD / no forces, no per-atom or per-grid energies); launcher -> kernel: it does
+    unsigned persist_blocks; // with defer, host -> launcher: the device's SM count (the launcher sizes the resident grid)
     double near_int[3];      // 1.8e-15 * cells per axis: fractions this close to 0 or 1 take the exact division
     double* atom_energies;   // [n_replicas][n_atoms] or null: each evaluated atom's energy, summed over the grids, stored
                              // (GridForce::getParticleAtomEnergies)

@@ -81,13 +81,13 @@ def report(tag, evals, t):
 names = sys.argv[1:] or ["modes", "strong", "double", "e2e", "c4", "c3", "c3sort"]
 MODES = ((gf.FORCE_FIXED_ADD, "fixed_add"), (gf.FORCE_F64_STORE, "f64_store"), (gf.FORCE_F32_STORE, "f32_store"), (NONE, "energy_only"))
 
-if any(n in names for n in ("modes", "strong", "double", "e2e")):
+if any(n in names for n in ("modes", "strong", "double", "e2e", "sweep")):
     w = W.c5_sharded_replicas()
     w2 = W.c5_sharded_replicas(pose_seed=W.SEED + 101)
     for precision, pname in ((gf.PRECISION_MIXED, "mixed"), (gf.PRECISION_DOUBLE, "double")):
         if precision == gf.PRECISION_DOUBLE and "double" not in names:
             continue
-        if precision == gf.PRECISION_MIXED and not any(n in names for n in ("modes", "strong", "e2e")):
+        if precision == gf.PRECISION_MIXED and not any(n in names for n in ("modes", "strong", "e2e", "sweep")):
             continue
         grids = [gf.Grid(dev, w.counts, w.spacing, w.origin, v, precision) for v in w.grids]
         k = gf.Kernel(dev, grids, w.scaling, oob_k=w.oob_k)
@@ -107,6 +107,14 @@ if any(n in names for n in ("modes", "strong", "double", "e2e")):
                     k.set_launch_overlap(pdl)
                     t = time_steps(k, r, w.n_atoms, sets, gf.FORCE_FIXED_ADD, iters=20 * n_gpu, graph=graph)
                     report(f"C5 shard 1/{n_gpu} ({r} replicas) pdl={int(pdl)} graph={int(graph)}", r * w.n_atoms * w.n_grids, t)
+        if "sweep" in names and precision == gf.PRECISION_MIXED:
+            # batch-size sweep on the C5 grids, launch overlap + graph: where the small-launch machinery matters
+            for r in (512, 1024, 2048, 3072, 4096, 6144, 8192, 12288, 16384):
+                n_sets = max(2, min(32, 65536 // r))
+                sets = [full[j % 2][(j // 2) * r:(j // 2 + 1) * r].contiguous() for j in range(n_sets)]
+                k.set_launch_overlap(True)
+                t = time_steps(k, r, w.n_atoms, sets, gf.FORCE_FIXED_ADD, iters=4 * n_sets, graph=True)
+                report(f"C5 grids, {r} replicas per launch, pdl=1 graph=1", r * w.n_atoms * w.n_grids, t)
         if "e2e" in names and precision == gf.PRECISION_MIXED:
             k.set_launch_overlap(False)
             pos_h = torch.from_numpy(w.pos.copy()).pin_memory()
