@@ -436,7 +436,9 @@ int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d
         static const bool defer_off = env_off("GFB_DEFER");
         const bool single = n_replicas == 1 && k->d_slots == nullptr;
         const bool add_or_none = d_forces == nullptr || force_mode == GFB_FORCE_FIXED_ADD || force_mode == GFB_FORCE_F64_ADD;
-        if (x.overlap && !defer_off && !single && add_or_none && !x.gather && !x.atom_energies && !d_grid_energies) {
+        const bool plain = k->d_particles == nullptr && n_particles == n_atoms && d_order == nullptr && k->d_slots == nullptr &&
+                           d_energies != nullptr && (reinterpret_cast<uintptr_t>(d_pos) & 15) == 0;
+        if (x.overlap && !defer_off && !single && plain && add_or_none && !x.gather && !x.atom_energies && !d_grid_energies) {
             p.defer = 1u;
             p.persist_blocks = (unsigned) k->dev->prop.multiProcessorCount;
         }

@@ -37,7 +37,10 @@ static void launch_lines4(const EvalParams& p_in, cudaStream_t stream) {
         }();
         // A block must be able to park ALL its tiles (GFB_PERSIST_DEFER): one that reaches its wait before the end stalls
         // there until the launch in front — which started at almost the same time — is over (measured: 11.1 -> 18.1 us).
-        static const double max_waves = env_double("GFB_PERSIST_MAX_WAVES", 3.0);   // 2.5 tiles per block 13.4 -> 10.9 us, 5 tiles 23.0 -> 24.3 us
+        // Tiles per block up to which the variant pays (C5 grids, 47-atom replicas, us per launch, one block per tile ->
+        // tile-striding): 4096 replicas 8.6 -> 6.2, 8192 (2.5 tiles) 13.4 -> 10.8, 12288 (3.8) 18.3 -> 15.9, 16384 (5.1)
+        // 23.2 -> 21.7, 32768 (10.2) 41.4 -> 47.0, 65536 83.2 -> 91.5: it runs 32 warps per SM instead of 40.
+        static const double max_waves = env_double("GFB_PERSIST_MAX_WAVES", 6.0);
         static const int max_depth = (int) env_double("GFB_PERSIST_MAX_DEPTH", 2.0);
         const double resident = (double) p.persist_blocks * per_sm;   // p.persist_blocks carries the SM count
         const double tiles = (double) blocks;
