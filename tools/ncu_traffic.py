@@ -1,7 +1,7 @@
 """DRAM bytes per launch of the profiled kernel out of `ncu --page raw --csv` files -> profiles/r2_traffic.json, keyed by
 the bench.py workload name and stamped with the hash of the kernel sources (bench.py reports `roofline.traffic` only while
 the sources still hash to what was profiled).
-usage: python tools/ncu_traffic.py KEY=raw.csv [KEY=raw.csv ...]     e.g. C5=profiles/r2_c5full_raw.csv"""
+usage: python tools/ncu_traffic.py KEY=raw.csv[=caveat] [...]     e.g. C5=profiles/r2b_c5full_raw.csv"""
 import csv
 import importlib.util
 import json
@@ -17,6 +17,9 @@ out_path = os.path.join(ROOT, "profiles", "r2_traffic.json")
 doc = json.load(open(out_path)) if os.path.exists(out_path) else {}
 for arg in sys.argv[1:]:
     key, path = arg.split("=", 1)
+    note = None
+    if "=" in path:      # KEY=raw.csv=free-text caveat carried into bench.py's traffic_source
+        path, note = path.split("=", 1)
     rows = list(csv.reader(open(path)))
     hdr, units = rows[0], rows[1]
     r = rows[2]
@@ -32,5 +35,7 @@ for arg in sys.argv[1:]:
                 "dram_bytes_per_launch": rd + wr, "duration_us_under_ncu": val("gpu__time_duration.sum"),
                 "source": os.path.relpath(path, ROOT) + " (ncu --set full --clock-control none --cache-control none, one warm launch)",
                 "source_sha256_16": bench.kernel_source_hash()}
+    if note:
+        doc[key]["source"] += "; " + note
     print(key, doc[key]["kernel"][:60], f"{(rd + wr) / 1e6:.1f} MB")
 json.dump(doc, open(out_path, "w"), indent=1, sort_keys=True)
