@@ -268,6 +268,8 @@ class DeviceLoop:
                 elif last and self.gather_mode == "push":
                     self.comm.gather_push(e.data_ptr(), self.r, self.lo, s)
                     self.comm.gather_wait(self.d_gathered.data_ptr(), s)
+                elif last and self.gather_mode == "ll":
+                    self.comm.gather(e.data_ptr(), self.r, self.lo, self.d_gathered.data_ptr(), s)
             if count:
                 self.set_evals[si] += 1
             self.last = (si, acc[j])
@@ -300,7 +302,7 @@ class DeviceLoop:
                 # N > 1: the host barrier lets the ranks go tens of microseconds apart, and the window's one collective
                 # (the energy gather) would be charged that skew. A device-side rendezvous in front of the first event
                 # starts all ranks within an NVLink round trip; it is held until this rank's window has been enqueued.
-                rendezvous = self.comm is not None and barrier is not None and self.gather_mode != "none" and RENDEZVOUS
+                rendezvous = self.comm is not None and barrier is not None and RENDEZVOUS
                 if rendezvous:
                     self.comm.rendezvous(self.stream.cuda_stream, hold=True)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -322,7 +324,7 @@ class DeviceLoop:
         self.kern.set_launch_overlap(False)
         if reduce_max is not None:
             out = reduce_max(out)
-        launches = steps + {"fused": 1, "push": 2}.get(self.gather_mode, 0)
+        launches = steps + {"fused": 1, "push": 2, "ll": 1}.get(self.gather_mode, 0)
         return out, launches
 
     def _count_replay(self, first, steps):
@@ -653,10 +655,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default=os.environ.get("GFB_BENCH_SCALING", "strong"), choices=["strong", "weak"],
                     help="N>1: strong = the named config (65,536 replicas in total, sharded); weak = 65,536 per GPU")
-    ap.add_argument("--energy-gather", default=os.environ.get("GFB_ENERGY_GATHER", "push"), choices=["push", "fused", "nccl"],
-                    help="N>1: the one gather of per-replica energies after the last step — push: peer stores over NVLink + "
-                         "arrival flags by a small kernel of this library behind the last launch (default, measured fastest); "
-                         "fused: the same stores from the tail of the last evaluation launch; nccl: ncclAllGather. The "
+    ap.add_argument("--energy-gather", default=os.environ.get("GFB_ENERGY_GATHER", "ll"), choices=["ll", "push", "fused", "nccl"],
+                    help="N>1: the one gather of per-replica energies after the last step — ll: ONE kernel of this library "
+                         "behind the last launch, flag-in-data packets over the NVLink peer mappings (publish + wait + copy-out, "
+                         "no fence, no flag round; default); push: peer stores + arrival flags by one kernel, wait + copy-out "
+                         "by a second; fused: the push from the tail of the last evaluation launch; nccl: ncclAllGather. The "
                          "result is checked against another method outside the timed region.")
     ap.add_argument("--windows", type=int, default=5, help="timed K-step windows (median reported)")
     ap.add_argument("--no-extras", action="store_true", help="skip C2/C3/C4/C5 variants and the CPU baseline (N=1 only)")
@@ -743,7 +746,7 @@ def main():
         # the gathered energies of the last window must equal the OTHER gather method's result on the same accumulators
         si, ai = loop.last
         other = torch.zeros(total, dtype=torch.float64, device=tdev)
-        if gather_mode in ("fused", "push"):
+        if gather_mode in ("fused", "push", "ll"):
             comm.all_gather(loop.d_e[ai].data_ptr(), other.data_ptr(), loop.r, stream.cuda_stream)
         else:
             dist.all_gather_into_tensor(other, loop.d_e[ai])

@@ -342,6 +342,12 @@ GFB_API int gfb_kernel_execute_device_gather(gfb_kernel* k, int n_replicas, int 
  * gather_offset and raises the arrival flags, stream-ordered after whatever produced d_energies. Same protocol as the
  * fused tail (one more small launch, nothing added to the evaluation kernel); pair it with gfb_comm_gather_wait. */
 GFB_API int gfb_comm_gather_push(gfb_comm* c, const double* d_energies, size_t count, size_t gather_offset, void* stream);
+/* The whole gather as ONE kernel, flag-in-data: every double travels to every rank as a 16-byte packet that carries the
+ * gather's sequence number in both 8-byte halves, so the data is its own arrival flag — no fence, no flag round, no
+ * second launch (NCCL's LL protocol, over this library's peer mappings). The kernel stores this rank's `count` values into
+ * every rank's packet array at gather_offset, then polls this rank's packet array until all count_total values of this
+ * gather have arrived and writes them to d_out. Every rank calls it once per gather, in the same order; capturable. */
+GFB_API int gfb_comm_gather(gfb_comm* c, const double* d_energies, size_t count, size_t gather_offset, double* d_out, void* stream);
 /* Waits (on `stream`, device side) until every rank's slice of the oldest gather not yet consumed has arrived, then
  * copies the complete [count_total] array into d_out (device memory of the caller). Gather sequence numbers live on the
  * device, so a launch/wait sequence captured with gfb_graph_* can be replayed. A peer that does not arrive within ~20 s

@@ -98,6 +98,7 @@ SIGNATURES = {
     "gfb_comm_gather_wait": (_i, [_vp, _vp, _vp]),
     "gfb_comm_gather_push": (_i, [_vp, _vp, _sz, _sz, _vp]),
     "gfb_comm_gather_status": (_i, [_vp]),
+    "gfb_comm_gather": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),
     "gfb_comm_rendezvous": (_i, [_vp, _i, _vp]),
     "gfb_comm_rendezvous_release": (_i, [_vp]),
     "gfb_multi_create": (_i, [_i, _pi, C.POINTER(_vp)]),
@@ -519,6 +520,10 @@ class Comm:
     def gather_push(self, d_energies, count, gather_offset, stream=0):
         """Stand-alone producer of the peer-store gather (same protocol as the fused tail, as its own small kernel)."""
         _check(load_library().gfb_comm_gather_push(self._h, _ptr(d_energies), count, gather_offset, _ptr(stream or None)))
+
+    def gather(self, d_energies, count, gather_offset, d_out, stream=0):
+        """The whole gather as one flag-in-data kernel: this rank's `count` values out to every rank, all count_total in to d_out."""
+        _check(load_library().gfb_comm_gather(self._h, _ptr(d_energies), count, gather_offset, _ptr(d_out), _ptr(stream or None)))
 
     def gather_wait(self, d_out, stream=0):
         """Enqueues the wait for the oldest unconsumed fused gather; the complete array is copied to device address d_out."""

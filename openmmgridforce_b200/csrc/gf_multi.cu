@@ -203,6 +203,65 @@ __global__ void __launch_bounds__(32) gf_rendezvous_kernel(GatherTable* gt, cons
     }
 }
 
+// Flag-in-data gather: publish + wait + copy-out in ONE kernel with no fence, no ticket and no flag round on the critical
+// path (the protocol NCCL calls LL). Every double travels as a 16-byte packet {lo32, seq, hi32, seq}: the 8-byte halves
+// are written atomically, so a consumer that sees seq in both halves holds the whole value — the data is its own arrival
+// flag. Each block first stores its share of this rank's slice into every peer's packet array (plain 16-byte stores over
+// the NVLink peer mappings, staggered start), then polls its share of THIS rank's packet array — all ranks' slices, its
+// own included — and writes the values to `out`. Critical path after the producing kernel: one L2 read, one NVLink
+// one-way trip, one poll. Packet arrays are double-buffered by the parity of seq: a rank can start gather k+2 only after
+// its gather k+1 has seen every peer's k+1 packets, which those peers sent after finishing their gather k (stream order),
+// i.e. after they stopped reading buffer k%2. seq lives in device memory (graph replay). Bounded spin as everywhere else.
+constexpr int kLLBlocks = 64;
+__global__ void __launch_bounds__(256) gf_gather_ll_kernel(GatherTable* gt, const double* src, int n, long long offset, double* out) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // src is complete (the evaluation launch in front)
+    const unsigned long long seq64 = *reinterpret_cast<volatile unsigned long long*>(&gt->ll_seq) + 1ull;
+    const unsigned seq = (unsigned) seq64;
+    const long long total = gt->count_total;
+    const long long buf = (long long) (seq & 1u) * total;
+    const int np = gt->n_peers, me = gt->my_rank;
+    const unsigned gtid = blockIdx.x * 256u + threadIdx.x, gsize = gridDim.x * 256u;
+    for (unsigned i = gtid; i < (unsigned) n; i += gsize) {
+        const double v = __ldcg(src + i);
+        const unsigned lo = (unsigned) __double2loint(v), hi = (unsigned) __double2hiint(v);
+        for (int r = 0; r < np; r++) {
+            char* base = reinterpret_cast<char*>(gt->peer_data[(me + 1 + r) % np]) + gt->ll_offset;
+            uint4* dst = reinterpret_cast<uint4*>(base) + buf + offset + i;
+            asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(seq), "r"(hi), "r"(seq) : "memory");
+        }
+    }
+    const uint4* mine = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(gt->peer_data[me]) + gt->ll_offset) + buf;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    bool ok = true;
+    for (long long j = gtid; j < total && ok; j += gsize) {
+        unsigned a, b, c, d;
+        for (unsigned spin = 0;; spin++) {
+            asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(mine + j) : "memory");
+            if (b == seq && d == seq) break;
+            if ((spin & 4095u) == 4095u) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 20000000000ull) {
+                    gt->timed_out = 1u;
+                    ok = false;
+                    break;
+                }
+            }
+        }
+        if (ok && out) out[j] = __hiloint2double((int) c, (int) a);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&gt->ll_ticket, 1u) == gridDim.x - 1) {   // every block has read ll_seq by now
+            gt->ll_seq = seq64;
+            gt->ll_ticket = 0;
+        }
+    }
+}
+
 // Launch with the programmatic-stream-serialization attribute (both gather kernels start with griddepcontrol.wait, so
 // the attribute only moves their block scheduling ahead of the previous kernel's end; the ordering is unchanged).
 template <typename... Args>
@@ -225,11 +284,12 @@ size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // This rank's gather memory: [2][count_total] doubles, then [2][kMaxPeers] arrival flags.
 struct GatherMem {
     void* base = nullptr;
-    size_t count_total = 0, flags_offset = 0, bytes = 0;
+    size_t count_total = 0, flags_offset = 0, ll_offset = 0, bytes = 0;
     int alloc(size_t count) {
         count_total = count;
         flags_offset = round_up(2 * count * sizeof(double), 256);
-        bytes = flags_offset + 3 * kMaxPeers * sizeof(unsigned long long);   // rows 0/1: gather parities, row 2: rendezvous
+        ll_offset = round_up(flags_offset + 3 * kMaxPeers * sizeof(unsigned long long), 256);   // flag rows 0/1: gather parities, 2: rendezvous
+        bytes = ll_offset + 2 * count * 16;                                                      // flag-in-data packets, [2][count]
         CUDA_TRY(cudaMalloc(&base, bytes));
         CUDA_TRY(cudaMemset(base, 0, bytes));
         return GFB_OK;
@@ -249,6 +309,7 @@ int upload_table(const GatherMem& mine, void* const* peer_base, int world, int r
         t.peer_flags[r] = reinterpret_cast<unsigned long long*>(static_cast<char*>(peer_base[r]) + mine.flags_offset);
     }
     t.count_total = (long long) mine.count_total;
+    t.ll_offset = (long long) mine.ll_offset;
     t.n_peers = world;
     t.my_rank = rank;
     if (!*d_table) CUDA_TRY(cudaMalloc((void**) d_table, sizeof t));
@@ -494,6 +555,18 @@ int gfb_comm_gather_push(gfb_comm* c, const double* d_energies, size_t count, si
     CUDA_TRY(cudaSetDevice(c->dev->ordinal));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->dev->stream;
     CUDA_TRY(launch_overlapped(gf_gather_push_kernel, kPushBlocks, 256, s, c->d_table, d_energies, (int) count, (long long) gather_offset));
+    g_launches++;
+    return GFB_OK;
+}
+
+int gfb_comm_gather(gfb_comm* c, const double* d_energies, size_t count, size_t gather_offset, double* d_out, void* stream) {
+    if (!c || !c->attached) return fail(GFB_ERR_INVALID, "gfb_comm_gather: communicator without attached gather memory");
+    if (!d_energies || count == 0 || !d_out) return fail(GFB_ERR_INVALID, "gfb_comm_gather: NULL or empty argument");
+    if (gather_offset + count > c->mem.count_total || count > 0x7fffffffull)
+        return fail(GFB_ERR_INVALID, "gfb_comm_gather: slice [%zu, +%zu) exceeds the gathered array (%zu)", gather_offset, count, c->mem.count_total);
+    CUDA_TRY(cudaSetDevice(c->dev->ordinal));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->dev->stream;
+    CUDA_TRY(launch_overlapped(gf_gather_ll_kernel, kLLBlocks, 256, s, c->d_table, d_energies, (int) count, (long long) gather_offset, d_out));
     g_launches++;
     return GFB_OK;
 }

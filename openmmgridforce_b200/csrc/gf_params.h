@@ -47,6 +47,12 @@ struct GatherTable {
     unsigned int copy_ticket;                    // copier blocks of the current gather that have finished their slice
     unsigned long long rendezvous;               // device-side rendezvous of all ranks completed so far (gf_rendezvous_kernel);
                                                  // its arrival flags are a third row of every rank's flag array
+    // Flag-in-data gather (gf_gather_ll_kernel): every rank's memory also holds [2][count_total] 16-byte packets
+    // {lo32, seq32, hi32, seq32} at byte offset ll_offset from peer_data[r]; a packet is valid for gather number seq once
+    // both of its 8-byte halves carry seq.
+    long long ll_offset;
+    unsigned long long ll_seq;                   // flag-in-data gathers completed by this rank
+    unsigned int ll_ticket;                      // blocks of the current flag-in-data gather that have finished
 };
 
 struct EvalParams {

@@ -56,7 +56,7 @@ def main():
     d_f = torch.zeros(3 * stride, dtype=torch.int64, device=tdev)
     d_e = [torch.zeros(width, dtype=torch.float64, device=tdev) for _ in range(2)]
     stream = torch.cuda.Stream(device=tdev)
-    fused, nccl = [], []
+    fused, nccl, ll = [], [], []
     torch.cuda.synchronize()
     with torch.cuda.stream(stream):
         for step in range(3):           # three gathers: both parities, and reuse of a parity
@@ -74,6 +74,9 @@ def main():
             got = torch.full((n_total,), float("nan"), dtype=torch.float64, device=tdev)
             comm.gather_wait(got.data_ptr(), stream.cuda_stream)
             fused.append(got)
+            got_ll = torch.full((n_total,), float("nan"), dtype=torch.float64, device=tdev)
+            comm.gather(cur.data_ptr(), r, lo, got_ll.data_ptr(), stream.cuda_stream)      # the one-kernel flag-in-data gather
+            ll.append(got_ll)
             padded = torch.empty(world * width, dtype=torch.float64, device=tdev)
             comm.all_gather(cur.data_ptr(), padded.data_ptr(), width, stream.cuda_stream)
             nccl.append(padded)
@@ -82,6 +85,7 @@ def main():
     stream.synchronize()
     comm.gather_status()
     np.savez(os.path.join(xdir, f"out{rank}.npz"), fused=torch.stack(fused).cpu().numpy(), nccl=torch.stack(nccl).cpu().numpy(),
+             ll=torch.stack(ll).cpu().numpy(),
              lo=lo, hi=hi, width=width, shifts=shifts)
     # leave together: a rank must not unmap its gather memory while a peer may still store into it
     put(os.path.join(xdir, f"done{rank}"), b"1")

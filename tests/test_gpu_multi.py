@@ -112,4 +112,5 @@ def test_comm_fused_gather_matches_nccl_and_oracle(oracle_built, world):
             padded = res[r]["nccl"][step]
             via_nccl = np.concatenate([padded[q * width:q * width + int(res[q]["hi"]) - int(res[q]["lo"])] for q in range(world)])
             assert np.array_equal(fused, via_nccl), (step, r)
+            assert np.array_equal(res[r]["ll"][step], via_nccl), (step, r)      # gfb_comm_gather (flag-in-data, one kernel)
             assert np.abs(fused - e_ref).max() <= 1e-6 * np.abs(e_ref).max(), (step, r)
