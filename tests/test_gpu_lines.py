@@ -305,3 +305,69 @@ def test_launch_overlap_pdl_gives_same_results(gpu_device, n_grids):
     k.close()
     for g in grids:
         g.close()
+
+
+@pytest.mark.parametrize("n_grids,n_replicas,mode", [
+    (3, 3000, "fixed"),      # 2 204 tiles of 64 atoms: pipeline depth 2 (half of the resident grid), ~1.9 tiles per block
+    (3, 9000, "fixed"),      # 6 610 tiles: 2.8 per block, every tile parked
+    (3, 12500, "fixed"),     # 9 180 tiles: 3.9 per block — blocks with a 4th tile take the wait inside the loop
+    (3, 9000, "none"),       # energy only
+    (3, 9000, "f64_add"),
+    (2, 9000, "fixed"),
+    (4, 9000, "fixed"),
+    (1, 9000, "fixed"),      # one grid, batched: 256-thread blocks
+])
+def test_tile_striding_launches_match_one_block_per_tile(gpu_device, n_grids, n_replicas, mode):
+    """Small launches under launch overlap run the tile-striding instantiation of the lines kernel (a resident grid, energy
+    sums parked in shared memory, one griddepcontrol.wait at the block's end; gf_launch_lines.cu picks grid and depth).
+    Over a sequence of back-to-back launches on rotating accumulators it must leave what serialized one-block-per-tile
+    launches leave: fixed-point forces bit for bit, energies to summation order, cleared accumulators cleared."""
+    import torch
+    import openmmgridforce_b200 as gf
+    from openmmgridforce_b200 import workloads as W
+    w = W.c5_sharded_replicas(n_local=n_replicas, n=64)
+    g4 = list(w.grids) + [w.grids[0][::-1].copy()]
+    s4 = np.concatenate([w.scaling, w.scaling[:1] * 0.5])
+    k4 = list(w.oob_k) + [w.oob_k[0]]
+    grids = [gf.Grid(gpu_device, w.counts, w.spacing, w.origin, v, gf.PRECISION_MIXED) for v in g4[:n_grids]]
+    k = gf.Kernel(gpu_device, grids, s4[:n_grids], oob_k=k4[:n_grids])
+    assert k.uses_lines_kernel()
+    tdev = torch.device("cuda:0")
+    r, a = w.n_replicas, w.n_atoms
+    n = r * a
+    stride = ((n + 31) // 32) * 32
+    rng = np.random.default_rng(11)
+    sets = [torch.from_numpy(w.pos + rng.uniform(-0.02, 0.02, size=3)).to(tdev) for _ in range(4)]
+    stream = torch.cuda.Stream()
+    fmode = {"fixed": gf.FORCE_FIXED_ADD, "f64_add": gf.FORCE_F64_ADD, "none": 0}[mode]
+    out = {}
+    for pdl in (False, True):
+        k.set_launch_overlap(pdl)
+        if mode == "fixed":
+            d_f = torch.zeros(3 * stride, dtype=torch.int64, device=tdev)
+        elif mode == "f64_add":
+            d_f = torch.zeros(3 * n, dtype=torch.float64, device=tdev)
+        else:
+            d_f = None
+        d_e = [torch.zeros(r, dtype=torch.float64, device=tdev) for _ in range(3)]
+        kept = []
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            for i in range(9):
+                k.execute_device(r, a, sets[i % 4].data_ptr(), d_e[i % 3].data_ptr(), None, d_f.data_ptr() if d_f is not None else None,
+                                 fmode, stride, None, stream.cuda_stream, d_energies_clear=d_e[(i + 1) % 3].data_ptr())
+                if i >= 6:
+                    kept.append(d_e[i % 3].clone())
+        stream.synchronize()
+        out[pdl] = (d_f.cpu().numpy() if d_f is not None else None, [x.cpu().numpy() for x in kept], d_e[0].cpu().numpy())
+    k.set_launch_overlap(False)
+    if mode == "fixed":
+        assert out[True][0].any() and np.array_equal(out[False][0], out[True][0])
+    elif mode == "f64_add":
+        assert np.abs(out[False][0] - out[True][0]).max() <= 1e-12 * np.abs(out[False][0]).max()
+    for e0, e1 in zip(out[False][1], out[True][1]):
+        assert np.abs(e0).max() > 0 and np.abs(e0 - e1).max() <= 1e-13 * np.abs(e0).max()
+    assert not out[True][2].any()          # accumulator 0 was cleared by the last launch (step 8 clears (8 + 1) % 3 = 0)
+    k.close()
+    for g in grids:
+        g.close()
