@@ -207,7 +207,7 @@ GFB_API int gfb_kernel_update_parameters(gfb_kernel* k, const double* scaling, c
 /* Which evaluation kernel a launch of this state uses: 1 = gf_eval_lines_kernel (MIXED, packed cells, one geometry,
  * 1-4 grids, no inv-power: the 2-4 grid case reads one 128-byte record per atom), 2 = gf_eval_lines_f64_kernel (DOUBLE,
  * same conditions, 2-4 grids, one 256-byte record per atom), 3 = gf_eval_bspline_kernel (MIXED B-spline records),
- * 0 = the general gf_eval_kernel. Introspection for tests and bench.py; no reference counterpart. */
+ * 4 = gf_eval_bspline_f64_kernel (DOUBLE B-spline records), 0 = the general gf_eval_kernel. Introspection for tests and bench.py; no reference counterpart. */
 GFB_API int gfb_kernel_eval_path(const gfb_kernel* k);
 
 /* Particle groups (GridForce::addParticleGroup / getParticleGroupEnergies, openmmapi/include/GridForce.h:433-508;

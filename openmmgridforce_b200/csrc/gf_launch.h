@@ -41,5 +41,9 @@ constexpr int kLinesF64BlockThreads = 128;
 void launch_bspline(const EvalParams& p, cudaStream_t stream);
 constexpr int kBsplineBlockThreads = 128;
 
+// gf_eval_bspline_f64_kernel (gf_eval_bspline_f64.cuh): DOUBLE B-spline records of one geometry.
+void launch_bspline_f64(const EvalParams& p, cudaStream_t stream);
+constexpr int kBsplineF64BlockThreads = 64;
+
 }  // namespace gfb
 #endif

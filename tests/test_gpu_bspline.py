@@ -70,6 +70,7 @@ def test_bspline_batched_replicas_mixed_geometries(gpu_device, oracle_built, pre
         port = oracle_built.PortOracle(counts, sp, og, grids_v, sc, oob_k=c["oob_k"], interpolation_method=1)
         ge_ref, f_ref = port.execute_batched(pos, n_threads=4)
         grids, k = _make(gf, gpu_device, c, precision)
+        assert k.eval_path() == (3 if precision == 0 else 4)      # the record kernels: gf_eval_bspline_kernel / _f64_kernel
         en, forces, ge = k.execute_host(pos, want_grid_energies=True)
         tol_e, tol_f = TOL[precision]
         assert np.abs(ge - ge_ref).max() <= tol_e * np.abs(ge_ref).max(), counts

@@ -358,3 +358,31 @@ def test_host_copy_probe_and_large_layout_refusal(gpu_device):
     rc = lib.gfb_grid_create_from_device(gpu_device._h, (C.c_int * 3)(n, n, n), (C.c_double * 3)(0.1, 0.1, 0.1),
                                          (C.c_double * 3)(0, 0, 0), C.c_void_p(0x1000), n ** 3, 0, gf.LAYOUT_BSPLINE, C.byref(h))
     assert rc == -4 and b"needs" in lib.gfb_last_error() and b"B-spline records" in lib.gfb_last_error()
+
+
+@pytest.mark.parametrize("precision", [0, 1], ids=["mixed", "double"])
+def test_release_cells_keeps_record_kernels_working(gpu_device, oracle_built, precision):
+    """gfb_grid_release_cells: once a kernel over 2-4 grids has woven the packed cells into its records, the per-grid copies
+    can be freed (3 x 192^3: 638 MB of 1.5 GB). The record kernels must give the same results afterwards, the grids must
+    report zero device bytes, and building another kernel on a released grid must fail with a clear error instead of
+    reading freed memory."""
+    import openmmgridforce_b200 as gf
+    from openmmgridforce_b200 import workloads as W
+    w = W.c5_sharded_replicas(n_local=300, n=48)
+    grids = [gf.Grid(gpu_device, w.counts, w.spacing, w.origin, v, precision) for v in w.grids]
+    k = gf.Kernel(gpu_device, grids, w.scaling, oob_k=w.oob_k)
+    assert k.eval_path() == (1 if precision == 0 else 2)
+    e0, f0, _ = k.execute_host(w.pos)
+    before = [g.device_bytes for g in grids]
+    assert all(b > 0 for b in before)
+    for g in grids:
+        g.release_cells()
+        g.release_cells()                      # idempotent
+    assert all(g.device_bytes == 0 for g in grids)
+    e1, f1, _ = k.execute_host(w.pos)
+    assert np.array_equal(f0, f1) and np.abs(e0 - e1).max() <= 1e-13 * np.abs(e0).max()
+    with pytest.raises(gf.GridForceB200Error, match="released its packed cells"):     # a new kernel would need them again
+        gf.Kernel(gpu_device, grids[:1], w.scaling[:1], oob_k=w.oob_k[:1])
+    k.close()
+    for g in grids:
+        g.close()
