@@ -222,7 +222,14 @@ GFB_API int gfb_kernel_set_energy_slots(gfb_kernel* k, const int* slots, int n_s
  * stream serialization (PDL): its blocks may start, fetch positions and grid records while the tail of the PREVIOUS
  * kernel on the same stream is still running, and wait for that kernel to complete before their first write. The
  * caller promises that d_pos is not written by the kernel launched immediately before on that stream (true for
- * back-to-back evaluations of resident replicas; NOT true right after an integrator kernel that moves the atoms).
+ * back-to-back evaluations of resident replicas; NOT true right after an integrator kernel that moves the atoms), and,
+ * for the ADD force modes, that this kernel's predecessor only ACCUMULATES into d_forces (the force atomics of an
+ * overlapped launch are issued before it waits; they commute with the predecessor's).
+ * Small launches (a batch of up to ~6 tiles of 64 atoms per resident block: 8,192 ligand replicas, say) of a plain state
+ * (no particle map, evaluation order or energy slots; ADD or no forces; no per-grid or per-atom energies) then run the
+ * tile-striding instantiation of gf_eval_lines_kernel: a grid that is resident all at once, whose blocks park their
+ * energy sums in shared memory and wait for the previous launch once, at their end — back-to-back
+ * launches of that size flow into one another instead of paying ~3 us of ramp and tail each.
  * Default off. No reference counterpart. */
 GFB_API int gfb_kernel_set_launch_overlap(gfb_kernel* k, int enable);
 
