@@ -16,13 +16,16 @@ bytes touched between two uses of the same data are the same at every N and exce
 
   value      device-resident inputs; K steps per window, W_n windows, CUDA events on the launching stream around each
              window, max over ranks per window, median over windows. The K-step loop (+ the final gather) is a CUDA graph
-             whose launches carry programmatic-dependent-launch edges; the same loop with direct launches and without
-             launch overlap is timed in the same run and reported under "variants".
+             whose launches carry programmatic-dependent-launch edges (small launches — a rank's shard at N >= 4 — then
+             run the tile-striding instantiation of the kernel); the same loop with direct launches and without launch
+             overlap is timed in the same run and reported under "variants".
   e2e        the same through the plugin's batched entry point GridForceBatch (pinned HOST positions in, energies + FP32
              forces out; H2D/D2H inside the timed region); FP64 forces, energy-only and the bare C ABI beside it.
   roofline   algorithmic bytes per evaluation (36 + 52/G bytes, G grids per atom) x evaluations per launch /
              average launch duration, against the measured HBM copy bandwidth in MEASURED_PEAKS.json
-The data path of an N > 1 run is the C ABI only (gfb_comm_*: fused in-kernel gather over peer memory, or ncclAllGather);
+The data path of an N > 1 run is the C ABI only (gfb_comm_*: the energy gather as one flag-in-data kernel over the NVLink
+peer mappings by default — push + wait, the fused tail of the last launch and ncclAllGather selectable — and a device-side
+rendezvous of the ranks in front of each timed window);
 torch.distributed is the launcher's bootstrap channel (NCCL id, IPC handles), the barrier and the max over ranks.
 Only the cpu_baseline leg and --impl reference load anything from oracle/ (the test-only CPU oracle); the cpu_baseline
 leg also uses it to CHECK a sample of the timed kernel's output — a mismatch refuses the JSON line.
