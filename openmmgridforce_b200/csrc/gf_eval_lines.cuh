@@ -358,21 +358,68 @@ __global__ void __launch_bounds__(lines_block(NG), lines_blocks_per_sm(NG, PERSI
         __syncwarp();
         const unsigned rbase = (warp_base + lane * 128u) ^ ((lane & 7u) << 4);   // 128-byte aligned base: xor == or
         if (inside) {
+            {   // (the one_grid lambda above serves the one-grid kernel only)
+                // Trilinear interpolation is linear in the corner values, and all NG grids share the cell and the
+                // fractions: the scaled corners are summed over the grids first (FP64: s * corner is exact to 1e-16,
+                // and nothing is rounded to FP32 before corners are differenced), and value and gradient are formed ONCE
+                // from the eight sums — 8 conversions + 8 DFMA per grid and 32 FP64 operations per atom instead of a
+                // full FP64 value and FP32 gradient interpolation per grid (168 -> ~105 instructions for three grids; the
+                // kernel is issue-bound on small launches). Forces come out of FP64 arithmetic on the stored corners.
+                double C[8];
 #pragma unroll
-            for (int g = 0; g < NG; g++) {
-                const double s = p.grid[g].scaling[ia];   // 47 x NG doubles: L1-resident
-                if (s != 0.0) {                           // :706
-                    float v[8];
-                    lds128(rbase ^ (32u * g), v);
-                    lds128(rbase ^ (32u * g + 16u), v + 4);
-                    one_grid(g, v, s);
+                for (int k = 0; k < 8; k++) C[k] = 0.0;
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    const double s = p.grid[g].scaling[ia];
+                    if (s != 0.0) {   // :706
+                        if (GE) {   // per-grid energies wanted: this grid's value on its own as well (the forces below are
+                                    // formed from the summed corners either way, so both instantiations give the same forces)
+                            float v[8];
+                            lds128(rbase ^ (32u * g), v);
+                            lds128(rbase ^ (32u * g + 16u), v + 4);
+                            e_g[GE ? g : 0] = s * trilinear_value_f64(v, dfx, dfy, dfz);
+#pragma unroll
+                            for (int k = 0; k < 8; k++) C[k] = fma(s, (double) v[k], C[k]);
+                        } else {
+                            float v[4];
+                            lds128(rbase ^ (32u * g), v);
+#pragma unroll
+                            for (int k = 0; k < 4; k++) C[k] = fma(s, (double) v[k], C[k]);
+                            lds128(rbase ^ (32u * g + 16u), v);
+#pragma unroll
+                            for (int k = 0; k < 4; k++) C[4 + k] = fma(s, (double) v[k], C[4 + k]);
+                        }
+                    }
+                }
+                const double ax = 1.0 - dfx, ay = 1.0 - dfy, az = 1.0 - dfz;
+                const double vmm = az * C[0] + dfz * C[1];   // z -> y -> x as :1044-1053
+                const double vmp = az * C[2] + dfz * C[3];
+                const double vpm = az * C[4] + dfz * C[5];
+                const double vpp = az * C[6] + dfz * C[7];
+                const double vm = ay * vmm + dfy * vmp;
+                const double vp = ay * vpm + dfy * vpp;
+                e_total = ax * vm + dfx * vp;                // :1061 summed over the grids
+                if (FMODE != kForceNone) {                   // :1066-1071
+                    const double gx = vp - vm;
+                    const double gy = (vmp - vmm) * ax + (vpp - vpm) * dfx;
+                    const double gz = ((C[1] - C[0]) * ay + (C[3] - C[2]) * dfy) * ax + ((C[5] - C[4]) * ay + (C[7] - C[6]) * dfy) * dfx;
+                    sx = (float) (gx * G.inv_spacing[0]);
+                    sy = (float) (gy * G.inv_spacing[1]);
+                    sz = (float) (gz * G.inv_spacing[2]);
                 }
             }
         }
     }
-    float Fx = -sx * (float) G.inv_spacing[0];   // :1072, :1082
-    float Fy = -sy * (float) G.inv_spacing[1];
-    float Fz = -sz * (float) G.inv_spacing[2];
+    float Fx, Fy, Fz;   // :1072, :1082
+    if (NG == 1) {
+        Fx = -sx * (float) G.inv_spacing[0];
+        Fy = -sy * (float) G.inv_spacing[1];
+        Fz = -sz * (float) G.inv_spacing[2];
+    } else {
+        Fx = -sx;
+        Fy = -sy;
+        Fz = -sz;
+    }
     if (active && !inside) {   // :1093-1117 (inside atoms with scale 0 take that branch too and add exactly 0)
         const double* mine = p.pos + 3 * (size_t) gidx;   // re-read (rare path): x, y, z need not stay in registers
         const RestraintAll<NG> r = restraint_all<NG>(p, mine[0], mine[1], mine[2]);
