@@ -846,6 +846,10 @@ def main():
                                           "note": "gfb_bench_host_copy, 64 MB pinned, every rank at the same time: the PCIe/host-memory share each GPU gets",
                                           "h2d_floor_ms_per_step": w.pos.nbytes / (min(r[0] for r in host_copy_all) * 1e9) * 1e3}},
                 "gpu_launches": int(launches * args.windows), "clocks": clocks, "cpu_binding": numa}
+        if ach > peak_gbs:
+            line["roofline"]["note"] = ("above 1: the denominator is the measured COPY bandwidth (equal read and write streams); this "
+                                        "launch's DRAM traffic is 80 % reads (roofline_measured_traffic: ncu's bytes for the same "
+                                        "launch over this run's launch time), and the HBM3e interface is nominally 7.7 TB/s")
         if weak is not None:
             line["weak_scaling"] = weak
         if world == 1 and not args.no_extras:
