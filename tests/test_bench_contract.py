@@ -54,6 +54,31 @@ def test_traffic_is_only_reported_for_the_profiled_sources(tmp_path, monkeypatch
     assert val is None and why
 
 
+def test_committed_traffic_file_matches_the_kernel_sources_and_captures():
+    """profiles/r2_traffic.json is what bench.py reports as roofline.traffic: every entry must carry the hash of the kernel
+    sources as they are in the tree (a stale capture is dropped, not reported), point at a committed ncu export and hold
+    that export's DRAM bytes; the physical roofline helper refuses lower-bound captures."""
+    import csv
+    import json
+    b = _bench()
+    doc = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+    assert {"C5", "C3", "C5_double", "C5_energy_only"} <= set(doc)
+    for key, entry in doc.items():
+        assert entry["source_sha256_16"] == b.kernel_source_hash(), key
+        raw = os.path.join(ROOT, entry["source"].split(" ")[0])
+        rows = list(csv.reader(open(raw)))
+        hdr, units, r = rows[0], rows[1], rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        total = sum(float(r[hdr.index(n)]) * scale[units[hdr.index(n)]] for n in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        assert abs(total - entry["dram_bytes_per_launch"]) <= 1e-6 * total, key
+        val, src = b.measured_traffic(key)
+        assert val == entry["dram_bytes_per_launch"]
+    c5 = doc["C5"]["dram_bytes_per_launch"]
+    assert abs(c5 / (9240576 * b.b_alg(3)) - 1.0) < 0.03          # the full launch moves what the algorithm needs
+    assert b.physical_roofline(c5, doc["C5"]["source"], 75.0, 6541.8)["frac"] > 0.9
+    assert b.physical_roofline(doc["C4"]["dram_bytes_per_launch"], doc["C4"]["source"], 6.5, 6541.8) is None
+
+
 def test_oracle_is_only_reached_from_the_cpu_legs():
     src = open(os.path.join(ROOT, "bench.py")).read()
     users = [m.start() for m in re.finditer(r"from oracle import bindings", src)]
