@@ -371,3 +371,42 @@ def test_tile_striding_launches_match_one_block_per_tile(gpu_device, n_grids, n_
     k.close()
     for g in grids:
         g.close()
+
+
+@pytest.mark.parametrize("atoms", [3, 33])
+def test_tile_striding_launch_many_replicas_per_warp_vs_oracle(gpu_device, oracle_built, atoms):
+    """The tile-striding instantiation with replicas shorter than (3 atoms: ten run heads per warp, every one parked) and
+    barely longer than a warp (33), out-of-grid atoms and zero scaling factors in the mix: device path under launch
+    overlap, energies and fixed-point forces of the LAST of four launches against the oracle."""
+    import torch
+    import openmmgridforce_b200 as gf
+    r = 36000 if atoms == 3 else 3300                  # ~108k atoms: more tiles than half the resident grid, fewer than six per block
+    c = _case(3, r, atoms, seed=21 + atoms)
+    ge_ref, f_ref = _oracle(oracle_built, c)
+    grids, k = _make(gf, gpu_device, c)
+    assert k.uses_lines_kernel()
+    k.set_launch_overlap(True)
+    tdev = torch.device("cuda:0")
+    n = r * atoms
+    stride = ((n + 31) // 32) * 32
+    d_pos = torch.from_numpy(c["pos"]).to(tdev)
+    d_f = torch.zeros(3 * stride, dtype=torch.int64, device=tdev)
+    d_e = [torch.zeros(r, dtype=torch.float64, device=tdev) for _ in range(2)]
+    d_out = torch.empty(n, 3, dtype=torch.float64, device=tdev)
+    stream = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    launches = 4
+    for i in range(launches):
+        k.execute_device(r, atoms, d_pos.data_ptr(), d_e[i % 2].data_ptr(), None, d_f.data_ptr(), gf.FORCE_FIXED_ADD, stride, None,
+                         stream.cuda_stream, d_energies_clear=d_e[(i + 1) % 2].data_ptr())
+    gpu_device.fixed_to_f64(d_f.data_ptr(), stride, n, d_out.data_ptr(), stream.cuda_stream)
+    stream.synchronize()
+    k.set_launch_overlap(False)
+    en = d_e[(launches - 1) % 2].cpu().numpy()
+    e_ref = ge_ref.sum(axis=1)
+    term = np.abs(ge_ref).max(axis=1)
+    assert (np.abs(en - e_ref) <= TOL_E * np.maximum(np.abs(e_ref), term)).all()
+    f = d_out.cpu().numpy().reshape(r, atoms, 3) / launches
+    assert np.abs(f - f_ref).max() <= TOL_F * np.abs(f_ref).max()
+    assert not d_e[launches % 2].cpu().numpy().any()             # cleared by the last launch
+    _close(grids, k)
