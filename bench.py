@@ -52,7 +52,9 @@ REPLICAS_PER_GPU = REPLICAS_TOTAL          # weak scaling, and N = 1
 N_ATOMS = 47
 N_GRIDS = 3
 GRID_N = 192
-RENDEZVOUS = os.environ.get("GFB_BENCH_RENDEZVOUS", "1") != "0"     # device-side start rendezvous of the timed windows (N > 1)
+# device-side start rendezvous of the timed windows (N > 1). The held kernel waits for a host write that follows the
+# enqueue of the window, so it is off when launches block the host (CUDA_LAUNCH_BLOCKING=1 would wait for the 20 s timeout).
+RENDEZVOUS = (os.environ.get("GFB_BENCH_RENDEZVOUS", "1") != "0" and os.environ.get("CUDA_LAUNCH_BLOCKING", "0") in ("", "0"))
 KERNEL_SOURCES = ("gf_eval_lines.cuh", "gf_eval_lines_f64.cuh", "gf_gather.cuh", "gf_kernels.cuh", "gf_params.h", "gf_launch_lines.cu")
 
 
