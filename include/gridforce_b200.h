@@ -383,7 +383,8 @@ GFB_API int gfb_comm_rendezvous_release(gfb_comm* c);
  *                            OpenMM's fixed-point buffer per device).
  *   gfb_multi_step           one evaluation of every shard (one launch per device); gather: 0 none, 1 ncclAllGather of
  *                            the energies on every device, 2 gather over peer memory fused into the evaluation kernel,
- *                            3 the same peer stores as a small kernel behind it (gfb_comm_gather_push's; the fastest).
+ *                            3 the same peer stores as a small kernel behind it (gfb_comm_gather_push's), 4 the one-kernel
+ *                            flag-in-data gather (gfb_comm_gather's; the fastest).
  *   gfb_multi_download       energies [n_replicas] as gathered on device `from_device` (after a gathering step; any
  *                            device holds all of them) and, when forces != NULL, the shards' forces as double [R][A][3]. */
 GFB_API int gfb_multi_create(int n_devices, const int* ordinals, gfb_multi** out);

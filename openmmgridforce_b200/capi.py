@@ -590,7 +590,8 @@ class Multi:
         self.n_replicas = pos.shape[0]
 
     def step(self, gather=0):
-        """gather: 0 none, 1 ncclAllGather, 2 peer-store gather fused into the evaluation kernel, 3 peer-store push kernel."""
+        """gather: 0 none, 1 ncclAllGather, 2 peer-store gather fused into the evaluation kernel, 3 peer-store push kernel, 4 the
+        one-kernel flag-in-data gather (gfb_comm_gather's kernel)."""
         _check(load_library().gfb_multi_step(self._h, gather))
 
     def download(self, from_device=0, want_forces=True):

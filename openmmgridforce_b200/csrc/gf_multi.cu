@@ -816,7 +816,7 @@ int gfb_multi_upload(gfb_multi* m, int n_replicas, const double* pos) {
 
 int gfb_multi_step(gfb_multi* m, int gather) {
     if (!m || m->shards.empty()) return fail(GFB_ERR_INVALID, "gfb_multi_step: call gfb_multi_upload first");
-    if (gather < 0 || gather > 3) return fail(GFB_ERR_INVALID, "gfb_multi_step: gather must be 0, 1, 2 or 3");
+    if (gather < 0 || gather > 4) return fail(GFB_ERR_INVALID, "gfb_multi_step: gather must be 0, 1, 2, 3 or 4");
     NcclApi* api = nullptr;
     if (gather == 1) {
         api = nccl_api();
@@ -856,6 +856,12 @@ int gfb_multi_step(gfb_multi* m, int gather) {
         for (int d = 0; d < m->n; d++) {
             MultiShard& s = m->shards[d];
             CUDA_TRY(cudaSetDevice(m->devs[d]->ordinal));
+            if (gather == 4) {   // flag-in-data: publish + wait + copy-out in one kernel per device
+                CUDA_TRY(launch_overlapped(gf_gather_ll_kernel, kLLBlocks, 256, m->devs[d]->stream, s.d_table, (const double*) s.d_e[cur],
+                                           s.hi - s.lo, (long long) s.lo, s.d_gathered));
+                g_launches++;
+                continue;
+            }
             if (gather == 3) {
                 CUDA_TRY(launch_overlapped(gf_gather_push_kernel, kPushBlocks, 256, m->devs[d]->stream, s.d_table, (const double*) s.d_e[cur],
                                            s.hi - s.lo, (long long) s.lo));

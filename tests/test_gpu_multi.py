@@ -56,7 +56,8 @@ def test_multi_host_path_matches_oracle(oracle_built, n_dev):
 @pytest.mark.parametrize("n_dev", [1, 2])
 def test_multi_resident_steps_and_gathers(oracle_built, n_dev):
     """Device-resident shards: one launch per device per step, energies gathered by ncclAllGather (1) and by the fused
-    in-kernel gather over peer memory (2) or the stand-alone push kernel (3); every device ends up with all energies; forces accumulate in fixed point."""
+    in-kernel gather over peer memory (2), the stand-alone push kernel (3) or the one-kernel flag-in-data gather (4); every
+    device ends up with all energies; forces accumulate in fixed point."""
     import openmmgridforce_b200 as gf
     if _n_gpus() < n_dev:
         pytest.skip(f"needs {n_dev} GPUs")
@@ -68,7 +69,7 @@ def test_multi_resident_steps_and_gathers(oracle_built, n_dev):
     m.build(w.scaling, oob_k=w.oob_k)
     m.upload(w.pos)
     steps = 0
-    for gather in (0, 2, 1, 3, 2, 3, 3):
+    for gather in (0, 2, 1, 3, 4, 2, 4, 4, 3):
         m.step(gather)
         steps += 1
         for d in range(n_dev):
