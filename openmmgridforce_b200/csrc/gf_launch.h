@@ -20,6 +20,8 @@ constexpr int kGeneralBlock = 256;
 // One explicit instantiation per grid count, each in its own object file (gf_launch_lines.cu with -DGFB_LINES_NG=k).
 template <int NG>
 void launch_lines_ng(const EvalParams& p, int fmode, int fpath, cudaStream_t stream);
+#ifndef GFB_LINES_NG   // the per-grid-count objects (gf_launch_lines.cu with -DGFB_LINES_NG=k) must not see this dispatcher: its
+                       // non-dependent calls would instantiate every grid count in every one of them
 inline void launch_lines(const EvalParams& p, int fmode, int fpath, cudaStream_t stream) {
     switch (p.n_grids) {
         case 1: launch_lines_ng<1>(p, fmode, fpath, stream); break;
@@ -28,6 +30,7 @@ inline void launch_lines(const EvalParams& p, int fmode, int fpath, cudaStream_t
         default: launch_lines_ng<4>(p, fmode, fpath, stream); break;
     }
 }
+#endif
 #ifndef GFB_LINES_BLOCK_MULTI
 #define GFB_LINES_BLOCK_MULTI 64
 #endif

@@ -1,4 +1,4 @@
-"""SASS evidence for the key kernels (no GPU needed): python tools/sass_summary.py > profiles/r1b_sass_summary.txt
+"""SASS evidence for the key kernels (no GPU needed): python tools/sass_summary.py > profiles/r2_sass_summary.txt
 Counts the memory / atomic / PDL / FP64 mnemonics of `cuobjdump -sass lib/libgridforce_b200.so` per kernel."""
 import collections
 import os
@@ -7,14 +7,21 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "openmmgridforce_b200", "lib", "libgridforce_b200.so")
-WANT = {
-    "_ZN3gfb20gf_eval_lines_kernelILi3ELi2ELi0ELb0ELb0EEEvNS_10EvalParamsE": "gf_eval_lines_kernel<3 grids, FIXED_ADD, red, batched> — the C5/C4 step",
-    "_ZN3gfb20gf_eval_lines_kernelILi1ELi2ELi1ELb1ELb0EEEvNS_10EvalParamsE": "gf_eval_lines_kernel<1 grid, FIXED_ADD, prefetch, single> — the C3 step",
-    "_ZN3gfb20gf_eval_lines_kernelILi3ELi0ELi0ELb0ELb0EEEvNS_10EvalParamsE": "gf_eval_lines_kernel<3 grids, F64_STORE> — host-path chunks (forces stored to pinned host memory)",
-    "_ZN3gfb22gf_eval_bspline_kernelILi2ELb0EEEvNS_10EvalParamsE": "gf_eval_bspline_kernel<FIXED_ADD, batched> — cubic B-spline bricks",
-    "_ZN3gfb14gf_eval_kernelIdLi1ELi3ELb1ELi2ELb0EEEvNS_10EvalParamsE": "gf_eval_kernel<double, CELLS, 3 grids, FIXED_ADD> — DOUBLE precision",
+WANT = {   # round-2 names (the lines kernel gained the PERSIST flag; substring match on the demangled-free symbol)
+    "gf_eval_lines_kernelILi3ELi2ELi0ELb0ELb0ELb0E": "gf_eval_lines_kernel<3 grids, FIXED_ADD, red, batched, PERSIST=0> — the C5 step (one block per tile)",
+    "gf_eval_lines_kernelILi3ELi2ELi0ELb0ELb0ELb1E": "gf_eval_lines_kernel<3 grids, FIXED_ADD, red, batched, PERSIST=1> — small launches under launch overlap (tile-striding)",
+    "gf_eval_lines_kernelILi1ELi2ELi1ELb1ELb0ELb0E": "gf_eval_lines_kernel<1 grid, FIXED_ADD, prefetch, single> — the C3 step",
+    "gf_eval_lines_kernelILi3ELi3ELi0ELb0ELb0ELb0E": "gf_eval_lines_kernel<3 grids, F32_STORE> — host-path chunks (FP32 forces stored to pinned host memory)",
+    "gf_eval_lines_kernelILi3ELi4ELi0ELb0ELb0ELb0E": "gf_eval_lines_kernel<3 grids, energy only>",
+    "gf_eval_lines_f64_kernelILi3ELi2ELb0ELb0E": "gf_eval_lines_f64_kernel<3 grids, FIXED_ADD> — DOUBLE 256-byte records",
+    "gf_eval_bspline_kernelILb0E": "gf_eval_bspline_kernel<batched> — MIXED cubic B-spline records",
+    "gf_eval_bspline_f64_kernelILb0E": "gf_eval_bspline_f64_kernel<batched> — DOUBLE cubic B-spline records",
+    "gf_gather_ll_kernel": "gf_gather_ll_kernel — the energy gather as one flag-in-data kernel over NVLink peer mappings",
+    "gf_gather_push_kernel": "gf_gather_push_kernel — peer stores + arrival flags",
+    "gf_gather_wait_kernel": "gf_gather_wait_kernel — waits for all ranks' flags, copies the gathered array out",
+    "gf_rendezvous_kernel": "gf_rendezvous_kernel — device-side rendezvous of all ranks",
 }
-PATS = ["LDGSTS.E.BYPASS.128", "LDG.E.ELL2.256", "LDG.E.EF.128", "LDG.E.EF.64", "LDS.128", "STS", "STG.E.128", "STG.E.64",
+PATS = ["LDGSTS.E.BYPASS.128", "LDG.E.ELL2.256", "LDG.E.LTC64B.ELL2.256", "LDG.E.128.STRONG.SYS", "STG.E.128.STRONG.SYS", "STG.E.64.STRONG.SYS", "LDG.E.64.STRONG.SYS", "LDS.64", "LDG.E.EF.128", "LDG.E.EF.64", "LDS.128", "STS", "STG.E.128", "STG.E.64",
         "REDG.E.ADD.64", "REDG.E.ADD.F64", "CCTL", "PREEXIT", "ACQBULK", "LDGDEPBAR", "DEPBAR", "DFMA", "DMUL", "DADD",
         "F2F.F64.F32", "FFMA", "SHFL", "BAR.SYNC", "WARPSYNC", "CALL"]
 NOTE = {"LDGSTS.E.BYPASS.128": "cp.async.cg 16 B (one granule of a 128-byte record / a brick row)",
@@ -23,17 +30,20 @@ NOTE = {"LDGSTS.E.BYPASS.128": "cp.async.cg 16 B (one granule of a 128-byte reco
         "PREEXIT": "griddepcontrol.launch_dependents", "ACQBULK": "griddepcontrol.wait", "CCTL": "prefetch.global.L2 (force lines)"}
 txt = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 print("cuobjdump -sass openmmgridforce_b200/lib/libgridforce_b200.so (sm_100a), instruction counts per kernel\n")
+seen = set()
 for f in re.split(r"\n\s*Function : ", txt)[1:]:
     name = f.split("\n", 1)[0].strip()
-    if name not in WANT:
+    key = next((k for k in WANT if k in name), None)
+    if key is None or key in seen:
         continue
+    seen.add(key)
     ins = re.findall(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", f)
     c = collections.Counter()
     for i in ins:
         for p in PATS:
             if i.startswith(p):
                 c[p] += 1
-    print(WANT[name])
+    print(WANT[key])
     print(f"  {name}: {len(ins)} SASS instructions")
     for p in PATS:
         if c[p]:
