@@ -1,6 +1,6 @@
 /* TEST INFRASTRUCTURE — see gridforce_oracle.h. Plain C99 restatement of
  * /root/reference/platforms/reference/src/ReferenceGridForceKernels.cpp:646-1121 (trilinear branch, and the cubic
- * B-spline branch :727-795 when gfo_grid.interp_method == 1).
+ * B-spline branch :727-795 when gfo_grid.interp_method == 1, the tricubic Hermite branch :796-893 when it is 2).
  * Build with -ffp-contract=off so a*b+c stays two roundings, as in the reference build. */
 #include "gridforce_oracle.h"
 
@@ -62,6 +62,108 @@ static double gfo_interp_bspline(const gfo_grid* g, double scale, const double* 
     return scale * interpolated;                                                             /* :793 */
 }
 
+/* Cubic Hermite basis and derivative (:68-77), same expressions. */
+static double he_h00(double t) { return (1.0 + 2.0 * t) * (1.0 - t) * (1.0 - t); }
+static double he_h10(double t) { return t * (1.0 - t) * (1.0 - t); }
+static double he_h01(double t) { return t * t * (3.0 - 2.0 * t); }
+static double he_h11(double t) { return t * t * (t - 1.0); }
+static double he_d00(double t) { return 6.0 * t * t - 6.0 * t; }
+static double he_d10(double t) { return 3.0 * t * t - 4.0 * t + 1.0; }
+static double he_d01(double t) { return -6.0 * t * t + 6.0 * t; }
+static double he_d11(double t) { return 3.0 * t * t - 2.0 * t; }
+
+/* A grid value by FLAT index, as the reference's tricubic branch forms them (:801-861). Neighbour indices past an axis
+ * end are not clamped there: iy+2 == ny or iz+2 == nz lands in the next row / x-slab (deterministic, reproduced here),
+ * and in the last x layer (ix == nx-2) ix+2 == nx lands past the end of the vector (UB in the reference). A read past the
+ * end returns 0 here — the CUDA layout carries a zero-filled guard slab for the same purpose. */
+static double gfo_flat(const gfo_grid* g, long long i) {
+    const long long n = (long long)g->counts[0] * g->counts[1] * g->counts[2];
+    return (i >= 0 && i < n) ? g->vals[i] : 0.0;
+}
+
+/* interpolation method 2 (:796-893): "tricubic Hermite" — cubic Hermite in x on the 4 cell edges with centred-difference
+ * x-derivatives, then in y and in z with one-sided differences of the partly interpolated values. Restated statement by
+ * statement, including what a derivation from scratch would not do: dvdy is formed on the z = iz plane only (:862), the
+ * y- and z-differences use the value basis alone for the neighbour rows (:852-855, :866-867), and the derivative
+ * estimates are switched off (0) in the first cell layer of an axis and in a one-point-wide band only (:817-832). */
+static double gfo_interp_tricubic(const gfo_grid* g, double scale, const double* pi, double* f, gfo_class* cls) {
+    const int nz = g->counts[2];
+    const int nyz = g->counts[1] * nz;
+    const double sx = g->spacing[0], sy = g->spacing[1], sz = g->spacing[2];
+    int k, idx[3];
+    double fr[3];
+    for (k = 0; k < 3; k++) {
+        idx[k] = (int)(pi[k] / g->spacing[k]);                   /* :708-710 */
+        fr[k] = (pi[k] / g->spacing[k]) - idx[k];                /* :713-715 */
+        if (idx[k] > g->counts[k] - 2) {                         /* quirk Q2, as in the trilinear branch */
+            idx[k] = g->counts[k] - 2;
+            fr[k] = (pi[k] / g->spacing[k]) - idx[k];
+        }
+    }
+    if (cls) { cls->cell[0] = idx[0]; cls->cell[1] = idx[1]; cls->cell[2] = idx[2]; }
+    {
+        const int ix = idx[0], iy = idx[1], iz = idx[2];
+        const double fx = fr[0], fy = fr[1], fz = fr[2];
+        const long long im = (long long)ix * nyz + (long long)iy * nz + iz;                  /* :801-804 */
+        const long long imp = im + nz, ip = im + nyz, ipp = ip + nz;
+        const double f000 = gfo_flat(g, im), f001 = gfo_flat(g, im + 1);                     /* :806-813 */
+        const double f010 = gfo_flat(g, imp), f011 = gfo_flat(g, imp + 1);
+        const double f100 = gfo_flat(g, ip), f101 = gfo_flat(g, ip + 1);
+        const double f110 = gfo_flat(g, ipp), f111 = gfo_flat(g, ipp + 1);
+        const int xin = ix > 0 && ix < g->counts[0] - 1;                                     /* :817-832 */
+        const int yin = iy > 0 && iy < g->counts[1] - 1;                                     /* :852-855 */
+        const int zin = iz > 0 && iz < g->counts[2] - 1;                                     /* :866-867 */
+        const double dx000 = xin ? (gfo_flat(g, im + nyz) - gfo_flat(g, im - nyz)) / (2.0 * sx) : 0.0;
+        const double dx001 = xin ? (gfo_flat(g, im + 1 + nyz) - gfo_flat(g, im + 1 - nyz)) / (2.0 * sx) : 0.0;
+        const double dx010 = xin ? (gfo_flat(g, imp + nyz) - gfo_flat(g, imp - nyz)) / (2.0 * sx) : 0.0;
+        const double dx011 = xin ? (gfo_flat(g, imp + 1 + nyz) - gfo_flat(g, imp + 1 - nyz)) / (2.0 * sx) : 0.0;
+        const double dx100 = xin ? (gfo_flat(g, im + 2 * (long long)nyz) - gfo_flat(g, im)) / (2.0 * sx) : 0.0;
+        const double dx101 = xin ? (gfo_flat(g, im + 1 + 2 * (long long)nyz) - gfo_flat(g, im + 1)) / (2.0 * sx) : 0.0;
+        const double dx110 = xin ? (gfo_flat(g, imp + 2 * (long long)nyz) - gfo_flat(g, imp)) / (2.0 * sx) : 0.0;
+        const double dx111 = xin ? (gfo_flat(g, imp + 1 + 2 * (long long)nyz) - gfo_flat(g, imp + 1)) / (2.0 * sx) : 0.0;
+        const double h00x = he_h00(fx), h01x = he_h01(fx), h10x = he_h10(fx), h11x = he_h11(fx);   /* :835-836 */
+        const double d00x = he_d00(fx), d01x = he_d01(fx), d10x = he_d10(fx), d11x = he_d11(fx);
+        const double v00 = h00x * f000 + h01x * f100 + h10x * dx000 * sx + h11x * dx100 * sx;      /* :838-841 */
+        const double v01 = h00x * f001 + h01x * f101 + h10x * dx001 * sx + h11x * dx101 * sx;
+        const double v10 = h00x * f010 + h01x * f110 + h10x * dx010 * sx + h11x * dx110 * sx;
+        const double v11 = h00x * f011 + h01x * f111 + h10x * dx011 * sx + h11x * dx111 * sx;
+        const double dv00 = d00x * f000 + d01x * f100 + d10x * dx000 * sx + d11x * dx100 * sx;     /* :843-846 */
+        const double dv01 = d00x * f001 + d01x * f101 + d10x * dx001 * sx + d11x * dx101 * sx;
+        const double dv10 = d00x * f010 + d01x * f110 + d10x * dx010 * sx + d11x * dx110 * sx;
+        const double dv11 = d00x * f011 + d01x * f111 + d10x * dx011 * sx + d11x * dx111 * sx;
+        const double dy00 = yin ? (v10 - (h00x * gfo_flat(g, im - nz) + h01x * gfo_flat(g, ip - nz))) / sy : 0.0;          /* :849-852 */
+        const double dy01 = yin ? (v11 - (h00x * gfo_flat(g, im + 1 - nz) + h01x * gfo_flat(g, ip + 1 - nz))) / sy : 0.0;
+        const double dy10 = yin ? ((h00x * gfo_flat(g, im + 2 * nz) + h01x * gfo_flat(g, ip + 2 * nz)) - v00) / sy : 0.0;
+        const double dy11 = yin ? ((h00x * gfo_flat(g, im + 1 + 2 * nz) + h01x * gfo_flat(g, ip + 1 + 2 * nz)) - v01) / sy : 0.0;
+        const double h00y = he_h00(fy), h01y = he_h01(fy), h10y = he_h10(fy), h11y = he_h11(fy);   /* :855-856 */
+        const double d00y = he_d00(fy), d01y = he_d01(fy), d10y = he_d10(fy), d11y = he_d11(fy);
+        const double v0 = h00y * v00 + h01y * v10 + h10y * dy00 * sy + h11y * dy10 * sy;           /* :858-859 */
+        const double v1 = h00y * v01 + h01y * v11 + h10y * dy01 * sy + h11y * dy11 * sy;
+        const double dvdx_0 = h00y * dv00 + h01y * dv10;                                            /* :861-862 */
+        const double dvdx_1 = h00y * dv01 + h01y * dv11;
+        double dvdy = (d00y * v00 + d01y * v10 + d10y * dy00 * sy + d11y * dy10 * sy);              /* :863 */
+        const double dz0 = zin ? (v1 - (h00y * (h00x * gfo_flat(g, im - 1) + h01x * gfo_flat(g, ip - 1)) +
+                                        h01y * (h00x * gfo_flat(g, imp - 1) + h01x * gfo_flat(g, ipp - 1)))) / sz : 0.0;   /* :866 */
+        const double dz1 = zin ? ((h00y * (h00x * gfo_flat(g, im + 2) + h01x * gfo_flat(g, ip + 2)) +
+                                   h01y * (h00x * gfo_flat(g, imp + 2) + h01x * gfo_flat(g, ipp + 2))) - v0) / sz : 0.0;   /* :867 */
+        const double h00z = he_h00(fz), h01z = he_h01(fz), h10z = he_h10(fz), h11z = he_h11(fz);   /* :870-871 */
+        const double d00z = he_d00(fz), d01z = he_d01(fz), d10z = he_d10(fz), d11z = he_d11(fz);
+        double interpolated = h00z * v0 + h01z * v1 + h10z * dz0 * sz + h11z * dz1 * sz;            /* :873 */
+        double dvdx = h00z * dvdx_0 + h01z * dvdx_1;                                                /* :875 */
+        double dvdz = d00z * v0 + d01z * v1 + d10z * dz0 * sz + d11z * dz1 * sz;                    /* :876 */
+        double grd[3];
+        if (g->inv_power > 0.0) {                                                                   /* :879-886 */
+            const double base = interpolated;
+            const double pf = g->inv_power * pow(base, g->inv_power - 1.0);
+            interpolated = pow(interpolated, g->inv_power);
+            dvdx *= pf; dvdy *= pf; dvdz *= pf;
+        }
+        grd[0] = dvdx / sx; grd[1] = dvdy / sy; grd[2] = dvdz / sz;                                 /* :889 */
+        if (f) for (k = 0; k < 3; k++) f[k] -= scale * grd[k];                                      /* :893 */
+        return scale * interpolated;                                                                /* :892 */
+    }
+}
+
 /* The inside branch for one atom (:706-1084). pi = position - origin. Returns scale * V and
  * subtracts scale * grad V from f[3]. */
 static double gfo_interp(const gfo_grid* g, double scale, const double* pi, double* f, gfo_class* cls) {
@@ -70,6 +172,7 @@ static double gfo_interp(const gfo_grid* g, double scale, const double* pi, doub
     int k, idx[3];
     double fr[3];
     if (g->interp_method == 1) return gfo_interp_bspline(g, scale, pi, f, cls);               /* :727 */
+    if (g->interp_method == 2) return gfo_interp_tricubic(g, scale, pi, f, cls);              /* :796 */
     for (k = 0; k < 3; k++) {
         idx[k] = (int)(pi[k] / g->spacing[k]);                   /* :708-710 */
         fr[k] = (pi[k] / g->spacing[k]) - idx[k];                /* :713-715 */

@@ -11,6 +11,7 @@
  *   :706-715   cell index and fraction (true FP64 division, truncation)
  *   :1022-1084 trilinear value (z -> y -> x), gradient, inv-power chain rule, accumulate
  *   :727-795   cubic B-spline branch (interpolation method 1): clamped 4x4x4 stencil
+ *   :796-893   tricubic Hermite branch (interpolation method 2): finite-difference derivatives, flat-index neighbours
  *   :1093-1117 out-of-grid harmonic restraint (also taken by inside atoms with scale == 0)
  */
 #ifndef GRIDFORCE_ORACLE_H_
@@ -27,7 +28,7 @@ typedef struct {
     const double* vals;   /* nx*ny*nz, x-major, z fastest                 (GridData.h:96-98) */
     double inv_power;     /* 0 = off; > 0: v <- pow(v, n) with chain rule (:1057-1059, :1076-1080) */
     double oob_k;         /* kJ/mol/nm^2, out-of-grid restraint           (GridForce.cpp:52 default 1e4) */
-    int interp_method;    /* 0 trilinear (:1016-1084), 1 cubic B-spline (:727-795) (GridForce::setInterpolationMethod) */
+    int interp_method;    /* 0 trilinear (:1016-1084), 1 cubic B-spline (:727-795), 2 tricubic Hermite (:796-893) (GridForce::setInterpolationMethod) */
 } gfo_grid;
 
 /* Per-atom classification record, for the bit-exact index tests. cell = -1 when the atom took the

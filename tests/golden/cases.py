@@ -128,6 +128,51 @@ def case_bspline_thin_grid():
                 scaling=rng.uniform(0.5, 1.5, size=(1, 200)), pos=pos, oob_k=[10000.0], inv_power=[0.0], interp=1)
 
 
+def _tricubic_safe(c, rng):
+    """Interpolation method 2 is undefined in the reference in the last x layer (ix == nx-2: the ix+2 neighbour is past the
+    end of the value vector, ReferenceGridForceKernels.cpp:825-832) and, like every method, on the upper faces (quirk Q2):
+    atoms there are moved to a random interior x. Everything else stays, the last y/z cells included."""
+    counts, sp, og = np.array(c["counts"]), np.array(c["spacing"]), np.array(c["origin"])
+    pos = c["pos"]
+    length = sp * (counts - 1)
+    px = pos[:, 0] - og[0]
+    bad = (px >= sp[0] * (counts[0] - 2) * (1 - 1e-9)) & (px <= length[0])
+    pos[bad, 0] = og[0] + rng.uniform(0.0, 1.0, size=int(bad.sum())) * sp[0] * (counts[0] - 2) * (1 - 1e-9)
+    for k in (1, 2):
+        on_face = pos[:, k] - og[k] == length[k]
+        pos[on_face, k] -= 0.25 * sp[k]
+    return c
+
+
+def case_tricubic_random_aniso():
+    """Tricubic Hermite (interpolation method 2, ReferenceGridForceKernels.cpp:796-893) on the random_aniso inputs plus
+    atoms in the first cells of every axis (derivative estimates switched off) and in the last y/z cells (neighbour reads
+    by flat index land in the next row / x-slab)."""
+    c = case_random_aniso()
+    counts, sp, og = np.array(c["counts"]), np.array(c["spacing"]), np.array(c["origin"])
+    rng = np.random.default_rng(41)
+    pos = c["pos"]
+    length = sp * (counts - 1)
+    pos[100:130] = og + rng.uniform(0.0, 1.0, size=(30, 3)) * sp                                   # first cells
+    pos[130:160, 1:] = (og + length - rng.uniform(1e-6, 1.0, size=(30, 3)) * sp)[:, 1:]            # last y and z cells
+    pos[160:175, 1] = (og + length - rng.uniform(1e-6, 1.0, size=(15, 3)) * sp)[:, 1]              # last y cells only
+    pos[175:190, 2] = (og + length - rng.uniform(1e-6, 1.0, size=(15, 3)) * sp)[:, 2]              # last z cells only
+    c["interp"] = 2
+    return _tricubic_safe(c, rng)
+
+
+def case_tricubic_ligand_three_grids():
+    c = case_ligand_three_grids()
+    c["interp"] = 2
+    return _tricubic_safe(c, np.random.default_rng(42))
+
+
+def case_tricubic_inv_power():
+    c = case_inv_power()
+    c["interp"] = 2
+    return _tricubic_safe(c, np.random.default_rng(43))
+
+
 CASES = {
     "ones_grid": case_ones_grid,
     "ramp_grid": case_ramp_grid,
@@ -139,6 +184,9 @@ CASES = {
     "bspline_ligand_three_grids": case_bspline_ligand_three_grids,
     "bspline_inv_power": case_bspline_inv_power,
     "bspline_thin_grid": case_bspline_thin_grid,
+    "tricubic_random_aniso": case_tricubic_random_aniso,
+    "tricubic_ligand_three_grids": case_tricubic_ligand_three_grids,
+    "tricubic_inv_power": case_tricubic_inv_power,
 }
 
 

@@ -170,6 +170,50 @@ def test_port_bspline_matches_reference_build_random(oracle_built):
         ref.close()
 
 
+def tricubic_positions(rng, counts, sp, og, n, outside_frac=0.05):
+    """Positions for interpolation method 2 that stay where the reference is defined: off the upper faces (quirk Q2)
+    and out of the last x layer (ix == nx-2 makes the reference read past the end of its value vector, :825-832); first
+    cells and the last cells in y and z (whose neighbour reads land in the next row / x-slab) are included."""
+    counts = np.array(counts)
+    length = np.array(sp) * (counts - 1)
+    hi = np.array([np.array(sp)[0] * (counts[0] - 2), length[1], length[2]]) * (1 - 1e-9)
+    pos = np.array(og) + rng.uniform(0.0, 1.0, size=(n, 3)) * hi
+    k = n // 5
+    pos[:k] = np.array(og) + rng.uniform(0.0, 1.0, size=(k, 3)) * np.array(sp)                         # first cells
+    pos[k:2 * k, 1:] = (np.array(og) + length - rng.uniform(1e-9, 1.0, size=(k, 3)) * np.array(sp))[:, 1:]   # last y/z cells
+    m = max(1, int(outside_frac * n))
+    pos[-m:] = np.array(og) + rng.uniform(-0.2, 1.2, size=(m, 3)) * length
+    inside_last_x = (pos[-m:, 0] - og[0] >= hi[0]) & (pos[-m:, 0] - og[0] <= length[0])
+    pos[-m:, 0] = np.where(inside_last_x, og[0] - 0.01, pos[-m:, 0])                                   # outside instead
+    return pos
+
+
+def test_port_tricubic_matches_reference_build_random(oracle_built):
+    """Interpolation method 2 (tricubic Hermite, :796-893) incl. the first cells (derivative estimates off) and the last
+    y/z cells (flat-index neighbours in the next row / slab), bit for bit, with and without inv-power."""
+    if not oracle_built.ref_available():
+        pytest.skip("oracle/_ref not built; golden vectors tricubic_* cover it")
+    rng = np.random.default_rng(11)
+    for trial in range(10):
+        counts = tuple(int(v) for v in rng.integers(4, 14, size=3))
+        sp = tuple(rng.uniform(0.01, 0.3, size=3))
+        og = tuple(rng.uniform(-2, 2, size=3))
+        n = int(rng.integers(20, 300))
+        grid = rng.normal(size=counts) * 10
+        inv_power = [0.0]
+        if trial % 3 == 2:
+            grid = np.abs(grid) + 0.5
+            inv_power = [3.0]
+        pos = tricubic_positions(rng, counts, sp, og, n)
+        sc = rng.normal(size=(1, n))
+        ref = oracle_built.RefOracle(n, counts, sp, og, [grid], sc, inv_power=inv_power, interpolation_method=2)
+        port = oracle_built.PortOracle(counts, sp, og, [grid], sc, inv_power=inv_power, interpolation_method=2)
+        er, fr = ref.execute(pos)
+        ep, fp, _ = port.execute(pos, 0)
+        assert er == ep and np.array_equal(fr, fp), trial
+        ref.close()
+
+
 def test_inv_power_transform_matches_reference(oracle_built):
     """RUNTIME inv-power mode: the restatement of GridForce::applyInvPowerTransformation against the reference's own
     method (where built) and against the committed fixture it produced."""
