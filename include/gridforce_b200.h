@@ -62,9 +62,15 @@ typedef enum { GFB_PRECISION_MIXED = 0, GFB_PRECISION_DOUBLE = 1 } gfb_precision
  *   BSPLINE cubic B-spline (method 1, :727-795): the index clamping of the 4x4x4 stencil is baked into a padded copy, and
  *          for every cell and padded x-plane a the 4x4 (y,z) windows of planes a and a+1 are stored back to back as one
  *          128-byte record (256 bytes in DOUBLE), so a stencil is 2 records = 2 full lines read with 8 (16) aligned
- *          32-byte loads of exactly its 64 values; 32x the raw grid. Never chosen by AUTO. */
+ *          32-byte loads of exactly its 64 values; 32x the raw grid. Never chosen by AUTO.
+ *   POINTS tricubic Hermite (method 2, :796-893): the x-major points as the API hands them (FP32 in MIXED, FP64 in
+ *          DOUBLE; 0.5x / 1x the raw grid) followed by one zero-filled x-slab. The reference forms this method's 32
+ *          neighbour reads by FLAT index without clamping, so in the last y/z cells they land in the next row / slab
+ *          (reproduced) and in the last x layer past the end of its vector (undefined there; zeros here). The
+ *          arithmetic is FP64 in both precisions. Never chosen by AUTO. */
 typedef enum {
-    GFB_LAYOUT_AUTO = 0, GFB_LAYOUT_CELLS = 1, GFB_LAYOUT_ROWS = 2, GFB_LAYOUT_PAIRS = 3, GFB_LAYOUT_BSPLINE = 4
+    GFB_LAYOUT_AUTO = 0, GFB_LAYOUT_CELLS = 1, GFB_LAYOUT_ROWS = 2, GFB_LAYOUT_PAIRS = 3, GFB_LAYOUT_BSPLINE = 4,
+    GFB_LAYOUT_POINTS = 5
 } gfb_layout;
 
 /* How execute writes forces.

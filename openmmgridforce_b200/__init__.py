@@ -28,6 +28,7 @@ from .capi import (  # noqa: F401
     LAYOUT_ROWS,
     LAYOUT_PAIRS,
     LAYOUT_BSPLINE,
+    LAYOUT_POINTS,
     LAYOUT_NAMES,
     library_path,
     load_library,

@@ -404,6 +404,115 @@ __device__ __forceinline__ void accumulate_bspline(const GridView& G, const Atom
     Fz -= sd * gz;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tricubic Hermite interpolation (GridForce::setInterpolationMethod(2); ReferenceGridForceKernels.cpp:796-893): cubic
+// Hermite along x on the cell's four x-edges with centred-difference x-derivatives, then along y and along z with
+// one-sided differences of the partly interpolated values against the value-basis interpolant of the neighbour rows.
+// 32 of the 64 points ix-1..ix+2 x iy-1..iy+2 x iz-1..iz+2 are read: 16 on the four x-lines of the cell's edges, 8 in
+// the rows iy-1 / iy+2, 8 at iz-1 / iz+2. What the reference does and a derivation from scratch would not is kept:
+// dvdy comes from the z = iz plane only (:863), and a derivative estimate is 0 in the first cell layer of its axis.
+//
+// Layout GFB_LAYOUT_POINTS: the raw x-major array in S plus one zero x-slab. The reference addresses the neighbours by
+// flat index without clamping (:817-867), so in the last y / z cell they are the first values of the next row / slab;
+// the same flat indices are formed here. In the last x layer its reads leave the vector (undefined); here they hit the
+// zero slab. Lower neighbours are only read where the reference reads them (ix, iy, iz > 0): nothing precedes the array.
+// Per stencil 12 (x,y) rows are touched, 2 or 4 consecutive z-values each: 12-16 sectors.
+// Arithmetic FP64 for both storage types; d*spacing products of the reference ((v1 - v0)/(2s) * s) are formed as
+// 0.5*(v1 - v0), equal to rounding.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void hermite_basis(double t, double h[4], double d[4]) {   // :68-77; order h00, h01, h10, h11
+    const double u = 1.0 - t, t2 = t * t;
+    h[0] = (1.0 + 2.0 * t) * u * u;
+    h[1] = t2 * (3.0 - 2.0 * t);
+    h[2] = t * u * u;
+    h[3] = t2 * (t - 1.0);
+    d[0] = 6.0 * t2 - 6.0 * t;
+    d[1] = -d[0];
+    d[2] = 3.0 * t2 - 4.0 * t + 1.0;
+    d[3] = 3.0 * t2 - 2.0 * t;
+}
+
+template <typename S>
+__device__ __forceinline__ void tricubic_interpolate(const GridView& G, const AtomCell& c, double& val, double& gx, double& gy,
+                                                     double& gz) {
+    const long long nz = G.nc[2] + 1;
+    const long long nyz = (long long) (G.nc[1] + 1) * nz;
+    const S* v = static_cast<const S*>(G.cells) + ((long long) c.ix * nyz + (long long) c.iy * nz + c.iz);   // &V[im], :801
+    const bool xin = c.ix > 0 && c.ix < G.nc[0];   // :817 (ix < counts-1 always holds for an inside atom)
+    const bool yin = c.iy > 0 && c.iy < G.nc[1];   // :849
+    const bool zin = c.iz > 0 && c.iz < G.nc[2];   // :866
+    double hx[4], dhx[4], hy[4], dhy[4], hz[4], dhz[4];
+    hermite_basis(c.fx, hx, dhx);
+    hermite_basis(c.fy, hy, dhy);
+    hermite_basis(c.fz, hz, dhz);
+    // x: the four edges (iy+j, iz+k), :806-846
+    double vv[2][2], dv[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const S* q = v + j * nz + k;
+            const double f0 = (double) __ldg(q), f1 = (double) __ldg(q + nyz);
+            double d0 = 0.0, d1 = 0.0;   // derivative x spacing at ix and ix+1
+            if (xin) {
+                d0 = 0.5 * (f1 - (double) __ldg(q - nyz));
+                d1 = 0.5 * ((double) __ldg(q + 2 * nyz) - f0);
+            }
+            vv[j][k] = hx[0] * f0 + hx[1] * f1 + hx[2] * d0 + hx[3] * d1;
+            dv[j][k] = dhx[0] * f0 + dhx[1] * f1 + dhx[2] * d0 + dhx[3] * d1;
+        }
+    }
+    // y: rows iy-1 and iy+2 interpolated in x with the value basis only, :849-863
+    double vk[2], dxk[2], dvdy = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        double dy0 = 0.0, dy1 = 0.0;
+        if (yin) {
+            const double rm = hx[0] * (double) __ldg(v - nz + k) + hx[1] * (double) __ldg(v + nyz - nz + k);
+            const double rp = hx[0] * (double) __ldg(v + 2 * nz + k) + hx[1] * (double) __ldg(v + nyz + 2 * nz + k);
+            dy0 = vv[1][k] - rm;
+            dy1 = rp - vv[0][k];
+        }
+        vk[k] = hy[0] * vv[0][k] + hy[1] * vv[1][k] + hy[2] * dy0 + hy[3] * dy1;
+        dxk[k] = hy[0] * dv[0][k] + hy[1] * dv[1][k];
+        if (k == 0) dvdy = dhy[0] * vv[0][0] + dhy[1] * vv[1][0] + dhy[2] * dy0 + dhy[3] * dy1;   // z = iz plane only, :863
+    }
+    // z: points iz-1 and iz+2 interpolated in x and y with the value basis only, :866-876
+    double dz0 = 0.0, dz1 = 0.0;
+    if (zin) {
+        const double zm = hy[0] * (hx[0] * (double) __ldg(v - 1) + hx[1] * (double) __ldg(v + nyz - 1)) +
+                          hy[1] * (hx[0] * (double) __ldg(v + nz - 1) + hx[1] * (double) __ldg(v + nyz + nz - 1));
+        const double zp = hy[0] * (hx[0] * (double) __ldg(v + 2) + hx[1] * (double) __ldg(v + nyz + 2)) +
+                          hy[1] * (hx[0] * (double) __ldg(v + nz + 2) + hx[1] * (double) __ldg(v + nyz + nz + 2));
+        dz0 = vk[1] - zm;
+        dz1 = zp - vk[0];
+    }
+    val = hz[0] * vk[0] + hz[1] * vk[1] + hz[2] * dz0 + hz[3] * dz1;          // :873
+    gx = hz[0] * dxk[0] + hz[1] * dxk[1];                                      // :875
+    gy = dvdy;
+    gz = dhz[0] * vk[0] + dhz[1] * vk[1] + dhz[2] * dz0 + dhz[3] * dz1;       // :876
+}
+
+// One grid's tricubic contribution for an inside atom (:796-893), same epilogue as accumulate_bspline.
+template <typename S>
+__device__ __forceinline__ void accumulate_tricubic(const GridView& G, const AtomCell& c, double sd, double& e_g, double& Fx,
+                                                    double& Fy, double& Fz) {
+    double dval, gx, gy, gz;
+    tricubic_interpolate<S>(G, c, dval, gx, gy, gz);
+    if (G.inv_power > 0.0) {  // :879-886
+        const double base = dval;
+        dval = pow(base, G.inv_power);
+        const double pf = G.inv_power * pow(base, G.inv_power - 1.0);
+        gx *= pf;
+        gy *= pf;
+        gz *= pf;
+    }
+    e_g = sd * dval;                     // :892
+    Fx -= sd * (gx / G.spacing[0]);      // :889, :893
+    Fy -= sd * (gy / G.spacing[1]);
+    Fz -= sd * (gz / G.spacing[2]);
+}
+
 // :1093-1117 — harmonic wall outside the grid (unscaled). Inside atoms with scale == 0 land here too and contribute
 // exactly 0 (quirk Q3). Rare (1-2 % of atoms): kept out of line so its FP64 temporaries do not cost registers.
 struct Restraint {
@@ -435,7 +544,7 @@ __device__ __forceinline__ void accumulate_restraint(const GridView& G, double x
 
 template <typename S, int LAYOUT, int NG>
 __host__ __device__ constexpr int eval_min_blocks() {
-    return LAYOUT == GFB_LAYOUT_BSPLINE ? 2 : ((NG == 1 && sizeof(S) == 4) ? 6 : 4);
+    return (LAYOUT == GFB_LAYOUT_BSPLINE || LAYOUT == GFB_LAYOUT_POINTS) ? 2 : ((NG == 1 && sizeof(S) == 4) ? 6 : 4);
 }
 
 template <typename S, int LAYOUT, int NG, bool SAME, bool SINGLE>
@@ -561,6 +670,8 @@ __global__ void __launch_bounds__(kBlock, eval_min_blocks<S, LAYOUT, NG>()) gf_e
                 if (c.inside && s != 0.0) {
                     if constexpr (LAYOUT == GFB_LAYOUT_BSPLINE) {
                         accumulate_bspline<S>(G, c, s, e_g, Fx, Fy, Fz);
+                    } else if constexpr (LAYOUT == GFB_LAYOUT_POINTS) {
+                        accumulate_tricubic<S>(G, c, s, e_g, Fx, Fy, Fz);
                     } else {
                         S v[8];
                         load_stencil<S, LAYOUT>(G, c.ix, c.iy, c.iz, v);

@@ -116,6 +116,14 @@ static __global__ void __launch_bounds__(256) gf_repack_bspline_kernel(const dou
     }
 }
 
+// POINTS (see tricubic_interpolate): the values as they are, in S, then n_guard zeros.
+template <typename S>
+static __global__ void __launch_bounds__(256) gf_repack_points_kernel(const double* __restrict__ vals, S* __restrict__ out,
+                                                               size_t n_points, size_t n_guard) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_points + n_guard; i += (size_t) gridDim.x * blockDim.x)
+        out[i] = i < n_points ? (S) vals[i] : (S) 0;
+}
+
 // GridForce::applyInvPowerTransformation (openmmapi/src/GridForce.cpp:262-268; CachedGridData.cpp:50-57): the RUNTIME
 // inv-power mode stores G -> sign(G) * |G|^(1/n) once, and the evaluation applies ^n. In place, FP64.
 static __global__ void __launch_bounds__(256) gf_inv_power_transform_kernel(double* __restrict__ vals, size_t n, double inv_n) {

@@ -65,7 +65,7 @@ public:
     double getGridCap() const;
     void setOutOfBoundsRestraint(double k);                 // kJ/mol/nm^2, default 10000
     double getOutOfBoundsRestraint() const;
-    void setInterpolationMethod(int method);                // 0 trilinear, 1 cubic B-spline run on this platform; 2, 3 throw at Context creation
+    void setInterpolationMethod(int method);                // 0 trilinear, 1 cubic B-spline, 2 tricubic run on this platform; 3 throws at Context creation
     int getInterpolationMethod() const;
 
     // ---- which particles ------------------------------------------------------------------------------------------

@@ -55,8 +55,9 @@ static unsigned long long hashWords(const void* data, size_t bytes, unsigned lon
 int b200LayoutForMethod(int interpolationMethod, const char* who) {
     if (interpolationMethod == 0) return GFB_LAYOUT_AUTO;        // trilinear
     if (interpolationMethod == 1) return GFB_LAYOUT_BSPLINE;     // cubic B-spline
-    throw OpenMMException(std::string(who) + ": interpolation methods 2 (tricubic) and 3 (quintic Hermite) need derivative "
-                          "grids and are not implemented on this platform; use 0 (trilinear) or 1 (cubic B-spline)");
+    if (interpolationMethod == 2) return GFB_LAYOUT_POINTS;      // tricubic Hermite (finite-difference derivatives)
+    throw OpenMMException(std::string(who) + ": interpolation method 3 (quintic Hermite) needs the 27 derivative grids and is "
+                          "not implemented on this platform; use 0 (trilinear), 1 (cubic B-spline) or 2 (tricubic)");
 }
 
 std::shared_ptr<SharedGrid> b200AcquireGrid(gfb_device* dev, int ordinal, int precision, int layout, const std::vector<int>& counts,

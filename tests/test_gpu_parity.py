@@ -18,7 +18,7 @@ import cases  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 TOL = {0: (1e-6, 1e-5), 1: (1e-12, 1e-12)}     # precision -> (energy, force)
-GOLDEN = sorted(n for n in cases.CASES if not n.startswith("bspline_"))      # trilinear cases; B-spline: test_gpu_bspline.py
+GOLDEN = sorted(n for n in cases.CASES if not n.startswith(("bspline_", "tricubic_")))      # trilinear cases; B-spline: test_gpu_bspline.py, tricubic: test_gpu_tricubic.py
 # (precision, layout): every device layout of include/gridforce_b200.h's gfb_layout, in both arithmetic modes
 MODES = [(0, 1), (0, 2), (0, 3), (1, 1), (1, 2)]
 MODE_IDS = ["mixed-cells", "mixed-rows", "mixed-pairs", "double-cells", "double-rows"]

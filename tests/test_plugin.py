@@ -163,7 +163,7 @@ def test_plugin_refuses_what_it_does_not_implement():
     c, _ = cases.load_golden("ramp_grid")
     platform = gfp.Platform.getPlatformByName("B200")
     system, forces = _build_system(gfp, c)
-    forces[0].setInterpolationMethod(2)               # tricubic needs derivative grids: loud refusal, no fallback
+    forces[0].setInterpolationMethod(3)               # quintic Hermite needs the 27 derivative grids: loud refusal, no fallback
     with pytest.raises(RuntimeError, match="not implemented on this platform"):
         gfp.Context(system, platform)
 

@@ -1,7 +1,9 @@
 """DRAM bytes per launch of the profiled kernel out of `ncu --page raw --csv` files -> profiles/r2_traffic.json, keyed by
 the bench.py workload name and stamped with the hash of the kernel sources (bench.py reports `roofline.traffic` only while
 the sources still hash to what was profiled).
-usage: python tools/ncu_traffic.py KEY=raw.csv[=caveat] [...]     e.g. C5=profiles/r2b_c5full_raw.csv"""
+usage: python tools/ncu_traffic.py KEY=raw.csv[=caveat] [...]     e.g. C5=profiles/r2b_c5full_raw.csv
+       python tools/ncu_traffic.py --restamp "why"     after tools/sass_identity.sh has shown that the profiled kernels'
+       SASS did not change although a hashed source file did: every entry gets the current hash and the reason."""
 import csv
 import importlib.util
 import json
@@ -15,6 +17,12 @@ spec.loader.exec_module(bench)
 
 out_path = os.path.join(ROOT, "profiles", "r2_traffic.json")
 doc = json.load(open(out_path)) if os.path.exists(out_path) else {}
+if len(sys.argv) >= 3 and sys.argv[1] == "--restamp":
+    for entry in doc.values():
+        entry.setdefault("restamped", []).append({"from": entry["source_sha256_16"], "to": bench.kernel_source_hash(), "why": sys.argv[2]})
+        entry["source_sha256_16"] = bench.kernel_source_hash()
+    json.dump(doc, open(out_path, "w"), indent=1, sort_keys=True)
+    sys.exit(0)
 for arg in sys.argv[1:]:
     key, path = arg.split("=", 1)
     note = None
