@@ -33,7 +33,7 @@ lib: $(LIBOUT)
 # One object per translation unit so that `make -j` builds the kernel families in parallel (the single-file build took
 # 90 s). Every header of csrc/ is a prerequisite of every object: an edit anywhere rebuilds, a stale .so cannot happen.
 CUDA_HDRS := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/gridforce_b200.h
-CUDA_OBJS := $(addprefix $(OBJDIR)/, gf_capi.o gf_grids.o gf_aux.o gf_multi.o gf_launch_general_f32.o gf_launch_general_f64.o \
+CUDA_OBJS := $(addprefix $(OBJDIR)/, gf_capi.o gf_grids.o gf_aux.o gf_multi.o gf_resident.o gf_launch_general_f32.o gf_launch_general_f64.o \
                gf_launch_lines_1.o gf_launch_lines_2.o gf_launch_lines_3.o gf_launch_lines_4.o gf_launch_records_f64.o gf_launch_bspline.o)
 
 $(OBJDIR)/gf_launch_lines_%.o: $(CSRC)/gf_launch_lines.cu $(CUDA_HDRS)

@@ -450,6 +450,16 @@ def run_single_ligand(gf, dev, steps=2000):
     f_h, _t2 = pinned_array(w.pos.shape)
     e_h, _t3 = pinned_array((1,))
     secs = time_e2e(lambda: kern.execute_host(pos_h, forces=f_h, energies_out=e_h), steps, 50)
+    e_launch, f_launch = float(e_h[0]), f_h.copy()
+    # The same calls with the resident evaluator (gfb_kernel_set_resident): a block stays on the GPU between steps, no
+    # launch and no synchronise per step.
+    kern.set_resident(True)
+    rsecs = time_e2e(lambda: kern.execute_host(pos_h, forces=f_h, energies_out=e_h), steps, 50)
+    resident = {"us_per_step": rsecs / steps * 1e6, "steps_per_s": steps / rsecs, "block_launches": kern.resident_launches(),
+                "gpu_us_last_step": dict(zip(("positions_in", "evaluation", "results_stored"), (float(v) for v in kern.resident_timeline()))),
+                "same_result_as_launch_path": bool(abs(float(e_h[0]) - e_launch) <= 1e-6 * abs(e_launch) and
+                                                   np.abs(f_h - f_launch).max() <= 1e-5 * np.abs(f_launch).max()),
+                "api": "gfb_kernel_execute_host after gfb_kernel_set_resident(1), ctypes loop"}
     kern.close()
     for g in grids:
         g.close()
@@ -465,16 +475,22 @@ def run_single_ligand(gf, dev, steps=2000):
             system.addParticle(1.0)
         for f in grid_forces_for(gfp, w):
             system.addForce(f)
-        ctx = gfp.Context(system, gfp.Platform.getPlatformByName("B200"))
-        ctx.setPositions(w.pos.reshape(-1, 3))
-        ctx.timeEvaluations(200)
-        psecs, _e = ctx.timeEvaluations(steps)
-        plugin = {"us_per_step": psecs * 1e6, "steps_per_s": 1.0 / psecs, "grid_force_limited_ns_per_day": 4e-6 * 86400.0 / psecs,
-                  "api": "B200 platform plugin: Context::calcForcesAndEnergy over 3 GridForces, C++ step loop"}
-        del ctx
+        for key, props in (("launch", None), ("resident", {"ResidentKernel": "true"})):
+            ctx = gfp.Context(system, gfp.Platform.getPlatformByName("B200"), props)
+            ctx.setPositions(w.pos.reshape(-1, 3))
+            ctx.timeEvaluations(200)
+            psecs, _e = ctx.timeEvaluations(steps)
+            entry = {"us_per_step": psecs * 1e6, "steps_per_s": 1.0 / psecs, "grid_force_limited_ns_per_day": 4e-6 * 86400.0 / psecs,
+                     "energy": _e}
+            if key == "launch":
+                plugin = dict(entry, api="B200 platform plugin: Context::calcForcesAndEnergy over 3 GridForces, C++ step loop")
+            else:
+                plugin["resident_kernel"] = dict(entry, api='the same Context created with {"ResidentKernel": "true"}')
+            del ctx
     except Exception as exc:      # reported, not fatal: the C-ABI figure above stands on its own
-        plugin = {"error": repr(exc)}
+        plugin = dict(plugin or {}, error=repr(exc))
     return {"workload": w.name, "us_per_step": secs / steps * 1e6, "steps_per_s": sps, "openmm_plugin_path": plugin,
+            "resident_evaluator": resident,
             "grid_force_limited_ns_per_day": sps * 4e-6 * 86400.0, "value": w.evals * sps, "unit": UNIT,
             "note": "latency-bound: one launch per step on host-mapped memory + one synchronize; upper bound on MD ns/day at 4 fs"}
 

@@ -71,6 +71,10 @@ SIGNATURES = {
     "gfb_kernel_set_energy_slots": (_i, [_vp, _vp, _i]),
     "gfb_kernel_eval_path": (_i, [_vp]),
     "gfb_kernel_set_launch_overlap": (_i, [_vp, _i]),
+    "gfb_kernel_set_resident": (_i, [_vp, _i, _ll]),
+    "gfb_kernel_resident_stop": (_i, [_vp]),
+    "gfb_kernel_resident_launches": (_ll, [_vp]),
+    "gfb_kernel_resident_timeline": (_i, [_vp, _vp]),
     "gfb_kernel_execute_host": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i]),
     "gfb_kernel_execute_device": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp]),
     "gfb_kernel_sort_atoms": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
@@ -372,6 +376,22 @@ class Kernel:
         """PDL for execute_device launches (see gfb_kernel_set_launch_overlap: positions must not come from the kernel
         launched just before)."""
         _check(load_library().gfb_kernel_set_launch_overlap(self._h, 1 if enable else 0))
+
+    def set_resident(self, enable=True, idle_us=0):
+        """gfb_kernel_set_resident: one-ligand-per-step host calls are served by a block that stays on the GPU."""
+        _check(load_library().gfb_kernel_set_resident(self._h, 1 if enable else 0, int(idle_us)))
+
+    def resident_stop(self):
+        _check(load_library().gfb_kernel_resident_stop(self._h))
+
+    def resident_launches(self):
+        return int(load_library().gfb_kernel_resident_launches(self._h))
+
+    def resident_timeline(self):
+        """Microseconds of the last resident step on the GPU: positions in, evaluation, results stored."""
+        out = np.zeros(3)
+        _check(load_library().gfb_kernel_resident_timeline(self._h, _ptr(out)))
+        return out
 
     def update_parameters(self, scaling=None, inv_power=None):
         sc = _host_f64(scaling).reshape(self.n_grids, self.n_atoms) if scaling is not None else None

@@ -242,6 +242,7 @@ int gfb_kernel_create(gfb_device* dev, int n_grids, gfb_grid* const* grids, int 
 int gfb_kernel_destroy(gfb_kernel* k) {
     if (!k) return GFB_OK;
     cudaSetDevice(k->dev->ordinal);
+    resident_destroy(k);
     cudaStreamSynchronize(k->dev->stream);
     cudaStreamSynchronize(k->dev->copy_stream);
     if (k->d_scaling) cudaFree(k->d_scaling);
@@ -264,6 +265,8 @@ int gfb_kernel_destroy(gfb_kernel* k) {
 int gfb_kernel_set_energy_slots(gfb_kernel* k, const int* slots, int n_slots) {
     if (!k) return fail(GFB_ERR_INVALID, "gfb_kernel_set_energy_slots: NULL kernel");
     CUDA_TRY(cudaSetDevice(k->dev->ordinal));
+    int rs = resident_stop(k);
+    if (rs != GFB_OK) return rs;
     if (!slots) {
         if (k->d_slots) cudaFree(k->d_slots);
         k->d_slots = nullptr;
@@ -289,6 +292,8 @@ int gfb_kernel_set_launch_overlap(gfb_kernel* k, int enable) {
 int gfb_kernel_update_parameters(gfb_kernel* k, const double* scaling, const double* inv_power) {
     if (!k) return fail(GFB_ERR_INVALID, "gfb_kernel_update_parameters: NULL kernel");
     CUDA_TRY(cudaSetDevice(k->dev->ordinal));
+    int rs = resident_stop(k);      // a resident block holds inv-power in its arguments and may hold scaling factors in L1
+    if (rs != GFB_OK) return rs;
     if (inv_power)
         for (int g = 0; g < k->n_grids; g++) {
             if (inv_power[g] < 0.0) return fail(GFB_ERR_INVALID, "gfb_kernel_update_parameters: inv_power[%d] < 0", g);
@@ -500,6 +505,8 @@ static int eval_block_threads(const gfb_kernel* k) {
 static int execute_host_small(gfb_kernel* k, int n_particles, const double* pos, double* energies, double* grid_energies,
                               void* forces, int force_mode) {
     gfb_device* dev = k->dev;
+    if (resident_enabled(k) && !k->want_atom_energies && force_mode != GFB_FORCE_F32_STORE)   // gfb_kernel_set_resident
+        return resident_step(k, n_particles, pos, energies, grid_energies, static_cast<double*>(forces), force_mode == GFB_FORCE_F64_ADD);
     const size_t np3 = (size_t) n_particles * 3;
     const int ng = k->n_grids;
     const size_t e_count = 1 + (size_t) ng;

@@ -113,6 +113,7 @@ struct gfb_kernel {
     bool unique_particles;   // no particle index occurs twice: a plain store per evaluated particle is the whole force
     bool want_atom_energies; // gfb_kernel_request_atom_energies
     long long atom_e_count;  // entries of d_atom_e written by the last host-path call
+    void* resident = nullptr;   // gfb::ResidentState (gf_resident.cu) once gfb_kernel_set_resident(enable) has been called
 };
 
 namespace gfb {
@@ -134,6 +135,12 @@ struct EvalExtra {
 int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos, double* d_energies,
                  double* d_grid_energies, void* d_forces, int force_mode, long long force_stride, const int* d_order,
                  double* d_energies_clear, cudaStream_t stream, const EvalExtra& x = EvalExtra());
+
+// Resident evaluator (gf_resident.cu): one ligand per MD step served by a block that stays on the GPU.
+bool resident_enabled(const gfb_kernel* k);     // switched on and this state qualifies
+int resident_step(gfb_kernel* k, int n_particles, const double* pos, double* energies, double* grid_energies, double* forces, bool add);
+int resident_stop(gfb_kernel* k);               // the block exits (parameters it caches are about to change); relaunched on demand
+void resident_destroy(gfb_kernel* k);
 }  // namespace gfb
 
 #endif

@@ -16,7 +16,11 @@ B200Platform::B200Platform() {
     platformProperties.push_back(DeviceIndex());
     platformProperties.push_back(Precision());
     setPropertyDefaultValue(DeviceIndex(), "0");
+    platformProperties.push_back(ResidentKernel());
+    platformProperties.push_back(ResidentIdleMicroseconds());
     setPropertyDefaultValue(Precision(), "mixed");
+    setPropertyDefaultValue(ResidentKernel(), "false");
+    setPropertyDefaultValue(ResidentIdleMicroseconds(), "100000");
 }
 
 void B200Platform::contextCreated(ContextImpl& context, const std::map<std::string, std::string>& properties) const {
@@ -55,7 +59,13 @@ KernelImpl* B200GridForceKernelFactory::createKernelImpl(std::string name, const
     if (prec != "mixed" && prec != "double")
         throw OpenMMException("B200 platform: Precision must be 'mixed' or 'double', got '" + prec + "'");
     const int device = atoi(b200.propertyFor(context, B200Platform::DeviceIndex()).c_str());
-    return new B200CalcGridForceKernel(name, platform, device, prec == "double" ? GFB_PRECISION_DOUBLE : GFB_PRECISION_MIXED, &context);
+    const std::string& res = b200.propertyFor(context, B200Platform::ResidentKernel());
+    if (res != "true" && res != "false")
+        throw OpenMMException("B200 platform: ResidentKernel must be 'true' or 'false', got '" + res + "'");
+    const long long idle = atoll(b200.propertyFor(context, B200Platform::ResidentIdleMicroseconds()).c_str());
+    B200CalcGridForceKernel* k = new B200CalcGridForceKernel(name, platform, device, prec == "double" ? GFB_PRECISION_DOUBLE : GFB_PRECISION_MIXED, &context);
+    k->setResident(res == "true", idle);
+    return k;
 }
 
 }  // namespace GridForcePlugin

@@ -60,6 +60,14 @@ int b200LayoutForMethod(int interpolationMethod, const char* who) {
                           "not implemented on this platform; use 0 (trilinear), 1 (cubic B-spline) or 2 (tricubic)");
 }
 
+void B200CalcGridForceKernel::applyResident(gfb_kernel* k) const {
+    if (!resident) return;
+    // GFB_ERR_UNSUPPORTED (B-spline / tricubic layouts, more than 256 atoms, repeated particles): that state keeps the
+    // launch-per-step path; the property is a request, not a requirement.
+    if (gfb_kernel_set_resident(k, 1, residentIdleUs) == GFB_ERR_CUDA)
+        throw OpenMMException(std::string("GridForce[B200]: resident evaluator: ") + gfb_last_error());
+}
+
 std::shared_ptr<SharedGrid> b200AcquireGrid(gfb_device* dev, int ordinal, int precision, int layout, const std::vector<int>& counts,
                                             const std::vector<double>& spacing, const double origin[3],
                                             const std::vector<double>& vals) {
@@ -313,6 +321,7 @@ void B200CalcGridForceKernel::build(const GridForce& force) {
     gfb_kernel* k = 0;
     check(gfb_kernel_create(dev, 1, &handle, (int) scaling.size(), scaling.data(), particles, &invPower, &oobK, &k), "kernel setup");
     kernels.push_back(k);
+    applyResident(k);
 
     // what a fused launch needs from this member, and which other kernels may share one with it
     scalingCopy = scaling;
@@ -427,6 +436,7 @@ double B200CalcGridForceKernel::executeFused(ContextImpl& context, const double*
         }
         check(gfb_kernel_create(dev, count, grids.data(), (int) scalingCopy.size(), scalingAll.data(),
                                 ligandCopy.empty() ? 0 : ligandCopy.data(), invPower.data(), oobK.data(), &fk), "fused kernel setup");
+        applyResident(fk);
     }
     double total = 0.0;
     std::vector<double> perGrid(count, 0.0);

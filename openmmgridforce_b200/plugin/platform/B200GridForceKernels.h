@@ -42,8 +42,16 @@ public:
     void copyParametersToContext(OpenMM::ContextImpl& context, const GridForce& force);
     std::vector<double> getParticleGroupEnergies();
     std::vector<double> getParticleAtomEnergies();
+    // Platform property "ResidentKernel": evaluation states that qualify (gfb_kernel_set_resident) keep a block on the GPU.
+    void setResident(bool on, long long idleMicroseconds) {
+        resident = on;
+        residentIdleUs = idleMicroseconds;
+    }
 
 private:
+    void applyResident(gfb_kernel* k) const;   // after gfb_kernel_create; states that do not qualify stay on the launch path
+    bool resident = false;
+    long long residentIdleUs = 100000;
     void release();
     void build(const GridForce& force);
     const OpenMM::System* system = 0;       // for the auto-derived inputs (NonbondedForce parameters)

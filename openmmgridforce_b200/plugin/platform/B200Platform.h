@@ -8,6 +8,9 @@
 // platforms/reference/src/ReferenceGridForceKernelFactory.cpp:44-72 relies on for the Reference platform):
 //   "DeviceIndex"  GPU ordinal, default "0"
 //   "Precision"    "mixed" (default) or "double"
+//   "ResidentKernel"  "false" (default) or "true": one-ligand-per-step evaluations are served by a block that stays on the
+//                  GPU between steps (gfb_kernel_set_resident: no launch, no synchronise per step)
+//   "ResidentIdleMicroseconds"  how long that block waits for the next step before it leaves the GPU, default "100000"
 // Per-Context values given to the Context constructor arrive in contextCreated() and win over the defaults;
 // getPropertyValue(context, name) reports what a Context uses.
 #ifndef B200_PLATFORM_H_
@@ -41,6 +44,14 @@ public:
     }
     static const std::string& Precision() {
         static const std::string key = "Precision";
+        return key;
+    }
+    static const std::string& ResidentKernel() {
+        static const std::string key = "ResidentKernel";
+        return key;
+    }
+    static const std::string& ResidentIdleMicroseconds() {
+        static const std::string key = "ResidentIdleMicroseconds";
         return key;
     }
 
