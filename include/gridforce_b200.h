@@ -242,12 +242,13 @@ GFB_API int gfb_kernel_set_launch_overlap(gfb_kernel* k, int enable);
 /* Resident evaluator for the one-ligand-per-MD-step case (BASELINE configs[1]; the call B200CalcGridForceKernel::execute
  * makes once per step, in place of ReferenceCalcGridForceKernel::execute, ReferenceGridForceKernels.cpp:646-1121).
  * With enable != 0, gfb_kernel_execute_host calls with n_replicas == 1 are served by ONE block that stays on the GPU and
- * is driven through a page-locked control block (positions in, step number; forces, energies and the step number out):
- * no kernel launch and no stream synchronisation per step. The block exits by itself after idle_us microseconds without
+ * is driven through page-locked memory both sides address (positions in, forces and energies out, every double a
+ * 16-byte packet that carries the step number in both halves, so the data is its own arrival flag): no kernel launch,
+ * no stream synchronisation, no fence and no separate command word per step. The block exits by itself after idle_us microseconds without
  * a step (<= 0: 100 000) and is launched again by the next one, so implicit device-wide synchronisations elsewhere in the
  * process (cudaFree, cudaDeviceSynchronize) wait at most that long; it is also stopped by
  * gfb_kernel_update_parameters, gfb_kernel_set_energy_slots, gfb_kernel_resident_stop and gfb_kernel_destroy.
- * Qualifies: trilinear packed cells (GFB_LAYOUT_CELLS, or the interleaved records after gfb_grid_release_cells), 1..256
+ * Qualifies: trilinear packed cells (GFB_LAYOUT_CELLS, or the interleaved records after gfb_grid_release_cells), 1..224
  * evaluated atoms with distinct particle indices, no energy slots, F64 force modes, no per-atom energies, and
  * CUDA_LAUNCH_BLOCKING unset; GFB_ERR_UNSUPPORTED otherwise (calls that do not qualify later on — several replicas, FP32
  * forces — take the normal path). Results are those of the general kernel's arithmetic (same device functions).
@@ -257,8 +258,8 @@ GFB_API int gfb_kernel_set_resident(gfb_kernel* k, int enable, long long idle_us
 GFB_API int gfb_kernel_resident_stop(gfb_kernel* k);
 GFB_API long long gfb_kernel_resident_launches(const gfb_kernel* k);
 /* Where the block spent the last resident step, from %globaltimer stamps it leaves in the control block, microseconds:
- * us[0] command seen -> positions on the GPU, us[1] -> all grids evaluated, us[2] -> results stored (before the release). */
-GFB_API int gfb_kernel_resident_timeline(const gfb_kernel* k, double us[3]);
+ * us[0] positions seen -> all grids evaluated, us[1] -> force and energy packets issued. */
+GFB_API int gfb_kernel_resident_timeline(const gfb_kernel* k, double us[2]);
 
 /* CalcGridForceKernel::execute for host-resident data (Reference-platform style), batched over replicas.
  *   pos       host [n_replicas][n_particles][3] doubles (std::vector<Vec3> layout)

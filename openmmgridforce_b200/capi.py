@@ -388,8 +388,8 @@ class Kernel:
         return int(load_library().gfb_kernel_resident_launches(self._h))
 
     def resident_timeline(self):
-        """Microseconds of the last resident step on the GPU: positions in, evaluation, results stored."""
-        out = np.zeros(3)
+        """Microseconds of the last resident step on the GPU: evaluation, result packets issued."""
+        out = np.zeros(2)
         _check(load_library().gfb_kernel_resident_timeline(self._h, _ptr(out)))
         return out
 

@@ -5,21 +5,25 @@
 //
 // Such a step is pure latency. execute_host_small (gf_capi.cu) already works on host-mapped memory with ONE launch and ONE
 // synchronise per step, and that launch + synchronise is what is left (~15 us). Here a single block stays resident on
-// the GPU and is driven through a page-locked control block that both sides address directly:
+// the GPU and talks to the host through page-locked memory both sides address directly, with the DATA AS ITS OWN FLAG
+// (the idea of gf_gather_ll_kernel, applied to PCIe): every double travels as a 16-byte packet
+//     { low 32 bits | tag << 32 ,  high 32 bits | tag << 32 },      tag = (step number << 2 | what is wanted) mod 2^32
+// so a packet whose two 8-byte halves both carry this step's tag is complete, whatever order the halves became visible
+// in. Nothing else is needed: no command word, no fence, no second round trip.
 //
-//   host:   positions -> ctl.pos, then cmd = step number | what is wanted (release)     spins on done_seq == n
-//   block:  thread 0 polls cmd over PCIe (ld.relaxed.sys, one fence when it changes); the block brings the positions in
-//           as contiguous 16-byte loads through shared memory, every thread evaluates its atom on all grids (the same
-//           device functions as gf_eval_kernel: classify, load_stencil, accumulate_inside, accumulate_restraint), the
-//           forces go out as contiguous 16-byte stores, the block sums the energies in a fixed order, and thread 0
-//           publishes done_seq = n with one st.release.sys.
+//   host:   writes the 3 x n_atoms position packets of step n                          then reads the result packets
+//   block:  its threads spin on the position packets (ld.relaxed.sys, 16 bytes each: the poll IS the position read),
+//           every thread evaluates its atom on all grids (the same device functions as gf_eval_kernel: classify,
+//           load_stencil, accumulate_inside, accumulate_restraint), forces and energies go back as packets
+//           (st.relaxed.sys, 16 bytes each), energies summed by the block in a fixed order.
 //
-// A step is then three PCIe trips (poll sees the command, positions come in, results go out) plus ~2 us of evaluation.
-// The block never holds the GPU: after `idle` microseconds without a command it clears ctl.alive and exits, and the next
-// step launches it again (so cudaFree / cudaDeviceSynchronize elsewhere in the process wait for at most that long);
-// every host-side wait is bounded and fails with an error instead of hanging.
+// A step is then one PCIe read that sees the positions, ~2.5 us of evaluation, and posted writes back. One extra thread
+// watches the control word (stop) and the clock: after `idle` microseconds without a step the block clears ctl.alive and
+// exits, and the next step launches it again (so cudaFree / cudaDeviceSynchronize / the driver loading another module
+// elsewhere in the process wait for at most that long); every host-side wait is bounded and fails with an error instead
+// of hanging.
 //
-// Opt-in (gfb_kernel_set_resident; platform property "ResidentKernel"): one replica, at most 256 evaluated atoms, no
+// Opt-in (gfb_kernel_set_resident; platform property "ResidentKernel"): one replica, at most 224 evaluated atoms, no
 // energy slots, trilinear packed cells (per-grid or interleaved records), either precision, inv-power included.
 #include <time.h>
 
@@ -27,6 +31,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "gf_handles.h"
 #include "gf_kernels.cuh"
@@ -36,62 +41,64 @@ using namespace gfb;
 namespace {
 
 constexpr unsigned long long kStop = ~0ull;
-constexpr int kMaxResidentAtoms = 256;    // one block; 255 registers per thread stay available (a ligand has ~50 atoms)
+constexpr int kMaxResidentAtoms = 224;    // + the watcher's warp = 256 threads: 255 registers per thread stay available (a ligand has ~50 atoms)
+
+struct Packet {                           // 16 bytes, 16-byte aligned
+    unsigned long long h[2];
+};
 
 // Page-locked, host- and device-addressable. Lines written by the host and lines written by the device are kept apart.
 struct ResidentCtl {
-    volatile unsigned long long cmd;        // host -> device: (step number << 2) | want bits (1 forces, 2 per-grid energies);
-                                            // kStop = exit now
+    volatile unsigned long long cmd;        // host -> device: kStop = exit now (anything else: keep going)
     unsigned char pad0[128 - 8];
-    volatile unsigned long long done_seq;   // device -> host: last step whose results are complete
     volatile unsigned long long alive;      // device -> host: cleared by the block right before it exits
-    unsigned char pad1[128 - 16];
-    double energies[1 + GFB_MAX_GRIDS];     // device -> host: total, then per grid
-    unsigned long long stamps[4];           // device -> host: %globaltimer (ns) of the last step: command seen, positions in,
-                                            // evaluated, results stored (gfb_kernel_resident_timeline)
-    unsigned char pad2[128 - (1 + GFB_MAX_GRIDS) * 8 - 32];
-    // followed by: double pos[3 * n_particles] (host -> device), padded to 128 bytes, double forces[3 * n_particles]
+    unsigned long long stamps[3];           // device -> host: %globaltimer (ns) of the last step: positions seen, evaluated,
+                                            // results stored (gfb_kernel_resident_timeline)
+    unsigned char pad1[128 - 32];
+    // followed by: Packet in[3 * n_atoms] (host -> device), padded to 128 bytes;
+    //              Packet out[3 * n_atoms + 1 + GFB_MAX_GRIDS] (device -> host): forces, total energy, per-grid energies
 };
-static_assert(sizeof(ResidentCtl) == 384, "three 128-byte lines");
+static_assert(sizeof(ResidentCtl) == 256, "two 128-byte lines");
 
 struct ResidentParams {
     GridView grid[GFB_MAX_GRIDS];
-    int n_grids, n_atoms, same_geom, n_particles;
-    const int* particles;              // [n_atoms] or null
+    int n_grids, n_atoms, same_geom, pad_;
     ResidentCtl* ctl;
-    const double* pos;                 // ctl.pos
-    double* forces;                    // ctl.forces
+    const Packet* in;
+    Packet* out;
     unsigned long long start_seq;      // last step already done when this launch starts
     unsigned long long idle_ns;
 };
+
+__host__ __device__ inline Packet pack(unsigned long long bits, unsigned tag) {
+    Packet p;
+    p.h[0] = (bits & 0xffffffffull) | ((unsigned long long) tag << 32);
+    p.h[1] = (bits >> 32) | ((unsigned long long) tag << 32);
+    return p;
+}
+__host__ __device__ inline bool packet_has(const Packet& p, unsigned tag) {
+    return (unsigned) (p.h[0] >> 32) == tag && (unsigned) (p.h[1] >> 32) == tag;
+}
+__host__ __device__ inline unsigned long long packet_bits(const Packet& p) { return (p.h[0] & 0xffffffffull) | (p.h[1] << 32); }
 
 __device__ __forceinline__ unsigned long long ld_relaxed_sys(const volatile unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
-__device__ __forceinline__ void st_release_sys(volatile unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ double ld_sys_f64(const double* p) {   // host memory the host has just written: never from a cache
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+__device__ __forceinline__ Packet ld_packet_sys(const Packet* p) {   // host memory the host is writing: never from a cache
+    Packet v;
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(v.h[0]), "=l"(v.h[1]) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ double2 ld_sys_f64x2(const double* p) {
-    double2 v;
-    asm volatile("ld.relaxed.sys.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_sys_f64(double* p, double v) {
-    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ void st_sys_f64x2(double* p, double2 v) {
-    asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+__device__ __forceinline__ void st_packet_sys(Packet* p, const Packet& v) {
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(v.h[0]), "l"(v.h[1]) : "memory");
 }
 __device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys(volatile unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
@@ -99,63 +106,73 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
+// blockDim.x = n_atoms rounded up to a warp + one more warp, whose first lane is the watcher.
 template <typename S>
-__global__ void __launch_bounds__(kMaxResidentAtoms, 1) gf_resident_kernel(const __grid_constant__ ResidentParams p) {
+__global__ void __launch_bounds__(kMaxResidentAtoms + 32, 1) gf_resident_kernel(const __grid_constant__ ResidentParams p) {
     constexpr bool EXACT = sizeof(S) == 8;
-    __shared__ unsigned long long s_cmd;
-    __shared__ unsigned long long s_t[3];
-    __shared__ double s_e[kMaxResidentAtoms / 32][1 + GFB_MAX_GRIDS];
-    __shared__ __align__(16) double s_xyz[3 * kMaxResidentAtoms + 2];    // positions in, then forces out (plain states)
+    __shared__ volatile int s_stop;
+    __shared__ unsigned s_want;
+    __shared__ unsigned long long s_t[2];
+    __shared__ double s_e[kMaxResidentAtoms / 32 + 1][1 + GFB_MAX_GRIDS];
+    __shared__ double s_xyz[3 * kMaxResidentAtoms];      // positions in, then forces out
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const unsigned n_warps = (blockDim.x + 31u) >> 5;
+    const unsigned n_workers = blockDim.x - 32u;          // threads that fetch, evaluate and send
+    const unsigned n_warps = n_workers >> 5;
+    const bool worker = tid < n_workers;
+    const bool watcher = tid == n_workers;
     const bool active = tid < (unsigned) p.n_atoms;
-    const int particle = active ? (p.particles ? p.particles[tid] : (int) tid) : 0;
-    // Plain state (every particle is an evaluated atom, in order): the 24*n bytes of positions come in, and the forces go
-    // out, as contiguous 16-byte accesses (full PCIe payloads) through shared memory instead of stride-24 doubles.
-    const bool plain = p.particles == nullptr && p.n_atoms == p.n_particles;
-    const unsigned n_pairs = (3u * (unsigned) p.n_atoms + 1u) >> 1;       // 16-byte units; the arrays are padded to 128 bytes
+    const unsigned n_in = 3u * (unsigned) p.n_atoms;
     ResidentCtl* ctl = p.ctl;
     unsigned long long expected = p.start_seq + 1;
+    if (tid == 0) s_stop = 0;
+    __syncthreads();
 
     for (;;) {
-        if (tid == 0) {
+        // ---- wait for step `expected`: its position packets are the signal ---------------------------------------------
+        const unsigned tag_hi = (unsigned) (expected << 2);            // the low two bits say what is wanted
+        if (worker) {
             const unsigned long long t0 = global_ns();
-            unsigned long long c;
-            for (;;) {
-                c = ld_relaxed_sys(&ctl->cmd);
-                if (c == kStop || (c >> 2) == expected) break;
-                if (global_ns() - t0 > p.idle_ns) {
-                    c = kStop;
-                    break;
+            for (unsigned i = tid; i < n_in; i += n_workers) {
+                for (;;) {
+                    const Packet q = ld_packet_sys(p.in + i);
+                    if (((unsigned) (q.h[0] >> 32) & ~3u) == tag_hi && (q.h[0] >> 32) == (q.h[1] >> 32)) {
+                        s_xyz[i] = __longlong_as_double((long long) packet_bits(q));
+                        if (i == 0) s_want = (unsigned) (q.h[0] >> 32) & 3u;
+                        break;
+                    }
+                    if (s_stop) break;
+                    if (global_ns() - t0 > p.idle_ns) {      // also bounds a step whose packets stop coming half-way
+                        s_stop = 1;
+                        break;
+                    }
                 }
             }
-            fence_sys();             // acquire: the positions written before the command are what the loads below see
-            s_cmd = c;
-            s_t[0] = global_ns();
+        } else if (watcher) {
+            const unsigned long long t0 = global_ns();
+            for (;;) {
+                const unsigned long long c = ld_relaxed_sys(&ctl->cmd);
+                const Packet q = ld_packet_sys(p.in);
+                if (c == kStop || global_ns() - t0 > p.idle_ns) {
+                    s_stop = 1;
+                    break;
+                }
+                if (((unsigned) (q.h[0] >> 32) & ~3u) == tag_hi && (q.h[0] >> 32) == (q.h[1] >> 32)) break;
+            }
         }
         __syncthreads();
-        const unsigned long long cmd = s_cmd;
-        if (cmd == kStop) break;
-        const unsigned long long want = cmd & 3ull;
+        if (s_stop) break;       // (a step whose packets arrived in the same instant is run by the next launch)
+        const unsigned want = s_want;
+        const unsigned tag = tag_hi | want;
+        if (tid == 0) s_t[0] = global_ns();
 
         double e_total = 0.0, Fx = 0.0, Fy = 0.0, Fz = 0.0;
         double e_grid[GFB_MAX_GRIDS];
         double x = 0.0, y = 0.0, z = 0.0;
-        if (plain) {
-            for (unsigned i = tid; i < n_pairs; i += blockDim.x) reinterpret_cast<double2*>(s_xyz)[i] = ld_sys_f64x2(p.pos + 2 * i);
-            __syncthreads();
-            if (active) {
-                x = s_xyz[3 * tid];
-                y = s_xyz[3 * tid + 1];
-                z = s_xyz[3 * tid + 2];
-            }
-            __syncthreads();         // s_xyz is reused for the forces
-        } else if (active) {
-            x = ld_sys_f64(p.pos + 3 * particle);
-            y = ld_sys_f64(p.pos + 3 * particle + 1);
-            z = ld_sys_f64(p.pos + 3 * particle + 2);
+        if (active) {
+            x = s_xyz[3 * tid];
+            y = s_xyz[3 * tid + 1];
+            z = s_xyz[3 * tid + 2];
         }
-        if (tid == 0) s_t[1] = global_ns();
         // Pass 1: classify and put every grid's stencil load in flight (the loads are independent round trips to L2/HBM);
         // pass 2: the arithmetic.
         AtomCell c[GFB_MAX_GRIDS];
@@ -185,54 +202,47 @@ __global__ void __launch_bounds__(kMaxResidentAtoms, 1) gf_resident_kernel(const
                 e_total += e_g;
             }
         }
-        if (tid == 0) s_t[2] = global_ns();
-        if (want & 1ull) {
-            if (plain) {
-                if (active) {
-                    s_xyz[3 * tid] = Fx;
-                    s_xyz[3 * tid + 1] = Fy;
-                    s_xyz[3 * tid + 2] = Fz;
-                }
-                __syncthreads();
-                for (unsigned i = tid; i < n_pairs; i += blockDim.x) st_sys_f64x2(p.forces + 2 * i, reinterpret_cast<double2*>(s_xyz)[i]);
-            } else if (active) {
-                st_sys_f64(p.forces + 3 * particle, Fx);
-                st_sys_f64(p.forces + 3 * particle + 1, Fy);
-                st_sys_f64(p.forces + 3 * particle + 2, Fz);
-            }
+        if (tid == 0) s_t[1] = global_ns();
+        // ---- results: forces as packets (contiguous 16-byte stores), energies summed lanes -> warps -> block ----------
+        __syncthreads();             // every worker has read its position out of s_xyz
+        if (active && (want & 1u)) {
+            s_xyz[3 * tid] = Fx;
+            s_xyz[3 * tid + 1] = Fy;
+            s_xyz[3 * tid + 2] = Fz;
         }
-        // energies: lanes -> warp -> block, always in the same order
+        if (worker) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) e_total += __shfl_xor_sync(kFull, e_total, o);
-        if (lane == 0) s_e[warp][0] = e_total;
-        if (want & 2ull) {
+            for (int o = 16; o > 0; o >>= 1) e_total += __shfl_xor_sync(kFull, e_total, o);
+            if (lane == 0) s_e[warp][0] = e_total;
+            if (want & 2u) {
 #pragma unroll
-            for (int g = 0; g < GFB_MAX_GRIDS; g++) {
-                if (g < p.n_grids) {
-                    double eg = e_grid[g];
+                for (int g = 0; g < GFB_MAX_GRIDS; g++) {
+                    if (g < p.n_grids) {
+                        double eg = e_grid[g];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) eg += __shfl_xor_sync(kFull, eg, o);
-                    if (lane == 0) s_e[warp][1 + g] = eg;
+                        for (int o = 16; o > 0; o >>= 1) eg += __shfl_xor_sync(kFull, eg, o);
+                        if (lane == 0) s_e[warp][1 + g] = eg;
+                    }
                 }
             }
         }
-        __syncthreads();             // every thread's force stores are issued and the warp sums are in shared memory
-        if (tid == 0) {
-            const int n_out = (want & 2ull) ? 1 + p.n_grids : 1;
+        __syncthreads();
+        if (worker && (want & 1u))
+            for (unsigned i = tid; i < n_in; i += n_workers)
+                st_packet_sys(p.out + i, pack((unsigned long long) __double_as_longlong(s_xyz[i]), tag));
+        if (watcher) {               // the spare thread sends the energies while the workers send the forces
+            const int n_out = (want & 2u) ? 1 + p.n_grids : 1;
             for (int j = 0; j < n_out; j++) {
                 double b = 0.0;
                 for (unsigned w = 0; w < n_warps; w++) b += s_e[w][j];
-                st_sys_f64(&ctl->energies[j], b);
+                st_packet_sys(p.out + n_in + j, pack((unsigned long long) __double_as_longlong(b), tag));
             }
             st_sys_u64(&ctl->stamps[0], s_t[0]);
             st_sys_u64(&ctl->stamps[1], s_t[1]);
-            st_sys_u64(&ctl->stamps[2], s_t[2]);
-            st_sys_u64(&ctl->stamps[3], global_ns());
-            // One release at system scope by one thread: the barrier above orders the other threads' stores before it
-            // (cumulativity), so the host that reads done_seq == n reads this step's forces and energies.
-            st_release_sys(&ctl->done_seq, expected);
+            st_sys_u64(&ctl->stamps[2], global_ns());
         }
         expected++;
+        __syncthreads();             // s_xyz / s_e are free again
     }
     if (tid == 0) st_release_sys(&ctl->alive, 0ull);
 }
@@ -243,16 +253,27 @@ double now_s() {
     return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
 }
 
+inline void store_packet(Packet* dst, const Packet& v) {   // two aligned 8-byte stores: each is atomic, the order is free
+    __atomic_store_n(&dst->h[0], v.h[0], __ATOMIC_RELAXED);
+    __atomic_store_n(&dst->h[1], v.h[1], __ATOMIC_RELAXED);
+}
+inline Packet load_packet(const Packet* src) {
+    Packet v;
+    v.h[0] = __atomic_load_n(&src->h[0], __ATOMIC_RELAXED);
+    v.h[1] = __atomic_load_n(&src->h[1], __ATOMIC_RELAXED);
+    return v;
+}
+
 }  // namespace
 
 namespace gfb {
 
 struct ResidentState {
     ResidentCtl* ctl = nullptr;      // cudaHostAlloc
-    size_t ctl_bytes = 0;
-    int n_particles = 0;
-    double* pos = nullptr;           // inside ctl
-    double* forces = nullptr;
+    Packet* in = nullptr;            // inside the same allocation
+    Packet* out = nullptr;
+    int n_atoms = 0;
+    std::vector<int> particles;      // host copy of the kernel's particle map (empty: atom a is particle a)
     cudaStream_t stream = nullptr;   // non-blocking: the block must not serialise with the device's other streams
     unsigned long long seq = 0;      // last step requested
     unsigned long long idle_us = 100000;
@@ -297,17 +318,16 @@ static int resident_launch(gfb_kernel* k, ResidentState* r) {
     }
     p.n_grids = k->n_grids;
     p.n_atoms = k->n_atoms;
-    p.n_particles = r->n_particles;
     p.same_geom = k->same_geom ? 1 : 0;
-    p.particles = k->d_particles;
     p.ctl = r->ctl;
-    p.pos = r->pos;
-    p.forces = r->forces;
+    p.in = r->in;
+    p.out = r->out;
     p.start_seq = r->seq - 1;        // the step just requested is the first one this launch runs
     p.idle_ns = r->idle_us * 1000ull;
+    r->ctl->cmd = 0;
     r->ctl->alive = 1;
     __atomic_thread_fence(__ATOMIC_SEQ_CST);
-    const unsigned threads = (unsigned) ((k->n_atoms + 31) / 32 * 32);
+    const unsigned threads = (unsigned) ((k->n_atoms + 31) / 32 * 32) + 32u;
     if (k->precision == GFB_PRECISION_DOUBLE) gf_resident_kernel<double><<<1, threads, 0, r->stream>>>(p);
     else gf_resident_kernel<float><<<1, threads, 0, r->stream>>>(p);
     g_launches++;
@@ -349,71 +369,92 @@ bool resident_enabled(const gfb_kernel* k) { return k->resident != nullptr && re
 int resident_step(gfb_kernel* k, int n_particles, const double* pos, double* energies, double* grid_energies, double* forces,
                   bool add) {
     ResidentState* r = static_cast<ResidentState*>(k->resident);
-    const size_t np3 = (size_t) n_particles * 3;
-    const size_t arr_bytes = (np3 * sizeof(double) + 127) & ~(size_t) 127;
-    if (!r->ctl || r->n_particles != n_particles) {
+    const int na = k->n_atoms;
+    const size_t n_in = 3 * (size_t) na;
+    if (!r->ctl || r->n_atoms != na) {
         int rc = resident_stop(k);
         if (rc != GFB_OK) return rc;
         if (r->ctl) cudaFreeHost(r->ctl);
         r->ctl = nullptr;
-        r->ctl_bytes = sizeof(ResidentCtl) + 2 * arr_bytes;
+        const size_t in_bytes = (n_in * sizeof(Packet) + 127) & ~(size_t) 127;
+        const size_t out_bytes = ((n_in + 1 + GFB_MAX_GRIDS) * sizeof(Packet) + 127) & ~(size_t) 127;
         void* mem = nullptr;
-        CUDA_TRY(cudaHostAlloc(&mem, r->ctl_bytes, cudaHostAllocMapped | cudaHostAllocPortable));
-        memset(mem, 0, r->ctl_bytes);
+        CUDA_TRY(cudaHostAlloc(&mem, sizeof(ResidentCtl) + in_bytes + out_bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(mem, 0, sizeof(ResidentCtl) + in_bytes + out_bytes);
         r->ctl = static_cast<ResidentCtl*>(mem);
-        r->pos = reinterpret_cast<double*>(static_cast<char*>(mem) + sizeof(ResidentCtl));
-        r->forces = reinterpret_cast<double*>(static_cast<char*>(mem) + sizeof(ResidentCtl) + arr_bytes);
-        r->n_particles = n_particles;
+        r->in = reinterpret_cast<Packet*>(static_cast<char*>(mem) + sizeof(ResidentCtl));
+        r->out = reinterpret_cast<Packet*>(static_cast<char*>(mem) + sizeof(ResidentCtl) + in_bytes);
+        r->n_atoms = na;
         r->seq = 0;
+        r->particles.clear();
+        if (k->d_particles) {
+            r->particles.resize((size_t) na);
+            CUDA_TRY(cudaMemcpy(r->particles.data(), k->d_particles, (size_t) na * sizeof(int), cudaMemcpyDeviceToHost));
+        }
     }
     if (!r->stream) CUDA_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
     ResidentCtl* ctl = r->ctl;
-    memcpy(r->pos, pos, np3 * sizeof(double));
-    if (np3 & 1) r->pos[np3] = 0.0;      // the block reads whole 16-byte units (the arrays are padded to 128 bytes)
-    // The block stores the forces of the evaluated particles only. STORE: the other entries must come back as they were;
-    // ADD: they must come back unchanged, i.e. the block's array contributes 0 there.
-    const bool all_written = !k->d_particles && k->n_atoms == n_particles;
-    if (forces && !all_written) {
-        if (add) memset(r->forces, 0, np3 * sizeof(double));
-        else memcpy(r->forces, forces, np3 * sizeof(double));
-    }
+    const int* hp = r->particles.empty() ? nullptr : r->particles.data();
     const unsigned long long n = ++r->seq;
-    __atomic_store_n(&ctl->cmd, (n << 2) | (forces ? 1ull : 0ull) | (grid_energies ? 2ull : 0ull), __ATOMIC_RELEASE);
+    const unsigned tag = (unsigned) (n << 2) | (forces ? 1u : 0u) | (grid_energies ? 2u : 0u);
+    for (int a = 0; a < na; a++) {
+        const double* src = pos + 3 * (size_t) (hp ? hp[a] : a);
+        for (int c = 0; c < 3; c++) {
+            unsigned long long bits;
+            memcpy(&bits, src + c, 8);
+            store_packet(r->in + 3 * (size_t) a + c, pack(bits, tag));
+        }
+    }
     if (!r->running || !__atomic_load_n(&ctl->alive, __ATOMIC_ACQUIRE)) {
         int rc = resident_launch(k, r);     // joins a block that has timed out, then starts one at this step
         if (rc != GFB_OK) return rc;
     }
-    // The answer arrives within microseconds; the wall-clock checks only bound a failure.
+    // Result packets, in the order they are needed: [forces] | total energy | [per-grid energies]. Each is awaited on its
+    // own; they arrive within microseconds, and the wall-clock checks only bound a failure.
+    const size_t first = forces ? 0 : n_in;
+    const size_t last = n_in + 1 + (grid_energies ? (size_t) k->n_grids : 0);
     double t0 = 0.0;
-    for (unsigned long long spins = 1;; spins++) {
-        if (__atomic_load_n(&ctl->done_seq, __ATOMIC_ACQUIRE) == n) break;
+    unsigned long long spins = 0;
+    for (size_t i = first; i < last;) {
+        const Packet q = load_packet(r->out + i);
+        if (packet_has(q, tag)) {
+            double v;
+            const unsigned long long bits = packet_bits(q);
+            memcpy(&v, &bits, 8);
+            if (i < n_in) {
+                const size_t a = i / 3, c = i - 3 * a;
+                double* dst = forces + 3 * (size_t) (hp ? hp[a] : (int) a) + c;
+                *dst = add ? *dst + v : v;
+            } else if (i == n_in) {
+                if (energies) energies[0] = v;
+            } else {
+                grid_energies[i - n_in - 1] = v;
+            }
+            i++;
+            continue;
+        }
         if (!__atomic_load_n(&ctl->alive, __ATOMIC_ACQUIRE)) {
-            // The block gave up waiting in the instant the command was posted. done_seq is final once alive is clear.
-            if (__atomic_load_n(&ctl->done_seq, __ATOMIC_ACQUIRE) == n) break;
+            // The block gave up waiting in the instant the step was posted (its exit is final once alive is clear, and it
+            // ran no part of this step: a block that stops does so before it evaluates). Start over with a new block.
+            if (packet_has(load_packet(r->out + i), tag)) continue;
             int rc = resident_launch(k, r);
             if (rc != GFB_OK) return rc;
             t0 = 0.0;
             continue;
         }
-        if ((spins & 0x3ffu) == 0) {
+        if ((++spins & 0x3ffu) == 0) {
             const double t = now_s();
             if (t0 == 0.0) t0 = t;
             if (t - t0 > 5.0) {
-                const cudaError_t q = cudaStreamQuery(r->stream);
+                const cudaError_t qe = cudaStreamQuery(r->stream);
                 __atomic_store_n(&ctl->cmd, kStop, __ATOMIC_RELEASE);
                 return fail(GFB_ERR_CUDA, "resident evaluator did not answer step %llu within 5 s (%s)", n,
-                            q == cudaErrorNotReady ? "block still running" : cudaGetErrorString(q));
+                            qe == cudaErrorNotReady ? "block still running" : cudaGetErrorString(qe));
             }
         }
 #if defined(__x86_64__)
         __builtin_ia32_pause();
 #endif
-    }
-    if (energies) energies[0] = ctl->energies[0];
-    if (grid_energies) memcpy(grid_energies, const_cast<double*>(ctl->energies) + 1, (size_t) k->n_grids * sizeof(double));
-    if (forces) {
-        if (add) for (size_t i = 0; i < np3; i++) forces[i] += r->forces[i];
-        else memcpy(forces, r->forces, np3 * sizeof(double));
     }
     return GFB_OK;
 }
@@ -452,12 +493,12 @@ int gfb_kernel_resident_stop(gfb_kernel* k) {
     return resident_stop(k);
 }
 
-int gfb_kernel_resident_timeline(const gfb_kernel* k, double us[3]) {
+int gfb_kernel_resident_timeline(const gfb_kernel* k, double us[2]) {
     if (!k || !us) return fail(GFB_ERR_INVALID, "gfb_kernel_resident_timeline: NULL argument");
     const ResidentState* r = static_cast<const ResidentState*>(k->resident);
     if (!r || !r->ctl || r->seq == 0) return fail(GFB_ERR_INVALID, "gfb_kernel_resident_timeline: no resident step has run");
     const unsigned long long* t = r->ctl->stamps;
-    for (int i = 0; i < 3; i++) us[i] = 1e-3 * (double) (long long) (t[i + 1] - t[i]);
+    for (int i = 0; i < 2; i++) us[i] = 1e-3 * (double) (long long) (t[i + 1] - t[i]);
     return GFB_OK;
 }
 

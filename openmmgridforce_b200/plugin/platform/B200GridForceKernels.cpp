@@ -62,7 +62,7 @@ int b200LayoutForMethod(int interpolationMethod, const char* who) {
 
 void B200CalcGridForceKernel::applyResident(gfb_kernel* k) const {
     if (!resident) return;
-    // GFB_ERR_UNSUPPORTED (B-spline / tricubic layouts, more than 256 atoms, repeated particles): that state keeps the
+    // GFB_ERR_UNSUPPORTED (B-spline / tricubic layouts, more than 224 atoms, repeated particles): that state keeps the
     // launch-per-step path; the property is a request, not a requirement.
     if (gfb_kernel_set_resident(k, 1, residentIdleUs) == GFB_ERR_CUDA)
         throw OpenMMException(std::string("GridForce[B200]: resident evaluator: ") + gfb_last_error());

@@ -66,7 +66,7 @@ def test_resident_steps_match_oracle_and_launch_path(gpu_device, oracle_built, p
         assert np.abs(ge[0] - ge2[0]).max() <= tol_e * scale and _rel_f(forces[0], forces2[0]) <= tol_f
     assert k.resident_launches() <= 2        # 1, unless the driver loaded another module meanwhile
     tl = k.resident_timeline()
-    assert np.all(tl >= 0.0) and tl.sum() < 1000.0        # microseconds on the GPU per step
+    assert tl.shape == (2,) and np.all(tl >= 0.0) and tl.sum() < 1000.0        # microseconds on the GPU per step
     # energy only, and forces only for a caller that wants no energies
     en, none, _ = k.execute_host(c["pos"], want_forces=False)
     assert none is None and abs(en[0] - k2.execute_host(c["pos"])[0][0]) <= tol_e * abs(en[0])
