@@ -20,8 +20,10 @@ WANT = {   # round-2 names (the lines kernel gained the PERSIST flag; substring 
     "gf_gather_push_kernel": "gf_gather_push_kernel — peer stores + arrival flags",
     "gf_gather_wait_kernel": "gf_gather_wait_kernel — waits for all ranks' flags, copies the gathered array out",
     "gf_rendezvous_kernel": "gf_rendezvous_kernel — device-side rendezvous of all ranks",
+    "gf_resident_kernelIfE": "gf_resident_kernel<float> — resident evaluator (one ligand per MD step), MIXED: packets polled and sent with 16-byte .SYS accesses, no MEMBAR",
+    "gf_eval_kernelIdLi5E": "gf_eval_kernel<double, POINTS> — tricubic Hermite (interpolation method 2), DOUBLE",
 }
-PATS = ["LDGSTS.E.BYPASS.128", "LDG.E.ELL2.256", "LDG.E.LTC64B.ELL2.256", "LDG.E.128.STRONG.SYS", "STG.E.128.STRONG.SYS", "STG.E.64.STRONG.SYS", "LDG.E.64.STRONG.SYS", "LDS.64", "LDG.E.EF.128", "LDG.E.EF.64", "LDS.128", "STS", "STG.E.128", "STG.E.64",
+PATS = ["MEMBAR", "LDGSTS.E.BYPASS.128", "LDG.E.ELL2.256", "LDG.E.LTC64B.ELL2.256", "LDG.E.128.STRONG.SYS", "STG.E.128.STRONG.SYS", "STG.E.64.STRONG.SYS", "LDG.E.64.STRONG.SYS", "LDS.64", "LDG.E.EF.128", "LDG.E.EF.64", "LDS.128", "STS", "STG.E.128", "STG.E.64",
         "REDG.E.ADD.64", "REDG.E.ADD.F64", "CCTL", "PREEXIT", "ACQBULK", "LDGDEPBAR", "DEPBAR", "DFMA", "DMUL", "DADD",
         "F2F.F64.F32", "FFMA", "SHFL", "BAR.SYNC", "WARPSYNC", "CALL"]
 NOTE = {"LDGSTS.E.BYPASS.128": "cp.async.cg 16 B (one granule of a 128-byte record / a brick row)",
