@@ -29,6 +29,7 @@ from .capi import (  # noqa: F401
     LAYOUT_PAIRS,
     LAYOUT_BSPLINE,
     LAYOUT_POINTS,
+    LAYOUT_HERMITE,
     LAYOUT_NAMES,
     library_path,
     load_library,

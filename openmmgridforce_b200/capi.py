@@ -17,8 +17,8 @@ FORCE_FIXED_ADD = 2
 FORCE_F32_STORE = 3
 COMM_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
-LAYOUT_AUTO, LAYOUT_CELLS, LAYOUT_ROWS, LAYOUT_PAIRS, LAYOUT_BSPLINE, LAYOUT_POINTS = 0, 1, 2, 3, 4, 5
-LAYOUT_NAMES = {0: "auto", 1: "cells", 2: "rows", 3: "pairs", 4: "bspline", 5: "points"}
+LAYOUT_AUTO, LAYOUT_CELLS, LAYOUT_ROWS, LAYOUT_PAIRS, LAYOUT_BSPLINE, LAYOUT_POINTS, LAYOUT_HERMITE = 0, 1, 2, 3, 4, 5, 6
+LAYOUT_NAMES = {0: "auto", 1: "cells", 2: "rows", 3: "pairs", 4: "bspline", 5: "points", 6: "hermite"}
 MAX_GRIDS = 8
 
 _LIB = None
@@ -369,7 +369,7 @@ class Kernel:
         return self.eval_path() == 1
 
     def eval_path(self):
-        """gfb_kernel_eval_path: 1 gf_eval_lines_kernel, 2 gf_eval_lines_f64_kernel, 3 gf_eval_bspline_kernel, 4 gf_eval_bspline_f64_kernel, 0 general."""
+        """gfb_kernel_eval_path: 1 gf_eval_lines_kernel, 2 gf_eval_lines_f64_kernel, 3 gf_eval_bspline_kernel, 4 gf_eval_bspline_f64_kernel, 5 the record kernel with the tricubic arithmetic, 0 general."""
         return int(load_library().gfb_kernel_eval_path(self._h))
 
     def set_launch_overlap(self, enable=True):

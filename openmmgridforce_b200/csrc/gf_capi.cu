@@ -371,12 +371,15 @@ bool lines_f64_eligible(const gfb_kernel* k) {
 }
 
 // gf_eval_bspline_kernel (gf_eval_bspline.cuh): MIXED B-spline tiles of one geometry, no evaluation order.
-static bool bspline_tiles_eligible(const gfb_kernel* k, const EvalParams& p) {
+// `layout` = GFB_LAYOUT_BSPLINE (method 1) or GFB_LAYOUT_HERMITE (method 2: the same kernel, other arithmetic).
+static bool record_tiles_eligible(const gfb_kernel* k, const EvalParams& p, int layout) {
     static const bool off = env_off("GFB_BSPLINE_TILES");   // 0: always the general kernel (A/B measurements)
-    if (off || k->precision != GFB_PRECISION_MIXED || k->grids[0]->layout != GFB_LAYOUT_BSPLINE || !k->same_geom) return false;
+    if (off || k->precision != GFB_PRECISION_MIXED || k->grids[0]->layout != layout || !k->same_geom) return false;
     if (p.order != nullptr) return false;
     return k->grids[0]->bytes / 128 < 0x7fffffffull;   // 32-bit record index
 }
+static bool bspline_tiles_eligible(const gfb_kernel* k, const EvalParams& p) { return record_tiles_eligible(k, p, GFB_LAYOUT_BSPLINE); }
+static bool tricubic_tiles_eligible(const gfb_kernel* k, const EvalParams& p) { return record_tiles_eligible(k, p, GFB_LAYOUT_HERMITE); }
 
 // gf_eval_bspline_f64_kernel (gf_eval_bspline_f64.cuh): DOUBLE B-spline records of one geometry, no evaluation order.
 static bool bspline_f64_eligible(const gfb_kernel* k, const EvalParams& p) {
@@ -436,6 +439,8 @@ int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d
     }
     if (bspline_tiles_eligible(k, p)) {
         launch_bspline(p, stream);
+    } else if (tricubic_tiles_eligible(k, p)) {
+        launch_tricubic_records(p, stream);
     } else if (bspline_f64_eligible(k, p)) {
         launch_bspline_f64(p, stream);
     } else if (lines) {
@@ -490,7 +495,7 @@ int check_exec_args(const char* fn, gfb_kernel* k, int n_replicas, int n_particl
 static int eval_block_threads(const gfb_kernel* k) {
     EvalParams probe;
     memset(&probe, 0, sizeof probe);
-    if (bspline_tiles_eligible(k, probe)) return kBsplineBlockThreads;
+    if (bspline_tiles_eligible(k, probe) || tricubic_tiles_eligible(k, probe)) return kBsplineBlockThreads;
     if (bspline_f64_eligible(k, probe)) return kBsplineF64BlockThreads;
     if (lines_eligible(k, probe)) return lines_block_threads(k->n_grids);
     return lines_f64_eligible(k) ? kLinesF64BlockThreads : kGeneralBlock;
@@ -528,7 +533,7 @@ static int execute_host_small(gfb_kernel* k, int n_particles, const double* pos,
     memset(&probe, 0, sizeof probe);
     // one block covers the ligand: its energy (and, in the record kernels, its per-grid energies) are plain stores
     const bool one_block = k->n_atoms <= eval_block_threads(k) &&
-                           (!grid_energies || !(bspline_tiles_eligible(k, probe) || bspline_f64_eligible(k, probe)));
+                           (!grid_energies || !(bspline_tiles_eligible(k, probe) || tricubic_tiles_eligible(k, probe) || bspline_f64_eligible(k, probe)));
     double* d_e = nullptr;
     if (!one_block) {   // several blocks (or per-grid energies): device accumulators, cleared here, fetched below
         if ((rc = k->d_energy.ensure(e_count * sizeof(double))) != GFB_OK) return rc;
@@ -582,6 +587,7 @@ int gfb_kernel_eval_path(const gfb_kernel* k) {
     if (lines_eligible(k, probe)) return 1;
     if (lines_f64_eligible(k)) return 2;
     if (bspline_tiles_eligible(k, probe)) return 3;
+    if (tricubic_tiles_eligible(k, probe)) return 5;
     return bspline_f64_eligible(k, probe) ? 4 : 0;
 }
 

@@ -1,5 +1,6 @@
 // Cubic B-spline evaluation kernel for MIXED-precision grids in the BSPLINE brick layout that share one geometry
-// (GridForce::setInterpolationMethod(1); reference platforms/reference/src/ReferenceGridForceKernels.cpp:727-795).
+// (GridForce::setInterpolationMethod(1); reference platforms/reference/src/ReferenceGridForceKernels.cpp:727-795), and,
+// with METHOD = 2, the tricubic Hermite evaluation (setInterpolationMethod(2), :796-893) on HERMITE records.
 // Everything else B-spline (DOUBLE precision, grids of different geometry, an evaluation order) runs
 // gf_eval_kernel<S, BSPLINE, ...> in gf_kernels.cuh, which holds the layout's description and the reference arithmetic.
 //
@@ -73,8 +74,30 @@ __device__ __forceinline__ void bspline_from_smem(unsigned rbase, unsigned sw, c
     }
 }
 
+// Tricubic Hermite (interpolation method 2) out of the same 256-byte smem region, for HERMITE records (filled by flat
+// index, gf_repack_bspline_kernel<float, true>): the point at offsets (i-1, r-1, k-1) is element k of granule 4*i + r.
+// 12 of the 16 granules are read (rows 1-2 of every x-plane, rows 0 and 3 of planes 1-2); arithmetic FP64 (tricubic_eval).
+struct TricubicSmem {
+    float g[4][4][4];      // [i][r][k]; entries of the four granules never read stay unset
+    __device__ __forceinline__ double operator()(int i, int r, int k) const { return (double) g[i][r][k]; }
+};
+__device__ __forceinline__ void tricubic_from_smem(unsigned rbase, unsigned sw, bool xin, bool yin, bool zin, const TricubicWeights& w,
+                                                   double& val, double& gx, double& gy, double& gz) {
+    TricubicSmem V;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            if ((r == 0 || r == 3) && (i == 0 || i == 3)) continue;      // corners of the (x,y) window: not part of the stencil
+            lds128(rbase + (((4u * i + r) << 4) ^ sw), V.g[i][r]);
+        }
+    }
+    tricubic_eval(V, xin, yin, zin, w, val, gx, gy, gz);
+}
+
 //   SINGLE  one replica and no energy slots (block-level energy reduction); the force mode is p.force_mode (launch-uniform)
-template <bool SINGLE>
+//   METHOD  1 cubic B-spline on BSPLINE records, 2 tricubic Hermite on HERMITE records (same fetch, other arithmetic)
+template <bool SINGLE, int METHOD>
 __global__ void __launch_bounds__(kBsBlock, GFB_BS_MINBLOCKS) gf_eval_bspline_kernel(const __grid_constant__ EvalParams p) {
     __shared__ __align__(128) unsigned char s_tiles[(kBsBlock / 32) * kBsWarpBytes];
 
@@ -124,7 +147,10 @@ __global__ void __launch_bounds__(kBsBlock, GFB_BS_MINBLOCKS) gf_eval_bspline_ke
     const unsigned sw = (lane & 7u) << 4;
 
     BsWeights wts;
-    bspline_weights(fc.fx, fc.fy, fc.fz, wts);
+    TricubicWeights tw;
+    if constexpr (METHOD == 1) bspline_weights(fc.fx, fc.fy, fc.fz, wts);
+    else tricubic_weights(fc.fx, fc.fy, fc.fz, tw);
+    const bool xin = fc.ix > 0 && fc.ix < G.nc[0], yin = fc.iy > 0 && fc.iy < G.nc[1], zin = fc.iz > 0 && fc.iz < G.nc[2];   // :817, :849, :866
 
     double e_total = 0.0;
     double Fx = 0.0, Fy = 0.0, Fz = 0.0;
@@ -155,7 +181,11 @@ __global__ void __launch_bounds__(kBsBlock, GFB_BS_MINBLOCKS) gf_eval_bspline_ke
         __syncwarp();
         // ---- evaluate -----------------------------------------------------------------------------------------------
         double e_g = 0.0;
-        if (interp) {
+        if (METHOD == 2 && interp) {
+            double val, gx, gy, gz;
+            tricubic_from_smem(rbase, sw, xin, yin, zin, tw, val, gx, gy, gz);
+            tricubic_epilogue(Gg, s, val, gx, gy, gz, e_g, Fx, Fy, Fz);      // :879-893
+        } else if (interp) {
             double val;
             float dx, dy, dz;
             bspline_from_smem(rbase, sw, wts, val, dx, dy, dz);

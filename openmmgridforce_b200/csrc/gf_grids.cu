@@ -22,9 +22,11 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
     *out = nullptr;
     if (precision != GFB_PRECISION_MIXED && precision != GFB_PRECISION_DOUBLE)
         return fail(GFB_ERR_INVALID, "gfb_grid_create: unknown precision %d", precision);
-    if (layout < GFB_LAYOUT_AUTO || layout > GFB_LAYOUT_POINTS) return fail(GFB_ERR_INVALID, "gfb_grid_create: unknown layout %d", layout);
+    if (layout < GFB_LAYOUT_AUTO || layout > GFB_LAYOUT_HERMITE) return fail(GFB_ERR_INVALID, "gfb_grid_create: unknown layout %d", layout);
     if (layout == GFB_LAYOUT_PAIRS && precision == GFB_PRECISION_DOUBLE)
         return fail(GFB_ERR_UNSUPPORTED, "gfb_grid_create: the PAIRS layout exists for MIXED precision only (use ROWS or CELLS)");
+    if (layout == GFB_LAYOUT_HERMITE && precision == GFB_PRECISION_DOUBLE)
+        return fail(GFB_ERR_UNSUPPORTED, "gfb_grid_create: the HERMITE record layout exists for MIXED precision only (use POINTS)");
     for (int k = 0; k < 3; k++) {
         if (counts[k] < 2) return fail(GFB_ERR_INVALID, "gfb_grid_create: counts[%d]=%d, need >= 2 points per axis", k, counts[k]);
         if (!(spacing[k] > 0.0) || !std::isfinite(spacing[k]))
@@ -68,7 +70,7 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
     } else if (layout == GFB_LAYOUT_POINTS) {   // the points themselves + one zero x-slab (tricubic_interpolate's flat-index reads)
         n_units = n_points + (size_t) counts[1] * counts[2];
         g->bytes = n_units * (precision == GFB_PRECISION_MIXED ? sizeof(float) : sizeof(double));
-    } else {   // BSPLINE: records (a < nx+1, iy < ny-1, iz < nz-1) of 2 planes x 4 rows x 4 values, one thread per row
+    } else {   // BSPLINE / HERMITE: records (a < nx+1, iy < ny-1, iz < nz-1) of 2 planes x 4 rows x 4 values, one thread per row
         g->row_chunks = counts[2] - 1;
         n_units = (size_t) (counts[0] + 1) * (counts[1] - 1) * (counts[2] - 1) * 8;
         g->bytes = n_units * 4 * (precision == GFB_PRECISION_MIXED ? sizeof(float) : sizeof(double));
@@ -86,7 +88,7 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
                 const int lay = layout;
                 delete g;
                 return fail(GFB_ERR_NOMEM, "gfb_grid_create: a %dx%dx%d grid in layout %d (%s) needs %.2f GB of device memory, %.2f GB are free%s",
-                            counts[0], counts[1], counts[2], lay, lay == GFB_LAYOUT_BSPLINE ? "B-spline records, 32x the raw grid" : "see gfb_layout",
+                            counts[0], counts[1], counts[2], lay, (lay == GFB_LAYOUT_BSPLINE || lay == GFB_LAYOUT_HERMITE) ? "records, 32x the raw grid" : "see gfb_layout",
                             need / 1e9, free_b / 1e9, lay == GFB_LAYOUT_CELLS ? "; GFB_LAYOUT_ROWS needs 1.14x the raw grid" : "");
             }
         } else {
@@ -119,8 +121,9 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
             if (mixed) gf_repack_points_kernel<float><<<blocks, 256, 0, dev->stream>>>(d_vals, cf, n_points, guard);
             else gf_repack_points_kernel<double><<<blocks, 256, 0, dev->stream>>>(d_vals, cd, n_points, guard);
         } else {
-            if (mixed) gf_repack_bspline_kernel<float><<<blocks, 256, 0, dev->stream>>>(d_vals, cf, counts[0], counts[1], counts[2]);
-            else gf_repack_bspline_kernel<double><<<blocks, 256, 0, dev->stream>>>(d_vals, cd, counts[0], counts[1], counts[2]);
+            if (layout == GFB_LAYOUT_HERMITE) gf_repack_bspline_kernel<float, true><<<blocks, 256, 0, dev->stream>>>(d_vals, cf, counts[0], counts[1], counts[2]);
+            else if (mixed) gf_repack_bspline_kernel<float, false><<<blocks, 256, 0, dev->stream>>>(d_vals, cf, counts[0], counts[1], counts[2]);
+            else gf_repack_bspline_kernel<double, false><<<blocks, 256, 0, dev->stream>>>(d_vals, cd, counts[0], counts[1], counts[2]);
         }
         g_launches++;
         err = cudaGetLastError();

@@ -432,34 +432,36 @@ __device__ __forceinline__ void hermite_basis(double t, double h[4], double d[4]
     d[3] = 3.0 * t2 - 2.0 * t;
 }
 
-template <typename S>
-__device__ __forceinline__ void tricubic_interpolate(const GridView& G, const AtomCell& c, double& val, double& gx, double& gy,
-                                                     double& gz) {
-    const long long nz = G.nc[2] + 1;
-    const long long nyz = (long long) (G.nc[1] + 1) * nz;
-    const S* v = static_cast<const S*>(G.cells) + ((long long) c.ix * nyz + (long long) c.iy * nz + c.iz);   // &V[im], :801
-    const bool xin = c.ix > 0 && c.ix < G.nc[0];   // :817 (ix < counts-1 always holds for an inside atom)
-    const bool yin = c.iy > 0 && c.iy < G.nc[1];   // :849
-    const bool zin = c.iz > 0 && c.iz < G.nc[2];   // :866
+// The arithmetic of :806-876 over an accessor V(i, r, k) = the point at offsets (i-1, r-1, k-1) from (ix, iy, iz),
+// i, r, k in 0..3 — always called with literal indices, so an accessor over registers costs nothing. Lower neighbours
+// (index 0) are only touched when xin / yin / zin hold, as in the reference.
+struct TricubicWeights {
     double hx[4], dhx[4], hy[4], dhy[4], hz[4], dhz[4];
-    hermite_basis(c.fx, hx, dhx);
-    hermite_basis(c.fy, hy, dhy);
-    hermite_basis(c.fz, hz, dhz);
+};
+__device__ __forceinline__ void tricubic_weights(double fx, double fy, double fz, TricubicWeights& w) {
+    hermite_basis(fx, w.hx, w.dhx);
+    hermite_basis(fy, w.hy, w.dhy);
+    hermite_basis(fz, w.hz, w.dhz);
+}
+template <typename Acc>
+__device__ __forceinline__ void tricubic_eval(const Acc& V, bool xin, bool yin, bool zin, const TricubicWeights& w, double& val,
+                                              double& gx, double& gy, double& gz) {
+    const double* hx = w.hx;
+    const double* hy = w.hy;
     // x: the four edges (iy+j, iz+k), :806-846
     double vv[2][2], dv[2][2];
 #pragma unroll
     for (int j = 0; j < 2; j++) {
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            const S* q = v + j * nz + k;
-            const double f0 = (double) __ldg(q), f1 = (double) __ldg(q + nyz);
+            const double f0 = V(1, 1 + j, 1 + k), f1 = V(2, 1 + j, 1 + k);
             double d0 = 0.0, d1 = 0.0;   // derivative x spacing at ix and ix+1
             if (xin) {
-                d0 = 0.5 * (f1 - (double) __ldg(q - nyz));
-                d1 = 0.5 * ((double) __ldg(q + 2 * nyz) - f0);
+                d0 = 0.5 * (f1 - V(0, 1 + j, 1 + k));
+                d1 = 0.5 * (V(3, 1 + j, 1 + k) - f0);
             }
             vv[j][k] = hx[0] * f0 + hx[1] * f1 + hx[2] * d0 + hx[3] * d1;
-            dv[j][k] = dhx[0] * f0 + dhx[1] * f1 + dhx[2] * d0 + dhx[3] * d1;
+            dv[j][k] = w.dhx[0] * f0 + w.dhx[1] * f1 + w.dhx[2] * d0 + w.dhx[3] * d1;
         }
     }
     // y: rows iy-1 and iy+2 interpolated in x with the value basis only, :849-863
@@ -468,37 +470,77 @@ __device__ __forceinline__ void tricubic_interpolate(const GridView& G, const At
     for (int k = 0; k < 2; k++) {
         double dy0 = 0.0, dy1 = 0.0;
         if (yin) {
-            const double rm = hx[0] * (double) __ldg(v - nz + k) + hx[1] * (double) __ldg(v + nyz - nz + k);
-            const double rp = hx[0] * (double) __ldg(v + 2 * nz + k) + hx[1] * (double) __ldg(v + nyz + 2 * nz + k);
+            const double rm = hx[0] * V(1, 0, 1 + k) + hx[1] * V(2, 0, 1 + k);
+            const double rp = hx[0] * V(1, 3, 1 + k) + hx[1] * V(2, 3, 1 + k);
             dy0 = vv[1][k] - rm;
             dy1 = rp - vv[0][k];
         }
         vk[k] = hy[0] * vv[0][k] + hy[1] * vv[1][k] + hy[2] * dy0 + hy[3] * dy1;
         dxk[k] = hy[0] * dv[0][k] + hy[1] * dv[1][k];
-        if (k == 0) dvdy = dhy[0] * vv[0][0] + dhy[1] * vv[1][0] + dhy[2] * dy0 + dhy[3] * dy1;   // z = iz plane only, :863
+        if (k == 0) dvdy = w.dhy[0] * vv[0][0] + w.dhy[1] * vv[1][0] + w.dhy[2] * dy0 + w.dhy[3] * dy1;   // z = iz plane only, :863
     }
     // z: points iz-1 and iz+2 interpolated in x and y with the value basis only, :866-876
     double dz0 = 0.0, dz1 = 0.0;
     if (zin) {
-        const double zm = hy[0] * (hx[0] * (double) __ldg(v - 1) + hx[1] * (double) __ldg(v + nyz - 1)) +
-                          hy[1] * (hx[0] * (double) __ldg(v + nz - 1) + hx[1] * (double) __ldg(v + nyz + nz - 1));
-        const double zp = hy[0] * (hx[0] * (double) __ldg(v + 2) + hx[1] * (double) __ldg(v + nyz + 2)) +
-                          hy[1] * (hx[0] * (double) __ldg(v + nz + 2) + hx[1] * (double) __ldg(v + nyz + nz + 2));
+        const double zm = hy[0] * (hx[0] * V(1, 1, 0) + hx[1] * V(2, 1, 0)) + hy[1] * (hx[0] * V(1, 2, 0) + hx[1] * V(2, 2, 0));
+        const double zp = hy[0] * (hx[0] * V(1, 1, 3) + hx[1] * V(2, 1, 3)) + hy[1] * (hx[0] * V(1, 2, 3) + hx[1] * V(2, 2, 3));
         dz0 = vk[1] - zm;
         dz1 = zp - vk[0];
     }
-    val = hz[0] * vk[0] + hz[1] * vk[1] + hz[2] * dz0 + hz[3] * dz1;          // :873
-    gx = hz[0] * dxk[0] + hz[1] * dxk[1];                                      // :875
+    val = w.hz[0] * vk[0] + w.hz[1] * vk[1] + w.hz[2] * dz0 + w.hz[3] * dz1;          // :873
+    gx = w.hz[0] * dxk[0] + w.hz[1] * dxk[1];                                          // :875
     gy = dvdy;
-    gz = dhz[0] * vk[0] + dhz[1] * vk[1] + dhz[2] * dz0 + dhz[3] * dz1;       // :876
+    gz = w.dhz[0] * vk[0] + w.dhz[1] * vk[1] + w.dhz[2] * dz0 + w.dhz[3] * dz1;       // :876
+}
+
+// POINTS: scalar reads by flat index.
+template <typename S>
+struct TricubicPoints {
+    const S* v;          // &V[im]
+    long long nz, nyz;
+    __device__ __forceinline__ double operator()(int i, int r, int k) const {
+        return (double) __ldg(v + (i - 1) * nyz + (r - 1) * nz + (k - 1));
+    }
+};
+// HERMITE records read into registers: b[i][4 * r + k] (load_brick order).
+template <typename S>
+struct TricubicBricks {
+    const S (*b)[16];
+    __device__ __forceinline__ double operator()(int i, int r, int k) const { return (double) b[i][4 * r + k]; }
+};
+
+// LAYOUT = GFB_LAYOUT_POINTS or GFB_LAYOUT_HERMITE (MIXED only: the BSPLINE record format, filled by flat index — see
+// gf_repack_bspline_kernel — so that a stencil is two full lines; gf_eval_bspline_kernel<.., 2> is its fast reader and
+// this one the fallback for grids of different geometry or an evaluation order).
+template <typename S, int LAYOUT>
+__device__ __forceinline__ void tricubic_interpolate(const GridView& G, const AtomCell& c, double& val, double& gx, double& gy,
+                                                     double& gz) {
+    const bool xin = c.ix > 0 && c.ix < G.nc[0];   // :817 (ix < counts-1 always holds for an inside atom)
+    const bool yin = c.iy > 0 && c.iy < G.nc[1];   // :849
+    const bool zin = c.iz > 0 && c.iz < G.nc[2];   // :866
+    TricubicWeights w;
+    tricubic_weights(c.fx, c.fy, c.fz, w);
+    if constexpr (LAYOUT == GFB_LAYOUT_POINTS) {
+        TricubicPoints<S> V;
+        V.nz = G.nc[2] + 1;
+        V.nyz = (long long) (G.nc[1] + 1) * V.nz;
+        V.v = static_cast<const S*>(G.cells) + ((long long) c.ix * V.nyz + (long long) c.iy * V.nz + c.iz);   // :801
+        tricubic_eval(V, xin, yin, zin, w, val, gx, gy, gz);
+    } else {
+        const S* rec = static_cast<const S*>(G.cells) + (((size_t) c.ix * G.nc[1] + c.iy) * G.nc[2] + c.iz) * 32;
+        const size_t plane2 = (size_t) G.nc[1] * G.nc[2] * 64;    // records two x-planes further on
+        S b[4][16];
+#pragma unroll
+        for (int i = 0; i < 4; i++) load_brick(rec + (i >> 1) * plane2 + (i & 1) * 16, b[i]);
+        TricubicBricks<S> V;
+        V.b = b;
+        tricubic_eval(V, xin, yin, zin, w, val, gx, gy, gz);
+    }
 }
 
 // One grid's tricubic contribution for an inside atom (:796-893), same epilogue as accumulate_bspline.
-template <typename S>
-__device__ __forceinline__ void accumulate_tricubic(const GridView& G, const AtomCell& c, double sd, double& e_g, double& Fx,
-                                                    double& Fy, double& Fz) {
-    double dval, gx, gy, gz;
-    tricubic_interpolate<S>(G, c, dval, gx, gy, gz);
+__device__ __forceinline__ void tricubic_epilogue(const GridView& G, double sd, double dval, double gx, double gy, double gz,
+                                                  double& e_g, double& Fx, double& Fy, double& Fz) {
     if (G.inv_power > 0.0) {  // :879-886
         const double base = dval;
         dval = pow(base, G.inv_power);
@@ -511,6 +553,13 @@ __device__ __forceinline__ void accumulate_tricubic(const GridView& G, const Ato
     Fx -= sd * (gx / G.spacing[0]);      // :889, :893
     Fy -= sd * (gy / G.spacing[1]);
     Fz -= sd * (gz / G.spacing[2]);
+}
+template <typename S, int LAYOUT>
+__device__ __forceinline__ void accumulate_tricubic(const GridView& G, const AtomCell& c, double sd, double& e_g, double& Fx,
+                                                    double& Fy, double& Fz) {
+    double dval, gx, gy, gz;
+    tricubic_interpolate<S, LAYOUT>(G, c, dval, gx, gy, gz);
+    tricubic_epilogue(G, sd, dval, gx, gy, gz, e_g, Fx, Fy, Fz);
 }
 
 // :1093-1117 — harmonic wall outside the grid (unscaled). Inside atoms with scale == 0 land here too and contribute
@@ -544,7 +593,7 @@ __device__ __forceinline__ void accumulate_restraint(const GridView& G, double x
 
 template <typename S, int LAYOUT, int NG>
 __host__ __device__ constexpr int eval_min_blocks() {
-    return (LAYOUT == GFB_LAYOUT_BSPLINE || LAYOUT == GFB_LAYOUT_POINTS) ? 2 : ((NG == 1 && sizeof(S) == 4) ? 6 : 4);
+    return (LAYOUT == GFB_LAYOUT_BSPLINE || LAYOUT == GFB_LAYOUT_POINTS || LAYOUT == GFB_LAYOUT_HERMITE) ? 2 : ((NG == 1 && sizeof(S) == 4) ? 6 : 4);
 }
 
 template <typename S, int LAYOUT, int NG, bool SAME, bool SINGLE>
@@ -670,8 +719,8 @@ __global__ void __launch_bounds__(kBlock, eval_min_blocks<S, LAYOUT, NG>()) gf_e
                 if (c.inside && s != 0.0) {
                     if constexpr (LAYOUT == GFB_LAYOUT_BSPLINE) {
                         accumulate_bspline<S>(G, c, s, e_g, Fx, Fy, Fz);
-                    } else if constexpr (LAYOUT == GFB_LAYOUT_POINTS) {
-                        accumulate_tricubic<S>(G, c, s, e_g, Fx, Fy, Fz);
+                    } else if constexpr (LAYOUT == GFB_LAYOUT_POINTS || LAYOUT == GFB_LAYOUT_HERMITE) {
+                        accumulate_tricubic<S, LAYOUT>(G, c, s, e_g, Fx, Fy, Fz);
                     } else {
                         S v[8];
                         load_stencil<S, LAYOUT>(G, c.ix, c.iy, c.iz, v);

@@ -42,6 +42,8 @@ constexpr int kLinesF64BlockThreads = 128;
 
 // gf_eval_bspline_kernel (gf_eval_bspline.cuh): MIXED B-spline records of one geometry.
 void launch_bspline(const EvalParams& p, cudaStream_t stream);
+// the same kernel with METHOD = 2: MIXED tricubic Hermite on HERMITE records of one geometry.
+void launch_tricubic_records(const EvalParams& p, cudaStream_t stream);
 constexpr int kBsplineBlockThreads = 128;
 
 // gf_eval_bspline_f64_kernel (gf_eval_bspline_f64.cuh): DOUBLE B-spline records of one geometry.

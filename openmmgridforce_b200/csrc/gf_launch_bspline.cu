@@ -9,8 +9,14 @@ static_assert(kBsBlock == kBsplineBlockThreads && kBsF64Block == kBsplineF64Bloc
 
 void launch_bspline(const EvalParams& p, cudaStream_t stream) {
     const unsigned blocks = (unsigned) ((p.total + kBsBlock - 1) / kBsBlock);
-    if (p.n_replicas == 1 && p.slots == nullptr) gf_eval_bspline_kernel<true><<<blocks, kBsBlock, 0, stream>>>(p);
-    else gf_eval_bspline_kernel<false><<<blocks, kBsBlock, 0, stream>>>(p);
+    if (p.n_replicas == 1 && p.slots == nullptr) gf_eval_bspline_kernel<true, 1><<<blocks, kBsBlock, 0, stream>>>(p);
+    else gf_eval_bspline_kernel<false, 1><<<blocks, kBsBlock, 0, stream>>>(p);
+}
+
+void launch_tricubic_records(const EvalParams& p, cudaStream_t stream) {
+    const unsigned blocks = (unsigned) ((p.total + kBsBlock - 1) / kBsBlock);
+    if (p.n_replicas == 1 && p.slots == nullptr) gf_eval_bspline_kernel<true, 2><<<blocks, kBsBlock, 0, stream>>>(p);
+    else gf_eval_bspline_kernel<false, 2><<<blocks, kBsBlock, 0, stream>>>(p);
 }
 
 void launch_bspline_f64(const EvalParams& p, cudaStream_t stream) {

@@ -95,7 +95,9 @@ static __global__ void __launch_bounds__(256) gf_repack_pairs_kernel(const doubl
 
 // BSPLINE records (see bspline_interpolate): one thread per (record, half h, row r): the 4 values
 // P[a+h][iy+r][iz+k] = V[clamp(a+h-1)][clamp(iy+r-1)][clamp(iz+k-1)], k = 0..3. a < nx+1, iy < ny-1, iz < nz-1.
-template <typename S>
+// FLAT (HERMITE records, tricubic_interpolate): the same records with P[a][b][c] = the value at flat index
+// ((a-1)*ny + (b-1))*nz + (c-1), 0 outside the array — how the reference's tricubic branch addresses its neighbours.
+template <typename S, bool FLAT>
 static __global__ void __launch_bounds__(256) gf_repack_bspline_kernel(const double* __restrict__ vals, S* __restrict__ out,
                                                                 int nx, int ny, int nz) {
     const size_t total = (size_t) (nx + 1) * (ny - 1) * (nz - 1) * 8;
@@ -107,10 +109,17 @@ static __global__ void __launch_bounds__(256) gf_repack_bspline_kernel(const dou
         t /= (nz - 1);
         const int iy = (int) (t % (ny - 1));
         const int a = (int) (t / (ny - 1));
+        S* o = out + c * 4;
+        if (FLAT) {
+            const long long n = (long long) nx * ny * nz;
+            const long long base = ((long long) (a + h - 1) * ny + (iy + r - 1)) * nz + (iz - 1);
+#pragma unroll
+            for (int k = 0; k < 4; k++) o[k] = (base + k >= 0 && base + k < n) ? (S) vals[base + k] : (S) 0;
+            continue;
+        }
         const int gx = min(max(a + h - 1, 0), nx - 1);
         const int gy = min(max(iy + r - 1, 0), ny - 1);
         const double* src = vals + ((size_t) gx * ny + gy) * nz;
-        S* o = out + c * 4;
 #pragma unroll
         for (int k = 0; k < 4; k++) o[k] = (S) src[min(max(iz + k - 1, 0), nz - 1)];
     }

@@ -52,10 +52,11 @@ static unsigned long long hashWords(const void* data, size_t bytes, unsigned lon
     return h ^ (h >> 32);
 }
 
-int b200LayoutForMethod(int interpolationMethod, const char* who) {
+int b200LayoutForMethod(int interpolationMethod, int precision, const char* who) {
     if (interpolationMethod == 0) return GFB_LAYOUT_AUTO;        // trilinear
     if (interpolationMethod == 1) return GFB_LAYOUT_BSPLINE;     // cubic B-spline
-    if (interpolationMethod == 2) return GFB_LAYOUT_POINTS;      // tricubic Hermite (finite-difference derivatives)
+    // tricubic Hermite (finite-difference derivatives): records in MIXED (two lines per stencil), raw points in DOUBLE
+    if (interpolationMethod == 2) return precision == GFB_PRECISION_MIXED ? GFB_LAYOUT_HERMITE : GFB_LAYOUT_POINTS;
     throw OpenMMException(std::string(who) + ": interpolation method 3 (quintic Hermite) needs the 27 derivative grids and is "
                           "not implemented on this platform; use 0 (trilinear), 1 (cubic B-spline) or 2 (tricubic)");
 }
@@ -177,7 +178,7 @@ void B200CalcGridForceKernel::build(const GridForce& force) {
     std::vector<int> counts;
     std::vector<double> spacing, vals, scaling;
     force.getGridParameters(counts, spacing, vals, scaling);
-    const int layout = b200LayoutForMethod(force.getInterpolationMethod(), "GridForce[B200]");
+    const int layout = b200LayoutForMethod(force.getInterpolationMethod(), precision, "GridForce[B200]");
     if (force.getTiledMode()) throw OpenMMException("GridForce[B200]: tiled grids are not supported on this platform");
     double origin[3];
     force.getGridOrigin(origin[0], origin[1], origin[2]);

@@ -67,7 +67,7 @@ void GridForceBatch::build() {
     size_t nAtoms = 0;
     for (size_t g = 0; g < forces.size(); g++) {
         const GridForce& f = *forces[g];
-        const int layout = b200LayoutForMethod(f.getInterpolationMethod(), "GridForceBatch");
+        const int layout = b200LayoutForMethod(f.getInterpolationMethod(), precision, "GridForceBatch");
         if (f.getInterpolationMethod() != forces[0]->getInterpolationMethod())
             throw OpenMMException("GridForceBatch: all forces must use the same interpolation method");
         std::vector<int> counts;

@@ -1,5 +1,6 @@
 """Scratch probe: device-resident step time of the cubic B-spline path on the C5 shape (R replicas x 47 atoms x 3 grids
-of 192^3) and C3 shape, CUDA events. Usage: python tools/bspline_perf.py [replicas]"""
+of 192^3), CUDA events. Usage: python tools/bspline_perf.py [replicas] [bspline|points|hermite]   (points / hermite =
+tricubic Hermite, interpolation method 2, on raw points / on records)"""
 import os
 import sys
 import numpy as np
@@ -9,13 +10,17 @@ import openmmgridforce_b200 as gf
 from openmmgridforce_b200 import workloads as W
 
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+LNAME = sys.argv[2] if len(sys.argv) > 2 else "bspline"
+LAYOUT = {"bspline": gf.LAYOUT_BSPLINE, "points": gf.LAYOUT_POINTS, "hermite": gf.LAYOUT_HERMITE}[LNAME]
 dev = gf.Device(0)
 tdev = torch.device("cuda:0")
 side = torch.cuda.Stream()
 torch.cuda.set_stream(side)
 w = W.c5_sharded_replicas(n_local=R)
 for prec, pname in ((0, "mixed"), (1, "double")):
-    grids = [gf.Grid(dev, w.counts, w.spacing, w.origin, v, prec, layout=gf.LAYOUT_BSPLINE) for v in w.grids]
+    if prec == 1 and LNAME == "hermite":
+        continue
+    grids = [gf.Grid(dev, w.counts, w.spacing, w.origin, v, prec, layout=LAYOUT) for v in w.grids]
     print(pname, "grid bytes", [g.device_bytes for g in grids])
     k = gf.Kernel(dev, grids, w.scaling, oob_k=w.oob_k)
     n = R * w.n_atoms
@@ -35,7 +40,7 @@ for prec, pname in ((0, "mixed"), (1, "double")):
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / iters * 1e3
-        print(f"bspline {pname} C5x{R} {fname}: {us:9.1f} us  {w.evals / us / 1e3:8.2f} G evals/s", flush=True)
+        print(f"{LNAME} {pname} C5x{R} path {k.eval_path()} {fname}: {us:9.1f} us  {w.evals / us / 1e3:8.2f} G evals/s", flush=True)
     k.close()
     for g in grids:
         g.close()
