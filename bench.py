@@ -515,16 +515,23 @@ def run_other_workload(torch, gf, dev, stream, name, steps, warmup, windows, pea
             precision = gf.PRECISION_DOUBLE
         elif name == "C5_energy_only":
             force_mode, forces = -1, False
-    grids = [gf.Grid(dev, w.counts, w.spacing, w.origin, v, precision) for v in w.grids]
+    # interpolation methods 1 and 2 on their record layouts (a stencil = two 128-byte records instead of one 32-byte slot)
+    layout = {"C5_bspline": gf.LAYOUT_BSPLINE, "C5_tricubic": gf.LAYOUT_HERMITE}.get(name)
+    grids = [gf.Grid(dev, w.counts, w.spacing, w.origin, v, precision, layout=layout) for v in w.grids]
     kern = gf.Kernel(dev, grids, w.scaling, oob_k=w.oob_k)
     loop = DeviceLoop(torch, gf, dev, kern, sets, w.n_atoms, stream, force_mode=force_mode)
     variants, _ = run_variants(loop, steps, warmup, windows, which=(VARIANTS[0], VARIANTS[3]))
     best = variants["pdl+graph"]
     rate = w.evals / (best["ms_per_step"] * 1e-3)
     bpe = b_alg(w.n_grids, 1 if precision == gf.PRECISION_DOUBLE else 0, forces)
+    if layout is not None:
+        bpe += 256.0 - 32.0      # two 128-byte records per evaluation in place of the 32-byte trilinear stencil
     ach = rate * bpe / 1e9
     traffic, traffic_src = measured_traffic(name)
-    out = {"workload": w.name + (" (DOUBLE precision)" if name == "C5_double" else " (energy only)" if name == "C5_energy_only" else ""),
+    suffix = {"C5_double": " (DOUBLE precision)", "C5_energy_only": " (energy only)",
+              "C5_bspline": " (cubic B-spline, interpolation method 1, BSPLINE records)",
+              "C5_tricubic": " (tricubic Hermite, interpolation method 2, HERMITE records)"}.get(name, "")
+    out = {"workload": w.name + suffix,
            "value": rate, "unit": UNIT, "us_per_step": best["ms_per_step"] * 1e3,
            "us_per_step_no_overlap_direct_launches": variants["plain"]["ms_per_step"] * 1e3,
            "eval_path": kern.eval_path(),
@@ -809,7 +816,7 @@ def main():
     extras = {}
     if rank == 0 and world == 1 and not args.no_extras:
         x_steps = max(20, min(args.steps, 200))
-        for name in ("C3", "C4", "C5_double", "C5_energy_only"):
+        for name in ("C3", "C4", "C5_double", "C5_energy_only", "C5_bspline", "C5_tricubic"):
             extras[name] = run_other_workload(torch, gf, dev, stream, name, x_steps, args.warmup, 3, peak_gbs, l2_gbs)
         extras["C2"] = run_single_ligand(gf, dev)
     clocks = sampler.stop()
