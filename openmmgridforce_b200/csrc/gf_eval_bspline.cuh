@@ -77,6 +77,13 @@ __device__ __forceinline__ void bspline_from_smem(unsigned rbase, unsigned sw, c
 // Tricubic Hermite (interpolation method 2) out of the same 256-byte smem region, for HERMITE records (filled by flat
 // index, gf_repack_bspline_kernel<float, true>): the point at offsets (i-1, r-1, k-1) is element k of granule 4*i + r.
 // 12 of the 16 granules are read (rows 1-2 of every x-plane, rows 0 and 3 of planes 1-2); arithmetic FP64 (tricubic_eval).
+// volatile: ptxas otherwise narrows the 16-byte loads of which only elements 1-2 are used (planes 0 and 3, rows 0 and 3) to
+// pairs of 4-byte loads, and 4-byte loads of this swizzle are 4-way bank conflicts (lanes l, l+8, l+16, l+24 share a
+// bank; a 16-byte load is served a quarter-warp at a time and has none): ncu counted 14.2 M conflicts per launch against
+// 0.13 M for the B-spline arithmetic on the same slice.
+__device__ __forceinline__ void lds128_whole(unsigned addr, float* v) {
+    asm volatile("ld.volatile.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
+}
 struct TricubicSmem {
     float g[4][4][4];      // [i][r][k]; entries of the four granules never read stay unset
     __device__ __forceinline__ double operator()(int i, int r, int k) const { return (double) g[i][r][k]; }
@@ -84,13 +91,16 @@ struct TricubicSmem {
 __device__ __forceinline__ void tricubic_from_smem(unsigned rbase, unsigned sw, bool xin, bool yin, bool zin, const TricubicWeights& w,
                                                    double& val, double& gx, double& gy, double& gz) {
     TricubicSmem V;
+    // in the order tricubic_eval consumes them: rows 1 and 2 of the four x-planes (x stage), then rows 0 and 3 of planes 1-2
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int r = 1; r <= 2; r++) {
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            if ((r == 0 || r == 3) && (i == 0 || i == 3)) continue;      // corners of the (x,y) window: not part of the stencil
-            lds128(rbase + (((4u * i + r) << 4) ^ sw), V.g[i][r]);
-        }
+        for (int i = 0; i < 4; i++) lds128_whole(rbase + (((4u * i + r) << 4) ^ sw), V.g[i][r]);
+    }
+#pragma unroll
+    for (int r = 0; r <= 3; r += 3) {
+#pragma unroll
+        for (int i = 1; i <= 2; i++) lds128_whole(rbase + (((4u * i + r) << 4) ^ sw), V.g[i][r]);
     }
     tricubic_eval(V, xin, yin, zin, w, val, gx, gy, gz);
 }

@@ -1,6 +1,7 @@
 """Small fixed launch sequence for ncu: a few device-resident launches of one configuration, rotating pose sets the way
 bench.py does (so that the captured launch sees the cache state of the timed loop, not a re-run of the same inputs).
-usage: profile_run.py {c3|c4|c5full|c5shard2|c5shard4|c5shard8} [precision] [force_mode (-1 = energy only)] [iters] [pdl]"""
+usage: profile_run.py {c3|c4|c5full|c5shard2|c5shard4|c5shard8} [precision] [force_mode (-1 = energy only)] [iters] [pdl]
+       [layout: auto|cells|rows|pairs|bspline|points|hermite]"""
 import os
 import sys
 
@@ -16,6 +17,7 @@ prec = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 fmode = int(sys.argv[3]) if len(sys.argv) > 3 else gf.FORCE_FIXED_ADD
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 6
 pdl = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+layout = {v: k for k, v in gf.LAYOUT_NAMES.items()}[sys.argv[6]] if len(sys.argv) > 6 else None
 dev = gf.Device(0)
 tdev = torch.device("cuda:0")
 side = torch.cuda.Stream()
@@ -35,7 +37,7 @@ else:
     w = W.c5_sharded_replicas(n_local=r)
     half = 0.5 * w.spacing[0] * 191
     sets = [w.pos] + [W.ligand_replicas(r, (half, half, half), seed=W.SEED + 7919 * j, escape_shift=(0.9, 0.0, 0.0)) for j in range(1, 2 * n_gpu)]
-grids = [gf.Grid(dev, w.counts, w.spacing, w.origin, v, prec) for v in w.grids]
+grids = [gf.Grid(dev, w.counts, w.spacing, w.origin, v, prec, layout=layout) for v in w.grids]
 k = gf.Kernel(dev, grids, w.scaling, oob_k=w.oob_k)
 k.set_launch_overlap(bool(pdl))
 R, P = w.n_replicas, w.n_atoms
