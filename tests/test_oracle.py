@@ -228,3 +228,25 @@ def test_inv_power_transform_matches_reference(oracle_built):
         for n in (2.0, 4.0, 3.5):
             ref, mode = oracle_built.ref_inv_power_transform(v, n)
             assert mode == 2 and np.array_equal(ref, oracle_built.port_inv_power_transform(v, n))
+
+
+def test_reference_method3_matrix_is_truncated():
+    """Why interpolation method 3 (triquintic Hermite, ReferenceGridForceKernels.cpp:895-1015) is refused instead of
+    reproduced: the 216 x 216 coefficient matrix the reference multiplies the 216 corner derivatives with
+    (platforms/reference/src/TriquinticMatrix.h) holds 31 initialised rows in the reference tree; the other 185 are
+    zero-initialised, so the "interpolant" ignores 180 of its 216 inputs (rank 31). There is no defined behaviour to match.
+    Reads the header where it lies (build container only)."""
+    import re
+    path = "/root/reference/platforms/reference/src/TriquinticMatrix.h"
+    if not os.path.exists(path):
+        pytest.skip("needs /root/reference")
+    text = open(path).read()
+    body = text[text.index("TRIQUINTIC_COEFFICIENTS[216][216] = {") + len("TRIQUINTIC_COEFFICIENTS[216][216] = {"):]
+    rows = re.findall(r"\{([^{}]*)\}", body[:body.rindex("};")])
+    m = np.zeros((216, 216))
+    for i, r in enumerate(rows[:216]):
+        vals = [float(x) for x in r.replace("\n", " ").split(",") if x.strip()]
+        m[i, :len(vals)] = vals
+    assert len(rows) < 216
+    assert np.linalg.matrix_rank(m) < 216
+    assert int((np.abs(m).sum(axis=0) == 0).sum()) > 100        # inputs that cannot influence the result
