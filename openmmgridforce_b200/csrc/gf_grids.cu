@@ -88,7 +88,7 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
                 const int lay = layout;
                 delete g;
                 return fail(GFB_ERR_NOMEM, "gfb_grid_create: a %dx%dx%d grid in layout %d (%s) needs %.2f GB of device memory, %.2f GB are free%s",
-                            counts[0], counts[1], counts[2], lay, (lay == GFB_LAYOUT_BSPLINE || lay == GFB_LAYOUT_HERMITE) ? "records, 32x the raw grid" : "see gfb_layout",
+                            counts[0], counts[1], counts[2], lay, lay == GFB_LAYOUT_BSPLINE ? "B-spline records, 32x the raw grid" : lay == GFB_LAYOUT_HERMITE ? "tricubic Hermite records, 32x the raw grid" : "see gfb_layout",
                             need / 1e9, free_b / 1e9, lay == GFB_LAYOUT_CELLS ? "; GFB_LAYOUT_ROWS needs 1.14x the raw grid" : "");
             }
         } else {
