@@ -158,6 +158,31 @@ def test_plugin_batch_entry_point_and_groups(oracle_built):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["mixed", "double"])
+@pytest.mark.parametrize("method", [1, 2])
+def test_plugin_batch_entry_point_other_interpolation_methods(oracle_built, method, precision):
+    """GridForceBatch with cubic B-spline (1) and tricubic Hermite (2) forces: 33 replicas x 3 forces in one launch, against
+    the oracle. MIXED runs the record kernels (BSPLINE / HERMITE records), DOUBLE the DOUBLE B-spline records and, for
+    method 2, the raw-points layout."""
+    import openmmgridforce_b200.gridforceplugin as gfp
+    c, _ = cases.load_golden("ligand_three_grids")            # FP32-representable grids
+    c = dict(c, interp=method)
+    platform = gfp.Platform.getPlatformByName("B200")
+    system, forces = _build_system(gfp, c)
+    context = gfp.Context(system, platform, {"Precision": precision})
+    rng = np.random.default_rng(method)
+    pos = np.stack([c["pos"] + rng.uniform(-0.3, 0.3, size=3) for _ in range(33)])
+    en, f = context.evaluateBatch(pos, precision=precision)
+    port = oracle_built.PortOracle(c["counts"], c["spacing"], c["origin"], c["grids"], c["scaling"], oob_k=c["oob_k"],
+                                   interpolation_method=method)
+    ge_ref, f_ref = port.execute_batched(pos)
+    te, tf = (1e-6, 1e-5) if precision == "mixed" else (1e-12, 1e-12)
+    scale = np.maximum(np.abs(ge_ref.sum(axis=1)), np.abs(ge_ref).max(axis=1))
+    assert (np.abs(en - ge_ref.sum(axis=1)) <= te * scale).all()
+    assert np.abs(f - f_ref).max() <= tf * np.abs(f_ref).max()
+
+
+@pytest.mark.gpu
 def test_plugin_refuses_what_it_does_not_implement():
     import openmmgridforce_b200.gridforceplugin as gfp
     c, _ = cases.load_golden("ramp_grid")
