@@ -68,8 +68,8 @@ typedef enum { GFB_PRECISION_MIXED = 0, GFB_PRECISION_DOUBLE = 1 } gfb_precision
  *          neighbour reads by FLAT index without clamping, so in the last y/z cells they land in the next row / slab
  *          (reproduced) and in the last x layer past the end of its vector (undefined there; zeros here). The
  *          arithmetic is FP64 in both precisions. Never chosen by AUTO.
- *   HERMITE tricubic Hermite on records, MIXED only: the BSPLINE record format (two 4x4 (y,z) windows of adjacent x-planes
- *          per cell and plane, 128 bytes, 32x the raw grid) filled by FLAT index instead of clamped indices, so that the
+ *   HERMITE tricubic Hermite on records: the BSPLINE record format (two 4x4 (y,z) windows of adjacent x-planes per cell
+ *          and plane, 128 bytes in MIXED, 256 in DOUBLE; 32x the raw grid) filled by FLAT index instead of clamped indices, so that the
  *          32 neighbours the method reads are inside the stencil's two full lines, with the reference's next-row /
  *          next-slab values at the upper y/z edges and zeros past the array. Same results as POINTS; 2 lines per
  *          stencil instead of 32 scalar loads. Never chosen by AUTO. */
@@ -218,8 +218,8 @@ GFB_API int gfb_kernel_update_parameters(gfb_kernel* k, const double* scaling, c
 /* Which evaluation kernel a launch of this state uses: 1 = gf_eval_lines_kernel (MIXED, packed cells, one geometry,
  * 1-4 grids, no inv-power: the 2-4 grid case reads one 128-byte record per atom), 2 = gf_eval_lines_f64_kernel (DOUBLE,
  * same conditions, 2-4 grids, one 256-byte record per atom), 3 = gf_eval_bspline_kernel (MIXED B-spline records),
- * 4 = gf_eval_bspline_f64_kernel (DOUBLE B-spline records), 5 = gf_eval_bspline_kernel<.., METHOD 2> (MIXED tricubic Hermite
- * on HERMITE records), 0 = the general gf_eval_kernel. Introspection for tests and bench.py; no reference counterpart. */
+ * 4 = gf_eval_bspline_f64_kernel (DOUBLE B-spline records), 5 / 6 = gf_eval_bspline_kernel<.., METHOD 2> /
+ * gf_eval_bspline_f64_kernel<.., METHOD 2> (MIXED / DOUBLE tricubic Hermite on HERMITE records), 0 = the general gf_eval_kernel. Introspection for tests and bench.py; no reference counterpart. */
 GFB_API int gfb_kernel_eval_path(const gfb_kernel* k);
 
 /* Particle groups (GridForce::addParticleGroup / getParticleGroupEnergies, openmmapi/include/GridForce.h:433-508;

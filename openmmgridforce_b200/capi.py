@@ -369,7 +369,7 @@ class Kernel:
         return self.eval_path() == 1
 
     def eval_path(self):
-        """gfb_kernel_eval_path: 1 gf_eval_lines_kernel, 2 gf_eval_lines_f64_kernel, 3 gf_eval_bspline_kernel, 4 gf_eval_bspline_f64_kernel, 5 the record kernel with the tricubic arithmetic, 0 general."""
+        """gfb_kernel_eval_path: 1 gf_eval_lines_kernel, 2 gf_eval_lines_f64_kernel, 3 gf_eval_bspline_kernel, 4 gf_eval_bspline_f64_kernel, 5 / 6 the MIXED / DOUBLE record kernels with the tricubic arithmetic, 0 general."""
         return int(load_library().gfb_kernel_eval_path(self._h))
 
     def set_launch_overlap(self, enable=True):

@@ -382,12 +382,14 @@ static bool bspline_tiles_eligible(const gfb_kernel* k, const EvalParams& p) { r
 static bool tricubic_tiles_eligible(const gfb_kernel* k, const EvalParams& p) { return record_tiles_eligible(k, p, GFB_LAYOUT_HERMITE); }
 
 // gf_eval_bspline_f64_kernel (gf_eval_bspline_f64.cuh): DOUBLE B-spline records of one geometry, no evaluation order.
-static bool bspline_f64_eligible(const gfb_kernel* k, const EvalParams& p) {
+static bool record_f64_eligible(const gfb_kernel* k, const EvalParams& p, int layout) {
     static const bool off = env_off("GFB_BSPLINE_TILES") || env_off("GFB_BSPLINE_F64");   // 0: the general kernel (A/B measurements)
-    if (off || k->precision != GFB_PRECISION_DOUBLE || k->grids[0]->layout != GFB_LAYOUT_BSPLINE || !k->same_geom) return false;
+    if (off || k->precision != GFB_PRECISION_DOUBLE || k->grids[0]->layout != layout || !k->same_geom) return false;
     if (p.order != nullptr) return false;
     return k->grids[0]->bytes / 256 < 0x7fffffffull;   // 32-bit record index
 }
+static bool bspline_f64_eligible(const gfb_kernel* k, const EvalParams& p) { return record_f64_eligible(k, p, GFB_LAYOUT_BSPLINE); }
+static bool tricubic_f64_eligible(const gfb_kernel* k, const EvalParams& p) { return record_f64_eligible(k, p, GFB_LAYOUT_HERMITE); }
 
 int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos, double* d_energies,
                  double* d_grid_energies, void* d_forces, int force_mode, long long force_stride, const int* d_order,
@@ -443,6 +445,8 @@ int enqueue_eval(gfb_kernel* k, int n_replicas, int n_particles, const double* d
         launch_tricubic_records(p, stream);
     } else if (bspline_f64_eligible(k, p)) {
         launch_bspline_f64(p, stream);
+    } else if (tricubic_f64_eligible(k, p)) {
+        launch_tricubic_records_f64(p, stream);
     } else if (lines) {
         p.lines = k->d_interleaved;
         static const bool ahead_off = env_off("GFB_POS_PREFETCH");   // A/B measurements
@@ -496,7 +500,7 @@ static int eval_block_threads(const gfb_kernel* k) {
     EvalParams probe;
     memset(&probe, 0, sizeof probe);
     if (bspline_tiles_eligible(k, probe) || tricubic_tiles_eligible(k, probe)) return kBsplineBlockThreads;
-    if (bspline_f64_eligible(k, probe)) return kBsplineF64BlockThreads;
+    if (bspline_f64_eligible(k, probe) || tricubic_f64_eligible(k, probe)) return kBsplineF64BlockThreads;
     if (lines_eligible(k, probe)) return lines_block_threads(k->n_grids);
     return lines_f64_eligible(k) ? kLinesF64BlockThreads : kGeneralBlock;
 }
@@ -533,7 +537,7 @@ static int execute_host_small(gfb_kernel* k, int n_particles, const double* pos,
     memset(&probe, 0, sizeof probe);
     // one block covers the ligand: its energy (and, in the record kernels, its per-grid energies) are plain stores
     const bool one_block = k->n_atoms <= eval_block_threads(k) &&
-                           (!grid_energies || !(bspline_tiles_eligible(k, probe) || tricubic_tiles_eligible(k, probe) || bspline_f64_eligible(k, probe)));
+                           (!grid_energies || !(bspline_tiles_eligible(k, probe) || tricubic_tiles_eligible(k, probe) || bspline_f64_eligible(k, probe) || tricubic_f64_eligible(k, probe)));
     double* d_e = nullptr;
     if (!one_block) {   // several blocks (or per-grid energies): device accumulators, cleared here, fetched below
         if ((rc = k->d_energy.ensure(e_count * sizeof(double))) != GFB_OK) return rc;
@@ -588,6 +592,7 @@ int gfb_kernel_eval_path(const gfb_kernel* k) {
     if (lines_f64_eligible(k)) return 2;
     if (bspline_tiles_eligible(k, probe)) return 3;
     if (tricubic_tiles_eligible(k, probe)) return 5;
+    if (tricubic_f64_eligible(k, probe)) return 6;
     return bspline_f64_eligible(k, probe) ? 4 : 0;
 }
 

@@ -1,4 +1,5 @@
 // DOUBLE-precision twin of gf_eval_bspline_kernel (gf_eval_bspline.cuh): cubic B-spline grids in the BSPLINE record layout
+// (METHOD 1) or tricubic Hermite grids in the HERMITE record layout (METHOD 2, :796-893, arithmetic tricubic_eval)
 // that share one geometry, no evaluation order (GridForce::setInterpolationMethod(1) on a "double" platform; reference
 // platforms/reference/src/ReferenceGridForceKernels.cpp:727-795, whose arithmetic is FP64 throughout).
 //
@@ -23,8 +24,41 @@ __device__ __forceinline__ void lds128_f64(unsigned addr, double* v) {
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(addr) : "memory");
 }
 
+// whole 16-byte loads whatever part of them the arithmetic uses (see lds128_whole in gf_eval_bspline.cuh)
+__device__ __forceinline__ void lds128_f64_whole(unsigned addr, double* v) {
+    asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(addr) : "memory");
+}
+// Tricubic Hermite (METHOD 2, HERMITE records filled by flat index) out of a lane's 512-byte region: the point at offsets
+// (i-1, r-1, k-1) is element k & 1 of granule 8*i + 2*r + (k >> 1). 24 of the 32 granules are read.
+struct TricubicSmemF64 {
+    double g[4][4][4];     // [i][r][k]; the four (x,y) corner rows stay unset
+    __device__ __forceinline__ double operator()(int i, int r, int k) const { return g[i][r][k]; }
+};
+__device__ __forceinline__ void tricubic_from_smem_f64(unsigned rbase, unsigned sw, bool xin, bool yin, bool zin, const TricubicWeights& w,
+                                                       double& val, double& gx, double& gy, double& gz) {
+    TricubicSmemF64 V;
+#pragma unroll
+    for (int r = 1; r <= 2; r++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            lds128_f64_whole(rbase + (((8u * i + 2u * r) << 4) ^ sw), V.g[i][r]);
+            lds128_f64_whole(rbase + (((8u * i + 2u * r + 1u) << 4) ^ sw), V.g[i][r] + 2);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r <= 3; r += 3) {
+#pragma unroll
+        for (int i = 1; i <= 2; i++) {
+            lds128_f64_whole(rbase + (((8u * i + 2u * r) << 4) ^ sw), V.g[i][r]);
+            lds128_f64_whole(rbase + (((8u * i + 2u * r + 1u) << 4) ^ sw), V.g[i][r] + 2);
+        }
+    }
+    tricubic_eval(V, xin, yin, zin, w, val, gx, gy, gz);
+}
+
 //   SINGLE  one replica and no energy slots (block-level energy reduction); the force mode is p.force_mode (launch-uniform)
-template <bool SINGLE>
+//   METHOD  1 cubic B-spline on BSPLINE records, 2 tricubic Hermite on HERMITE records (same fetch, other arithmetic)
+template <bool SINGLE, int METHOD>
 __global__ void __launch_bounds__(kBsF64Block, 6) gf_eval_bspline_f64_kernel(const __grid_constant__ EvalParams p) {
     __shared__ __align__(128) unsigned char s_tiles[(kBsF64Block / 32) * kBsF64WarpBytes];
 
@@ -73,9 +107,15 @@ __global__ void __launch_bounds__(kBsF64Block, 6) gf_eval_bspline_f64_kernel(con
 
     // per-atom weights, used for every grid (:741-748)
     double bx[4], dbx[4], by[4], dby[4], bz[4], dbz[4];
-    bspline_basis(c.fx, bx, dbx);
-    bspline_basis(c.fy, by, dby);
-    bspline_basis(c.fz, bz, dbz);
+    TricubicWeights tw;
+    if constexpr (METHOD == 1) {
+        bspline_basis(c.fx, bx, dbx);
+        bspline_basis(c.fy, by, dby);
+        bspline_basis(c.fz, bz, dbz);
+    } else {
+        tricubic_weights(c.fx, c.fy, c.fz, tw);
+    }
+    const bool xin = c.ix > 0 && c.ix < G.nc[0], yin = c.iy > 0 && c.iy < G.nc[1], zin = c.iz > 0 && c.iz < G.nc[2];   // :817, :849, :866
 
     double e_total = 0.0;
     double Fx = 0.0, Fy = 0.0, Fz = 0.0;
@@ -107,7 +147,11 @@ __global__ void __launch_bounds__(kBsF64Block, 6) gf_eval_bspline_f64_kernel(con
         __syncwarp();
         // ---- evaluate: bspline_interpolate<double>, operation for operation ---------------------------------------------
         double e_g = 0.0;
-        if (interp) {
+        if (METHOD == 2 && interp) {
+            double val, gx, gy, gz;
+            tricubic_from_smem_f64(rbase, sw, xin, yin, zin, tw, val, gx, gy, gz);
+            tricubic_epilogue(Gg, s, val, gx, gy, gz, e_g, Fx, Fy, Fz);      // :879-893
+        } else if (interp) {
             double val = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
 #pragma unroll
             for (int i = 0; i < 4; i++) {

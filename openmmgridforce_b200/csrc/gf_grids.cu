@@ -25,8 +25,6 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
     if (layout < GFB_LAYOUT_AUTO || layout > GFB_LAYOUT_HERMITE) return fail(GFB_ERR_INVALID, "gfb_grid_create: unknown layout %d", layout);
     if (layout == GFB_LAYOUT_PAIRS && precision == GFB_PRECISION_DOUBLE)
         return fail(GFB_ERR_UNSUPPORTED, "gfb_grid_create: the PAIRS layout exists for MIXED precision only (use ROWS or CELLS)");
-    if (layout == GFB_LAYOUT_HERMITE && precision == GFB_PRECISION_DOUBLE)
-        return fail(GFB_ERR_UNSUPPORTED, "gfb_grid_create: the HERMITE record layout exists for MIXED precision only (use POINTS)");
     for (int k = 0; k < 3; k++) {
         if (counts[k] < 2) return fail(GFB_ERR_INVALID, "gfb_grid_create: counts[%d]=%d, need >= 2 points per axis", k, counts[k]);
         if (!(spacing[k] > 0.0) || !std::isfinite(spacing[k]))
@@ -121,7 +119,8 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
             if (mixed) gf_repack_points_kernel<float><<<blocks, 256, 0, dev->stream>>>(d_vals, cf, n_points, guard);
             else gf_repack_points_kernel<double><<<blocks, 256, 0, dev->stream>>>(d_vals, cd, n_points, guard);
         } else {
-            if (layout == GFB_LAYOUT_HERMITE) gf_repack_bspline_kernel<float, true><<<blocks, 256, 0, dev->stream>>>(d_vals, cf, counts[0], counts[1], counts[2]);
+            if (layout == GFB_LAYOUT_HERMITE && mixed) gf_repack_bspline_kernel<float, true><<<blocks, 256, 0, dev->stream>>>(d_vals, cf, counts[0], counts[1], counts[2]);
+            else if (layout == GFB_LAYOUT_HERMITE) gf_repack_bspline_kernel<double, true><<<blocks, 256, 0, dev->stream>>>(d_vals, cd, counts[0], counts[1], counts[2]);
             else if (mixed) gf_repack_bspline_kernel<float, false><<<blocks, 256, 0, dev->stream>>>(d_vals, cf, counts[0], counts[1], counts[2]);
             else gf_repack_bspline_kernel<double, false><<<blocks, 256, 0, dev->stream>>>(d_vals, cd, counts[0], counts[1], counts[2]);
         }

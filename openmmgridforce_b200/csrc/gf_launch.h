@@ -48,6 +48,7 @@ constexpr int kBsplineBlockThreads = 128;
 
 // gf_eval_bspline_f64_kernel (gf_eval_bspline_f64.cuh): DOUBLE B-spline records of one geometry.
 void launch_bspline_f64(const EvalParams& p, cudaStream_t stream);
+void launch_tricubic_records_f64(const EvalParams& p, cudaStream_t stream);   // METHOD = 2 on DOUBLE HERMITE records
 constexpr int kBsplineF64BlockThreads = 64;
 
 }  // namespace gfb

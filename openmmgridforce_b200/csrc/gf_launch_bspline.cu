@@ -21,8 +21,14 @@ void launch_tricubic_records(const EvalParams& p, cudaStream_t stream) {
 
 void launch_bspline_f64(const EvalParams& p, cudaStream_t stream) {
     const unsigned blocks = (unsigned) ((p.total + kBsF64Block - 1) / kBsF64Block);
-    if (p.n_replicas == 1 && p.slots == nullptr) gf_eval_bspline_f64_kernel<true><<<blocks, kBsF64Block, 0, stream>>>(p);
-    else gf_eval_bspline_f64_kernel<false><<<blocks, kBsF64Block, 0, stream>>>(p);
+    if (p.n_replicas == 1 && p.slots == nullptr) gf_eval_bspline_f64_kernel<true, 1><<<blocks, kBsF64Block, 0, stream>>>(p);
+    else gf_eval_bspline_f64_kernel<false, 1><<<blocks, kBsF64Block, 0, stream>>>(p);
+}
+
+void launch_tricubic_records_f64(const EvalParams& p, cudaStream_t stream) {
+    const unsigned blocks = (unsigned) ((p.total + kBsF64Block - 1) / kBsF64Block);
+    if (p.n_replicas == 1 && p.slots == nullptr) gf_eval_bspline_f64_kernel<true, 2><<<blocks, kBsF64Block, 0, stream>>>(p);
+    else gf_eval_bspline_f64_kernel<false, 2><<<blocks, kBsF64Block, 0, stream>>>(p);
 }
 
 }  // namespace gfb

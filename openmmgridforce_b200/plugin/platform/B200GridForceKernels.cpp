@@ -55,8 +55,10 @@ static unsigned long long hashWords(const void* data, size_t bytes, unsigned lon
 int b200LayoutForMethod(int interpolationMethod, int precision, const char* who) {
     if (interpolationMethod == 0) return GFB_LAYOUT_AUTO;        // trilinear
     if (interpolationMethod == 1) return GFB_LAYOUT_BSPLINE;     // cubic B-spline
-    // tricubic Hermite (finite-difference derivatives): records in MIXED (two lines per stencil), raw points in DOUBLE
-    if (interpolationMethod == 2) return precision == GFB_PRECISION_MIXED ? GFB_LAYOUT_HERMITE : GFB_LAYOUT_POINTS;
+    // tricubic Hermite (finite-difference derivatives): records (two full lines per stencil in MIXED, four in DOUBLE);
+    // GFB_LAYOUT_POINTS (the raw points, 32 scalar loads per stencil) stays available through the C ABI for memory-lean use
+    (void) precision;
+    if (interpolationMethod == 2) return GFB_LAYOUT_HERMITE;
     throw OpenMMException(std::string(who) + ": interpolation method 3 (quintic Hermite) needs the 27 derivative grids and is "
                           "not implemented on this platform; use 0 (trilinear), 1 (cubic B-spline) or 2 (tricubic)");
 }

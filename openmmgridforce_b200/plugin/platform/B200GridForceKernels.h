@@ -23,7 +23,7 @@ struct SharedGrid {
 };
 
 gfb_device* b200Device(int ordinal);    // process-wide, opened on first use; throws OpenMMException
-// GridForce::getInterpolationMethod -> device layout: 0 trilinear (AUTO), 1 cubic B-spline (BSPLINE records), 2 tricubic Hermite (HERMITE records in MIXED, POINTS in DOUBLE); 3 throws.
+// GridForce::getInterpolationMethod -> device layout: 0 trilinear (AUTO), 1 cubic B-spline (BSPLINE records), 2 tricubic Hermite (HERMITE records); 3 throws.
 int b200LayoutForMethod(int interpolationMethod, int precision, const char* who);
 std::shared_ptr<SharedGrid> b200AcquireGrid(gfb_device* dev, int ordinal, int precision, int layout, const std::vector<int>& counts,
                                             const std::vector<double>& spacing, const double origin[3],

@@ -25,9 +25,14 @@ def _rel_f(f, ref):
     return np.abs(f - ref).max() / max(np.abs(ref).max(), 1e-300)
 
 
-# (precision, layout): raw points in both precisions, HERMITE records (MIXED only)
-MODES = [(0, 5), (1, 5), (0, 6)]
-MODE_IDS = ["mixed-points", "double-points", "mixed-records"]
+# (precision, layout): raw points and HERMITE records, both precisions
+MODES = [(0, 5), (1, 5), (0, 6), (1, 6)]
+MODE_IDS = ["mixed-points", "double-points", "mixed-records", "double-records"]
+
+
+def _path(gf, precision, layout):
+    """gfb_kernel_eval_path of a one-geometry state: the record kernels for HERMITE, the general kernel for POINTS."""
+    return 0 if layout != gf.LAYOUT_HERMITE else (5 if precision == 0 else 6)
 
 
 def _make(gf, dev, c, precision, particles=None, layout=5):
@@ -56,7 +61,7 @@ def test_tricubic_golden_vectors(gpu_device, name, mode):
     c, ref = cases.load_golden(name)
     assert c["interp"] == 2
     grids, k = _make(gf, gpu_device, c, precision, layout=layout)
-    assert all(g.layout == layout for g in grids) and k.eval_path() == (5 if layout == gf.LAYOUT_HERMITE else 0)
+    assert all(g.layout == layout for g in grids) and k.eval_path() == _path(gf, precision, layout)
     en, forces, ge = k.execute_host(c["pos"], want_grid_energies=True)
     tol_e, tol_f = TOL[precision]
     floor = 0.0
@@ -89,7 +94,7 @@ def test_tricubic_batched_replicas(gpu_device, oracle_built, mode):
         port = oracle_built.PortOracle(counts, sp, og, grids_v, sc, oob_k=c["oob_k"], interpolation_method=2)
         ge_ref, f_ref = port.execute_batched(pos, n_threads=4)
         grids, k = _make(gf, gpu_device, c, precision, layout=layout)
-        assert k.eval_path() == (5 if layout == gf.LAYOUT_HERMITE else 0)
+        assert k.eval_path() == _path(gf, precision, layout)
         en, forces, ge = k.execute_host(pos, want_grid_energies=True)
         tol = 1e-10 if precision == 0 else 1e-12
         assert np.abs(ge - ge_ref).max() <= tol * np.abs(ge_ref).max(), counts
@@ -98,13 +103,13 @@ def test_tricubic_batched_replicas(gpu_device, oracle_built, mode):
         _close(grids, k)
 
 
-@pytest.mark.parametrize("mode", [(1, 5), (0, 6)], ids=["double-points", "mixed-records"])
+@pytest.mark.parametrize("mode", [(1, 5), (0, 6), (1, 6)], ids=["double-points", "mixed-records", "double-records"])
 @pytest.mark.parametrize("counts", [(2, 2, 2), (2, 3, 7), (3, 2, 4), (4, 4, 4), (9, 5, 6)])
 def test_tricubic_edges_and_thin_grids(gpu_device, oracle_built, counts, mode):
     """Every cell of small grids — first layers (derivative estimates off), last y/z cells (neighbours by flat index in
     the next row / slab), the last x layer (the reference reads past its vector there; the oracle, the zero guard slab
     of the POINTS layout and the flat-index fill of the HERMITE records all supply 0), atoms on the faces and outside —
-    against the oracle: DOUBLE points at 1e-12, MIXED records on an FP32-representable grid at 1e-10."""
+    against the oracle: DOUBLE at 1e-12, MIXED records on an FP32-representable grid at 1e-10."""
     import openmmgridforce_b200 as gf
     precision, layout = mode
     rng = np.random.default_rng(sum(counts))
@@ -130,7 +135,8 @@ def test_tricubic_edges_and_thin_grids(gpu_device, oracle_built, counts, mode):
     _close(grids, k)
 
 
-def test_tricubic_records_general_kernel_fallback(gpu_device, oracle_built):
+@pytest.mark.parametrize("precision", [0, 1], ids=["mixed", "double"])
+def test_tricubic_records_general_kernel_fallback(gpu_device, oracle_built, precision):
     """HERMITE records of two DIFFERENT geometries in one state: the record kernel does not qualify, the general kernel
     reads the records (tricubic_interpolate<float, HERMITE>); and an evaluation order on a one-geometry state."""
     import torch
@@ -141,7 +147,7 @@ def test_tricubic_records_general_kernel_fallback(gpu_device, oracle_built):
     grids_v = [(rng.normal(size=cnt) * 3).astype(np.float32).astype(np.float64) for cnt, _ in geoms]
     sc = rng.uniform(0.5, 1.5, size=(2, n))
     pos = rng.uniform(-0.05, 0.95, size=(n, 3))
-    grids = [gf.Grid(gpu_device, cnt, sp, (0.0, 0.0, 0.0), v, 0, layout=gf.LAYOUT_HERMITE) for (cnt, sp), v in zip(geoms, grids_v)]
+    grids = [gf.Grid(gpu_device, cnt, sp, (0.0, 0.0, 0.0), v, precision, layout=gf.LAYOUT_HERMITE) for (cnt, sp), v in zip(geoms, grids_v)]
     k = gf.Kernel(gpu_device, grids, sc)
     assert k.eval_path() == 0
     en, forces, ge = k.execute_host(pos, want_grid_energies=True)
@@ -155,7 +161,7 @@ def test_tricubic_records_general_kernel_fallback(gpu_device, oracle_built):
     _close(grids, k)
     # one geometry + an evaluation order -> general kernel as well
     cnt, sp = geoms[0]
-    g1 = [gf.Grid(gpu_device, cnt, sp, (0.0, 0.0, 0.0), grids_v[0], 0, layout=gf.LAYOUT_HERMITE)]
+    g1 = [gf.Grid(gpu_device, cnt, sp, (0.0, 0.0, 0.0), grids_v[0], precision, layout=gf.LAYOUT_HERMITE)]
     k1 = gf.Kernel(gpu_device, g1, sc[:1])
     port = oracle_built.PortOracle(cnt, sp, (0.0, 0.0, 0.0), [grids_v[0]], sc[:1], interpolation_method=2)
     e_ref, f_ref, _ = port.execute(pos, 0)
@@ -213,11 +219,10 @@ def test_tricubic_memory_footprint_and_layout_mix(gpu_device):
         g = gf.Grid(gpu_device, counts, (0.1, 0.1, 0.1), (0, 0, 0), np.zeros(counts), precision, layout=gf.LAYOUT_POINTS)
         assert g.device_bytes == points * size
         g.close()
-    g = gf.Grid(gpu_device, counts, (0.1, 0.1, 0.1), (0, 0, 0), np.zeros(counts), 0, layout=gf.LAYOUT_HERMITE)
-    assert g.device_bytes == (counts[0] + 1) * (counts[1] - 1) * (counts[2] - 1) * 128        # the BSPLINE record format
-    g.close()
-    with pytest.raises(gf.GridForceB200Error, match="MIXED precision only"):
-        gf.Grid(gpu_device, counts, (0.1, 0.1, 0.1), (0, 0, 0), np.zeros(counts), 1, layout=gf.LAYOUT_HERMITE)
+    for precision, size in ((0, 128), (1, 256)):                                                  # the BSPLINE record format
+        g = gf.Grid(gpu_device, counts, (0.1, 0.1, 0.1), (0, 0, 0), np.zeros(counts), precision, layout=gf.LAYOUT_HERMITE)
+        assert g.device_bytes == (counts[0] + 1) * (counts[1] - 1) * (counts[2] - 1) * size
+        g.close()
     with pytest.raises(gf.GridForceB200Error):
         gf.Kernel(gpu_device, [gf.Grid(gpu_device, counts, (0.1, 0.1, 0.1), (0, 0, 0), np.zeros(counts), 0, layout=gf.LAYOUT_POINTS),
                                gf.Grid(gpu_device, counts, (0.1, 0.1, 0.1), (0, 0, 0), np.zeros(counts), 0, layout=gf.LAYOUT_CELLS)],

@@ -18,8 +18,6 @@ side = torch.cuda.Stream()
 torch.cuda.set_stream(side)
 w = W.c5_sharded_replicas(n_local=R)
 for prec, pname in ((0, "mixed"), (1, "double")):
-    if prec == 1 and LNAME == "hermite":
-        continue
     grids = [gf.Grid(dev, w.counts, w.spacing, w.origin, v, prec, layout=LAYOUT) for v in w.grids]
     print(pname, "grid bytes", [g.device_bytes for g in grids])
     k = gf.Kernel(dev, grids, w.scaling, oob_k=w.oob_k)
