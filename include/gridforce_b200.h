@@ -72,10 +72,14 @@ typedef enum { GFB_PRECISION_MIXED = 0, GFB_PRECISION_DOUBLE = 1 } gfb_precision
  *          and plane, 128 bytes in MIXED, 256 in DOUBLE; 32x the raw grid) filled by FLAT index instead of clamped indices, so that the
  *          32 neighbours the method reads are inside the stencil's two full lines, with the reference's next-row /
  *          next-slab values at the upper y/z edges and zeros past the array. Same results as POINTS; 2 lines per
- *          stencil instead of 32 scalar loads. Never chosen by AUTO. */
+ *          stencil instead of 32 scalar loads. Never chosen by AUTO.
+ *   BSPLINE_POINTS cubic B-spline (method 1) on the raw points (FP32 / FP64, 0.5x / 1x the raw grid), indices clamped
+ *          when they are formed, 64 scalar loads per stencil in the general kernel: the memory-lean counterpart of
+ *          BSPLINE for grids whose records (32x) do not fit — the platform falls back to it, and to POINTS for method 2,
+ *          when the record copy is refused with GFB_ERR_NOMEM. Same results as BSPLINE. Never chosen by AUTO. */
 typedef enum {
     GFB_LAYOUT_AUTO = 0, GFB_LAYOUT_CELLS = 1, GFB_LAYOUT_ROWS = 2, GFB_LAYOUT_PAIRS = 3, GFB_LAYOUT_BSPLINE = 4,
-    GFB_LAYOUT_POINTS = 5, GFB_LAYOUT_HERMITE = 6
+    GFB_LAYOUT_POINTS = 5, GFB_LAYOUT_HERMITE = 6, GFB_LAYOUT_BSPLINE_POINTS = 7
 } gfb_layout;
 
 /* How execute writes forces.

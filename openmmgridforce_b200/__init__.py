@@ -30,6 +30,7 @@ from .capi import (  # noqa: F401
     LAYOUT_BSPLINE,
     LAYOUT_POINTS,
     LAYOUT_HERMITE,
+    LAYOUT_BSPLINE_POINTS,
     LAYOUT_NAMES,
     library_path,
     load_library,

@@ -17,8 +17,8 @@ FORCE_FIXED_ADD = 2
 FORCE_F32_STORE = 3
 COMM_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
-LAYOUT_AUTO, LAYOUT_CELLS, LAYOUT_ROWS, LAYOUT_PAIRS, LAYOUT_BSPLINE, LAYOUT_POINTS, LAYOUT_HERMITE = 0, 1, 2, 3, 4, 5, 6
-LAYOUT_NAMES = {0: "auto", 1: "cells", 2: "rows", 3: "pairs", 4: "bspline", 5: "points", 6: "hermite"}
+LAYOUT_AUTO, LAYOUT_CELLS, LAYOUT_ROWS, LAYOUT_PAIRS, LAYOUT_BSPLINE, LAYOUT_POINTS, LAYOUT_HERMITE, LAYOUT_BSPLINE_POINTS = 0, 1, 2, 3, 4, 5, 6, 7
+LAYOUT_NAMES = {0: "auto", 1: "cells", 2: "rows", 3: "pairs", 4: "bspline", 5: "points", 6: "hermite", 7: "bspline_points"}
 MAX_GRIDS = 8
 
 _LIB = None

@@ -22,7 +22,7 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
     *out = nullptr;
     if (precision != GFB_PRECISION_MIXED && precision != GFB_PRECISION_DOUBLE)
         return fail(GFB_ERR_INVALID, "gfb_grid_create: unknown precision %d", precision);
-    if (layout < GFB_LAYOUT_AUTO || layout > GFB_LAYOUT_HERMITE) return fail(GFB_ERR_INVALID, "gfb_grid_create: unknown layout %d", layout);
+    if (layout < GFB_LAYOUT_AUTO || layout > GFB_LAYOUT_BSPLINE_POINTS) return fail(GFB_ERR_INVALID, "gfb_grid_create: unknown layout %d", layout);
     if (layout == GFB_LAYOUT_PAIRS && precision == GFB_PRECISION_DOUBLE)
         return fail(GFB_ERR_UNSUPPORTED, "gfb_grid_create: the PAIRS layout exists for MIXED precision only (use ROWS or CELLS)");
     for (int k = 0; k < 3; k++) {
@@ -65,6 +65,9 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
         g->row_chunks = (counts[2] - 2) / 3 + 1;
         n_units = (size_t) counts[0] * (counts[1] - 1) * g->row_chunks;
         g->bytes = n_units * 32;
+    } else if (layout == GFB_LAYOUT_BSPLINE_POINTS) {   // the points themselves (clamped indexing needs no guard)
+        n_units = n_points;
+        g->bytes = n_units * (precision == GFB_PRECISION_MIXED ? sizeof(float) : sizeof(double));
     } else if (layout == GFB_LAYOUT_POINTS) {   // the points themselves + one zero x-slab (tricubic_interpolate's flat-index reads)
         n_units = n_points + (size_t) counts[1] * counts[2];
         g->bytes = n_units * (precision == GFB_PRECISION_MIXED ? sizeof(float) : sizeof(double));
@@ -114,8 +117,8 @@ static int grid_create_common(gfb_device* dev, const int counts[3], const double
             else gf_repack_rows_kernel<double><<<blocks, 256, 0, dev->stream>>>(d_vals, cd, counts[0], counts[1], counts[2], g->row_chunks);
         } else if (layout == GFB_LAYOUT_PAIRS) {
             gf_repack_pairs_kernel<<<blocks, 256, 0, dev->stream>>>(d_vals, cf, counts[0], counts[1], counts[2], g->row_chunks);
-        } else if (layout == GFB_LAYOUT_POINTS) {
-            const size_t guard = (size_t) counts[1] * counts[2];
+        } else if (layout == GFB_LAYOUT_POINTS || layout == GFB_LAYOUT_BSPLINE_POINTS) {
+            const size_t guard = layout == GFB_LAYOUT_POINTS ? (size_t) counts[1] * counts[2] : 0;
             if (mixed) gf_repack_points_kernel<float><<<blocks, 256, 0, dev->stream>>>(d_vals, cf, n_points, guard);
             else gf_repack_points_kernel<double><<<blocks, 256, 0, dev->stream>>>(d_vals, cd, n_points, guard);
         } else {

@@ -372,14 +372,63 @@ __device__ __forceinline__ void bspline_interpolate(const GridView& G, int ix, i
     }
 }
 
-// One grid's B-spline contribution for an inside atom (:727-795), same epilogue as accumulate_inside.
+// The same sums over the raw points (GFB_LAYOUT_BSPLINE_POINTS), indices clamped when they are formed as the reference
+// does (:754-775): 64 scalar loads per stencil, 1/64 of the records' memory — the fallback for grids whose records do
+// not fit. The atom's cell comes from classify(), which maps the upper face to (n-2, fraction 1); the reference uses
+// (n-1, fraction 0) there: the same 4x4x4 polynomial on the clamped neighbourhood (deviations table).
 template <typename S>
+__device__ __forceinline__ void bspline_interpolate_points(const GridView& G, int ix, int iy, int iz, double fx, double fy, double fz,
+                                                           double& val, S& gx, S& gy, S& gz) {
+    constexpr bool F64 = sizeof(S) == 8;
+    double bx[4], dbx[4], by[4], dby[4], bz[4], dbz[4];
+    bspline_basis(fx, bx, dbx);
+    bspline_basis(fy, by, dby);
+    bspline_basis(fz, bz, dbz);
+    const int nx = G.nc[0] + 1, ny = G.nc[1] + 1, nz = G.nc[2] + 1;
+    const S* base = static_cast<const S*>(G.cells);
+    int zi[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) zi[k] = min(max(iz - 1 + k, 0), nz - 1);
+    val = 0.0;
+    gx = gy = gz = (S) 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const size_t px = (size_t) min(max(ix - 1 + i, 0), nx - 1) * ny;
+        double pv = 0.0;
+        S pdy = (S) 0, pdz = (S) 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const S* row = base + (px + (size_t) min(max(iy - 1 + r, 0), ny - 1)) * nz;
+            double rz = 0.0;
+            S rzs = (S) 0, drz = (S) 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const S v = __ldg(row + zi[k]);
+                rz = fma(bz[k], (double) v, rz);
+                if (!F64) rzs = fma((S) bz[k], v, rzs);
+                drz = fma((S) dbz[k], v, drz);
+            }
+            if (F64) rzs = (S) rz;
+            pv = fma(by[r], rz, pv);
+            pdy = fma((S) dby[r], rzs, pdy);
+            pdz = fma((S) by[r], drz, pdz);
+        }
+        val = fma(bx[i], pv, val);
+        gx = fma((S) dbx[i], (S) pv, gx);
+        gy = fma((S) bx[i], pdy, gy);
+        gz = fma((S) bx[i], pdz, gz);
+    }
+}
+
+// One grid's B-spline contribution for an inside atom (:727-795), same epilogue as accumulate_inside.
+template <typename S, int LAYOUT = GFB_LAYOUT_BSPLINE>
 __device__ __forceinline__ void accumulate_bspline(const GridView& G, const AtomCell& c, double sd, double& e_g, double& Fx,
                                                    double& Fy, double& Fz) {
     constexpr bool EXACT = sizeof(S) == 8;
     double dval;
     S dx, dy, dz;
-    bspline_interpolate<S>(G, c.ix, c.iy, c.iz, c.fx, c.fy, c.fz, dval, dx, dy, dz);
+    if constexpr (LAYOUT == GFB_LAYOUT_BSPLINE_POINTS) bspline_interpolate_points<S>(G, c.ix, c.iy, c.iz, c.fx, c.fy, c.fz, dval, dx, dy, dz);
+    else bspline_interpolate<S>(G, c.ix, c.iy, c.iz, c.fx, c.fy, c.fz, dval, dx, dy, dz);
     double gx, gy, gz;
     if (EXACT) {  // :790
         gx = (double) dx / G.spacing[0];
@@ -593,7 +642,7 @@ __device__ __forceinline__ void accumulate_restraint(const GridView& G, double x
 
 template <typename S, int LAYOUT, int NG>
 __host__ __device__ constexpr int eval_min_blocks() {
-    return (LAYOUT == GFB_LAYOUT_BSPLINE || LAYOUT == GFB_LAYOUT_POINTS || LAYOUT == GFB_LAYOUT_HERMITE) ? 2 : ((NG == 1 && sizeof(S) == 4) ? 6 : 4);
+    return (LAYOUT == GFB_LAYOUT_BSPLINE || LAYOUT >= GFB_LAYOUT_POINTS) ? 2 : ((NG == 1 && sizeof(S) == 4) ? 6 : 4);
 }
 
 template <typename S, int LAYOUT, int NG, bool SAME, bool SINGLE>
@@ -717,8 +766,8 @@ __global__ void __launch_bounds__(kBlock, eval_min_blocks<S, LAYOUT, NG>()) gf_e
                 if (!SAME) c = classify<EXACT>(G, x, y, z);
                 const double s = NG > 0 ? sd[NG > 0 ? g : 0] : G.scaling[ia];
                 if (c.inside && s != 0.0) {
-                    if constexpr (LAYOUT == GFB_LAYOUT_BSPLINE) {
-                        accumulate_bspline<S>(G, c, s, e_g, Fx, Fy, Fz);
+                    if constexpr (LAYOUT == GFB_LAYOUT_BSPLINE || LAYOUT == GFB_LAYOUT_BSPLINE_POINTS) {
+                        accumulate_bspline<S, LAYOUT>(G, c, s, e_g, Fx, Fy, Fz);
                     } else if constexpr (LAYOUT == GFB_LAYOUT_POINTS || LAYOUT == GFB_LAYOUT_HERMITE) {
                         accumulate_tricubic<S, LAYOUT>(G, c, s, e_g, Fx, Fy, Fz);
                     } else {

@@ -24,6 +24,7 @@ void launch_general_f32(const EvalParams& p, int layout, bool same, cudaStream_t
     if (layout == GFB_LAYOUT_BSPLINE) launch_eval3<float, GFB_LAYOUT_BSPLINE, 0, false>(p, stream);   // each grid classified on its own
     else if (layout == GFB_LAYOUT_POINTS) launch_eval3<float, GFB_LAYOUT_POINTS, 0, false>(p, stream);
     else if (layout == GFB_LAYOUT_HERMITE) launch_eval3<float, GFB_LAYOUT_HERMITE, 0, false>(p, stream);
+    else if (layout == GFB_LAYOUT_BSPLINE_POINTS) launch_eval3<float, GFB_LAYOUT_BSPLINE_POINTS, 0, false>(p, stream);
     else if (layout == GFB_LAYOUT_CELLS) launch_eval2<float, GFB_LAYOUT_CELLS>(p, same, stream);
     else if (layout == GFB_LAYOUT_ROWS) launch_eval2<float, GFB_LAYOUT_ROWS>(p, same, stream);
     else launch_eval2<float, GFB_LAYOUT_PAIRS>(p, same, stream);
@@ -33,6 +34,7 @@ void launch_general_f64(const EvalParams& p, int layout, bool same, cudaStream_t
     if (layout == GFB_LAYOUT_BSPLINE) launch_eval3<double, GFB_LAYOUT_BSPLINE, 0, false>(p, stream);
     else if (layout == GFB_LAYOUT_POINTS) launch_eval3<double, GFB_LAYOUT_POINTS, 0, false>(p, stream);
     else if (layout == GFB_LAYOUT_HERMITE) launch_eval3<double, GFB_LAYOUT_HERMITE, 0, false>(p, stream);
+    else if (layout == GFB_LAYOUT_BSPLINE_POINTS) launch_eval3<double, GFB_LAYOUT_BSPLINE_POINTS, 0, false>(p, stream);
     else if (layout == GFB_LAYOUT_CELLS) launch_eval2<double, GFB_LAYOUT_CELLS>(p, same, stream);
     else launch_eval2<double, GFB_LAYOUT_ROWS>(p, same, stream);
 }

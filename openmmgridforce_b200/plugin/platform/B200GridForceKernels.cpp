@@ -96,8 +96,18 @@ std::shared_ptr<SharedGrid> b200AcquireGrid(gfb_device* dev, int ordinal, int pr
     std::shared_ptr<SharedGrid> hit = cache[key.str()].lock();
     if (hit) return hit;
     gfb_grid* g = 0;
-    check(gfb_grid_create(dev, counts.data(), spacing.data(), origin, vals.data(), vals.size(), precision, layout, &g),
-          "grid upload");
+    // Record layouts are 32x the raw grid. When that copy does not fit (GFB_ERR_NOMEM, said before any allocation), or
+    // B200_COMPACT_LAYOUTS=1 asks for it, the same method runs on the raw points through the general kernel.
+    static const bool compact = [] {
+        const char* e = getenv("B200_COMPACT_LAYOUTS");
+        return e && e[0] == '1';
+    }();
+    const int lean = layout == GFB_LAYOUT_BSPLINE ? GFB_LAYOUT_BSPLINE_POINTS : (layout == GFB_LAYOUT_HERMITE ? GFB_LAYOUT_POINTS : layout);
+    int rc = (compact && lean != layout) ? GFB_ERR_NOMEM
+                                         : gfb_grid_create(dev, counts.data(), spacing.data(), origin, vals.data(), vals.size(), precision, layout, &g);
+    if (rc == GFB_ERR_NOMEM && lean != layout)
+        rc = gfb_grid_create(dev, counts.data(), spacing.data(), origin, vals.data(), vals.size(), precision, lean, &g);
+    check(rc, "grid upload");
     std::shared_ptr<SharedGrid> made(new SharedGrid(g));
     cache[key.str()] = made;
     return made;

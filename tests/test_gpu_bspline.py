@@ -23,8 +23,8 @@ def _rel_f(f, ref):
     return np.abs(f - ref).max() / max(np.abs(ref).max(), 1e-300)
 
 
-def _make(gf, dev, c, precision, particles=None):
-    grids = [gf.Grid(dev, c["counts"], c["spacing"], c["origin"], g, precision, layout=gf.LAYOUT_BSPLINE) for g in c["grids"]]
+def _make(gf, dev, c, precision, particles=None, layout=4):
+    grids = [gf.Grid(dev, c["counts"], c["spacing"], c["origin"], g, precision, layout=layout) for g in c["grids"]]
     k = gf.Kernel(dev, grids, c["scaling"], particles=particles, inv_power=c["inv_power"], oob_k=c["oob_k"])
     return grids, k
 
@@ -43,6 +43,26 @@ def test_bspline_golden_vectors(gpu_device, name, precision):
     assert c["interp"] == 1
     grids, k = _make(gf, gpu_device, c, precision)
     assert all(g.layout == gf.LAYOUT_BSPLINE for g in grids) and not k.uses_lines_kernel()
+    en, forces, ge = k.execute_host(c["pos"], want_grid_energies=True)
+    tol_e, tol_f = TOL[precision]
+    for g in range(len(grids)):
+        assert abs(ge[0, g] - ref["grid_energies"][g]) <= tol_e * abs(ref["grid_energies"][g]), (name, g)
+    assert abs(en[0] - ref["energy"]) <= tol_e * abs(ref["energy"])
+    assert _rel_f(forces[0], ref["forces"]) <= tol_f
+    _close(grids, k)
+
+
+@pytest.mark.parametrize("precision", [0, 1], ids=["mixed", "double"])
+@pytest.mark.parametrize("name", BSPLINE)
+def test_bspline_on_raw_points_golden_vectors(gpu_device, name, precision):
+    """GFB_LAYOUT_BSPLINE_POINTS: the same method on the raw points with clamped indexing (general kernel) — the layout the
+    platform falls back to when the 32x record copy does not fit. Same tolerances, same golden vectors (incl. the thin
+    grid where every index clamps, and the upper faces)."""
+    import openmmgridforce_b200 as gf
+    c, ref = cases.load_golden(name)
+    grids, k = _make(gf, gpu_device, c, precision, layout=gf.LAYOUT_BSPLINE_POINTS)
+    points = int(np.prod(c["counts"]))
+    assert all(g.device_bytes == points * (4 if precision == 0 else 8) for g in grids) and k.eval_path() == 0
     en, forces, ge = k.execute_host(c["pos"], want_grid_energies=True)
     tol_e, tol_f = TOL[precision]
     for g in range(len(grids)):

@@ -183,6 +183,35 @@ def test_plugin_batch_entry_point_other_interpolation_methods(oracle_built, meth
 
 
 @pytest.mark.gpu
+def test_plugin_compact_layouts_when_records_do_not_fit():
+    """Record layouts (methods 1 and 2) are 32x the raw grid; when that copy is refused (GFB_ERR_NOMEM) the platform runs
+    the same method on the raw points. B200_COMPACT_LAYOUTS=1 takes that branch on purpose: a fresh interpreter (the switch
+    is read once) evaluates the B-spline and tricubic golden cases through the plugin in both precisions."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = """
+import os, sys, numpy as np
+sys.path.insert(0, os.path.join(%r, "tests", "golden")); sys.path.insert(0, os.path.join(%r, "tests")); sys.path.insert(0, %r)
+import cases
+import openmmgridforce_b200.gridforceplugin as gfp
+from test_plugin import _build_system
+for name in ("bspline_random_aniso", "bspline_thin_grid", "tricubic_random_aniso", "tricubic_inv_power"):
+    for precision, te, tf in (("mixed", 1e-6, 1e-5), ("double", 1e-12, 1e-12)):
+        c, ref = cases.load_golden(name)
+        system, forces = _build_system(gfp, c)
+        ctx = gfp.Context(system, gfp.Platform.getPlatformByName("B200"), {"Precision": precision})
+        ctx.setPositions(c["pos"])
+        st = ctx.getState(getEnergy=True, getForces=True)
+        assert abs(st.getPotentialEnergy() - ref["energy"]) <= te * abs(ref["energy"]), (name, precision)
+        assert np.abs(st.getForces() - ref["forces"]).max() <= tf * np.abs(ref["forces"]).max(), (name, precision)
+print("compact ok")
+""" % (root, root, root)
+    env = dict(os.environ, B200_COMPACT_LAYOUTS="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "compact ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.gpu
 def test_plugin_refuses_what_it_does_not_implement():
     import openmmgridforce_b200.gridforceplugin as gfp
     c, _ = cases.load_golden("ramp_grid")

@@ -1,5 +1,5 @@
 """Scratch probe: device-resident step time of the cubic B-spline path on the C5 shape (R replicas x 47 atoms x 3 grids
-of 192^3), CUDA events. Usage: python tools/bspline_perf.py [replicas] [bspline|points|hermite]   (points / hermite =
+of 192^3), CUDA events. Usage: python tools/bspline_perf.py [replicas] [bspline|bspline_points|points|hermite]   (points / hermite =
 tricubic Hermite, interpolation method 2, on raw points / on records)"""
 import os
 import sys
@@ -11,7 +11,7 @@ from openmmgridforce_b200 import workloads as W
 
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 LNAME = sys.argv[2] if len(sys.argv) > 2 else "bspline"
-LAYOUT = {"bspline": gf.LAYOUT_BSPLINE, "points": gf.LAYOUT_POINTS, "hermite": gf.LAYOUT_HERMITE}[LNAME]
+LAYOUT = {v: k for k, v in gf.LAYOUT_NAMES.items()}[LNAME]      # bspline | bspline_points | hermite | points
 dev = gf.Device(0)
 tdev = torch.device("cuda:0")
 side = torch.cuda.Stream()
