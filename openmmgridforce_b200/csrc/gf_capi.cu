@@ -505,22 +505,24 @@ static int eval_block_threads(const gfb_kernel* k) {
     return lines_f64_eligible(k) ? kLinesF64BlockThreads : kGeneralBlock;
 }
 
-// One replica of at most a few thousand particles — a ligand evaluated once per MD step (BASELINE configs[1]; what
-// B200CalcGridForceKernel::execute issues). Such a call is pure latency, so instead of H2D copy -> kernel -> D2H copies
+// A few thousand particles in all — one ligand evaluated once per MD step (BASELINE configs[1]; what
+// B200CalcGridForceKernel::execute issues), or a handful of replicas of it (example/input.json: nstate = 21 — the size of a
+// sampler.py sweep through GridForceBatch). Such a call is pure latency, so instead of H2D copy -> kernel -> D2H copies
 // (6-7 driver calls, 3 trips through the copy engines) the kernel works on HOST-MAPPED pinned memory directly: it reads
 // the positions over PCIe, stores the forces over PCIe and — when one block covers the ligand — stores the energy too.
 // One launch + one synchronize per call. The caller's forces are combined on the host from the kernel's stores
 // (STORE: staged copy of the caller's array with the evaluated entries overwritten; ADD: caller's value + kernel's).
-static int execute_host_small(gfb_kernel* k, int n_particles, const double* pos, double* energies, double* grid_energies,
-                              void* forces, int force_mode) {
+static int execute_host_small(gfb_kernel* k, int n_replicas, int n_particles, const double* pos, double* energies,
+                              double* grid_energies, void* forces, int force_mode) {
     gfb_device* dev = k->dev;
-    if (resident_enabled(k) && !k->want_atom_energies && force_mode != GFB_FORCE_F32_STORE)   // gfb_kernel_set_resident
+    if (n_replicas == 1 && resident_enabled(k) && !k->want_atom_energies && force_mode != GFB_FORCE_F32_STORE)   // gfb_kernel_set_resident
         return resident_step(k, n_particles, pos, energies, grid_energies, static_cast<double*>(forces), force_mode == GFB_FORCE_F64_ADD);
-    const size_t np3 = (size_t) n_particles * 3;
+    const size_t R = (size_t) n_replicas;
+    const size_t np3 = R * (size_t) n_particles * 3;
     const int ng = k->n_grids;
-    const size_t e_count = 1 + (size_t) ng;
+    const size_t e_count = R * (1 + (size_t) ng);                           // [R totals | R x ng per grid], as the batch path lays them out
     const size_t e_off = (2 * np3 + 15) & ~(size_t) 15;                    // doubles: [pos | forces | pad | energies | atom energies]
-    const size_t ae_count = k->want_atom_energies ? (size_t) k->n_atoms : 0;
+    const size_t ae_count = k->want_atom_energies ? R * (size_t) k->n_atoms : 0;
     int rc = k->h_small.ensure((e_off + e_count + ae_count) * sizeof(double));
     if (rc != GFB_OK) return rc;
     double* h_pos = static_cast<double*>(k->h_small.ptr);
@@ -535,27 +537,38 @@ static int execute_host_small(gfb_kernel* k, int n_particles, const double* pos,
     }
     EvalParams probe;
     memset(&probe, 0, sizeof probe);
-    // one block covers the ligand: its energy (and, in the record kernels, its per-grid energies) are plain stores
-    const bool one_block = k->n_atoms <= eval_block_threads(k) &&
+    // one replica that one block covers: its energy (and, in the record kernels, its per-grid energies) are plain stores
+    const bool one_block = n_replicas == 1 && k->n_atoms <= eval_block_threads(k) &&
                            (!grid_energies || !(bspline_tiles_eligible(k, probe) || tricubic_tiles_eligible(k, probe) || bspline_f64_eligible(k, probe) || tricubic_f64_eligible(k, probe)));
+    // Several blocks or replicas (or per-grid energies): the energies are sums over blocks, accumulated with red.add.f64.
+    // For up to 16 accumulators (4 replicas x 3 grids) they are the HOST-MAPPED array itself (zeroed here by the host; the
+    // GPU's atomics on mapped memory are atomic among its own threads, which is all that is needed while the host waits):
+    // no memset and no copy on the stream, the call stays one launch + one synchronise (2 replicas: 34.9 -> 24.9 us).
+    // Each such atomic is a PCIe round trip, though (~1.3 us, serialised per address): at 8 replicas it is a draw and at
+    // 21 it loses (49 against 36 us; profiles/logs_r2/r2v17_small_batch_*), so larger arrays accumulate on the device
+    // and come back with one D2H copy. GFB_SMALL_HOST_ATOMICS=0: always the device route (A/B measurements).
+    static const bool host_atomics_off = env_off("GFB_SMALL_HOST_ATOMICS");
+    const bool host_acc = !one_block && !host_atomics_off && e_count <= 16;
     double* d_e = nullptr;
-    if (!one_block) {   // several blocks (or per-grid energies): device accumulators, cleared here, fetched below
+    if (host_acc) {
+        memset(h_e, 0, e_count * sizeof(double));
+    } else if (!one_block) {
         if ((rc = k->d_energy.ensure(e_count * sizeof(double))) != GFB_OK) return rc;
         d_e = static_cast<double*>(k->d_energy.ptr);
         CUDA_TRY(cudaMemsetAsync(d_e, 0, e_count * sizeof(double), dev->stream));
     }
     // cudaHostAlloc memory is mapped into the device's address space at the same address (unified addressing)
-    double* e_dst = one_block ? h_e : d_e;
+    double* e_dst = (one_block || host_acc) ? h_e : d_e;
     EvalExtra x;
     x.energy_store = one_block;
     x.atom_energies = ae_count ? h_e + e_count : nullptr;
-    rc = enqueue_eval(k, 1, n_particles, h_pos, e_dst, grid_energies ? e_dst + 1 : nullptr, forces ? h_f : nullptr,
+    rc = enqueue_eval(k, n_replicas, n_particles, h_pos, e_dst, grid_energies ? e_dst + R : nullptr, forces ? h_f : nullptr,
                       f32 ? GFB_FORCE_F32_STORE : GFB_FORCE_F64_STORE, 0, nullptr, nullptr, dev->stream, x);
     if (rc != GFB_OK) return rc;
-    if (!one_block) CUDA_TRY(cudaMemcpyAsync(h_e, d_e, e_count * sizeof(double), cudaMemcpyDeviceToHost, dev->stream));
+    if (d_e) CUDA_TRY(cudaMemcpyAsync(h_e, d_e, e_count * sizeof(double), cudaMemcpyDeviceToHost, dev->stream));
     CUDA_TRY(cudaStreamSynchronize(dev->stream));
-    if (energies) energies[0] = h_e[0];
-    if (grid_energies) memcpy(grid_energies, h_e + 1, ng * sizeof(double));
+    if (energies) memcpy(energies, h_e, R * sizeof(double));
+    if (grid_energies) memcpy(grid_energies, h_e + R, R * ng * sizeof(double));
     if (ae_count) {
         if ((rc = k->d_atom_e.ensure(ae_count * sizeof(double))) != GFB_OK) return rc;
         CUDA_TRY(cudaMemcpy(k->d_atom_e.ptr, h_e + e_count, ae_count * sizeof(double), cudaMemcpyHostToDevice));
@@ -665,8 +678,10 @@ int gfb_kernel_execute_host(gfb_kernel* k, int n_replicas, int n_particles, cons
     CUDA_TRY(cudaSetDevice(dev->ordinal));
 
     static const bool small_off = env_off("GFB_SMALL_PATH");   // 0: always take the copy pipeline (A/B measurements)
-    if (!small_off && n_replicas == 1 && k->d_slots == nullptr && k->unique_particles && n_particles <= 4096 && k->n_atoms > 0)
-        return execute_host_small(k, n_particles, pos, energies, grid_energies, forces, force_mode);
+    static const bool small_batch_off = env_off("GFB_SMALL_BATCH");   // 0: the host-mapped path for single replicas only (A/B)
+    if (!small_off && (n_replicas == 1 || !small_batch_off) && k->d_slots == nullptr && k->unique_particles &&
+        (long long) n_replicas * n_particles <= 4096 && k->n_atoms > 0)
+        return execute_host_small(k, n_replicas, n_particles, pos, energies, grid_energies, forces, force_mode);
 
     const bool f32 = force_mode == GFB_FORCE_F32_STORE;
     const size_t fsz = f32 ? sizeof(float) : sizeof(double);      // bytes per force component
