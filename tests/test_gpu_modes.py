@@ -11,6 +11,8 @@
 
 Tolerances (BASELINE.json north_star): MIXED energies 1e-6 relative, forces 1e-5 relative (max-norm); DOUBLE 1e-12.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -383,6 +385,40 @@ def test_release_cells_keeps_record_kernels_working(gpu_device, oracle_built, pr
     assert np.array_equal(f0, f1) and np.abs(e0 - e1).max() <= 1e-13 * np.abs(e0).max()
     with pytest.raises(gf.GridForceB200Error, match="released its packed cells"):     # a new kernel would need them again
         gf.Kernel(gpu_device, grids[:1], w.scaling[:1], oob_k=w.oob_k[:1])
+    k.close()
+    for g in grids:
+        g.close()
+
+
+@pytest.mark.parametrize("precision", [0, 1], ids=["mixed", "double"])
+@pytest.mark.parametrize("n_replicas", [2, 4, 5, 21, 87])
+def test_small_batches_on_host_mapped_memory(gpu_device, oracle_built, n_replicas, precision):
+    """gfb_kernel_execute_host with a handful of replicas (<= 4096 particles in all): one launch on host-mapped staging;
+    up to 16 accumulators (4 replicas x 3 grids + totals) the energies are summed in the mapped array itself, beyond that
+    on the device. Energies, per-grid energies, forces (STORE and ADD) and the energy-only call against the oracle."""
+    import openmmgridforce_b200 as gf
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import cases
+    c, _ = cases.load_golden("ligand_three_grids")
+    rng = np.random.default_rng(n_replicas)
+    pos = np.stack([c["pos"] + rng.uniform(-0.6, 0.6, size=3) for _ in range(n_replicas)])
+    port = oracle_built.PortOracle(c["counts"], c["spacing"], c["origin"], c["grids"], c["scaling"], oob_k=c["oob_k"])
+    ge_ref, f_ref = port.execute_batched(pos)
+    grids = [gf.Grid(gpu_device, c["counts"], c["spacing"], c["origin"], g, precision) for g in c["grids"]]
+    k = gf.Kernel(gpu_device, grids, c["scaling"], oob_k=c["oob_k"])
+    te, tf = (1e-6, 1e-5) if precision == 0 else (1e-12, 1e-12)
+    scale = np.maximum(np.abs(ge_ref.sum(axis=1)), np.abs(ge_ref).max(axis=1))
+    for _ in range(3):                                   # repeated calls: accumulators start from zero every time
+        en, f, ge = k.execute_host(pos, want_grid_energies=True)
+        assert (np.abs(en - ge_ref.sum(axis=1)) <= te * scale).all()
+        assert (np.abs(ge - ge_ref) <= te * scale[:, None]).all()
+        assert np.abs(f - f_ref).max() <= tf * np.abs(f_ref).max()
+    acc = np.ones_like(pos)
+    k.execute_host(pos, forces=acc, force_mode=gf.FORCE_F64_ADD)
+    assert np.abs(acc - (1.0 + f_ref)).max() <= tf * np.abs(f_ref).max()
+    e0, none, _ = k.execute_host(pos, want_forces=False)
+    assert none is None and (np.abs(e0 - ge_ref.sum(axis=1)) <= te * scale).all()
     k.close()
     for g in grids:
         g.close()
