@@ -121,6 +121,9 @@ typedef struct {
     int32_t cell[3];     /* (ix,iy,iz), or -1,-1,-1 when the restraint branch is taken */
 } gfb_class;
 
+/* Library plumbing; no reference counterpart. gfb_last_error() is the text the plugin puts into its OpenMMException — the
+ * reference reports every failure that way (e.g. openmmapi/src/GridForce.cpp:193, 306;
+ * platforms/cuda/src/CudaGridForceKernels.cpp:387-403). */
 GFB_API int gfb_version(void);
 GFB_API const char* gfb_last_error(void);
 GFB_API int gfb_device_count(int* count);
@@ -139,7 +142,8 @@ GFB_API int gfb_device_synchronize(gfb_device* dev);
  * doubles. counts >= 2 on every axis. */
 GFB_API int gfb_grid_create(gfb_device* dev, const int counts[3], const double spacing[3], const double origin[3],
                             const double* vals, size_t n_vals, int precision, int layout, gfb_grid** out);
-/* Same, from a DEVICE pointer to doubles (x-major); stream-ordered on the device's stream. */
+/* Same, from a DEVICE pointer to doubles (x-major); stream-ordered on the device's stream. What the reference CUDA platform
+ * does after its own GPU grid generation (platforms/cuda/src/CudaGridForceKernels.cpp:482-486 uploads; :520-600 generates in place). */
 GFB_API int gfb_grid_create_from_device(gfb_device* dev, const int counts[3], const double spacing[3],
                                         const double origin[3], const double* d_vals, size_t n_vals,
                                         int precision, int layout, gfb_grid** out);
@@ -165,7 +169,8 @@ GFB_API int gfb_gridfile_read_values(const char* path, double* vals, size_t n_va
  * with_trailer = 1 -> GridData::saveToFile (adds i32 0 and the origin again). deriv_count is written as 0. */
 GFB_API int gfb_gridfile_write(const char* path, const gfb_gridfile_header* header, const double* vals, size_t n_vals,
                                int with_trailer);
-/* File -> device grid in one call, streamed through pinned staging in 32 MB pieces (no full host copy). */
+/* File -> device grid in one call, streamed through pinned staging in 32 MB pieces (no full host copy). Replaces
+ * GridForce::loadFromFile (openmmapi/src/GridForce.cpp:495-692) followed by the kernel's upload of the values. */
 GFB_API int gfb_grid_create_from_file(gfb_device* dev, const char* path, int precision, int layout, gfb_grid** out,
                                       gfb_gridfile_header* header_out);
 
@@ -268,7 +273,7 @@ GFB_API int gfb_kernel_set_resident(gfb_kernel* k, int enable, long long idle_us
 GFB_API int gfb_kernel_resident_stop(gfb_kernel* k);
 GFB_API long long gfb_kernel_resident_launches(const gfb_kernel* k);
 /* Where the block spent the last resident step, from %globaltimer stamps it leaves in the control block, microseconds:
- * us[0] positions seen -> all grids evaluated, us[1] -> force and energy packets issued. */
+ * us[0] positions seen -> all grids evaluated, us[1] -> force and energy packets issued. No reference counterpart. */
 GFB_API int gfb_kernel_resident_timeline(const gfb_kernel* k, double us[2]);
 
 /* CalcGridForceKernel::execute for host-resident data (Reference-platform style), batched over replicas.
@@ -299,7 +304,9 @@ GFB_API int gfb_host_unregister(void* ptr);
 GFB_API int gfb_kernel_request_atom_energies(gfb_kernel* k, int enable);
 GFB_API int gfb_kernel_get_atom_energies(gfb_kernel* k, double* out, size_t n);
 
-/* CalcGridForceKernel::execute for device-resident data (CUDA-platform style): enqueues ONE kernel on
+/* CalcGridForceKernel::execute (openmmapi/include/GridForceKernels.h:63-71) for device-resident data, CUDA-platform
+ * style — what CudaCalcGridForceKernel::execute does with cu.getPosq() / cu.getLongForceBuffer()
+ * (platforms/cuda/src/CudaGridForceKernels.cpp:787-879, launch at :975-978): enqueues ONE kernel on
  * `stream` (a cudaStream_t; NULL = the device's own stream) and returns without synchronising.
  *   d_pos          device [n_replicas][n_particles][3] doubles
  *   d_energies     device [n_replicas] doubles, ACCUMULATED into (caller zeroes), or NULL
@@ -316,17 +323,19 @@ GFB_API int gfb_kernel_execute_device(gfb_kernel* k, int n_replicas, int n_parti
 
 /* Order of the atoms by the brick of grid cells they sit in (grid 0; bricks of 4^3 cells numbered along a Morton
  * curve), so neighbouring lanes read neighbouring lines. Positions move less than a cell per MD step, so the order is
- * reused for many steps. Own counting sort (histogram, scan, scatter): three small kernels, no library.
+ * reused for many steps. Own counting sort (histogram, scan, scatter): three small kernels, no library. No reference counterpart (BASELINE.json north_star item 2).
  * d_order: device out [n_replicas*n_atoms], a permutation of the flattened [replica][atom] list. Stream-ordered. */
 GFB_API int gfb_kernel_sort_atoms(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos,
                                   int* d_order, void* stream);
 
 /* Runs only the classification stage on the device (same device function the evaluation uses) for grid
- * `grid_index`: host out cls [n_replicas*n_atoms]. Used by the bit-exact index parity tests. */
+ * `grid_index`: host out cls [n_replicas*n_atoms]. Used by the bit-exact index parity tests against
+ * platforms/reference/src/ReferenceGridForceKernels.cpp:687-715 (origin shift, inclusive inside test, index and fraction). */
 GFB_API int gfb_kernel_classify_host(gfb_kernel* k, int grid_index, int n_replicas, int n_particles,
                                      const double* pos, gfb_class* cls);
 
-/* Converts an OpenMM-style fixed-point force buffer to doubles [n][3] on the device (stream-ordered). */
+/* Converts an OpenMM-style fixed-point force buffer (value = (long long)(f * 2^32), component-planar;
+ * platforms/cuda/src/kernels/gridForce.cu:487-499) to doubles [n][3] on the device (stream-ordered). */
 GFB_API int gfb_forces_fixed_to_f64(gfb_device* dev, const void* d_fixed, long long force_stride, long long n,
                                     double* d_out, void* stream);
 
@@ -379,19 +388,22 @@ GFB_API int gfb_comm_all_gather(gfb_comm* c, const double* d_send, double* d_rec
 GFB_API int gfb_comm_gather_alloc(gfb_comm* c, size_t count_total, unsigned char handle_out[GFB_IPC_HANDLE_BYTES]);
 GFB_API int gfb_comm_gather_attach(gfb_comm* c, const unsigned char* handles /* [world_size][GFB_IPC_HANDLE_BYTES], rank order */);
 /* As gfb_kernel_execute_device (no per-grid energies, no evaluation order) + the fused gather of d_energies
- * (n_replicas * n_slots doubles) into every rank's gathered array at element gather_offset. */
+ * (n_replicas * n_slots doubles) into every rank's gathered array at element gather_offset. No reference counterpart: the
+ * reference evaluates replicas one Context after the other on one device (example/sampler.py:153-164). */
 GFB_API int gfb_kernel_execute_device_gather(gfb_kernel* k, int n_replicas, int n_particles, const double* d_pos,
                                              double* d_energies, void* d_forces, int force_mode, long long force_stride,
                                              double* d_energies_clear, gfb_comm* c, size_t gather_offset, void* stream);
 /* The producer side as a kernel of its own: copies `count` doubles from d_energies into every rank's gathered array at
  * gather_offset and raises the arrival flags, stream-ordered after whatever produced d_energies. Same protocol as the
- * fused tail (one more small launch, nothing added to the evaluation kernel); pair it with gfb_comm_gather_wait. */
+ * fused tail (one more small launch, nothing added to the evaluation kernel); pair it with gfb_comm_gather_wait. No reference
+ * counterpart (the gather of SURVEY.md 8(e); the reference collects energies in a Python list, example/sampler.py:153-164). */
 GFB_API int gfb_comm_gather_push(gfb_comm* c, const double* d_energies, size_t count, size_t gather_offset, void* stream);
 /* The whole gather as ONE kernel, flag-in-data: every double travels to every rank as a 16-byte packet that carries the
  * gather's sequence number in both 8-byte halves, so the data is its own arrival flag — no fence, no flag round, no
  * second launch (NCCL's LL protocol, over this library's peer mappings). The kernel stores this rank's `count` values into
  * every rank's packet array at gather_offset, then polls this rank's packet array until all count_total values of this
- * gather have arrived and writes them to d_out. Every rank calls it once per gather, in the same order; capturable. */
+ * gather have arrived and writes them to d_out. Every rank calls it once per gather, in the same order; capturable.
+ * No reference counterpart (the "final gather of per-replica energies" of BASELINE.json's north_star). */
 GFB_API int gfb_comm_gather(gfb_comm* c, const double* d_energies, size_t count, size_t gather_offset, double* d_out, void* stream);
 /* Waits (on `stream`, device side) until every rank's slice of the oldest gather not yet consumed has arrived, then
  * copies the complete [count_total] array into d_out (device memory of the caller). Gather sequence numbers live on the
@@ -410,8 +422,9 @@ GFB_API int gfb_comm_gather_status(gfb_comm* c);   /* GFB_OK, or GFB_ERR_CUDA af
 GFB_API int gfb_comm_rendezvous(gfb_comm* c, int hold, void* stream);
 GFB_API int gfb_comm_rendezvous_release(gfb_comm* c);
 
-/* One process, n_devices GPUs. add_grid uploads and repacks the grid on every device; build creates one evaluation
- * state per device (arguments as gfb_kernel_create, identity particles).
+/* One process, n_devices GPUs: what replaces the sequential loop over replica Contexts of the reference's sampler
+ * (example/sampler.py:130-164). add_grid uploads and repacks the grid on every device; build creates one
+ * evaluation state per device (arguments as gfb_kernel_create, identity particles).
  *   gfb_multi_execute_host   pos host [n_replicas][n_atoms][3] -> energies host [n_replicas], forces host (layout of
  *                            force_mode, STORE modes; NULL = energy only). Replicas are block-partitioned over the
  *                            devices; one host thread per device drives that device's gfb_kernel_execute_host on its
@@ -440,7 +453,7 @@ GFB_API int gfb_multi_download(gfb_multi* m, int from_device, double* energies, 
 GFB_API unsigned long long gfb_launch_count(void);
 
 /* Microbenchmark used for the roofline denominator: random 32-byte-sector gather over `bytes` of device
- * memory (n_loads loads per launch, `reps` launches, CUDA-event timed). Returns GB/s through *gbs. */
+ * memory (n_loads loads per launch, `reps` launches, CUDA-event timed). Returns GB/s through *gbs. No reference counterpart. */
 GFB_API int gfb_bench_sector_gather(gfb_device* dev, size_t bytes, long long n_loads, int reps, double* gbs);
 /* Pinned-host <-> device copy bandwidth of this process on this GPU's link: gbs[0] H2D alone, gbs[1] D2H alone, gbs[2]
  * both directions at once (sum). bench.py prints it beside the end-to-end figure (every rank measures at the same time,
