@@ -252,6 +252,7 @@ int gfb_kernel_destroy(gfb_kernel* k) {
     k->d_pos.release();
     k->d_forces.release();
     k->d_energy.release();
+    k->d_small_e.release();
     k->d_cls.release();
     k->d_sort.release();
     k->d_atom_e.release();
@@ -550,12 +551,31 @@ static int execute_host_small(gfb_kernel* k, int n_replicas, int n_particles, co
     static const bool host_atomics_off = env_off("GFB_SMALL_HOST_ATOMICS");
     const bool host_acc = !one_block && !host_atomics_off && e_count <= 16;
     double* d_e = nullptr;
+    double* d_clear = nullptr;     // the accumulator of the NEXT call, zero-filled by this launch (saves a memset per call)
     if (host_acc) {
         memset(h_e, 0, e_count * sizeof(double));
     } else if (!one_block) {
-        if ((rc = k->d_energy.ensure(e_count * sizeof(double))) != GFB_OK) return rc;
-        d_e = static_cast<double*>(k->d_energy.ptr);
-        CUDA_TRY(cudaMemsetAsync(d_e, 0, e_count * sizeof(double), dev->stream));
+        // Two accumulator arrays take turns. Without per-grid energies only the R totals are used, and the launch that
+        // accumulates into one array clears the other's totals (EvalParams::energies_clear), so a steady sequence of such
+        // calls needs no memset; anything else (first call, more replicas than last time, per-grid energies) memsets.
+        if ((rc = k->d_small_e.ensure(2 * e_count * sizeof(double))) != GFB_OK) return rc;
+        double* base = static_cast<double*>(k->d_small_e.ptr);
+        if (k->small_stride != e_count || k->small_base != base) {      // the arrays moved or changed size: nothing is known to be zero
+            k->small_base = base;
+            k->small_stride = e_count;
+            k->small_zeroed = 0;
+            k->small_toggle = 0;
+        }
+        d_e = base + (size_t) k->small_toggle * e_count;
+        const size_t need = grid_energies ? e_count : R;
+        if (grid_energies || k->small_zeroed < need) CUDA_TRY(cudaMemsetAsync(d_e, 0, need * sizeof(double), dev->stream));
+        if (!grid_energies) {
+            d_clear = base + (size_t) (k->small_toggle ^ 1) * e_count;
+            k->small_zeroed = R;               // after this launch the other array's first R entries are zero
+        } else {
+            k->small_zeroed = 0;
+        }
+        k->small_toggle ^= 1;
     }
     // cudaHostAlloc memory is mapped into the device's address space at the same address (unified addressing)
     double* e_dst = (one_block || host_acc) ? h_e : d_e;
@@ -563,9 +583,12 @@ static int execute_host_small(gfb_kernel* k, int n_replicas, int n_particles, co
     x.energy_store = one_block;
     x.atom_energies = ae_count ? h_e + e_count : nullptr;
     rc = enqueue_eval(k, n_replicas, n_particles, h_pos, e_dst, grid_energies ? e_dst + R : nullptr, forces ? h_f : nullptr,
-                      f32 ? GFB_FORCE_F32_STORE : GFB_FORCE_F64_STORE, 0, nullptr, nullptr, dev->stream, x);
-    if (rc != GFB_OK) return rc;
-    if (d_e) CUDA_TRY(cudaMemcpyAsync(h_e, d_e, e_count * sizeof(double), cudaMemcpyDeviceToHost, dev->stream));
+                      f32 ? GFB_FORCE_F32_STORE : GFB_FORCE_F64_STORE, 0, nullptr, d_clear, dev->stream, x);
+    if (rc != GFB_OK) {
+        k->small_zeroed = 0;
+        return rc;
+    }
+    if (d_e) CUDA_TRY(cudaMemcpyAsync(h_e, d_e, (grid_energies ? e_count : R) * sizeof(double), cudaMemcpyDeviceToHost, dev->stream));
     CUDA_TRY(cudaStreamSynchronize(dev->stream));
     if (energies) memcpy(energies, h_e, R * sizeof(double));
     if (grid_energies) memcpy(grid_energies, h_e + R, R * ng * sizeof(double));

@@ -113,6 +113,12 @@ struct gfb_kernel {
     bool unique_particles;   // no particle index occurs twice: a plain store per evaluated particle is the whole force
     bool want_atom_energies; // gfb_kernel_request_atom_energies
     long long atom_e_count;  // entries of d_atom_e written by the last host-path call
+    // execute_host_small's two alternating device accumulator arrays (d_small_e): entries per array, which one is next,
+    // and how many leading entries of the next one are known to be zero
+    gfb::DeviceBuffer d_small_e;
+    double* small_base = nullptr;
+    size_t small_stride = 0, small_zeroed = 0;
+    int small_toggle = 0;
     void* resident = nullptr;   // gfb::ResidentState (gf_resident.cu) once gfb_kernel_set_resident(enable) has been called
 };
 

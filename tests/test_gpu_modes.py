@@ -419,6 +419,23 @@ def test_small_batches_on_host_mapped_memory(gpu_device, oracle_built, n_replica
     assert np.abs(acc - (1.0 + f_ref)).max() <= tf * np.abs(f_ref).max()
     e0, none, _ = k.execute_host(pos, want_forces=False)
     assert none is None and (np.abs(e0 - ge_ref.sum(axis=1)) <= te * scale).all()
+    # a run of calls without per-grid energies on moving poses (the two device accumulator arrays take turns and each
+    # launch clears the other's totals), with a per-grid call and a smaller batch in between
+    for step in range(6):
+        p2 = pos + rng.uniform(-0.05, 0.05, size=3)
+        g2, f2 = port.execute_batched(p2)
+        s2 = np.maximum(np.abs(g2.sum(axis=1)), np.abs(g2).max(axis=1))
+        if step == 3:
+            en, f, ge = k.execute_host(p2, want_grid_energies=True)
+            assert (np.abs(ge - g2) <= te * s2[:, None]).all()
+        elif step == 4 and n_replicas > 2:
+            en, f, _ = k.execute_host(p2[:-1])
+            assert (np.abs(en - g2.sum(axis=1)[:-1]) <= te * s2[:-1]).all()
+            continue
+        else:
+            en, f, _ = k.execute_host(p2)
+        assert (np.abs(en - g2.sum(axis=1)) <= te * s2).all(), step
+        assert np.abs(f - f2).max() <= tf * np.abs(f2).max()
     k.close()
     for g in grids:
         g.close()
