@@ -230,6 +230,45 @@ def test_inv_power_transform_matches_reference(oracle_built):
             assert mode == 2 and np.array_equal(ref, oracle_built.port_inv_power_transform(v, n))
 
 
+def test_tricubic_known_answers(oracle_built):
+    """Interpolation method 2 (:796-893) on fields whose answer can be written down, which also records what this branch
+    of the reference is and is not: a constant field is reproduced exactly with zero force; a linear field
+    V = 2x + 4y + 6z + 1 is reproduced in VALUE at cell midpoints and its x-force everywhere in the interior, but the
+    y- and z-differences of the branch (one-sided, against neighbour rows interpolated with the value basis only,
+    :849-867) are not derivative estimates of the field: at a midpoint the y- and z-forces come out at HALF the field's
+    gradient, and off the midpoints the value itself is off. The restatement is bit-exact with the reference build on
+    random inputs (test_port_tricubic_matches_reference_build_random); this test pins the same behaviour by hand."""
+    counts, sp = (9, 9, 9), (0.1, 0.1, 0.1)
+    i, j, k = np.meshgrid(*(np.arange(n) * 0.1 for n in counts), indexing="ij")
+    rng = np.random.default_rng(3)
+    pos = rng.uniform(0.0, 0.8, size=(60, 3)) * (1 - 1e-9)
+    pos[:, 0] *= 0.875                                              # not the last x layer (its ix+2 neighbours are past the vector)
+    sc = rng.uniform(0.5, 1.5, size=(1, 60))
+    const = oracle_built.PortOracle(counts, sp, (0.0, 0.0, 0.0), [np.full(counts, 3.25)], sc, interpolation_method=2)
+    e, f, _ = const.execute(pos, 0)
+    assert abs(e - 3.25 * sc.sum()) <= 1e-12 * abs(e) and np.abs(f).max() <= 1e-9
+    grid = 2 * i + 4 * j + 6 * k + 1
+    cells = rng.integers(1, 7, size=(40, 3))                        # interior cells 1..6
+    mid = (cells + 0.5) * 0.1
+    one = np.ones((1, 40))
+    lin = oracle_built.PortOracle(counts, sp, (0.0, 0.0, 0.0), [grid], one, interpolation_method=2)
+    f_all = np.zeros((40, 3))
+    for a in range(40):                                              # per-atom energies: one atom at a time
+        pa = np.zeros((40, 3)) - 1.0                                 # the others outside (restraint, not interpolation)
+        pa[a] = mid[a]
+        ea, fa, _ = lin.execute(pa, 0)
+        outside = 39 * 3 * 0.5 * 10000.0 * 1.0                       # 39 atoms at (-1,-1,-1): k/2 * dev^2 per axis
+        v = 2 * mid[a, 0] + 4 * mid[a, 1] + 6 * mid[a, 2] + 1
+        assert abs((ea - outside) - v) <= 1e-9, a
+        f_all[a] = fa[a]
+    assert np.abs(f_all - np.array([-2.0, -2.0, -3.0])).max() <= 1e-9
+    off = np.array([[0.33, 0.41, 0.27]])
+    one1 = oracle_built.PortOracle(counts, sp, (0.0, 0.0, 0.0), [grid], np.ones((1, 1)), interpolation_method=2)
+    e_off, f_off, _ = one1.execute(off, 0)
+    assert abs(f_off[0, 0] + 2.0) <= 1e-9                            # x: centred differences + cubic Hermite, exact
+    assert abs(e_off - 4.92) > 1e-3                                  # the value is NOT the field's off the midpoints
+
+
 def test_reference_method3_matrix_is_truncated():
     """Why interpolation method 3 (triquintic Hermite, ReferenceGridForceKernels.cpp:895-1015) is refused instead of
     reproduced: the 216 x 216 coefficient matrix the reference multiplies the 216 corner derivatives with
